@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (REPO, os.path.join(REPO, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import grasptrajopt_b200  # noqa: E402
+
+grasptrajopt_b200.install_compat()
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+ASSETS = os.path.join(REPO, "grasptrajopt_b200", "assets")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def assets_dir():
+    return ASSETS
