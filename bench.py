@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- trajectories/sec of the batched grasp-trajectory solver (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic problems: all problems of the batch are solved
+to convergence (LM iterations of the fused linearise kernel + the block-tridiagonal step kernel).
+N=1 workload: BASELINE config C2 (Panda tabletop, 256 candidate grasps x 30 knots, 2000 surface points, 128^3 SDF).
+N>1 (launched by torchrun, one rank per GPU): every rank solves its own C2-sized shard (weak scaling; problems are
+independent, no collective inside the solve) and the converged trajectories are exchanged with ONE NCCL all-gather.
+
+`value`  = converged trajectories / device time of the solves, inputs already resident in HBM (CUDA events on the
+           library's stream, max over ranks).
+`e2e`    = the same through the public C-ABI call gto_solve_batch with pinned HOST buffers: H2D of the per-problem
+           inputs, solve, D2H of Q/dQ/cost inside the timed region (wall clock between device synchronisations).
+`--impl reference` times the CPU oracle port of the same path on the host cores (the reference's CasADi/IPOPT path
+cannot be installed offline -- see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "trajectories/sec (batched grasp NLPs to convergence)"
+UNIT = "trajectories/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=str, default="C2")
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the batch (debug only; makes the number invalid)")
+    ap.add_argument("--cpu-sample", type=int, default=-1, help="problems in the cpu_baseline sample (-1: auto, 0: skip)")
+    ap.add_argument("--no-jrows", action="store_true", help="secondary mode: do not materialise Jacobian rows")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(w, prof, n_fields_per_launch=2):
+    """Jacobian rows + residual written once (exact count from the device), both fields read once
+    per launch, trajectory read + step written per problem-iteration."""
+    t = w.table
+    field_bytes = sum(int(np.prod(w.fields[s].cost.shape)) * 4 for s in sorted(w.fields)[:n_fields_per_launch])
+    units = prof["problem_iterations"]
+    return prof["jrow_bytes"] + prof["linearize_launches_with_work"] * field_bytes + units * 8 * t.nopt * w.batch.T
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_oracle_sample(w, idx):
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import gto_oracle as O
+    from helpers import problems_from_workload
+
+    out = []
+    for p in problems_from_workload(w, idx):
+        r = O.solve_lm(p)
+        out.append((r.status, r.iters, r.cost))
+    return out
+
+
+def _cpu_worker(args):
+    config, scale, idx = args
+    from grasptrajopt_b200 import workloads as W
+
+    w = W.make_workload(config, scale=scale)
+    return cpu_oracle_sample(w, idx)
+
+
+def time_cpu(config, scale, nsample, B, nproc):
+    """Oracle port on `nproc` host processes over a bounded sample of the same workload."""
+    import multiprocessing as mp
+
+    idx = list(np.linspace(0, B - 1, nsample).astype(int))
+    chunks = [idx[i::nproc] for i in range(nproc) if idx[i::nproc]]
+    t0 = time.perf_counter()
+    if len(chunks) == 1:
+        res = [_cpu_worker((config, scale, chunks[0]))]
+    else:
+        with mp.get_context("spawn").Pool(len(chunks)) as pool:
+            res = pool.map(_cpu_worker, [(config, scale, c) for c in chunks])
+    dt = time.perf_counter() - t0
+    flat = [r for c in res for r in c]
+    conv = sum(1 for r in flat if r[0] == 0)
+    return dt, conv, len(flat), len(chunks)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path.  CasADi/IPOPT are not installable offline, so this is the oracle port
+    (same reduced problem, projected LM, float64 NumPy) on all host cores; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from grasptrajopt_b200 import workloads as W
+
+    ncpu = os.cpu_count() or 1
+    w = W.make_workload(args.config, scale=args.scale)
+    B = w.batch.B
+    nsample = max(1, min(B, ncpu))
+    for _ in range(max(0, min(args.warmup, 1))):
+        time_cpu(args.config, args.scale, nsample, B, min(ncpu, nsample))
+    tot_t, tot_conv = 0.0, 0
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        dt, conv, n, nproc = time_cpu(args.config, args.scale, nsample, B, min(ncpu, nsample))
+        tot_t += dt
+        tot_conv += conv
+    value = tot_conv / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": w.description, "config": args.config},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(ncpu, nsample), "kind": "port",
+                         "sample": f"{nsample} of {B} problems per step, oracle/gto_oracle.py solve_lm, one process per core (wall clock incl. workload regeneration per process)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference CasADi/IPOPT path not installable offline; published wall-clock is ~0.1 trajectories/s (BASELINE.md)",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from grasptrajopt_b200 import capi, workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    # weak scaling: every rank owns a C2-sized shard generated from its own seed stream
+    idx = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[args.config.upper()]
+    scale = args.scale / world if args.config.upper() == "C5" else args.scale  # C5 is the fixed-size (strong) sweep
+    w = W.make_workload(args.config, scale=scale, seed=idx + 1000 * rank if world > 1 else None)
+    b = w.batch
+    if args.no_jrows:
+        b.flags |= capi.FLAG_NO_JROWS
+    B = b.B
+    ctx = capi.GtoContext(local)
+    ctx.set_robot(w.table)
+    for slot, cf in w.fields.items():
+        ctx.set_field(slot, cf.cost, cf.origin, cf.pitch)
+    opts = capi.default_options()
+
+    # pinned host staging for the end-to-end arm
+    def pin(a):
+        tns = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return tns.numpy(), tns
+
+    keep = []
+    for name in ("qc", "q_seed", "goal_tf", "base_position"):
+        arr, tns = pin(getattr(b, name))
+        setattr(b, name, arr)
+        keep.append(tns)
+
+    nfl = w.table.nopt * b.T + 2
+    gathered = torch.empty((world * B, nfl), dtype=torch.float32, device=f"cuda:{local}") if world > 1 else None
+
+    class _DevArr:  # wrap the library's device buffer for torch.distributed without a copy
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    def exchange():
+        if world > 1:
+            ptr, n = ctx.result_device_ptr()
+            local_res = torch.as_tensor(_DevArr(ptr, (B, n)), device=f"cuda:{local}")
+            dist.all_gather_into_tensor(gathered, local_res)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    ctx.upload_batch(b)
+    for _ in range(args.warmup):
+        ctx.solve_resident(opts)
+        exchange()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_ms, lin_ms, step_ms, launches, conv = 0.0, 0.0, 0.0, 0, 0
+    prof_acc = {"jrow_bytes": 0, "problem_iterations": 0, "linearize_launches_with_work": 0, "linearize_launches": 0}
+    t0 = time.perf_counter()
+    xch_ms = 0.0
+    for _ in range(args.steps):
+        ctx.solve_resident(opts)
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            exchange()
+            e1.record()
+            e1.synchronize()
+            xch_ms += e0.elapsed_time(e1)
+        p = ctx.profile()
+        dev_ms += p["solve_ms"]
+        lin_ms += p["linearize_ms"]
+        step_ms += p["step_ms"]
+        launches += p["linearize_launches"] + p["step_launches"] + 2
+        for k in prof_acc:
+            prof_acc[k] += p[k]
+    sync_all()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    res = ctx.download_batch()
+    conv = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
+    iters_hist = np.bincount(res["iters"], minlength=1).tolist()
+    step_dev_ms = dev_ms + xch_ms  # device time of this rank: solves (library events) + all-gather (torch events)
+
+    # ---- e2e: public API with host buffers ----
+    for _ in range(min(args.warmup, 2)):
+        ctx.solve_batch(b, opts)
+    sync_all()
+    t1 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        r2 = ctx.solve_batch(b, opts)
+        exchange()
+        p = ctx.profile()
+        h2d, d2h = p["h2d_bytes"], p["d2h_bytes"]
+    sync_all()
+    e2e_ms = 1e3 * (time.perf_counter() - t1)
+    clocks = sampler.stop()
+    conv2 = int(np.sum(r2["status"] == capi.STATUS_CONVERGED))
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([step_dev_ms, e2e_ms, float(conv), float(conv2), wall_ms], dtype=torch.float64, device=f"cuda:{local}")
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        step_dev_ms, e2e_ms, wall_ms = float(mx[0]), float(mx[1]), float(mx[4])
+        conv_tot, conv2_tot = int(sm[2]), int(sm[3])
+    else:
+        conv_tot, conv2_tot = conv, conv2
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg = algorithmic_bytes(w, prof_acc)
+        achieved = alg / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0
+        value = conv_tot * args.steps / (step_dev_ms * 1e-3)
+        e2e_value = conv2_tot * args.steps / (e2e_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config.upper() == "C5" else "weak",
+            "vs_baseline": None, "dtype": "f32 (point kernel; TF32 tensor-core J^T J) + f64 (trajectory, step solve)", "data": "synthetic",
+            "config": {"workload": w.description, "config": args.config.upper(), "problems_per_gpu": B, "knots": b.T, "surface_points": w.table.npoints,
+                       "field": list(next(iter(w.fields.values())).cost.shape), "materialize_jacobian_rows": not args.no_jrows,
+                       "l2": "working set per iteration (Jacobian rows, >=0.4 GB) exceeds the 126 MB L2; no explicit flush",
+                       "convergence": f"|dq|inf<={opts.tol_step:g} or |proj grad|inf<={opts.tol_grad:g}, max_iter={opts.max_iter}",
+                       "converged": conv_tot, "problems": B * world, "iterations_histogram": iters_hist, "wall_ms_per_step": wall_ms / args.steps,
+                       "scale": args.scale},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "timing": "wall clock between device synchronisations around gto_solve_batch with pinned host buffers"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": alg / args.steps, "kernel_ms_per_step": lin_ms / args.steps,
+                         "kernel_share_of_step": lin_ms / dev_ms if dev_ms else None, "step_kernel_ms_per_step": step_ms / args.steps,
+                         "launches_per_step": prof_acc["linearize_launches"] / args.steps},
+            "clocks": clocks,
+        }
+        # CPU baseline on rank 0 at N=1 only: bounded sample of the same workload
+        if world == 1 and args.cpu_sample != 0:
+            ns = args.cpu_sample if args.cpu_sample > 0 else 2
+            dt, cconv, n, nproc = time_cpu(args.config, scale, ns, B, 1)
+            line["cpu_baseline"] = {"value": cconv / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{ns} of {B} problems of the same workload, oracle/gto_oracle.py solve_lm (float64 NumPy), 1 process"}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,1698 @@
+// gto_b200.cu -- CUDA kernels (sm_100a) + C-ABI of libgto_b200.so.  See include/gto_b200.h.
+//
+// Hot path of IRVLUTD/GraspTrajOpt re-designed for B200 (reference citations are file:line in the reference tree):
+//   k_linearize   ONE fused kernel per Gauss-Newton iteration: chain FK of every link (optas/models.py:826-868,
+//                 gto/gto_models.py:83-101) -> world points (gto/gto_planner.py:111-128) -> trilinear SDF value + gradient
+//                 from a shared-memory brick staged by TMA (replaces the nearest-node gather gto/gto_models.py:174-187 and
+//                 gto/sdf_callback.py) -> obstacle / goal / stand-off residuals (gto_planner.py:86-131) -> chained analytic
+//                 Jacobian rows (geometric Jacobian, optas/models.py:1203-1268) -> coalesced fp32 row stores to HBM ->
+//                 per-knot Gauss-Newton blocks: J^T J on the tensor cores (mma.sync m16n8k8 TF32; an 8x8..16x16 output cannot
+//                 fill a tcgen05 M=64 tile), J^T r and the cost in fp32 with warp-shuffle reduction.
+//   k_step        per problem: step acceptance (Levenberg-Marquardt, Nielsen damping), projected bound handling
+//                 (optas/builder.py:472-510), block-tridiagonal factor/solve in fp64 (the velocity term gto_planner.py:134-135
+//                 couples neighbouring knots), next trial point.  Replaces IPOPT (optas/solver.py:384-400).
+//   k_init / k_finalize   constraint elimination (gto_planner.py:59-72) and result unpacking (optas/solver.py:126-159).
+// There is no CPU fallback: every entry point fails with GTO_ERR_NO_DEVICE without a CUDA device.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/gto_b200.h"
+
+#define NCLASS 3
+#define BRICK_MAX 24
+// SDF brick edge per class (one TMA tensor map per field and class: the box size is baked into the descriptor)
+__host__ __device__ __forceinline__ int kBrickClassDev(int k) { return k == 0 ? 8 : (k == 1 ? 16 : 24); }
+#define MAX_FIELDS 4096
+#define MAX_CHUNKS 1024
+#define LIN_MAX_WARPS 8
+
+// ------------------------------------------------------------------------------------------------------------------
+// device-side tables
+// ------------------------------------------------------------------------------------------------------------------
+struct RobotDev {
+  int ndof, nopt, nmov, nlinks, npoints;
+  int opt_qidx[GTO_MAX_OPT];
+  int opt_mov[GTO_MAX_OPT];
+  int mov_parent[GTO_MAX_MOV], mov_type[GTO_MAX_MOV], mov_qidx[GTO_MAX_MOV], mov_opt[GTO_MAX_MOV];
+  float mov_origin[GTO_MAX_MOV][12];
+  float mov_axis[GTO_MAX_MOV][4];
+  int link_mov[GTO_MAX_LINKS];
+  float link_tf[GTO_MAX_LINKS][12];
+  int link_pt_start[GTO_MAX_LINKS], link_pt_count[GTO_MAX_LINKS];
+  unsigned link_optmask[GTO_MAX_LINKS];
+  float link_center[GTO_MAX_LINKS][4];  // AABB of the link's points in its visual frame
+  float link_half[GTO_MAX_LINKS][4];
+  int link_chunk0[GTO_MAX_LINKS + 1];   // chunk range per link
+  int grip_mov;
+  float grip_tf[12];
+  int grip_pt_start, grip_pt_count;
+  unsigned grip_optmask;
+  int nchunks;
+  double lo[GTO_MAX_OPT], hi[GTO_MAX_OPT];
+};
+
+struct FieldDev {
+  const float* data;  // [nx][ny][nzp]
+  int nx, ny, nz, nzp;
+  float ox, oy, oz, inv_pitch;
+  int has_tma;
+};
+
+struct LinParams {
+  const RobotDev* robot;
+  const int* chunk_start;  // [nchunks] first point of each 32-point chunk
+  const int* chunk_count;  // [nchunks]
+  const float* px;
+  const float* py;
+  const float* pz;
+  const float* q;          // [B][T][ndof] configuration at which to linearise
+  const float* goal_tf;    // [B][2][12]
+  const float* base;       // [B][4]
+  const int* field_ids;    // [B][2]
+  const FieldDev* fields;
+  const CUtensorMap* tmaps;  // [MAX_FIELDS][NCLASS]
+  const int* active;       // problem ids (NULL: identity)
+  const int* nactive;      // device counter (NULL: use nproblems)
+  int nproblems;
+  int b0;                  // first problem of the chunk (rows buffer is indexed by b - b0)
+  const int* bufsel;       // [B] accepted buffer per problem; output goes to the other one (NULL: buffer 0)
+  float* H;                // [2][Bcap][T][nopt*nopt]
+  float* g;                // [2][Bcap][T][nopt]
+  float* costp;            // [2][Bcap][T]
+  long long buf_stride_H, buf_stride_g, buf_stride_c;
+  float* rows;             // [Bchunk][nrows][RS] or NULL
+  long long rows_per_problem;
+  int T, t_lo, knot_standoff, use_standoff, collision;
+  float sw_obs, sw_goal;
+  unsigned flags;
+  int brick_max;           // largest brick edge that fits the shared memory carve-out
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA (cp.async.bulk.tensor) + TF32 MMA
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();  // a lost transaction must abort the launch, never hang the device
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// shared-memory carve-up of k_linearize
+// ------------------------------------------------------------------------------------------------------------------
+struct LinShared {
+  float frames[GTO_MAX_LINKS][12];   // visual frame of each collision link (robot base frame)
+  float Tm[GTO_MAX_MOV][12];         // movable joint frames
+  float A[GTO_MAX_MOV][12];          // origin * motion of each movable joint
+  float tw[GTO_MAX_OPT][8];          // (omega.xyz, -, m.xyz, -) per optimised joint
+  float gripf[12];
+  float goal[2][12];
+  float basep[4];
+  int brick_lo[GTO_MAX_LINKS][3];
+  int brick_cls[GTO_MAX_LINKS];      // class index, -1: no brick
+  float red[LIN_MAX_WARPS][GTO_MAX_OPT * GTO_MAX_OPT + GTO_MAX_OPT + 2];
+  unsigned long long mbar;
+};
+
+// Trilinear value + analytic gradient.  The brick is a cube of edge `bB` whose lower corner is
+// grid index (bl[0], bl[1], bl[2]); lookups whose 8 corners are not all inside it go to global memory.
+__device__ __forceinline__ void sdf_trilinear(const FieldDev& f, const float* __restrict__ brick, int bB, const int* bl, float wx,
+                                              float wy, float wz, float& val, float& gx, float& gy, float& gz) {
+  float ux = (wx - f.ox) * f.inv_pitch, uy = (wy - f.oy) * f.inv_pitch, uz = (wz - f.oz) * f.inv_pitch;
+  int ix = min(max((int)floorf(ux), 0), f.nx - 2);
+  int iy = min(max((int)floorf(uy), 0), f.ny - 2);
+  int iz = min(max((int)floorf(uz), 0), f.nz - 2);
+  float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
+  const bool inx = (fx >= 0.f) && (fx <= 1.f), iny = (fy >= 0.f) && (fy <= 1.f), inz = (fz >= 0.f) && (fz <= 1.f);
+  fx = fminf(fmaxf(fx, 0.f), 1.f);
+  fy = fminf(fmaxf(fy, 0.f), 1.f);
+  fz = fminf(fmaxf(fz, 0.f), 1.f);
+  float c000, c001, c010, c011, c100, c101, c110, c111;
+  int lx = ix - bl[0], ly = iy - bl[1], lz = iz - bl[2];
+  if (bB > 0 && lx >= 0 && ly >= 0 && lz >= 0 && lx <= bB - 2 && ly <= bB - 2 && lz <= bB - 2) {
+    const float* p = brick + (lx * bB + ly) * bB + lz;
+    const int sy = bB, sx = bB * bB;
+    c000 = p[0]; c001 = p[1]; c010 = p[sy]; c011 = p[sy + 1];
+    c100 = p[sx]; c101 = p[sx + 1]; c110 = p[sx + sy]; c111 = p[sx + sy + 1];
+  } else {
+    const float* p = f.data + ((long long)ix * f.ny + iy) * f.nzp + iz;
+    const long long sy = f.nzp, sx = (long long)f.ny * f.nzp;
+    c000 = __ldg(p); c001 = __ldg(p + 1); c010 = __ldg(p + sy); c011 = __ldg(p + sy + 1);
+    c100 = __ldg(p + sx); c101 = __ldg(p + sx + 1); c110 = __ldg(p + sx + sy); c111 = __ldg(p + sx + sy + 1);
+  }
+  // interpolate along z, then y, then x (same association order as the oracle)
+  const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+  const float z00 = fmaf(fz, d00, c000), z01 = fmaf(fz, d01, c010), z10 = fmaf(fz, d10, c100), z11 = fmaf(fz, d11, c110);
+  const float y0 = fmaf(fy, z01 - z00, z00), y1 = fmaf(fy, z11 - z10, z10);
+  val = fmaf(fx, y1 - y0, y0);
+  const float dy0 = z01 - z00, dy1 = z11 - z10;
+  const float dz0 = fmaf(fy, d01 - d00, d00), dz1 = fmaf(fy, d11 - d10, d10);
+  gx = inx ? (y1 - y0) * f.inv_pitch : 0.f;
+  gy = iny ? fmaf(fx, dy1 - dy0, dy0) * f.inv_pitch : 0.f;
+  gz = inz ? fmaf(fx, dz1 - dz0, dz0) * f.inv_pitch : 0.f;
+}
+
+// 3x4 product C = A * B (both [R|t] row-major, implicit last row 0 0 0 1)
+__device__ __forceinline__ void mul34(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float s = A[r * 4 + 0] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c];
+      if (c == 3) s += A[r * 4 + 3];
+      C[r * 4 + c] = s;
+    }
+  }
+}
+
+// Warp-level: add this chunk's rows (staged in shared memory as [32][RS]) into the tensor-core accumulators.
+// A[m][k] = J[point k][col m], B[k][n] = J[point k][col n]  =>  D = J^T J.  NP = 8: one 16x8 tile (rows 8..15 unused);
+// NP = 16: two n-tiles.
+template <int NP>
+__device__ __forceinline__ void mma_rows(const float* st, int RS, int nrows32, float (&acc0)[4], float (&acc1)[4], int lane) {
+  const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    if (ks * 8 >= nrows32) break;
+    const float* r0 = st + (ks * 8 + tq) * RS;
+    const float* r1 = r0 + 4 * RS;
+    const uint32_t a0 = f2tf32(r0[gq]), a2 = f2tf32(r1[gq]);
+    if (NP == 8) {
+      mma_tf32_16x8x8(acc0, a0, 0u, a2, 0u, a0, a2);
+    } else {
+      const uint32_t a1 = f2tf32(r0[gq + 8]), a3 = f2tf32(r1[gq + 8]);
+      mma_tf32_16x8x8(acc0, a0, a1, a2, a3, a0, a2);
+      mma_tf32_16x8x8(acc1, a0, a1, a2, a3, a1, a3);
+    }
+  }
+}
+
+// Warp-level: copy `nfl` floats of staged rows to global memory with coalesced stores (128-bit when aligned).
+__device__ __forceinline__ void store_rows(float* __restrict__ dst, const float* st, int nfl, int lane) {
+  if ((((uintptr_t)dst & 15) == 0) && ((nfl & 3) == 0)) {
+    const float4* s4 = reinterpret_cast<const float4*>(st);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < (nfl >> 2); i += 32) __stcs(d4 + i, s4[i]);
+  } else {
+    for (int i = lane; i < nfl; i += 32) __stcs(dst + i, st[i]);
+  }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __grid_constant__ LinParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  LinShared& S = *reinterpret_cast<LinShared*>(smem_raw);
+  const RobotDev& R = *p.robot;
+  const int nopt = R.nopt, RS = nopt + 1;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // carve: [LinShared | brick (128B aligned) | staging per warp]
+  size_t off = (sizeof(LinShared) + 127) & ~(size_t)127;
+  float* brick = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)p.brick_max * p.brick_max * p.brick_max * sizeof(float);
+  off = (off + 127) & ~(size_t)127;
+  const int st_floats = ((32 * RS + 16 + 31) / 32) * 32;
+  float* stage = reinterpret_cast<float*>(smem_raw + off) + warp * st_floats;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(&S.mbar);
+
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t mbar_phase = 0;
+
+  const int nknots = p.T - p.t_lo;
+  const int nprob = p.nactive ? *p.nactive : p.nproblems;
+  const long long nitems = (long long)nprob * nknots;
+  const bool use_brick = !(p.flags & GTO_FLAG_NO_BRICK);
+  const bool use_tma = use_brick && !(p.flags & GTO_FLAG_NO_TMA);
+  const int gq = lane >> 2, tq = lane & 3;
+
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int a = (int)(item / nknots);
+    const int t = p.t_lo + (int)(item - (long long)a * nknots);
+    const int b = p.active ? p.active[a] : a;
+    const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
+    const float* q = p.q + ((long long)b * p.T + t) * R.ndof;
+    const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
+    const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
+
+    __syncthreads();  // previous item fully consumed (frames, reduction scratch)
+
+    // ---------------- forward kinematics by warp 0 ----------------
+    if (warp == 0) {
+      if (lane < R.nmov) {  // A_j = origin_j * motion_j(q_j)
+        const float qj = q[R.mov_qidx[lane]];
+        const float ax = R.mov_axis[lane][0], ay = R.mov_axis[lane][1], az = R.mov_axis[lane][2];
+        float M[12];
+        if (R.mov_type[lane] == GTO_JOINT_REVOLUTE) {  // Rodrigues: I + s K + (1-c) K^2
+          float s, c;
+          sincosf(qj, &s, &c);
+          const float v = 1.f - c;
+          M[0] = 1.f - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.f;
+          M[4] = s * az + v * ax * ay;          M[5] = 1.f - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.f;
+          M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.f - v * (ax * ax + ay * ay); M[11] = 0.f;
+        } else {
+          M[0] = 1.f; M[1] = 0.f; M[2] = 0.f; M[3] = qj * ax;
+          M[4] = 0.f; M[5] = 1.f; M[6] = 0.f; M[7] = qj * ay;
+          M[8] = 0.f; M[9] = 0.f; M[10] = 1.f; M[11] = qj * az;
+        }
+        float C[12];
+        mul34(R.mov_origin[lane], M, C);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) S.A[lane][e] = C[e];
+      }
+      __syncwarp();
+      for (int j = 0; j < R.nmov; ++j) {  // sequential along the tree, 12 lanes per product
+        if (lane < 12) {
+          const int r = lane >> 2, c = lane & 3;
+          const int pj = R.mov_parent[j];
+          float s;
+          if (pj < 0) {
+            s = S.A[j][lane];
+          } else {
+            const float* P = S.Tm[pj];
+            s = P[r * 4 + 0] * S.A[j][c] + P[r * 4 + 1] * S.A[j][4 + c] + P[r * 4 + 2] * S.A[j][8 + c];
+            if (c == 3) s += P[r * 4 + 3];
+          }
+          S.Tm[j][lane] = s;
+        }
+        __syncwarp();
+      }
+      if (lane < R.nlinks) {  // visual frames + brick placement
+        const int mj = R.link_mov[lane];
+        float F[12];
+        if (mj < 0) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) F[e] = R.link_tf[lane][e];
+        } else {
+          mul34(S.Tm[mj], R.link_tf[lane], F);
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) S.frames[lane][e] = F[e];
+        int cls = -1;
+        if (fid >= 0 && use_brick) {
+          const FieldDev& f = p.fields[fid];
+          const float* cc = R.link_center[lane];
+          const float* hh = R.link_half[lane];
+          const float bp[3] = {p.base[4 * b + 0], p.base[4 * b + 1], p.base[4 * b + 2]};
+          const float org[3] = {f.ox, f.oy, f.oz};
+          int need = 0, lo3[3];
+#pragma unroll
+          for (int ax3 = 0; ax3 < 3; ++ax3) {
+            const float cw = F[ax3 * 4 + 0] * cc[0] + F[ax3 * 4 + 1] * cc[1] + F[ax3 * 4 + 2] * cc[2] + F[ax3 * 4 + 3] + bp[ax3];
+            const float hw = fabsf(F[ax3 * 4 + 0]) * hh[0] + fabsf(F[ax3 * 4 + 1]) * hh[1] + fabsf(F[ax3 * 4 + 2]) * hh[2] + 1e-4f;
+            const int lo = (int)floorf((cw - hw - org[ax3]) * f.inv_pitch);
+            const int hi = (int)floorf((cw + hw - org[ax3]) * f.inv_pitch);
+            lo3[ax3] = lo;
+            need = max(need, hi - lo + 2);
+          }
+          cls = NCLASS - 1;
+#pragma unroll
+          for (int k = NCLASS - 1; k >= 0; --k)
+            if (kBrickClassDev(k) >= need) cls = k;
+          while (cls > 0 && kBrickClassDev(cls) > p.brick_max) --cls;
+          const int Bc = kBrickClassDev(cls);
+          if (Bc > p.brick_max) cls = -1;
+          if (cls >= 0 && need > Bc) {  // partial coverage: centre the brick, the rest reads global memory
+#pragma unroll
+            for (int ax3 = 0; ax3 < 3; ++ax3) lo3[ax3] += (need - Bc) / 2;
+          }
+          S.brick_lo[lane][0] = lo3[0]; S.brick_lo[lane][1] = lo3[1]; S.brick_lo[lane][2] = lo3[2];
+        }
+        S.brick_cls[lane] = cls;
+      }
+      if (lane < nopt) {  // joint twists: v(W) = omega x W + m
+        const int j = R.opt_mov[lane];
+        float om[3] = {0.f, 0.f, 0.f}, mm[3] = {0.f, 0.f, 0.f};
+        if (j >= 0) {
+          const float* Tj = S.Tm[j];
+          const float ax = R.mov_axis[j][0], ay = R.mov_axis[j][1], az = R.mov_axis[j][2];
+          const float zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
+          const float zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
+          const float zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
+          if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
+            const float ox = Tj[3], oy = Tj[7], oz = Tj[11];
+            om[0] = zx; om[1] = zy; om[2] = zz;
+            mm[0] = oy * zz - oz * zy; mm[1] = oz * zx - ox * zz; mm[2] = ox * zy - oy * zx;  // o x z
+          } else {
+            mm[0] = zx; mm[1] = zy; mm[2] = zz;
+          }
+        }
+        S.tw[lane][0] = om[0]; S.tw[lane][1] = om[1]; S.tw[lane][2] = om[2]; S.tw[lane][3] = 0.f;
+        S.tw[lane][4] = mm[0]; S.tw[lane][5] = mm[1]; S.tw[lane][6] = mm[2]; S.tw[lane][7] = 0.f;
+      }
+      if (lane == 31) {
+        float F[12];
+        if (R.grip_mov < 0) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) F[e] = R.grip_tf[e];
+        } else {
+          mul34(S.Tm[R.grip_mov], R.grip_tf, F);
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) S.gripf[e] = F[e];
+      }
+      if (lane < 24) S.goal[lane / 12][lane % 12] = p.goal_tf[(long long)b * 24 + lane];
+      if (lane >= 24 && lane < 27) S.basep[lane - 24] = p.base[4 * b + (lane - 24)];
+    }
+    __syncthreads();
+
+    // ---------------- per-thread accumulators for this (problem, knot) ----------------
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    float gacc[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) gacc[k] = 0.f;
+    float cacc = 0.f;
+    float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
+
+    // ---------------- obstacle rows, link by link ----------------
+    if (p.collision) {
+      const float bx = S.basep[0], by = S.basep[1], bz = S.basep[2];
+      for (int l = 0; l < R.nlinks; ++l) {
+        const int cls = (fid >= 0) ? S.brick_cls[l] : -1;
+        const int bB = (cls >= 0) ? kBrickClassDev(cls) : 0;
+        if (fid >= 0 && cls >= 0) {
+          __syncthreads();  // everyone is done with the previous brick
+          if (use_tma && p.fields[fid].has_tma) {
+            if (threadIdx.x == 0) {
+              mbar_expect_tx(mbar, (uint32_t)(bB * bB * bB * sizeof(float)));
+              tma_load_3d(brick, p.tmaps + (long long)fid * NCLASS + cls, S.brick_lo[l][2], S.brick_lo[l][1], S.brick_lo[l][0], mbar);
+            }
+            mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1;
+          } else {
+            const FieldDev& f = p.fields[fid];
+            const int n3 = bB * bB * bB;
+            for (int i = threadIdx.x; i < n3; i += blockDim.x) {
+              const int lz = i % bB, ly = (i / bB) % bB, lx = i / (bB * bB);
+              const int gx_ = S.brick_lo[l][0] + lx, gy_ = S.brick_lo[l][1] + ly, gz_ = S.brick_lo[l][2] + lz;
+              float v = 0.f;
+              if (gx_ >= 0 && gy_ >= 0 && gz_ >= 0 && gx_ < f.nx && gy_ < f.ny && gz_ < f.nz)
+                v = __ldg(f.data + ((long long)gx_ * f.ny + gy_) * f.nzp + gz_);
+              brick[i] = v;
+            }
+            __syncthreads();
+          }
+        }
+        const unsigned mask = R.link_optmask[l];
+        const float* F = S.frames[l];
+        for (int ch = R.link_chunk0[l] + warp; ch < R.link_chunk0[l + 1]; ch += nwarps) {
+          const int p0 = p.chunk_start[ch], cnt = p.chunk_count[ch];
+          const bool act = lane < cnt;
+          float J[NP];
+#pragma unroll
+          for (int k = 0; k < NP; ++k) J[k] = 0.f;
+          float r = 0.f;
+          if (act && fid >= 0) {
+            const float x = __ldg(p.px + p0 + lane), y = __ldg(p.py + p0 + lane), z = __ldg(p.pz + p0 + lane);
+            const float wbx = F[0] * x + F[1] * y + F[2] * z + F[3];
+            const float wby = F[4] * x + F[5] * y + F[6] * z + F[7];
+            const float wbz = F[8] * x + F[9] * y + F[10] * z + F[11];
+            float val, gx, gy, gz;
+            sdf_trilinear(p.fields[fid], brick, bB, S.brick_lo[l], wbx + bx, wby + by, wbz + bz, val, gx, gy, gz);
+            r = p.sw_obs * val;
+            gx *= p.sw_obs; gy *= p.sw_obs; gz *= p.sw_obs;
+            // row_k = grad . (omega_k x W + m_k) = omega_k . (W x grad) + m_k . grad
+            const float nx = wby * gz - wbz * gy, ny = wbz * gx - wbx * gz, nz = wbx * gy - wby * gx;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              if (k < nopt && ((mask >> k) & 1u)) {
+                const float4 o4 = *reinterpret_cast<const float4*>(&S.tw[k][0]);
+                const float4 m4 = *reinterpret_cast<const float4*>(&S.tw[k][4]);
+                J[k] = o4.x * nx + o4.y * ny + o4.z * nz + m4.x * gx + m4.y * gy + m4.z * gz;
+              }
+            }
+          }
+          cacc = fmaf(r, r, cacc);
+#pragma unroll
+          for (int k = 0; k < NP; ++k) {
+            if (k < nopt) {
+              gacc[k] = fmaf(J[k], r, gacc[k]);
+              stage[lane * RS + k] = J[k];
+            }
+          }
+          stage[lane * RS + nopt] = r;
+          __syncwarp();
+          mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
+          if (rows_b) store_rows(rows_b + ((long long)t * R.npoints + p0) * RS, stage, cnt * RS, lane);
+          __syncwarp();
+        }
+      }
+    }
+
+    // ---------------- goal / stand-off rows (gripper point set, plain link frame, no base offset) ----------------
+    if (is_goal || is_stand) {
+      const int Pg = R.grip_pt_count;
+      const long long obs_rows = p.collision ? (long long)p.T * R.npoints : 0;
+      const float* Fg = S.gripf;
+      const unsigned mask = R.grip_optmask;
+      for (int which = 0; which < 2; ++which) {
+        if (which == 0 && !is_goal) continue;
+        if (which == 1 && !is_stand) continue;
+        const float* M = S.goal[which];
+        const long long rbase = obs_rows + (which == 1 ? 3LL * Pg : 0);
+        const int nch = (Pg + 31) / 32;
+        for (int ch = warp; ch < nch; ch += nwarps) {
+          const int k0 = ch * 32, cnt = min(32, Pg - k0);
+          const bool act = lane < cnt;
+          float w3[3] = {0.f, 0.f, 0.f}, r3[3] = {0.f, 0.f, 0.f};
+          if (act) {
+            const int pi = R.grip_pt_start + k0 + lane;
+            const float x = __ldg(p.px + pi), y = __ldg(p.py + pi), z = __ldg(p.pz + pi);
+#pragma unroll
+            for (int a3 = 0; a3 < 3; ++a3) {
+              w3[a3] = Fg[a3 * 4 + 0] * x + Fg[a3 * 4 + 1] * y + Fg[a3 * 4 + 2] * z + Fg[a3 * 4 + 3];
+              const float tg = M[a3 * 4 + 0] * x + M[a3 * 4 + 1] * y + M[a3 * 4 + 2] * z + M[a3 * 4 + 3];
+              r3[a3] = p.sw_goal * (w3[a3] - tg);
+            }
+          }
+#pragma unroll
+          for (int a3 = 0; a3 < 3; ++a3) {  // rows ordered [axis][point]: each pass writes 32 contiguous rows
+            float J[NP];
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              J[k] = 0.f;
+              if (act && k < nopt && ((mask >> k) & 1u)) {
+                const float4 o4 = *reinterpret_cast<const float4*>(&S.tw[k][0]);
+                const float4 m4 = *reinterpret_cast<const float4*>(&S.tw[k][4]);
+                float v;  // (omega x W + m)[a3]
+                if (a3 == 0) v = o4.y * w3[2] - o4.z * w3[1] + m4.x;
+                else if (a3 == 1) v = o4.z * w3[0] - o4.x * w3[2] + m4.y;
+                else v = o4.x * w3[1] - o4.y * w3[0] + m4.z;
+                J[k] = p.sw_goal * v;
+              }
+            }
+            const float r = r3[a3];
+            cacc = fmaf(r, r, cacc);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              if (k < nopt) {
+                gacc[k] = fmaf(J[k], r, gacc[k]);
+                stage[lane * RS + k] = J[k];
+              }
+            }
+            stage[lane * RS + nopt] = r;
+            __syncwarp();
+            mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
+            if (rows_b) store_rows(rows_b + (rbase + (long long)a3 * Pg + k0) * RS, stage, cnt * RS, lane);
+            __syncwarp();
+          }
+        }
+      }
+    }
+
+    // ---------------- reduce over lanes / warps, write the per-knot Gauss-Newton block ----------------
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cacc += __shfl_xor_sync(0xffffffffu, cacc, o);
+    {
+      float* red = S.red[warp];
+      // accumulator fragment layout: acc[0]:(row gq, col 2tq) acc[1]:(gq, 2tq+1) acc[2]:(gq+8, 2tq) acc[3]:(gq+8, 2tq+1)
+      const int c0 = 2 * tq;
+      if (gq < nopt) {
+        if (c0 < nopt) red[gq * nopt + c0] = acc0[0];
+        if (c0 + 1 < nopt) red[gq * nopt + c0 + 1] = acc0[1];
+      }
+      if (NP == 16) {
+        if (gq + 8 < nopt) {
+          if (c0 < nopt) red[(gq + 8) * nopt + c0] = acc0[2];
+          if (c0 + 1 < nopt) red[(gq + 8) * nopt + c0 + 1] = acc0[3];
+        }
+        if (gq < nopt) {
+          if (c0 + 8 < nopt) red[gq * nopt + c0 + 8] = acc1[0];
+          if (c0 + 9 < nopt) red[gq * nopt + c0 + 9] = acc1[1];
+        }
+        if (gq + 8 < nopt) {
+          if (c0 + 8 < nopt) red[(gq + 8) * nopt + c0 + 8] = acc1[2];
+          if (c0 + 9 < nopt) red[(gq + 8) * nopt + c0 + 9] = acc1[3];
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          if (k < nopt) red[nopt * nopt + k] = gacc[k];
+        red[nopt * nopt + nopt] = cacc;
+      }
+    }
+    __syncthreads();
+    {
+      const int nH = nopt * nopt, ntot = nH + nopt + 1;
+      for (int i = threadIdx.x; i < ntot; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarps; ++w) s += S.red[w][i];
+        const long long bt = (long long)b * p.T + t;
+        if (i < nH) p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
+        else if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
+        else p.costp[obuf * p.buf_stride_c + bt] = s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_init: eliminate the equality constraints (gto/gto_planner.py:59-72): optimised rows of knots 0,1 = qc; clip the seed
+// to the position limits (:138); parameter-joint entries are kept from the seed (optas/solver.py:126-159).
+// ------------------------------------------------------------------------------------------------------------------
+struct StateParams {
+  const RobotDev* robot;
+  int B, T;
+  double dt, w_vel;
+  const double* qc;      // [B][ndof]
+  const double* q_seed;  // [B][T][ndof]
+  double* Qc;            // [B][T][nopt] accepted point
+  double* Qt;            // [B][T][nopt] trial point
+  float* q_trial;        // [B][T][ndof] what k_linearize reads
+  int* bufsel;
+  double *F, *Fp, *lam, *nu, *pred, *stepn;
+  int *iters, *status;
+  double lambda0;
+  int project;
+  // finalize
+  double* outQ;
+  double* outdQ;
+  double* outcost;
+  float* result;  // [B][nopt*T+2]
+};
+
+__global__ void k_init(const StateParams p) {
+  const RobotDev& R = *p.robot;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.B * p.T) return;
+  const int b = (int)(i / p.T), t = (int)(i % p.T);
+  const double* s = p.q_seed + i * R.ndof;
+  float* qt = p.q_trial + i * R.ndof;
+  for (int j = 0; j < R.ndof; ++j) qt[j] = (float)s[j];
+  if (!p.project) return;
+  for (int k = 0; k < R.nopt; ++k) {
+    const int j = R.opt_qidx[k];
+    double v = fmin(fmax(s[j], R.lo[k]), R.hi[k]);
+    if (t < 2) v = p.qc[(long long)b * R.ndof + j];
+    p.Qc[i * R.nopt + k] = v;
+    p.Qt[i * R.nopt + k] = v;
+    qt[j] = (float)v;
+  }
+  if (t == 0) {
+    p.bufsel[b] = 0;
+    p.F[b] = 0.0; p.Fp[b] = 0.0; p.lam[b] = p.lambda0; p.nu[b] = 2.0; p.pred[b] = 0.0; p.stepn[b] = 0.0;
+    p.iters[b] = 0; p.status[b] = -1;
+  }
+}
+
+__global__ void k_finalize(const StateParams p) {
+  const RobotDev& R = *p.robot;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.B * p.T) return;
+  const int b = (int)(i / p.T), t = (int)(i % p.T);
+  const int n = R.nopt;
+  const double* s = p.q_seed + i * R.ndof;
+  double* Q = p.outQ + i * R.ndof;
+  for (int j = 0; j < R.ndof; ++j) Q[j] = s[j];
+  for (int k = 0; k < n; ++k) {
+    const double v = p.Qc[i * n + k];
+    Q[R.opt_qidx[k]] = v;
+    p.result[(long long)b * (n * p.T + 2) + t * n + k] = (float)v;
+  }
+  if (t < p.T - 1) {
+    double* dQ = p.outdQ + ((long long)b * (p.T - 1) + t) * R.ndof;
+    for (int j = 0; j < R.ndof; ++j) dQ[j] = 0.0;
+    for (int k = 0; k < n; ++k) dQ[R.opt_qidx[k]] = (p.Qc[(i + 1) * n + k] - p.Qc[i * n + k]) / p.dt;
+  }
+  if (t == 0) {
+    p.outcost[b] = p.F[b];
+    p.result[(long long)b * (n * p.T + 2) + n * p.T] = (float)p.F[b];
+    p.result[(long long)b * (n * p.T + 2) + n * p.T + 1] = (float)p.status[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_step: one warp per active problem.  Mirrors oracle/gto_oracle.py solve_lm / lm_step (float64).
+// ------------------------------------------------------------------------------------------------------------------
+struct StepParams {
+  const RobotDev* robot;
+  int T;
+  double dt, w_vel;
+  int max_iter;
+  double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps;
+  double* Qc;
+  double* Qt;
+  float* q_trial;
+  const float* H;
+  const float* g;
+  const float* costp;
+  long long buf_stride_H, buf_stride_g, buf_stride_c;
+  int* bufsel;
+  double *F, *Fp, *lam, *nu, *pred, *stepn;
+  int *iters, *status;
+  const int* active_in;
+  const int* nactive_in;
+  int* active_out;
+  int* nactive_out;
+  double* Sinv;          // [B][m][n*n]
+  double* vv;            // [B][m][n]
+  double* gt;            // [B][m][n]
+  double* dd;            // [B][m][n]
+  unsigned char* fixed;  // [B][m][n]
+  int iter;              // number of LM steps already taken by the problems in the active list
+};
+
+#define STEP_WARPS 4
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
+  __shared__ double sS[STEP_WARPS][2][GTO_MAX_OPT * GTO_MAX_OPT];
+  __shared__ double sU[STEP_WARPS][GTO_MAX_OPT];
+  __shared__ double sV[STEP_WARPS][GTO_MAX_OPT];
+  const RobotDev& R = *p.robot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_idx = blockIdx.x * STEP_WARPS + warp;
+  if (a_idx >= *p.nactive_in) return;
+  const int b = p.active_in[a_idx];
+  const int n = R.nopt, T = p.T, m = T - 2, nn = n * n;
+  const double a2 = p.w_vel / (p.dt * p.dt);
+  double* Xc = p.Qc + (long long)b * T * n;
+  double* Xt = p.Qt + (long long)b * T * n;
+  int cur = p.bufsel[b];
+  const int it = p.iter;
+  double lam = p.lam[b], nu = p.nu[b];
+
+  // ---------------- evaluate the trial point produced by the previous call ----------------
+  {
+    const int tri = 1 - cur;
+    const float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
+    double s = 0.0;
+    for (int t = lane; t < T; t += 32) s += (double)ct[t];
+    const double Fp_t = warp_sum(s);
+    s = 0.0;
+    for (int i = lane; i < (T - 1) * n; i += 32) {
+      const double d = Xt[i + n] - Xt[i];
+      s += d * d;
+    }
+    const double Ft = Fp_t + a2 * warp_sum(s);
+    int done = -1;  // -1: keep running, otherwise final status
+    if (!isfinite(Ft)) {
+      done = GTO_STATUS_NAN;
+    } else if (it == 0) {  // initial point: accept unconditionally
+      cur = tri;
+      if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
+    } else {
+      const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
+      const double ared = 0.5 * (Fcur - Ft);
+      const double noise = p.noise_rel * fmax(Fpcur, Fp_t);
+      if (pred > 0.0 && ared + noise >= p.eta * pred) {
+        const double rho = ared / pred;
+        for (int i = lane; i < T * n; i += 32) Xc[i] = Xt[i];
+        cur = tri;
+        if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
+        const double w = 2.0 * fmin(rho, 1.0) - 1.0;
+        lam = fmax(p.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - w * w * w));
+        nu = 2.0;
+        if (step <= p.tol_step) done = GTO_STATUS_CONVERGED;
+      } else {
+        if (pred <= 0.0 && step <= p.tol_step) {
+          done = GTO_STATUS_CONVERGED;
+        } else {
+          lam = fmin(p.lambda_max, lam * nu);
+          nu *= 2.0;
+          if (lam >= p.lambda_max) done = GTO_STATUS_STALLED;
+        }
+      }
+    }
+    if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
+    if (done >= 0) {
+      if (lane == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
+      return;
+    }
+  }
+  __syncwarp();
+
+  // ---------------- next damped projected Gauss-Newton step from the accepted point ----------------
+  const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn;
+  const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
+  double* gt = p.gt + (long long)b * m * n;
+  double* dd = p.dd + (long long)b * m * n;
+  double* vv = p.vv + (long long)b * m * n;
+  double* Sg = p.Sinv + (long long)b * m * nn;
+  unsigned char* fx = p.fixed + (long long)b * m * n;
+
+  double pgmax = 0.0;
+  for (int idx = lane; idx < m * n; idx += 32) {
+    const int i = idx / n, k = idx - i * n, t = i + 2;
+    double gv = Xc[t * n + k] - Xc[(t - 1) * n + k];
+    if (t < T - 1) gv -= Xc[(t + 1) * n + k] - Xc[t * n + k];
+    const double gtv = (double)gc[t * n + k] + a2 * gv;
+    const double x = Xc[t * n + k];
+    const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
+    gt[idx] = gtv;
+    fx[idx] = fixed ? 1 : 0;
+    if (!fixed) pgmax = fmax(pgmax, fabs(gtv));
+  }
+  pgmax = warp_max(pgmax);
+  if (2.0 * pgmax <= p.tol_grad) {
+    if (lane == 0) { p.status[b] = GTO_STATUS_CONVERGED; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
+    return;
+  }
+  __syncwarp();
+
+  double* U = sU[warp];
+  double* V = sV[warp];
+  bool ok = false;
+  for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
+    ok = true;
+    // forward sweep (block Thomas): S_i = D_i - C_i Sinv_{i-1} C_i ; u_i = b_i - C_i v_{i-1} ; v_i = Sinv_i u_i
+    for (int i = 0; i < m && ok; ++i) {
+      const int t = i + 2;
+      const double cnt = (t < T - 1) ? 2.0 : 1.0;
+      double* Sc = sS[warp][i & 1];
+      const double* Sp = sS[warp][(i + 1) & 1];
+      for (int e = lane; e < nn; e += 32) {
+        const int r = e / n, c = e - r * n;
+        const bool fr = fx[i * n + r], fc = fx[i * n + c];
+        double v = (double)Hc[t * nn + e];
+        if (r == c) {
+          v += a2 * cnt;
+          v += lam * v;
+        }
+        if (fr || fc) v = (r == c) ? 1.0 : 0.0;
+        if (i > 0) {
+          const double cr = (fr || fx[(i - 1) * n + r]) ? 0.0 : a2;
+          const double cc = (fc || fx[(i - 1) * n + c]) ? 0.0 : a2;
+          v -= cr * cc * Sp[e];
+        }
+        Sc[e] = v;
+      }
+      if (lane < n) {
+        const bool fr = fx[i * n + lane];
+        double u = fr ? 0.0 : -gt[i * n + lane];
+        if (i > 0) {
+          const double cr = (fr || fx[(i - 1) * n + lane]) ? 0.0 : a2;
+          u += cr * V[lane];
+        }
+        U[lane] = u;
+      }
+      __syncwarp();
+      // in-place Gauss-Jordan inverse of the SPD block
+      for (int k = 0; k < n; ++k) {
+        const double piv = Sc[k * n + k];
+        if (!(piv > 0.0)) { ok = false; break; }
+        const double ip = 1.0 / piv;
+        double nv[(GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32];
+        int cntv = 0;
+        for (int e = lane; e < nn; e += 32, ++cntv) {
+          const int r = e / n, c = e - r * n;
+          double v;
+          if (r == k && c == k) v = ip;
+          else if (r == k) v = Sc[e] * ip;
+          else if (c == k) v = -Sc[e] * ip;
+          else v = Sc[e] - Sc[r * n + k] * Sc[k * n + c] * ip;
+          nv[cntv] = v;
+        }
+        __syncwarp();
+        cntv = 0;
+        for (int e = lane; e < nn; e += 32, ++cntv) Sc[e] = nv[cntv];
+        __syncwarp();
+      }
+      if (!ok) break;
+      for (int e = lane; e < nn; e += 32) Sg[i * nn + e] = Sc[e];
+      double v = 0.0;
+      if (lane < n) {
+        for (int c = 0; c < n; ++c) v += Sc[lane * n + c] * U[c];
+        vv[i * n + lane] = v;
+      }
+      __syncwarp();
+      if (lane < n) V[lane] = v;
+      __syncwarp();
+    }
+    if (!ok) {
+      lam = fmin(p.lambda_max, lam * 10.0);  // not positive definite: add damping and refactor
+      __syncwarp();
+    }
+  }
+  if (!ok) {
+    if (lane == 0) { p.status[b] = GTO_STATUS_NAN; p.iters[b] = it; }
+    return;
+  }
+  // backward sweep: x_i = v_i + Sinv_i (c_{i+1} o x_{i+1}); trial point = clip(X + x)
+  double stepmax = 0.0, gdot = 0.0;
+  for (int i = m - 1; i >= 0; --i) {
+    const int t = i + 2;
+    double x = 0.0;
+    if (lane < n) {
+      x = vv[i * n + lane];
+      if (i < m - 1) {
+        double s = 0.0;
+        for (int c = 0; c < n; ++c) {
+          const double cc = (fx[i * n + c] || fx[(i + 1) * n + c]) ? 0.0 : a2;
+          s += Sg[i * nn + lane * n + c] * cc * U[c];
+        }
+        x += s;
+      }
+    }
+    __syncwarp();
+    if (lane < n) {
+      U[lane] = x;  // unclipped solution feeds the recursion
+      const double xc = Xc[t * n + lane];
+      const double xn = fmin(fmax(xc + x, R.lo[lane]), R.hi[lane]);
+      const double d = xn - xc;
+      Xt[t * n + lane] = xn;
+      p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[lane]] = (float)xn;
+      dd[i * n + lane] = d;
+      stepmax = fmax(stepmax, fabs(d));
+      gdot += gt[i * n + lane] * d;
+    }
+    __syncwarp();
+  }
+  stepmax = warp_max(stepmax);
+  gdot = warp_sum(gdot);
+  // predicted reduction with the undamped, unmasked model: -(g.d + 0.5 d^T A d)
+  double quad = 0.0;
+  for (int idx = lane; idx < m * nn; idx += 32) {
+    const int i = idx / nn, e = idx - i * nn, r = e / n, c = e - r * n, t = i + 2;
+    double h = (double)Hc[t * nn + e];
+    if (r == c) h += a2 * ((t < T - 1) ? 2.0 : 1.0);
+    quad += h * dd[i * n + r] * dd[i * n + c];
+  }
+  for (int idx = lane; idx < (m - 1) * n; idx += 32) quad -= 2.0 * a2 * dd[idx] * dd[idx + n];
+  quad = warp_sum(quad);
+  if (lane == 0) {
+    p.pred[b] = -(gdot + 0.5 * quad);
+    p.stepn[b] = stepmax;
+    p.lam[b] = lam;
+    p.nu[b] = nu;
+    p.iters[b] = it + 1;
+    const int slot = atomicAdd(p.nactive_out, 1);
+    p.active_out[slot] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_plan_cost: nearest-node cost of whole plans (seed ranking, gto/gto_models.py:204-215; clip-then-truncate indexing of
+// points_to_offsets_numpy :190-201).  One block per (plan, knot).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_plan_cost(const RobotDev* robot, const float* px, const float* py, const float* pz, const float* q, int T,
+                            FieldDev f, float bx, float by, float bz, double* cost) {
+  __shared__ float Tm[GTO_MAX_MOV][12];
+  __shared__ float frames[GTO_MAX_LINKS][12];
+  __shared__ double part[32];
+  const RobotDev& R = *robot;
+  const int n = blockIdx.x / T, t = blockIdx.x % T;
+  const float* qq = q + ((long long)n * T + t) * R.ndof;
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < R.nmov; ++j) {
+      const float qj = qq[R.mov_qidx[j]];
+      const float ax = R.mov_axis[j][0], ay = R.mov_axis[j][1], az = R.mov_axis[j][2];
+      float M[12], A[12];
+      if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
+        float s, c;
+        sincosf(qj, &s, &c);
+        const float v = 1.f - c;
+        M[0] = 1.f - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay; M[2] = s * ay + v * ax * az; M[3] = 0.f;
+        M[4] = s * az + v * ax * ay; M[5] = 1.f - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az; M[7] = 0.f;
+        M[8] = -s * ay + v * ax * az; M[9] = s * ax + v * ay * az; M[10] = 1.f - v * (ax * ax + ay * ay); M[11] = 0.f;
+      } else {
+        M[0] = 1.f; M[1] = 0.f; M[2] = 0.f; M[3] = qj * ax;
+        M[4] = 0.f; M[5] = 1.f; M[6] = 0.f; M[7] = qj * ay;
+        M[8] = 0.f; M[9] = 0.f; M[10] = 1.f; M[11] = qj * az;
+      }
+      mul34(R.mov_origin[j], M, A);
+      if (R.mov_parent[j] < 0) {
+        for (int e = 0; e < 12; ++e) Tm[j][e] = A[e];
+      } else {
+        float C[12];
+        mul34(Tm[R.mov_parent[j]], A, C);
+        for (int e = 0; e < 12; ++e) Tm[j][e] = C[e];
+      }
+    }
+    for (int l = 0; l < R.nlinks; ++l) {
+      if (R.link_mov[l] < 0) {
+        for (int e = 0; e < 12; ++e) frames[l][e] = R.link_tf[l][e];
+      } else {
+        float C[12];
+        mul34(Tm[R.link_mov[l]], R.link_tf[l], C);
+        for (int e = 0; e < 12; ++e) frames[l][e] = C[e];
+      }
+    }
+  }
+  __syncthreads();
+  double s = 0.0;
+  for (int l = 0; l < R.nlinks; ++l) {
+    const float* F = frames[l];
+    for (int i = threadIdx.x; i < R.link_pt_count[l]; i += blockDim.x) {
+      const int pi = R.link_pt_start[l] + i;
+      const float x = px[pi], y = py[pi], z = pz[pi];
+      const float wx = F[0] * x + F[1] * y + F[2] * z + F[3] + bx;
+      const float wy = F[4] * x + F[5] * y + F[6] * z + F[7] + by;
+      const float wz = F[8] * x + F[9] * y + F[10] * z + F[11] + bz;
+      const int ix = (int)fminf(fmaxf((wx - f.ox) * f.inv_pitch, 0.f), (float)(f.nx - 1));
+      const int iy = (int)fminf(fmaxf((wy - f.oy) * f.inv_pitch, 0.f), (float)(f.ny - 1));
+      const int iz = (int)fminf(fmaxf((wz - f.oz) * f.inv_pitch, 0.f), (float)(f.nz - 1));
+      s += (double)f.data[((long long)ix * f.ny + iy) * f.nzp + iz];
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+    atomicAdd(cost + n, tot);
+  }
+}
+
+// ==================================================================================================================
+// host side: context + C-ABI
+// ==================================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct FieldHost {
+  float* data = nullptr;
+  int nx = 0, ny = 0, nz = 0, nzp = 0;
+  double origin[3] = {0, 0, 0};
+  double pitch = 0;
+  bool set = false;
+};
+
+struct gto_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  PFN_encodeTiled encode = nullptr;
+  // robot
+  bool has_robot = false;
+  RobotDev robot_h;
+  RobotDev* robot_d = nullptr;
+  DevBuf<float> px, py, pz;
+  DevBuf<int> chunk_start, chunk_count;
+  int lin_warps = 8;
+  double max_link_diag = 0.0;  // largest |half extent|_2 over links
+  // fields
+  std::vector<FieldHost> fields;
+  FieldDev* fields_d = nullptr;
+  CUtensorMap* tmaps_d = nullptr;
+  double min_pitch = 0.0;
+  // batch (resident)
+  bool has_batch = false;
+  bool solved = false;
+  int B = 0, T = 0;
+  double dt = 0, w_goal = 1, w_obs = 10, w_vel = 0.01;
+  int standoff_offset = -10, use_standoff = 1, collision = 1;
+  unsigned flags = 0;
+  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, vv, gt, dd, outQ, outdQ, outcost;
+  DevBuf<float> q_trial, goal_tf, base, H, g, costp, rows, result;
+  DevBuf<int> field_ids, bufsel, iters, status, active, nactive;
+  DevBuf<unsigned char> fixedm;
+  int* h_counter = nullptr;  // pinned
+  long long rows_per_problem = 0;
+  int Bchunk = 0;
+  // profiling
+  gto_profile prof;
+  std::vector<cudaEvent_t> ev;
+};
+
+static int fail(gto_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int gto_abi_version(void) { return GTO_ABI_VERSION; }
+
+extern "C" void gto_default_options(gto_options* o) {
+  if (!o) return;
+  o->max_iter = 100;
+  o->tol_step = 1e-6;
+  o->tol_grad = 1e-6;
+  o->lambda0 = 1e-3;
+  o->lambda_min = 1e-9;
+  o->lambda_max = 1e9;
+  o->eta = 1e-4;
+  o->noise_rel = 1e-6;
+  o->bound_eps = 1e-12;
+  o->check_every = 4;
+}
+
+extern "C" const char* gto_last_error(gto_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int gto_create(gto_ctx** out, int device) {
+  if (!out) return GTO_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return GTO_ERR_NO_DEVICE;  // no CPU fallback, by design
+  if (device < 0 || device >= ndev) return GTO_ERR_INVALID;
+  gto_ctx* ctx = new gto_ctx();
+  ctx->device = device;
+  memset(&ctx->prof, 0, sizeof(ctx->prof));
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return GTO_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return GTO_ERR_CUDA; }
+  if (prop.major < 10) {  // kernels are built for sm_100a only
+    delete ctx;
+    return GTO_ERR_NO_DEVICE;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GTO_ERR_CUDA; }
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+    ctx->encode = (PFN_encodeTiled)fn;
+  ctx->fields.resize(MAX_FIELDS);
+  if (cudaMalloc((void**)&ctx->robot_d, sizeof(RobotDev)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->fields_d, sizeof(FieldDev) * MAX_FIELDS) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->tmaps_d, sizeof(CUtensorMap) * MAX_FIELDS * NCLASS) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_counter, sizeof(int) * 4) != cudaSuccess) {
+    gto_destroy(ctx);
+    return GTO_ERR_NOMEM;
+  }
+  cudaMemset(ctx->fields_d, 0, sizeof(FieldDev) * MAX_FIELDS);
+  *out = ctx;
+  return GTO_OK;
+}
+
+extern "C" void gto_destroy(gto_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& f : ctx->fields)
+    if (f.data) cudaFree(f.data);
+  for (auto e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->robot_d) cudaFree(ctx->robot_d);
+  if (ctx->fields_d) cudaFree(ctx->fields_d);
+  if (ctx->tmaps_d) cudaFree(ctx->tmaps_d);
+  if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
+  ctx->px.release(); ctx->py.release(); ctx->pz.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
+  ctx->qc.release(); ctx->q_seed.release(); ctx->Qc.release(); ctx->Qt.release(); ctx->F.release(); ctx->Fp.release();
+  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release(); ctx->vv.release();
+  ctx->gt.release(); ctx->dd.release(); ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
+  ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
+  ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->fixedm.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
+  if (!ctx || !r) return GTO_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (r->nopt < 1 || r->nopt > GTO_MAX_OPT || r->nmov < 1 || r->nmov > GTO_MAX_MOV || r->nlinks < 1 || r->nlinks > GTO_MAX_LINKS ||
+      r->ndof < r->nopt || r->npoints < 1)
+    return fail(ctx, GTO_ERR_INVALID, "robot table sizes out of range");
+  RobotDev& h = ctx->robot_h;
+  memset(&h, 0, sizeof(h));
+  h.ndof = r->ndof; h.nopt = r->nopt; h.nmov = r->nmov; h.nlinks = r->nlinks; h.npoints = r->npoints;
+  for (int k = 0; k < r->nopt; ++k) {
+    if (r->opt_qidx[k] < 0 || r->opt_qidx[k] >= r->ndof) return fail(ctx, GTO_ERR_INVALID, "opt_qidx out of range");
+    h.opt_qidx[k] = r->opt_qidx[k];
+    h.opt_mov[k] = -1;
+    h.lo[k] = r->lo[k];
+    h.hi[k] = r->hi[k];
+    if (!(h.lo[k] <= h.hi[k])) return fail(ctx, GTO_ERR_INVALID, "joint limits must satisfy lo <= hi");
+  }
+  for (int j = 0; j < r->nmov; ++j) {
+    if (r->mov_parent[j] >= j) return fail(ctx, GTO_ERR_INVALID, "movable joints must be listed parents first");
+    if (r->mov_type[j] != GTO_JOINT_REVOLUTE && r->mov_type[j] != GTO_JOINT_PRISMATIC) return fail(ctx, GTO_ERR_INVALID, "unsupported joint type");
+    if (r->mov_qidx[j] < 0 || r->mov_qidx[j] >= r->ndof) return fail(ctx, GTO_ERR_INVALID, "mov_qidx out of range");
+    h.mov_parent[j] = r->mov_parent[j]; h.mov_type[j] = r->mov_type[j]; h.mov_qidx[j] = r->mov_qidx[j]; h.mov_opt[j] = r->mov_opt[j];
+    for (int e = 0; e < 12; ++e) h.mov_origin[j][e] = (float)r->mov_origin[j * 12 + e];
+    for (int e = 0; e < 3; ++e) h.mov_axis[j][e] = (float)r->mov_axis[j * 3 + e];
+    if (r->mov_opt[j] >= 0) {
+      if (r->mov_opt[j] >= r->nopt) return fail(ctx, GTO_ERR_INVALID, "mov_opt out of range");
+      h.opt_mov[r->mov_opt[j]] = j;
+    }
+  }
+  std::vector<float> hx(r->npoints), hy(r->npoints), hz(r->npoints);
+  for (int i = 0; i < r->npoints; ++i) { hx[i] = r->points[3 * i]; hy[i] = r->points[3 * i + 1]; hz[i] = r->points[3 * i + 2]; }
+  std::vector<int> cs, cc;
+  ctx->max_link_diag = 0.0;
+  int max_chunks_per_link = 1;
+  for (int l = 0; l < r->nlinks; ++l) {
+    const int s = r->link_pt_start[l], n = r->link_pt_count[l];
+    if (s < 0 || n < 0 || s + n > r->npoints || r->link_mov[l] >= r->nmov) return fail(ctx, GTO_ERR_INVALID, "link table out of range");
+    h.link_mov[l] = r->link_mov[l]; h.link_pt_start[l] = s; h.link_pt_count[l] = n; h.link_optmask[l] = r->link_optmask[l];
+    for (int e = 0; e < 12; ++e) h.link_tf[l][e] = (float)r->link_tf[l * 12 + e];
+    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = s; i < s + n; ++i) {
+      const float v[3] = {hx[i], hy[i], hz[i]};
+      for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], v[a]); mx[a] = std::max(mx[a], v[a]); }
+    }
+    double diag = 0;
+    for (int a = 0; a < 3; ++a) {
+      h.link_center[l][a] = n ? 0.5f * (mn[a] + mx[a]) : 0.f;
+      h.link_half[l][a] = n ? 0.5f * (mx[a] - mn[a]) : 0.f;
+      diag += (double)h.link_half[l][a] * h.link_half[l][a];
+    }
+    ctx->max_link_diag = std::max(ctx->max_link_diag, sqrt(diag));
+    h.link_chunk0[l] = (int)cs.size();
+    for (int o = 0; o < n; o += 32) { cs.push_back(s + o); cc.push_back(std::min(32, n - o)); }
+    max_chunks_per_link = std::max(max_chunks_per_link, (n + 31) / 32);
+  }
+  h.link_chunk0[r->nlinks] = (int)cs.size();
+  h.nchunks = (int)cs.size();
+  if (h.nchunks > MAX_CHUNKS * 64) return fail(ctx, GTO_ERR_INVALID, "too many surface points");
+  h.grip_mov = r->grip_mov; h.grip_pt_start = r->grip_pt_start; h.grip_pt_count = r->grip_pt_count; h.grip_optmask = r->grip_optmask;
+  if (r->grip_pt_start < 0 || r->grip_pt_count < 1 || r->grip_pt_start + r->grip_pt_count > r->npoints || r->grip_mov >= r->nmov)
+    return fail(ctx, GTO_ERR_INVALID, "gripper point set out of range");
+  for (int e = 0; e < 12; ++e) h.grip_tf[e] = (float)r->grip_tf[e];
+  // warps per CTA: least idle lanes when a link's chunks are dealt round-robin to the warps
+  int best = 8;
+  double best_eff = 0;
+  for (int w = 4; w <= LIN_MAX_WARPS; ++w) {
+    double used = 0, slots = 0;
+    for (int l = 0; l < r->nlinks; ++l) {
+      const int c = (r->link_pt_count[l] + 31) / 32;
+      used += c;
+      slots += (double)((c + w - 1) / w) * w;
+    }
+    const double eff = slots > 0 ? used / slots : 1;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+  }
+  ctx->lin_warps = best;
+  CK(ctx->px.ensure(r->npoints)); CK(ctx->py.ensure(r->npoints)); CK(ctx->pz.ensure(r->npoints));
+  CK(ctx->chunk_start.ensure(cs.size())); CK(ctx->chunk_count.ensure(cs.size()));
+  CK(cudaMemcpy(ctx->px.p, hx.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->py.p, hy.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->pz.p, hz.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->chunk_start.p, cs.data(), sizeof(int) * cs.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->chunk_count.p, cc.data(), sizeof(int) * cc.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->robot_d, &h, sizeof(RobotDev), cudaMemcpyHostToDevice));
+  ctx->has_robot = true;
+  ctx->has_batch = false;
+  return GTO_OK;
+}
+
+extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const int32_t dims[3], const double origin[3], double pitch) {
+  if (!ctx || !cost || !dims || !origin) return GTO_ERR_INVALID;
+  if (slot < 0 || slot >= MAX_FIELDS) return fail(ctx, GTO_ERR_INVALID, "field slot out of range");
+  if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2 || !(pitch > 0)) return fail(ctx, GTO_ERR_INVALID, "field needs >= 2 nodes per axis and pitch > 0");
+  CK(cudaSetDevice(ctx->device));
+  FieldHost& f = ctx->fields[slot];
+  const int nzp = (dims[2] + 3) & ~3;  // TMA: global strides must be multiples of 16 bytes
+  const size_t n = (size_t)dims[0] * dims[1] * nzp;
+  if (f.data && (size_t)f.nx * f.ny * f.nzp != n) { cudaFree(f.data); f.data = nullptr; }
+  if (!f.data) CK(cudaMalloc((void**)&f.data, n * sizeof(float)));
+  CK(cudaMemset(f.data, 0, n * sizeof(float)));
+  CK(cudaMemcpy2D(f.data, (size_t)nzp * sizeof(float), cost, (size_t)dims[2] * sizeof(float), (size_t)dims[2] * sizeof(float),
+                  (size_t)dims[0] * dims[1], cudaMemcpyHostToDevice));
+  f.nx = dims[0]; f.ny = dims[1]; f.nz = dims[2]; f.nzp = nzp; f.pitch = pitch; f.set = true;
+  for (int a = 0; a < 3; ++a) f.origin[a] = origin[a];
+  FieldDev d;
+  d.data = f.data; d.nx = f.nx; d.ny = f.ny; d.nz = f.nz; d.nzp = nzp;
+  d.ox = (float)origin[0]; d.oy = (float)origin[1]; d.oz = (float)origin[2]; d.inv_pitch = (float)(1.0 / pitch);
+  d.has_tma = 0;
+  if (ctx->encode) {
+    CUtensorMap maps[NCLASS];
+    bool ok = true;
+    for (int c = 0; c < NCLASS && ok; ++c) {
+      const cuuint64_t gdim[3] = {(cuuint64_t)f.nz, (cuuint64_t)f.ny, (cuuint64_t)f.nx};
+      const cuuint64_t gstr[2] = {(cuuint64_t)nzp * sizeof(float), (cuuint64_t)f.ny * nzp * sizeof(float)};
+      const cuuint32_t Bc = (cuuint32_t)kBrickClassDev(c);
+      const cuuint32_t box[3] = {Bc, Bc, Bc};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult rc = ctx->encode(&maps[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)f.data, gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ok = (rc == CUDA_SUCCESS);
+    }
+    if (ok) {
+      CK(cudaMemcpy(ctx->tmaps_d + (size_t)slot * NCLASS, maps, sizeof(maps), cudaMemcpyHostToDevice));
+      d.has_tma = 1;
+    }
+  }
+  CK(cudaMemcpy(ctx->fields_d + slot, &d, sizeof(d), cudaMemcpyHostToDevice));
+  ctx->min_pitch = 0.0;
+  for (auto& ff : ctx->fields)
+    if (ff.set) ctx->min_pitch = (ctx->min_pitch == 0.0) ? ff.pitch : std::min(ctx->min_pitch, ff.pitch);
+  return GTO_OK;
+}
+
+static long long rows_per_problem(const gto_ctx* c) {
+  const RobotDev& R = c->robot_h;
+  return (c->collision ? (long long)c->T * R.npoints : 0) + 3LL * R.grip_pt_count * (1 + (c->use_standoff ? 1 : 0));
+}
+
+static int validate_batch(gto_ctx* ctx, const gto_batch_in* in) {
+  if (!ctx->has_robot) return fail(ctx, GTO_ERR_STATE, "gto_set_robot has not been called");
+  if (!in || in->B < 1 || in->T < 3 || !(in->dt > 0) || !in->qc || !in->q_seed || !in->goal_tf)
+    return fail(ctx, GTO_ERR_INVALID, "batch needs B >= 1, T >= 3, dt > 0 and qc/q_seed/goal_tf");
+  const int ks = in->T + in->standoff_offset;
+  if (in->use_standoff && (ks < 0 || ks >= in->T)) return fail(ctx, GTO_ERR_INVALID, "stand-off knot outside the trajectory");
+  if (in->collision_avoidance) {
+    if (!in->field_all || !in->field_obs) return fail(ctx, GTO_ERR_INVALID, "collision_avoidance needs field_all/field_obs");
+    for (int b = 0; b < in->B; ++b)
+      for (int w = 0; w < 2; ++w) {
+        const int s = w ? in->field_obs[b] : in->field_all[b];
+        if (s >= MAX_FIELDS || (s >= 0 && !ctx->fields[s].set)) return fail(ctx, GTO_ERR_INVALID, "batch references a field slot that was never set");
+      }
+  }
+  return GTO_OK;
+}
+
+extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
+  if (!ctx) return GTO_ERR_INVALID;
+  int rc = validate_batch(ctx, in);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const RobotDev& R = ctx->robot_h;
+  const int B = in->B, T = in->T, n = R.nopt, nd = R.ndof, m = T - 2;
+  ctx->B = B; ctx->T = T; ctx->dt = in->dt;
+  ctx->w_goal = in->w_goal; ctx->w_obs = in->w_obs; ctx->w_vel = in->w_vel;
+  ctx->standoff_offset = in->standoff_offset; ctx->use_standoff = in->use_standoff; ctx->collision = in->collision_avoidance;
+  ctx->flags = in->flags;
+  ctx->has_batch = false;
+  ctx->solved = false;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(ctx->qc.ensure((size_t)B * nd)); CK(ctx->q_seed.ensure((size_t)B * T * nd));
+  CK(ctx->goal_tf.ensure((size_t)B * 24)); CK(ctx->base.ensure((size_t)B * 4)); CK(ctx->field_ids.ensure((size_t)B * 2));
+  CK(ctx->Qc.ensure((size_t)B * T * n)); CK(ctx->Qt.ensure((size_t)B * T * n)); CK(ctx->q_trial.ensure((size_t)B * T * nd));
+  CK(ctx->F.ensure(B)); CK(ctx->Fp.ensure(B)); CK(ctx->lam.ensure(B)); CK(ctx->nu.ensure(B)); CK(ctx->pred.ensure(B)); CK(ctx->stepn.ensure(B));
+  CK(ctx->bufsel.ensure(B)); CK(ctx->iters.ensure(B)); CK(ctx->status.ensure(B)); CK(ctx->active.ensure((size_t)2 * B));
+  CK(ctx->H.ensure((size_t)2 * B * T * n * n)); CK(ctx->g.ensure((size_t)2 * B * T * n)); CK(ctx->costp.ensure((size_t)2 * B * T));
+  CK(ctx->Sinv.ensure((size_t)B * m * n * n)); CK(ctx->vv.ensure((size_t)B * m * n)); CK(ctx->gt.ensure((size_t)B * m * n));
+  CK(ctx->dd.ensure((size_t)B * m * n)); CK(ctx->fixedm.ensure((size_t)B * m * n));
+  CK(ctx->outQ.ensure((size_t)B * T * nd)); CK(ctx->outdQ.ensure((size_t)B * (T - 1) * nd)); CK(ctx->outcost.ensure(B));
+  CK(ctx->result.ensure((size_t)B * (n * T + 2)));
+  // host-side repacking of the small per-problem inputs (float32 copies for the point kernel)
+  std::vector<float> gtf((size_t)B * 24), bs((size_t)B * 4, 0.f);
+  std::vector<int> fid((size_t)B * 2, -1);
+  for (size_t i = 0; i < gtf.size(); ++i) gtf[i] = (float)in->goal_tf[i];
+  for (int b = 0; b < B; ++b) {
+    if (in->base_position)
+      for (int a = 0; a < 3; ++a) bs[4 * b + a] = (float)in->base_position[3 * b + a];
+    if (in->collision_avoidance) { fid[2 * b] = in->field_all[b]; fid[2 * b + 1] = in->field_obs[b]; }
+  }
+  CK(cudaEventRecord(e0, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->qc.p, in->qc, sizeof(double) * B * nd, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->q_seed.p, in->q_seed, sizeof(double) * B * T * nd, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->goal_tf.p, gtf.data(), sizeof(float) * gtf.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->base.p, bs.data(), sizeof(float) * bs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->field_ids.p, fid.data(), sizeof(int) * fid.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx->prof.h2d_ms = ms;
+  ctx->prof.h2d_bytes = (long long)sizeof(double) * B * nd * (1 + T) + sizeof(float) * (gtf.size() + bs.size()) + sizeof(int) * fid.size();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->rows_per_problem = rows_per_problem(ctx);
+  ctx->has_batch = true;
+  return GTO_OK;
+}
+
+static int pick_brick_max(const gto_ctx* ctx) {
+  if (ctx->min_pitch <= 0) return kBrickClassDev(0);
+  const int need = (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 3;
+  int cls = NCLASS - 1;
+  for (int k = NCLASS - 1; k >= 0; --k)
+    if (kBrickClassDev(k) >= need) cls = k;
+  return kBrickClassDev(cls);
+}
+
+static size_t lin_smem_bytes(const gto_ctx* ctx, int brick_max, int warps) {
+  const int RS = ctx->robot_h.nopt + 1;
+  size_t off = (sizeof(LinShared) + 127) & ~(size_t)127;
+  off += (size_t)brick_max * brick_max * brick_max * sizeof(float);
+  off = (off + 127) & ~(size_t)127;
+  const int st_floats = ((32 * RS + 16 + 31) / 32) * 32;
+  off += (size_t)warps * st_floats * sizeof(float);
+  return off;
+}
+
+// launches one linearisation on ctx->stream
+static int launch_linearize(gto_ctx* ctx, const float* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
+                            float* rows, int t_lo, unsigned flags) {
+  const RobotDev& R = ctx->robot_h;
+  LinParams p;
+  memset(&p, 0, sizeof(p));
+  p.robot = ctx->robot_d; p.chunk_start = ctx->chunk_start.p; p.chunk_count = ctx->chunk_count.p;
+  p.px = ctx->px.p; p.py = ctx->py.p; p.pz = ctx->pz.p;
+  p.q = q; p.goal_tf = ctx->goal_tf.p; p.base = ctx->base.p; p.field_ids = ctx->field_ids.p;
+  p.fields = ctx->fields_d; p.tmaps = ctx->tmaps_d;
+  p.active = active; p.nactive = nactive; p.nproblems = nproblems; p.b0 = b0; p.bufsel = bufsel;
+  p.H = ctx->H.p; p.g = ctx->g.p; p.costp = ctx->costp.p;
+  p.buf_stride_H = (long long)ctx->B * ctx->T * R.nopt * R.nopt;
+  p.buf_stride_g = (long long)ctx->B * ctx->T * R.nopt;
+  p.buf_stride_c = (long long)ctx->B * ctx->T;
+  p.rows = rows; p.rows_per_problem = ctx->rows_per_problem;
+  p.T = ctx->T; p.t_lo = t_lo; p.knot_standoff = ctx->T + ctx->standoff_offset; p.use_standoff = ctx->use_standoff;
+  p.collision = ctx->collision;
+  p.sw_obs = (float)sqrt(ctx->w_obs); p.sw_goal = (float)sqrt(ctx->w_goal);
+  p.flags = flags;
+  int bm = pick_brick_max(ctx);
+  size_t smem = lin_smem_bytes(ctx, bm, ctx->lin_warps);
+  while (smem > (size_t)ctx->max_smem_optin / 2 && bm > kBrickClassDev(0)) {  // keep two CTAs per SM
+    bm = (bm == 24) ? 16 : 8;
+    smem = lin_smem_bytes(ctx, bm, ctx->lin_warps);
+  }
+  p.brick_max = bm;
+  const int threads = ctx->lin_warps * 32;
+  int occ = 1;
+  cudaError_t e;
+  if (R.nopt <= 8) {
+    e = cudaFuncSetAttribute(k_linearize<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize<8>, threads, smem);
+  } else {
+    e = cudaFuncSetAttribute(k_linearize<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize<16>, threads, smem);
+  }
+  if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("linearize launch setup: ") + cudaGetErrorString(e));
+  if (occ < 1) return fail(ctx, GTO_ERR_CUDA, "linearize kernel does not fit on an SM");
+  const long long max_items = (long long)nproblems * (ctx->T - t_lo);
+  const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
+  if (R.nopt <= 8) k_linearize<8><<<grid, threads, smem, ctx->stream>>>(p);
+  else k_linearize<16><<<grid, threads, smem, ctx->stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize launch: ") + cudaGetErrorString(e));
+  return GTO_OK;
+}
+
+static cudaEvent_t get_event(gto_ctx* ctx, size_t i) {
+  while (ctx->ev.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev.push_back(e);
+  }
+  return ctx->ev[i];
+}
+
+extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!ctx->has_batch) return fail(ctx, GTO_ERR_STATE, "no batch uploaded");
+  CK(cudaSetDevice(ctx->device));
+  gto_options o;
+  gto_default_options(&o);
+  if (user_opts) o = *user_opts;
+  if (o.max_iter < 1 || o.check_every < 1) return fail(ctx, GTO_ERR_INVALID, "max_iter and check_every must be >= 1");
+  const RobotDev& R = ctx->robot_h;
+  const int B = ctx->B, T = ctx->T, n = R.nopt;
+  const bool want_rows = !(ctx->flags & GTO_FLAG_NO_JROWS);
+  // Jacobian-row buffer: problems are processed in chunks that fit the budget
+  const char* env = getenv("GTO_JROWS_BUDGET_MB");
+  const double budget = (env ? atof(env) : 24576.0) * 1048576.0;
+  const double per_problem = (double)ctx->rows_per_problem * (n + 1) * sizeof(float);
+  int Bchunk = B;
+  if (want_rows) {
+    Bchunk = (int)std::max(1.0, std::min((double)B, floor(budget / per_problem)));
+    CK(ctx->rows.ensure((size_t)Bchunk * ctx->rows_per_problem * (n + 1)));
+  }
+  ctx->Bchunk = Bchunk;
+  CK(ctx->nactive.ensure((size_t)o.max_iter + 3));
+
+  StateParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.robot = ctx->robot_d; sp.B = B; sp.T = T; sp.dt = ctx->dt; sp.w_vel = ctx->w_vel;
+  sp.qc = ctx->qc.p; sp.q_seed = ctx->q_seed.p; sp.Qc = ctx->Qc.p; sp.Qt = ctx->Qt.p; sp.q_trial = ctx->q_trial.p;
+  sp.bufsel = ctx->bufsel.p; sp.F = ctx->F.p; sp.Fp = ctx->Fp.p; sp.lam = ctx->lam.p; sp.nu = ctx->nu.p; sp.pred = ctx->pred.p;
+  sp.stepn = ctx->stepn.p; sp.iters = ctx->iters.p; sp.status = ctx->status.p; sp.lambda0 = o.lambda0; sp.project = 1;
+  sp.outQ = ctx->outQ.p; sp.outdQ = ctx->outdQ.p; sp.outcost = ctx->outcost.p; sp.result = ctx->result.p;
+
+  StepParams st;
+  memset(&st, 0, sizeof(st));
+  st.robot = ctx->robot_d; st.T = T; st.dt = ctx->dt; st.w_vel = ctx->w_vel; st.max_iter = o.max_iter;
+  st.tol_step = o.tol_step; st.tol_grad = o.tol_grad; st.lambda_min = o.lambda_min; st.lambda_max = o.lambda_max; st.eta = o.eta;
+  st.noise_rel = o.noise_rel; st.bound_eps = o.bound_eps;
+  st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;
+  st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
+  st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;
+  st.stepn = ctx->stepn.p; st.iters = ctx->iters.p; st.status = ctx->status.p;
+  st.Sinv = ctx->Sinv.p; st.vv = ctx->vv.p; st.gt = ctx->gt.p; st.dd = ctx->dd.p; st.fixed = ctx->fixedm.p;
+
+  gto_profile& pf = ctx->prof;
+  pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
+  pf.linearize_launches = pf.step_launches = pf.iterations = 0;
+  pf.knot_items = 0; pf.jrow_bytes = 0; pf.problem_iterations = 0; pf.linearize_launches_with_work = 0;
+  std::vector<int> h_nact((size_t)o.max_iter + 3);
+  size_t nev = 0;
+  std::vector<int> ev_kind;  // per recorded interval: 0 linearize, 1 step
+  cudaEvent_t ev_begin = get_event(ctx, nev++);
+  CK(cudaEventRecord(ev_begin, ctx->stream));
+  {
+    const long long tot = (long long)B * T;
+    k_init<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(sp);
+    CK(cudaGetLastError());
+  }
+  std::vector<int> ident(B);
+  for (int b = 0; b < B; ++b) ident[b] = b;
+
+  for (int b0 = 0; b0 < B; b0 += Bchunk) {
+    const int nb = std::min(Bchunk, B - b0);
+    int* act0 = ctx->active.p;
+    int* act1 = ctx->active.p + B;
+    CK(cudaMemsetAsync(ctx->nactive.p, 0, sizeof(int) * ((size_t)o.max_iter + 3), ctx->stream));
+    CK(cudaMemcpyAsync(act0, ident.data() + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->nactive.p, &nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    int host_active = nb;
+    for (int it = 0; it <= o.max_iter; ++it) {
+      int* ain = (it & 1) ? act1 : act0;
+      int* aout = (it & 1) ? act0 : act1;
+      cudaEvent_t a = get_event(ctx, nev++), bE = get_event(ctx, nev++), c = get_event(ctx, nev++);
+      CK(cudaEventRecord(a, ctx->stream));
+      int rc = launch_linearize(ctx, ctx->q_trial.p, ain, ctx->nactive.p + it, nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
+                                it == 0 ? 0 : 2, ctx->flags);
+      if (rc) return rc;
+      CK(cudaEventRecord(bE, ctx->stream));
+      st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
+      st.iter = it;
+      k_step<<<(nb + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, ctx->stream>>>(st);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(c, ctx->stream));
+      ev_kind.push_back(0);
+      pf.linearize_launches++;
+      pf.step_launches++;
+      pf.iterations = std::max(pf.iterations, it);
+      if (((it + 1) % o.check_every) == 0 || it == o.max_iter) {
+        CK(cudaMemcpyAsync(ctx->h_counter, ctx->nactive.p + it + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        host_active = ctx->h_counter[0];
+        if (host_active == 0) break;
+      }
+    }
+    // exact work accounting for the roofline: problems active in every linearise launch of this chunk
+    CK(cudaMemcpyAsync(h_nact.data(), ctx->nactive.p, sizeof(int) * h_nact.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int it = 0; it <= o.max_iter; ++it) {
+      const long long na = h_nact[it];
+      if (na <= 0) break;
+      pf.problem_iterations += na;
+      pf.linearize_launches_with_work++;
+      pf.knot_items += na * (it == 0 ? T : T - 2);
+      if (want_rows)
+        pf.jrow_bytes += na * (it == 0 ? ctx->rows_per_problem : ctx->rows_per_problem - 2LL * (ctx->collision ? R.npoints : 0)) * (n + 1) * 4;
+    }
+  }
+  {
+    const long long tot = (long long)B * T;
+    k_finalize<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(sp);
+    CK(cudaGetLastError());
+  }
+  cudaEvent_t ev_end = get_event(ctx, nev++);
+  CK(cudaEventRecord(ev_end, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+  pf.solve_ms = ms;
+  for (size_t i = 0; i < ev_kind.size(); ++i) {
+    float m1 = 0, m2 = 0;
+    cudaEventElapsedTime(&m1, ctx->ev[1 + 3 * i], ctx->ev[2 + 3 * i]);
+    cudaEventElapsedTime(&m2, ctx->ev[2 + 3 * i], ctx->ev[3 + 3 * i]);
+    pf.linearize_ms += m1;
+    pf.step_ms += m2;
+  }
+  ctx->solved = true;
+  return GTO_OK;
+}
+
+extern "C" int gto_download_batch(gto_ctx* ctx, gto_batch_out* out) {
+  if (!ctx || !out) return GTO_ERR_INVALID;
+  if (!ctx->solved) return fail(ctx, GTO_ERR_STATE, "no solved batch to download");
+  CK(cudaSetDevice(ctx->device));
+  const int B = ctx->B, T = ctx->T, nd = ctx->robot_h.ndof;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, ctx->stream));
+  long long bytes = 0;
+  if (out->Q) { CK(cudaMemcpyAsync(out->Q, ctx->outQ.p, sizeof(double) * B * T * nd, cudaMemcpyDeviceToHost, ctx->stream)); bytes += sizeof(double) * B * T * nd; }
+  if (out->dQ) { CK(cudaMemcpyAsync(out->dQ, ctx->outdQ.p, sizeof(double) * B * (T - 1) * nd, cudaMemcpyDeviceToHost, ctx->stream)); bytes += sizeof(double) * B * (T - 1) * nd; }
+  if (out->cost) { CK(cudaMemcpyAsync(out->cost, ctx->outcost.p, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream)); bytes += sizeof(double) * B; }
+  if (out->iters) { CK(cudaMemcpyAsync(out->iters, ctx->iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream)); bytes += sizeof(int) * B; }
+  if (out->status) { CK(cudaMemcpyAsync(out->status, ctx->status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream)); bytes += sizeof(int) * B; }
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx->prof.d2h_ms = ms;
+  ctx->prof.d2h_bytes = bytes;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return GTO_OK;
+}
+
+extern "C" int gto_solve_batch(gto_ctx* ctx, const gto_batch_in* in, const gto_options* opts, gto_batch_out* out) {
+  int rc = gto_upload_batch(ctx, in);
+  if (rc) return rc;
+  rc = gto_solve_resident(ctx, opts);
+  if (rc) return rc;
+  return gto_download_batch(ctx, out);
+}
+
+extern "C" int gto_result_device_ptr(gto_ctx* ctx, void** ptr, int64_t* nfloats) {
+  if (!ctx || !ptr) return GTO_ERR_INVALID;
+  if (!ctx->solved) return fail(ctx, GTO_ERR_STATE, "no solved batch");
+  *ptr = (void*)ctx->result.p;
+  if (nfloats) *nfloats = (int64_t)ctx->robot_h.nopt * ctx->T + 2;
+  return GTO_OK;
+}
+
+extern "C" int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out* out) {
+  if (!ctx || !out) return GTO_ERR_INVALID;
+  int rc = gto_upload_batch(ctx, in);
+  if (rc) return rc;
+  const RobotDev& R = ctx->robot_h;
+  const int B = ctx->B, T = ctx->T, n = R.nopt;
+  const size_t nrows = (size_t)B * ctx->rows_per_problem * (n + 1);
+  if (out->rows) CK(ctx->rows.ensure(nrows));
+  StateParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.robot = ctx->robot_d; sp.B = B; sp.T = T; sp.q_seed = ctx->q_seed.p; sp.q_trial = ctx->q_trial.p; sp.project = 0;
+  const long long tot = (long long)B * T;
+  k_init<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(sp);
+  CK(cudaGetLastError());
+  rc = launch_linearize(ctx, ctx->q_trial.p, nullptr, nullptr, B, 0, nullptr, out->rows ? ctx->rows.p : nullptr, 0, ctx->flags);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (out->rows) CK(cudaMemcpy(out->rows, ctx->rows.p, nrows * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out->H) CK(cudaMemcpy(out->H, ctx->H.p, sizeof(float) * B * T * n * n, cudaMemcpyDeviceToHost));
+  if (out->g) CK(cudaMemcpy(out->g, ctx->g.p, sizeof(float) * B * T * n, cudaMemcpyDeviceToHost));
+  if (out->cost) CK(cudaMemcpy(out->cost, ctx->costp.p, sizeof(float) * B * T, cudaMemcpyDeviceToHost));
+  return GTO_OK;
+}
+
+extern "C" int gto_get_profile(gto_ctx* ctx, gto_profile* prof) {
+  if (!ctx || !prof) return GTO_ERR_INVALID;
+  *prof = ctx->prof;
+  return GTO_OK;
+}
+
+extern "C" int gto_plan_cost(gto_ctx* ctx, int32_t nplans, int32_t T, const double* plans, int32_t slot, const double base_position[3],
+                             double* cost, double* dist) {
+  if (!ctx || !plans || !cost || nplans < 1 || T < 1) return GTO_ERR_INVALID;
+  if (!ctx->has_robot) return fail(ctx, GTO_ERR_STATE, "gto_set_robot has not been called");
+  if (slot < 0 || slot >= MAX_FIELDS || !ctx->fields[slot].set) return fail(ctx, GTO_ERR_INVALID, "field slot not set");
+  CK(cudaSetDevice(ctx->device));
+  const int nd = ctx->robot_h.ndof;
+  const size_t nq = (size_t)nplans * T * nd;
+  std::vector<float> qf(nq);
+  for (size_t i = 0; i < nq; ++i) qf[i] = (float)plans[i];
+  float* dq = nullptr;
+  double* dc = nullptr;
+  CK(cudaMalloc((void**)&dq, nq * sizeof(float)));
+  if (cudaMalloc((void**)&dc, nplans * sizeof(double)) != cudaSuccess) { cudaFree(dq); return fail(ctx, GTO_ERR_NOMEM, "plan cost buffer"); }
+  cudaMemcpyAsync(dq, qf.data(), nq * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemsetAsync(dc, 0, nplans * sizeof(double), ctx->stream);
+  FieldDev f;
+  cudaMemcpyAsync(&f, ctx->fields_d + slot, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  const float bx = base_position ? (float)base_position[0] : 0.f, by = base_position ? (float)base_position[1] : 0.f,
+              bz = base_position ? (float)base_position[2] : 0.f;
+  k_plan_cost<<<nplans * T, 128, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, dq, T, f, bx, by, bz, dc);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cost, dc, nplans * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dq);
+  cudaFree(dc);
+  if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_plan_cost: ") + cudaGetErrorString(e));
+  if (dist)
+    for (int i = 0; i < nplans; ++i) {
+      double s = 0;
+      for (int j = 0; j < nd; ++j) {
+        const double d = plans[((size_t)i * T) * nd + j] - plans[((size_t)i * T + T - 1) * nd + j];
+        s += d * d;
+      }
+      dist[i] = sqrt(s);
+    }
+  return GTO_OK;
+}

@@ -278,7 +278,7 @@ def build_robot_table(
     return table
 
 
-def prepend_planar_base(table: RobotTable, xlim=(-2.0, 2.0), ylim=(-2.0, 2.0), yawlim=(-np.pi, np.pi)) -> RobotTable:
+def prepend_planar_base(table: RobotTable, xlim=(-0.6, 0.6), ylim=(-0.6, 0.6), yawlim=(-np.pi, np.pi)) -> RobotTable:
     """"10-DoF mobile" variant (BASELINE config C4): the base pose (x, y, yaw) becomes three
     virtual optimised joints in front of the tree -- the single-trajectory analogue of the
     reference's ``BasePlanner`` ``TaskModel(dim=3)`` (``gto/base_planner.py:23,44-51``)."""

@@ -136,3 +136,64 @@ def sample_goals(table: RobotTable, qc: np.ndarray, n: int, rng: np.random.Gener
     QG = QS.copy()
     QG[:, table.opt_qidx] = np.clip(QS[:, table.opt_qidx] + rng.normal(0.0, seed_noise, size=(n, table.nopt)), table.lo, table.hi)
     return RT, QS, QG
+
+
+def sample_grasps_around(table: RobotTable, qc: np.ndarray, center, n: int, rng: np.random.Generator, approach_axis: str = "z",
+                         reach: float = 0.10, pos_tol: float = 0.03, approach_dir=(0.0, 0.0, -1.0), min_cos: float = 0.3,
+                         boxes=(), clearance: float = 0.02, seed_noise: float = 0.05, max_rounds: int = 400, batch: int = 8192):
+    """Candidate grasps of ONE object (BASELINE "candidate grasps"): configurations q* whose grasp point -- ``reach``
+    metres ahead of the gripper frame along its approach axis -- lies within ``pos_tol`` of ``center`` and whose approach
+    axis points roughly along ``approach_dir``.  Reachable by construction: all optimised joints but the first revolute
+    one are drawn uniformly within their limits, and that joint is then solved in closed form so that the grasp point
+    swings onto the object's azimuth.  Returns (RT [n,4,4] pose of link_ee, q_star [n,ndof], q_goal_seed [n,ndof])."""
+    from .kinematics import fk_movable, gripper_frames, ee_frames
+    from .robot_table import JOINT_REVOLUTE
+
+    qc = np.asarray(qc, dtype=np.float64)
+    center = np.asarray(center, dtype=np.float64)
+    adir = np.asarray(approach_dir, dtype=np.float64)
+    adir = adir / np.linalg.norm(adir)
+    ax = "xyz".index(approach_axis)
+    j0 = next(j for j in range(table.nmov) if table.mov_opt[j] >= 0 and table.mov_type[j] == JOINT_REVOLUTE)
+    k0 = int(table.mov_opt[j0])
+    keepQ = []
+    for _ in range(max_rounds):
+        q = np.tile(qc, (batch, 1))
+        q[:, table.opt_qidx] = rng.uniform(table.lo, table.hi, size=(batch, table.nopt))
+        q[:, table.opt_qidx[k0]] = 0.0
+        Tm = fk_movable(table, q)
+        o = Tm[:, j0, :3, 3]
+        z = Tm[:, j0, :3, :3] @ table.mov_axis[j0]
+        Tg = gripper_frames(table, q)
+        p = Tg[:, :3, 3] + reach * Tg[:, :3, ax]
+
+        def cyl(v):
+            d = v - o
+            h = np.sum(d * z, axis=1)
+            rv = d - h[:, None] * z
+            return h, rv
+
+        hp, rp = cyl(p)
+        hc, rc = cyl(center[None, :])
+        rpn, rcn = np.linalg.norm(rp, axis=1), np.linalg.norm(rc, axis=1)
+        ok = (np.abs(hp - hc) < pos_tol) & (np.abs(rpn - rcn) < pos_tol) & (rpn > 1e-3)
+        theta = np.arctan2(np.sum(np.cross(rp, rc) * z, axis=1), np.sum(rp * rc, axis=1))
+        ok &= (theta >= table.lo[k0]) & (theta <= table.hi[k0])
+        q = q[ok]
+        q[:, table.opt_qidx[k0]] = theta[ok]
+        if q.shape[0] == 0:
+            continue
+        Tg = gripper_frames(table, q)
+        good = (Tg[:, :3, ax] @ adir) > min_cos
+        if len(boxes):
+            good &= box_sdf(Tg[:, :3, 3], boxes) >= clearance
+        keepQ.append(q[good])
+        if sum(x.shape[0] for x in keepQ) >= n:
+            break
+    QS = np.concatenate(keepQ)[:n] if keepQ else np.zeros((0, table.ndof))
+    if QS.shape[0] < n:
+        raise RuntimeError(f"only {QS.shape[0]} of {n} candidate grasps found")
+    RT = ee_frames(table, QS)
+    QG = QS.copy()
+    QG[:, table.opt_qidx] = np.clip(QS[:, table.opt_qidx] + rng.normal(0.0, seed_noise, size=(n, table.nopt)), table.lo, table.hi)
+    return RT, QS, QG

@@ -428,15 +428,15 @@ def linearize(p: Problem, Q: np.ndarray, need_jac: bool = True) -> Linearization
 
 def pack_rows(p: Problem, lin: Linearization) -> np.ndarray:
     """Dense Jacobian rows in the C-ABI layout ``[rows][nopt+1]`` = ``[J | r]`` with rows
-    ordered: obstacle ``[t][point]`` (if collision_avoidance), goal ``[k][axis]``, stand-off
-    ``[k][axis]`` (include/gto_b200.h, ``gto_eval_batch``)."""
+    ordered: obstacle ``[t][point]`` (if collision_avoidance), goal ``[axis][k]``, stand-off
+    ``[axis][k]`` (include/gto_b200.h, ``gto_eval_batch``)."""
     n = p.table.nopt
     blocks = []
     if p.collision_avoidance:
         blocks.append(np.concatenate([lin.J_obs.reshape(-1, n), lin.r_obs.reshape(-1, 1)], axis=1))
-    blocks.append(np.concatenate([lin.J_goal.reshape(-1, n), lin.r_goal.reshape(-1, 1)], axis=1))
+    blocks.append(np.concatenate([np.transpose(lin.J_goal, (1, 0, 2)).reshape(-1, n), lin.r_goal.T.reshape(-1, 1)], axis=1))
     if p.use_standoff:
-        blocks.append(np.concatenate([lin.J_stand.reshape(-1, n), lin.r_stand.reshape(-1, 1)], axis=1))
+        blocks.append(np.concatenate([np.transpose(lin.J_stand, (1, 0, 2)).reshape(-1, n), lin.r_stand.T.reshape(-1, 1)], axis=1))
     return np.concatenate(blocks, axis=0)
 
 
@@ -477,6 +477,7 @@ class SolverOptions:
 STATUS_CONVERGED = 0
 STATUS_MAX_ITER = 1
 STATUS_NAN = 2
+STATUS_STALLED = 3
 
 
 def _system(p: Problem, Qx: np.ndarray, lin: Linearization):
@@ -534,7 +535,8 @@ def _matvec(D, off, x):
 
 
 def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: SolverOptions):
-    """One damped projected Gauss-Newton step.  Returns (trial Qx, d [m,n], pred, |proj grad|_inf)."""
+    """One damped projected Gauss-Newton step.  Returns (trial Qx, d [m,n], pred, |proj grad|_inf);
+    the trial is ``None`` when the projected gradient is already below ``tol_grad``."""
     tb = p.table
     D, a2, gt = _system(p, Qx, lin)
     X = Qx[2:]
@@ -543,6 +545,8 @@ def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: So
     fixed = at_lo | at_hi
     pg = np.where(fixed, 0.0, gt)
     pgnorm = 2.0 * float(np.max(np.abs(pg))) if pg.size else 0.0
+    if pgnorm <= opts.tol_grad:
+        return None, np.zeros_like(gt), 0.0, pgnorm
     Dd = D.copy()
     m, n = gt.shape
     for i in range(m):
@@ -629,8 +633,11 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
     hist = [F]
     it = 0
     while it < opts.max_iter:
-        it += 1
         Qx_trial, d, pred, pgnorm = lm_step(p, Q[:, oi], lin, lam, opts)
+        if Qx_trial is None:
+            status = STATUS_CONVERGED
+            break
+        it += 1
         Qt = Q.copy()
         Qt[:, oi] = Qx_trial
         lin_t = linearize(p, Qt)
@@ -658,6 +665,7 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
             lam = min(opts.lambda_max, lam * nu)
             nu *= 2.0
             if lam >= opts.lambda_max:
+                status = STATUS_STALLED
                 break
     Qf, dQ = unpack_solution(p, Q)
     return SolveResult(Qf, dQ, F, it, status, hist)
