@@ -44,6 +44,10 @@ struct RobotDev {
   int mov_parent[GTO_MAX_MOV], mov_type[GTO_MAX_MOV], mov_qidx[GTO_MAX_MOV], mov_opt[GTO_MAX_MOV];
   float mov_origin[GTO_MAX_MOV][12];
   float mov_axis[GTO_MAX_MOV][4];
+  double mov_origin_d[GTO_MAX_MOV][12];
+  double mov_axis_d[GTO_MAX_MOV][4];
+  double link_tf_d[GTO_MAX_LINKS][12];
+  double grip_tf_d[12];
   int link_mov[GTO_MAX_LINKS];
   float link_tf[GTO_MAX_LINKS][12];
   int link_pt_start[GTO_MAX_LINKS], link_pt_count[GTO_MAX_LINKS];
@@ -73,8 +77,8 @@ struct LinParams {
   const float* px;
   const float* py;
   const float* pz;
-  const float* q;          // [B][T][ndof] configuration at which to linearise
-  const float* goal_tf;    // [B][2][12]
+  const double* q;         // [B][T][ndof] configuration at which to linearise
+  const double* goal_tf;   // [B][2][12]
   const float* base;       // [B][4]
   const int* field_ids;    // [B][2]
   const FieldDev* fields;
@@ -144,12 +148,12 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint
 // shared-memory carve-up of k_linearize
 // ------------------------------------------------------------------------------------------------------------------
 struct LinShared {
+  double Tm[GTO_MAX_MOV][12];        // movable joint frames (float64)
+  double A[GTO_MAX_MOV][12];         // origin * motion of each movable joint
   float frames[GTO_MAX_LINKS][12];   // visual frame of each collision link (robot base frame)
-  float Tm[GTO_MAX_MOV][12];         // movable joint frames
-  float A[GTO_MAX_MOV][12];          // origin * motion of each movable joint
   float tw[GTO_MAX_OPT][8];          // (omega.xyz, -, m.xyz, -) per optimised joint
   float gripf[12];
-  float goal[2][12];
+  float goal[2][12];                 // gripper frame minus goal / stand-off frame (difference formed in float64)
   float basep[4];
   int brick_lo[GTO_MAX_LINKS][3];
   int brick_cls[GTO_MAX_LINKS];      // class index, -1: no brick
@@ -196,12 +200,13 @@ __device__ __forceinline__ void sdf_trilinear(const FieldDev& f, const float* __
 }
 
 // 3x4 product C = A * B (both [R|t] row-major, implicit last row 0 0 0 1)
-__device__ __forceinline__ void mul34(const float* A, const float* B, float* C) {
+template <typename TA, typename TB, typename TC>
+__device__ __forceinline__ void mul34(const TA* A, const TB* B, TC* C) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float s = A[r * 4 + 0] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c];
+      TC s = A[r * 4 + 0] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c];
       if (c == 3) s += A[r * 4 + 3];
       C[r * 4 + c] = s;
     }
@@ -276,32 +281,34 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
     const int t = p.t_lo + (int)(item - (long long)a * nknots);
     const int b = p.active ? p.active[a] : a;
     const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
-    const float* q = p.q + ((long long)b * p.T + t) * R.ndof;
+    const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
     const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
     const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
 
     __syncthreads();  // previous item fully consumed (frames, reduction scratch)
 
-    // ---------------- forward kinematics by warp 0 ----------------
+    // ---------------- forward kinematics by warp 0, in float64 ----------------
+    // The trajectory lives in float64 (k_step); doing the chain in float64 keeps the coherent frame error out of the
+    // goal residual, so the projected-gradient stopping test stays meaningful.  Frames are rounded to float32 once.
     if (warp == 0) {
       if (lane < R.nmov) {  // A_j = origin_j * motion_j(q_j)
-        const float qj = q[R.mov_qidx[lane]];
-        const float ax = R.mov_axis[lane][0], ay = R.mov_axis[lane][1], az = R.mov_axis[lane][2];
-        float M[12];
+        const double qj = q[R.mov_qidx[lane]];
+        const double ax = R.mov_axis_d[lane][0], ay = R.mov_axis_d[lane][1], az = R.mov_axis_d[lane][2];
+        double M[12];
         if (R.mov_type[lane] == GTO_JOINT_REVOLUTE) {  // Rodrigues: I + s K + (1-c) K^2
-          float s, c;
-          sincosf(qj, &s, &c);
-          const float v = 1.f - c;
-          M[0] = 1.f - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.f;
-          M[4] = s * az + v * ax * ay;          M[5] = 1.f - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.f;
-          M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.f - v * (ax * ax + ay * ay); M[11] = 0.f;
+          double s, c;
+          sincos(qj, &s, &c);
+          const double v = 1.0 - c;
+          M[0] = 1.0 - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.0;
+          M[4] = s * az + v * ax * ay;          M[5] = 1.0 - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.0;
+          M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
         } else {
-          M[0] = 1.f; M[1] = 0.f; M[2] = 0.f; M[3] = qj * ax;
-          M[4] = 0.f; M[5] = 1.f; M[6] = 0.f; M[7] = qj * ay;
-          M[8] = 0.f; M[9] = 0.f; M[10] = 1.f; M[11] = qj * az;
+          M[0] = 1.0; M[1] = 0.0; M[2] = 0.0; M[3] = qj * ax;
+          M[4] = 0.0; M[5] = 1.0; M[6] = 0.0; M[7] = qj * ay;
+          M[8] = 0.0; M[9] = 0.0; M[10] = 1.0; M[11] = qj * az;
         }
-        float C[12];
-        mul34(R.mov_origin[lane], M, C);
+        double C[12];
+        mul34(R.mov_origin_d[lane], M, C);
 #pragma unroll
         for (int e = 0; e < 12; ++e) S.A[lane][e] = C[e];
       }
@@ -310,11 +317,11 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
         if (lane < 12) {
           const int r = lane >> 2, c = lane & 3;
           const int pj = R.mov_parent[j];
-          float s;
+          double s;
           if (pj < 0) {
             s = S.A[j][lane];
           } else {
-            const float* P = S.Tm[pj];
+            const double* P = S.Tm[pj];
             s = P[r * 4 + 0] * S.A[j][c] + P[r * 4 + 1] * S.A[j][4 + c] + P[r * 4 + 2] * S.A[j][8 + c];
             if (c == 3) s += P[r * 4 + 3];
           }
@@ -324,15 +331,19 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
       }
       if (lane < R.nlinks) {  // visual frames + brick placement
         const int mj = R.link_mov[lane];
-        float F[12];
+        double Fd[12];
         if (mj < 0) {
 #pragma unroll
-          for (int e = 0; e < 12; ++e) F[e] = R.link_tf[lane][e];
+          for (int e = 0; e < 12; ++e) Fd[e] = R.link_tf_d[lane][e];
         } else {
-          mul34(S.Tm[mj], R.link_tf[lane], F);
+          mul34(S.Tm[mj], R.link_tf_d[lane], Fd);
         }
+        float F[12];
 #pragma unroll
-        for (int e = 0; e < 12; ++e) S.frames[lane][e] = F[e];
+        for (int e = 0; e < 12; ++e) {
+          F[e] = (float)Fd[e];
+          S.frames[lane][e] = F[e];
+        }
         int cls = -1;
         if (fid >= 0 && use_brick) {
           const FieldDev& f = p.fields[fid];
@@ -345,8 +356,9 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
           for (int ax3 = 0; ax3 < 3; ++ax3) {
             const float cw = F[ax3 * 4 + 0] * cc[0] + F[ax3 * 4 + 1] * cc[1] + F[ax3 * 4 + 2] * cc[2] + F[ax3 * 4 + 3] + bp[ax3];
             const float hw = fabsf(F[ax3 * 4 + 0]) * hh[0] + fabsf(F[ax3 * 4 + 1]) * hh[1] + fabsf(F[ax3 * 4 + 2]) * hh[2] + 1e-4f;
-            const int lo = (int)floorf((cw - hw - org[ax3]) * f.inv_pitch);
+            int lo = (int)floorf((cw - hw - org[ax3]) * f.inv_pitch);
             const int hi = (int)floorf((cw + hw - org[ax3]) * f.inv_pitch);
+            if (ax3 == 2) lo &= ~3;  // TMA: the innermost start coordinate must be 16-byte aligned
             lo3[ax3] = lo;
             need = max(need, hi - lo + 2);
           }
@@ -360,6 +372,7 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
           if (cls >= 0 && need > Bc) {  // partial coverage: centre the brick, the rest reads global memory
 #pragma unroll
             for (int ax3 = 0; ax3 < 3; ++ax3) lo3[ax3] += (need - Bc) / 2;
+            lo3[2] &= ~3;
           }
           S.brick_lo[lane][0] = lo3[0]; S.brick_lo[lane][1] = lo3[1]; S.brick_lo[lane][2] = lo3[2];
         }
@@ -367,36 +380,39 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
       }
       if (lane < nopt) {  // joint twists: v(W) = omega x W + m
         const int j = R.opt_mov[lane];
-        float om[3] = {0.f, 0.f, 0.f}, mm[3] = {0.f, 0.f, 0.f};
+        double om[3] = {0.0, 0.0, 0.0}, mm[3] = {0.0, 0.0, 0.0};
         if (j >= 0) {
-          const float* Tj = S.Tm[j];
-          const float ax = R.mov_axis[j][0], ay = R.mov_axis[j][1], az = R.mov_axis[j][2];
-          const float zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
-          const float zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
-          const float zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
+          const double* Tj = S.Tm[j];
+          const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
+          const double zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
+          const double zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
+          const double zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
           if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
-            const float ox = Tj[3], oy = Tj[7], oz = Tj[11];
+            const double ox = Tj[3], oy = Tj[7], oz = Tj[11];
             om[0] = zx; om[1] = zy; om[2] = zz;
             mm[0] = oy * zz - oz * zy; mm[1] = oz * zx - ox * zz; mm[2] = ox * zy - oy * zx;  // o x z
           } else {
             mm[0] = zx; mm[1] = zy; mm[2] = zz;
           }
         }
-        S.tw[lane][0] = om[0]; S.tw[lane][1] = om[1]; S.tw[lane][2] = om[2]; S.tw[lane][3] = 0.f;
-        S.tw[lane][4] = mm[0]; S.tw[lane][5] = mm[1]; S.tw[lane][6] = mm[2]; S.tw[lane][7] = 0.f;
+        S.tw[lane][0] = (float)om[0]; S.tw[lane][1] = (float)om[1]; S.tw[lane][2] = (float)om[2]; S.tw[lane][3] = 0.f;
+        S.tw[lane][4] = (float)mm[0]; S.tw[lane][5] = (float)mm[1]; S.tw[lane][6] = (float)mm[2]; S.tw[lane][7] = 0.f;
       }
-      if (lane == 31) {
-        float F[12];
+      if (lane == 31) {  // gripper link frame and its difference to the two goal frames, formed in float64
+        double F[12];
         if (R.grip_mov < 0) {
 #pragma unroll
-          for (int e = 0; e < 12; ++e) F[e] = R.grip_tf[e];
+          for (int e = 0; e < 12; ++e) F[e] = R.grip_tf_d[e];
         } else {
-          mul34(S.Tm[R.grip_mov], R.grip_tf, F);
+          mul34(S.Tm[R.grip_mov], R.grip_tf_d, F);
         }
 #pragma unroll
-        for (int e = 0; e < 12; ++e) S.gripf[e] = F[e];
+        for (int e = 0; e < 12; ++e) {
+          S.gripf[e] = (float)F[e];
+          S.goal[0][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + e]);
+          S.goal[1][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + 12 + e]);
+        }
       }
-      if (lane < 24) S.goal[lane / 12][lane % 12] = p.goal_tf[(long long)b * 24 + lane];
       if (lane >= 24 && lane < 27) S.basep[lane - 24] = p.base[4 * b + (lane - 24)];
     }
     __syncthreads();
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
       for (int which = 0; which < 2; ++which) {
         if (which == 0 && !is_goal) continue;
         if (which == 1 && !is_stand) continue;
-        const float* M = S.goal[which];
+        const float* Dg = S.goal[which];
         const long long rbase = obs_rows + (which == 1 ? 3LL * Pg : 0);
         const int nch = (Pg + 31) / 32;
         for (int ch = warp; ch < nch; ch += nwarps) {
@@ -506,8 +522,8 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
 #pragma unroll
             for (int a3 = 0; a3 < 3; ++a3) {
               w3[a3] = Fg[a3 * 4 + 0] * x + Fg[a3 * 4 + 1] * y + Fg[a3 * 4 + 2] * z + Fg[a3 * 4 + 3];
-              const float tg = M[a3 * 4 + 0] * x + M[a3 * 4 + 1] * y + M[a3 * 4 + 2] * z + M[a3 * 4 + 3];
-              r3[a3] = p.sw_goal * (w3[a3] - tg);
+              // residual = (F_gripper - F_goal) x: no cancellation between two O(1 m) positions
+              r3[a3] = p.sw_goal * (Dg[a3 * 4 + 0] * x + Dg[a3 * 4 + 1] * y + Dg[a3 * 4 + 2] * z + Dg[a3 * 4 + 3]);
             }
           }
 #pragma unroll
@@ -609,7 +625,7 @@ struct StateParams {
   const double* q_seed;  // [B][T][ndof]
   double* Qc;            // [B][T][nopt] accepted point
   double* Qt;            // [B][T][nopt] trial point
-  float* q_trial;        // [B][T][ndof] what k_linearize reads
+  double* q_trial;       // [B][T][ndof] what k_linearize reads (float64: FK runs in double)
   int* bufsel;
   double *F, *Fp, *lam, *nu, *pred, *stepn;
   int *iters, *status;
@@ -628,8 +644,8 @@ __global__ void k_init(const StateParams p) {
   if (i >= (long long)p.B * p.T) return;
   const int b = (int)(i / p.T), t = (int)(i % p.T);
   const double* s = p.q_seed + i * R.ndof;
-  float* qt = p.q_trial + i * R.ndof;
-  for (int j = 0; j < R.ndof; ++j) qt[j] = (float)s[j];
+  double* qt = p.q_trial + i * R.ndof;
+  for (int j = 0; j < R.ndof; ++j) qt[j] = s[j];
   if (!p.project) return;
   for (int k = 0; k < R.nopt; ++k) {
     const int j = R.opt_qidx[k];
@@ -637,7 +653,7 @@ __global__ void k_init(const StateParams p) {
     if (t < 2) v = p.qc[(long long)b * R.ndof + j];
     p.Qc[i * R.nopt + k] = v;
     p.Qt[i * R.nopt + k] = v;
-    qt[j] = (float)v;
+    qt[j] = v;
   }
   if (t == 0) {
     p.bufsel[b] = 0;
@@ -683,10 +699,10 @@ struct StepParams {
   double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps;
   double* Qc;
   double* Qt;
-  float* q_trial;
+  double* q_trial;
   const float* H;
   const float* g;
-  const float* costp;
+  float* costp;
   long long buf_stride_H, buf_stride_g, buf_stride_c;
   int* bufsel;
   double *F, *Fp, *lam, *nu, *pred, *stepn;
@@ -695,15 +711,10 @@ struct StepParams {
   const int* nactive_in;
   int* active_out;
   int* nactive_out;
-  double* Sinv;          // [B][m][n*n]
-  double* vv;            // [B][m][n]
-  double* gt;            // [B][m][n]
-  double* dd;            // [B][m][n]
-  unsigned char* fixed;  // [B][m][n]
-  int iter;              // number of LM steps already taken by the problems in the active list
+  double* Sinv_g;  // [B][m][n*n] global scratch, used only when the factor does not fit shared memory
+  int sinv_in_smem;
+  int iter;        // number of LM steps already taken by the problems in the active list
 };
-
-#define STEP_WARPS 4
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -716,17 +727,36 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
-  __shared__ double sS[STEP_WARPS][2][GTO_MAX_OPT * GTO_MAX_OPT];
-  __shared__ double sU[STEP_WARPS][GTO_MAX_OPT];
-  __shared__ double sV[STEP_WARPS][GTO_MAX_OPT];
+// One warp (= one CTA) per active problem; the whole block-tridiagonal system of the problem lives in shared memory:
+//   X [T][n] f64 | gt [m][n] f64 | vv [m][n] f64 | dd [m][n] f64 | Sinv [m][n*n] f64 (or global) | S [2][n*n] f64 | U,V [16] f64
+//   | Hs [m][n*n] f32 | fx [m][n] u8
+__host__ __device__ inline size_t step_smem_bytes(int T, int n, bool sinv_in_smem) {
+  const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
+  size_t d = (size_t)T * n + 3 * m * n + (sinv_in_smem ? m * nn : 0) + 2 * nn + 32;
+  size_t bytes = d * sizeof(double) + m * nn * sizeof(float) + m * n;
+  return (bytes + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(32) k_step(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char step_smem[];
   const RobotDev& R = *p.robot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a_idx = blockIdx.x * STEP_WARPS + warp;
+  const int lane = threadIdx.x;
+  const int a_idx = blockIdx.x;
   if (a_idx >= *p.nactive_in) return;
   const int b = p.active_in[a_idx];
   const int n = R.nopt, T = p.T, m = T - 2, nn = n * n;
   const double a2 = p.w_vel / (p.dt * p.dt);
+  double* X = reinterpret_cast<double*>(step_smem);
+  double* gt = X + (size_t)T * n;
+  double* vv = gt + (size_t)m * n;
+  double* dd = vv + (size_t)m * n;
+  double* Sinv = p.sinv_in_smem ? dd + (size_t)m * n : p.Sinv_g + (size_t)b * m * nn;
+  double* S2 = (p.sinv_in_smem ? Sinv + (size_t)m * nn : dd + (size_t)m * n);
+  double* U = S2 + 2 * nn;
+  double* V = U + 16;
+  float* Hs = reinterpret_cast<float*>(V + 16);
+  unsigned char* fx = reinterpret_cast<unsigned char*>(Hs + (size_t)m * nn);
+
   double* Xc = p.Qc + (long long)b * T * n;
   double* Xt = p.Qt + (long long)b * T * n;
   int cur = p.bufsel[b];
@@ -736,7 +766,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
   // ---------------- evaluate the trial point produced by the previous call ----------------
   {
     const int tri = 1 - cur;
-    const float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
+    float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
     double s = 0.0;
     for (int t = lane; t < T; t += 32) s += (double)ct[t];
     const double Fp_t = warp_sum(s);
@@ -750,6 +780,8 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
     if (!isfinite(Ft)) {
       done = GTO_STATUS_NAN;
     } else if (it == 0) {  // initial point: accept unconditionally
+      // knots 0 and 1 never move and are linearised only once: mirror their cost into the other buffer
+      if (lane < 2) p.costp[cur * p.buf_stride_c + (long long)b * T + lane] = ct[lane];
       cur = tri;
       if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
     } else {
@@ -783,22 +815,20 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
   }
   __syncwarp();
 
-  // ---------------- next damped projected Gauss-Newton step from the accepted point ----------------
+  // ---------------- stage the accepted point and its Gauss-Newton blocks in shared memory ----------------
   const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn;
   const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
-  double* gt = p.gt + (long long)b * m * n;
-  double* dd = p.dd + (long long)b * m * n;
-  double* vv = p.vv + (long long)b * m * n;
-  double* Sg = p.Sinv + (long long)b * m * nn;
-  unsigned char* fx = p.fixed + (long long)b * m * n;
+  for (int i = lane; i < T * n; i += 32) X[i] = Xc[i];
+  for (int i = lane; i < m * nn; i += 32) Hs[i] = Hc[2 * nn + i];
+  __syncwarp();
 
   double pgmax = 0.0;
   for (int idx = lane; idx < m * n; idx += 32) {
     const int i = idx / n, k = idx - i * n, t = i + 2;
-    double gv = Xc[t * n + k] - Xc[(t - 1) * n + k];
-    if (t < T - 1) gv -= Xc[(t + 1) * n + k] - Xc[t * n + k];
+    double gv = X[t * n + k] - X[(t - 1) * n + k];
+    if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
     const double gtv = (double)gc[t * n + k] + a2 * gv;
-    const double x = Xc[t * n + k];
+    const double x = X[t * n + k];
     const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
     gt[idx] = gtv;
     fx[idx] = fixed ? 1 : 0;
@@ -811,21 +841,20 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
   }
   __syncwarp();
 
-  double* U = sU[warp];
-  double* V = sV[warp];
+  // ---------------- damped projected Gauss-Newton step: block Thomas algorithm in float64 ----------------
   bool ok = false;
   for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
     ok = true;
-    // forward sweep (block Thomas): S_i = D_i - C_i Sinv_{i-1} C_i ; u_i = b_i - C_i v_{i-1} ; v_i = Sinv_i u_i
+    // forward sweep: S_i = D_i - C_i Sinv_{i-1} C_i ; u_i = b_i - C_i v_{i-1} ; v_i = Sinv_i u_i
     for (int i = 0; i < m && ok; ++i) {
       const int t = i + 2;
       const double cnt = (t < T - 1) ? 2.0 : 1.0;
-      double* Sc = sS[warp][i & 1];
-      const double* Sp = sS[warp][(i + 1) & 1];
+      double* Sc = p.sinv_in_smem ? Sinv + (size_t)i * nn : S2 + (size_t)(i & 1) * nn;
+      const double* Sp = p.sinv_in_smem ? Sinv + (size_t)(i - 1) * nn : S2 + (size_t)((i + 1) & 1) * nn;
       for (int e = lane; e < nn; e += 32) {
         const int r = e / n, c = e - r * n;
         const bool fr = fx[i * n + r], fc = fx[i * n + c];
-        double v = (double)Hc[t * nn + e];
+        double v = (double)Hs[i * nn + e];
         if (r == c) {
           v += a2 * cnt;
           v += lam * v;
@@ -854,23 +883,30 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
         if (!(piv > 0.0)) { ok = false; break; }
         const double ip = 1.0 / piv;
         double nv[(GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32];
-        int cntv = 0;
-        for (int e = lane; e < nn; e += 32, ++cntv) {
-          const int r = e / n, c = e - r * n;
-          double v;
-          if (r == k && c == k) v = ip;
-          else if (r == k) v = Sc[e] * ip;
-          else if (c == k) v = -Sc[e] * ip;
-          else v = Sc[e] - Sc[r * n + k] * Sc[k * n + c] * ip;
-          nv[cntv] = v;
+#pragma unroll
+        for (int j = 0; j < (GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32; ++j) {
+          const int e = lane + 32 * j;
+          if (e < nn) {
+            const int r = e / n, c = e - r * n;
+            double v;
+            if (r == k && c == k) v = ip;
+            else if (r == k) v = Sc[e] * ip;
+            else if (c == k) v = -Sc[e] * ip;
+            else v = Sc[e] - Sc[r * n + k] * Sc[k * n + c] * ip;
+            nv[j] = v;
+          }
         }
         __syncwarp();
-        cntv = 0;
-        for (int e = lane; e < nn; e += 32, ++cntv) Sc[e] = nv[cntv];
+#pragma unroll
+        for (int j = 0; j < (GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32; ++j) {
+          const int e = lane + 32 * j;
+          if (e < nn) Sc[e] = nv[j];
+        }
         __syncwarp();
       }
       if (!ok) break;
-      for (int e = lane; e < nn; e += 32) Sg[i * nn + e] = Sc[e];
+      if (!p.sinv_in_smem)
+        for (int e = lane; e < nn; e += 32) Sinv[(size_t)i * nn + e] = Sc[e];
       double v = 0.0;
       if (lane < n) {
         for (int c = 0; c < n; ++c) v += Sc[lane * n + c] * U[c];
@@ -897,22 +933,23 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
     if (lane < n) {
       x = vv[i * n + lane];
       if (i < m - 1) {
+        const double* Si = Sinv + (size_t)i * nn;
         double s = 0.0;
         for (int c = 0; c < n; ++c) {
           const double cc = (fx[i * n + c] || fx[(i + 1) * n + c]) ? 0.0 : a2;
-          s += Sg[i * nn + lane * n + c] * cc * U[c];
+          s += Si[lane * n + c] * cc * U[c];
         }
         x += s;
       }
     }
     __syncwarp();
     if (lane < n) {
-      U[lane] = x;  // unclipped solution feeds the recursion
-      const double xc = Xc[t * n + lane];
+      U[lane] = x;  // the unclipped solution feeds the recursion
+      const double xc = X[t * n + lane];
       const double xn = fmin(fmax(xc + x, R.lo[lane]), R.hi[lane]);
       const double d = xn - xc;
       Xt[t * n + lane] = xn;
-      p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[lane]] = (float)xn;
+      p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[lane]] = xn;
       dd[i * n + lane] = d;
       stepmax = fmax(stepmax, fabs(d));
       gdot += gt[i * n + lane] * d;
@@ -925,7 +962,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(const StepParams p) {
   double quad = 0.0;
   for (int idx = lane; idx < m * nn; idx += 32) {
     const int i = idx / nn, e = idx - i * nn, r = e / n, c = e - r * n, t = i + 2;
-    double h = (double)Hc[t * nn + e];
+    double h = (double)Hs[idx];
     if (r == c) h += a2 * ((t < T - 1) ? 2.0 : 1.0);
     quad += h * dd[i * n + r] * dd[i * n + c];
   }
@@ -1078,10 +1115,10 @@ struct gto_ctx {
   double dt = 0, w_goal = 1, w_obs = 10, w_vel = 0.01;
   int standoff_offset = -10, use_standoff = 1, collision = 1;
   unsigned flags = 0;
-  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, vv, gt, dd, outQ, outdQ, outcost;
-  DevBuf<float> q_trial, goal_tf, base, H, g, costp, rows, result;
+  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, outQ, outdQ, outcost;
+  DevBuf<double> q_trial, goal_tf;
+  DevBuf<float> base, H, g, costp, rows, result;
   DevBuf<int> field_ids, bufsel, iters, status, active, nactive;
-  DevBuf<unsigned char> fixedm;
   int* h_counter = nullptr;  // pinned
   long long rows_per_problem = 0;
   int Bchunk = 0;
@@ -1167,11 +1204,11 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   ctx->px.release(); ctx->py.release(); ctx->pz.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
   ctx->qc.release(); ctx->q_seed.release(); ctx->Qc.release(); ctx->Qt.release(); ctx->F.release(); ctx->Fp.release();
-  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release(); ctx->vv.release();
-  ctx->gt.release(); ctx->dd.release(); ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
+  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release();
+  ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
-  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->fixedm.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1198,8 +1235,8 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
     if (r->mov_type[j] != GTO_JOINT_REVOLUTE && r->mov_type[j] != GTO_JOINT_PRISMATIC) return fail(ctx, GTO_ERR_INVALID, "unsupported joint type");
     if (r->mov_qidx[j] < 0 || r->mov_qidx[j] >= r->ndof) return fail(ctx, GTO_ERR_INVALID, "mov_qidx out of range");
     h.mov_parent[j] = r->mov_parent[j]; h.mov_type[j] = r->mov_type[j]; h.mov_qidx[j] = r->mov_qidx[j]; h.mov_opt[j] = r->mov_opt[j];
-    for (int e = 0; e < 12; ++e) h.mov_origin[j][e] = (float)r->mov_origin[j * 12 + e];
-    for (int e = 0; e < 3; ++e) h.mov_axis[j][e] = (float)r->mov_axis[j * 3 + e];
+    for (int e = 0; e < 12; ++e) { h.mov_origin[j][e] = (float)r->mov_origin[j * 12 + e]; h.mov_origin_d[j][e] = r->mov_origin[j * 12 + e]; }
+    for (int e = 0; e < 3; ++e) { h.mov_axis[j][e] = (float)r->mov_axis[j * 3 + e]; h.mov_axis_d[j][e] = r->mov_axis[j * 3 + e]; }
     if (r->mov_opt[j] >= 0) {
       if (r->mov_opt[j] >= r->nopt) return fail(ctx, GTO_ERR_INVALID, "mov_opt out of range");
       h.opt_mov[r->mov_opt[j]] = j;
@@ -1214,7 +1251,7 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
     const int s = r->link_pt_start[l], n = r->link_pt_count[l];
     if (s < 0 || n < 0 || s + n > r->npoints || r->link_mov[l] >= r->nmov) return fail(ctx, GTO_ERR_INVALID, "link table out of range");
     h.link_mov[l] = r->link_mov[l]; h.link_pt_start[l] = s; h.link_pt_count[l] = n; h.link_optmask[l] = r->link_optmask[l];
-    for (int e = 0; e < 12; ++e) h.link_tf[l][e] = (float)r->link_tf[l * 12 + e];
+    for (int e = 0; e < 12; ++e) { h.link_tf[l][e] = (float)r->link_tf[l * 12 + e]; h.link_tf_d[l][e] = r->link_tf[l * 12 + e]; }
     float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
     for (int i = s; i < s + n; ++i) {
       const float v[3] = {hx[i], hy[i], hz[i]};
@@ -1237,7 +1274,7 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
   h.grip_mov = r->grip_mov; h.grip_pt_start = r->grip_pt_start; h.grip_pt_count = r->grip_pt_count; h.grip_optmask = r->grip_optmask;
   if (r->grip_pt_start < 0 || r->grip_pt_count < 1 || r->grip_pt_start + r->grip_pt_count > r->npoints || r->grip_mov >= r->nmov)
     return fail(ctx, GTO_ERR_INVALID, "gripper point set out of range");
-  for (int e = 0; e < 12; ++e) h.grip_tf[e] = (float)r->grip_tf[e];
+  for (int e = 0; e < 12; ++e) { h.grip_tf[e] = (float)r->grip_tf[e]; h.grip_tf_d[e] = r->grip_tf[e]; }
   // warps per CTA: least idle lanes when a link's chunks are dealt round-robin to the warps
   int best = 8;
   double best_eff = 0;
@@ -1284,7 +1321,7 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
   d.data = f.data; d.nx = f.nx; d.ny = f.ny; d.nz = f.nz; d.nzp = nzp;
   d.ox = (float)origin[0]; d.oy = (float)origin[1]; d.oz = (float)origin[2]; d.inv_pitch = (float)(1.0 / pitch);
   d.has_tma = 0;
-  if (ctx->encode) {
+  if (ctx->encode && !getenv("GTO_DISABLE_TMA")) {
     CUtensorMap maps[NCLASS];
     bool ok = true;
     for (int c = 0; c < NCLASS && ok; ++c) {
@@ -1353,14 +1390,12 @@ extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
   CK(ctx->F.ensure(B)); CK(ctx->Fp.ensure(B)); CK(ctx->lam.ensure(B)); CK(ctx->nu.ensure(B)); CK(ctx->pred.ensure(B)); CK(ctx->stepn.ensure(B));
   CK(ctx->bufsel.ensure(B)); CK(ctx->iters.ensure(B)); CK(ctx->status.ensure(B)); CK(ctx->active.ensure((size_t)2 * B));
   CK(ctx->H.ensure((size_t)2 * B * T * n * n)); CK(ctx->g.ensure((size_t)2 * B * T * n)); CK(ctx->costp.ensure((size_t)2 * B * T));
-  CK(ctx->Sinv.ensure((size_t)B * m * n * n)); CK(ctx->vv.ensure((size_t)B * m * n)); CK(ctx->gt.ensure((size_t)B * m * n));
-  CK(ctx->dd.ensure((size_t)B * m * n)); CK(ctx->fixedm.ensure((size_t)B * m * n));
+  (void)m;
   CK(ctx->outQ.ensure((size_t)B * T * nd)); CK(ctx->outdQ.ensure((size_t)B * (T - 1) * nd)); CK(ctx->outcost.ensure(B));
   CK(ctx->result.ensure((size_t)B * (n * T + 2)));
   // host-side repacking of the small per-problem inputs (float32 copies for the point kernel)
-  std::vector<float> gtf((size_t)B * 24), bs((size_t)B * 4, 0.f);
+  std::vector<float> bs((size_t)B * 4, 0.f);
   std::vector<int> fid((size_t)B * 2, -1);
-  for (size_t i = 0; i < gtf.size(); ++i) gtf[i] = (float)in->goal_tf[i];
   for (int b = 0; b < B; ++b) {
     if (in->base_position)
       for (int a = 0; a < 3; ++a) bs[4 * b + a] = (float)in->base_position[3 * b + a];
@@ -1369,7 +1404,7 @@ extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
   CK(cudaEventRecord(e0, ctx->stream));
   CK(cudaMemcpyAsync(ctx->qc.p, in->qc, sizeof(double) * B * nd, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->q_seed.p, in->q_seed, sizeof(double) * B * T * nd, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->goal_tf.p, gtf.data(), sizeof(float) * gtf.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->goal_tf.p, in->goal_tf, sizeof(double) * B * 24, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->base.p, bs.data(), sizeof(float) * bs.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->field_ids.p, fid.data(), sizeof(int) * fid.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(e1, ctx->stream));
@@ -1377,7 +1412,7 @@ extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   ctx->prof.h2d_ms = ms;
-  ctx->prof.h2d_bytes = (long long)sizeof(double) * B * nd * (1 + T) + sizeof(float) * (gtf.size() + bs.size()) + sizeof(int) * fid.size();
+  ctx->prof.h2d_bytes = (long long)sizeof(double) * B * (nd * (1 + T) + 24) + sizeof(float) * bs.size() + sizeof(int) * fid.size();
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   ctx->rows_per_problem = rows_per_problem(ctx);
   ctx->has_batch = true;
@@ -1404,7 +1439,7 @@ static size_t lin_smem_bytes(const gto_ctx* ctx, int brick_max, int warps) {
 }
 
 // launches one linearisation on ctx->stream
-static int launch_linearize(gto_ctx* ctx, const float* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
+static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
                             float* rows, int t_lo, unsigned flags) {
   const RobotDev& R = ctx->robot_h;
   LinParams p;
@@ -1500,7 +1535,16 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
   st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;
   st.stepn = ctx->stepn.p; st.iters = ctx->iters.p; st.status = ctx->status.p;
-  st.Sinv = ctx->Sinv.p; st.vv = ctx->vv.p; st.gt = ctx->gt.p; st.dd = ctx->dd.p; st.fixed = ctx->fixedm.p;
+  size_t step_smem = step_smem_bytes(T, n, true);
+  st.sinv_in_smem = 1;
+  if (step_smem > (size_t)ctx->max_smem_optin) {  // long horizon x many joints: keep the factor in global scratch
+    st.sinv_in_smem = 0;
+    step_smem = step_smem_bytes(T, n, false);
+    if (step_smem > (size_t)ctx->max_smem_optin) return fail(ctx, GTO_ERR_INVALID, "T * nopt^2 too large for the step kernel");
+    CK(ctx->Sinv.ensure((size_t)B * (T - 2) * n * n));
+  }
+  st.Sinv_g = ctx->Sinv.p;
+  CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1538,7 +1582,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       CK(cudaEventRecord(bE, ctx->stream));
       st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
       st.iter = it;
-      k_step<<<(nb + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, ctx->stream>>>(st);
+      k_step<<<nb, 32, step_smem, ctx->stream>>>(st);
       CK(cudaGetLastError());
       CK(cudaEventRecord(c, ctx->stream));
       ev_kind.push_back(0);

@@ -682,6 +682,8 @@ def solve_scipy(p: Problem, xtol: float = 1e-14, gtol: float = 1e-12, max_nfev: 
     Q0 = initial_trajectory(p)
     sv = np.sqrt(p.w_vel) / p.dt
 
+    dense = (T - 2) * n <= 400
+
     def unpack(x):
         Q = Q0.copy()
         Q[2:, oi] = x.reshape(T - 2, n)
@@ -718,13 +720,13 @@ def solve_scipy(p: Problem, xtol: float = 1e-14, gtol: float = 1e-12, max_nfev: 
                     J[base + t * n + k, (t + 1 - 2) * n + k] = sv
                 if t >= 2:
                     J[base + t * n + k, (t - 2) * n + k] = -sv
-        return J.tocsr()
+        return J.toarray() if dense else J.tocsr()
 
     x0 = Q0[2:, oi].reshape(-1)
     lo = np.tile(tb.lo, T - 2)
     hi = np.tile(tb.hi, T - 2)
     x0 = np.clip(x0, lo + 1e-12, hi - 1e-12)
-    res = least_squares(fun, x0, jac=jac, bounds=(lo, hi), method="trf", xtol=xtol, ftol=1e-15, gtol=gtol, max_nfev=max_nfev, tr_solver="exact" if (T - 2) * n <= 400 else "lsmr", x_scale=1.0)
+    res = least_squares(fun, x0, jac=jac, bounds=(lo, hi), method="trf", xtol=xtol, ftol=1e-15, gtol=gtol, max_nfev=max_nfev, tr_solver="exact" if dense else "lsmr", x_scale=1.0)
     # tr_solver exact needs dense J
     Q = unpack(res.x)
     return Q, 2.0 * res.cost, res
