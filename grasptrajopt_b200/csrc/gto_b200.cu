@@ -737,6 +737,11 @@ __host__ __device__ inline size_t step_smem_bytes(int T, int n, bool sinv_in_sme
   return (bytes + 15) & ~(size_t)15;
 }
 
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// NP = padded block order (8 or 16).  Lane r < NP owns row r of the current diagonal block in registers; the
+// Gauss-Jordan inverse runs on warp shuffles (no shared-memory round trips inside the serial recurrence).
+template <int NP>
 __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   extern __shared__ __align__(16) unsigned char step_smem[];
   const RobotDev& R = *p.robot;
@@ -752,9 +757,7 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   double* dd = vv + (size_t)m * n;
   double* Sinv = p.sinv_in_smem ? dd + (size_t)m * n : p.Sinv_g + (size_t)b * m * nn;
   double* S2 = (p.sinv_in_smem ? Sinv + (size_t)m * nn : dd + (size_t)m * n);
-  double* U = S2 + 2 * nn;
-  double* V = U + 16;
-  float* Hs = reinterpret_cast<float*>(V + 16);
+  float* Hs = reinterpret_cast<float*>(S2 + 2 * nn + 32);
   unsigned char* fx = reinterpret_cast<unsigned char*>(Hs + (size_t)m * nn);
 
   double* Xc = p.Qc + (long long)b * T * n;
@@ -823,16 +826,19 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   __syncwarp();
 
   double pgmax = 0.0;
-  for (int idx = lane; idx < m * n; idx += 32) {
-    const int i = idx / n, k = idx - i * n, t = i + 2;
-    double gv = X[t * n + k] - X[(t - 1) * n + k];
-    if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
-    const double gtv = (double)gc[t * n + k] + a2 * gv;
-    const double x = X[t * n + k];
-    const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
-    gt[idx] = gtv;
-    fx[idx] = fixed ? 1 : 0;
-    if (!fixed) pgmax = fmax(pgmax, fabs(gtv));
+  {
+    const int krow = lane % n, irow0 = lane / n, istride = 32 / n;  // lanes >= istride*n idle in this loop
+    for (int i = irow0; i < m && lane < istride * n; i += istride) {
+      const int k = krow, t = i + 2, idx = i * n + k;
+      double gv = X[t * n + k] - X[(t - 1) * n + k];
+      if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
+      const double gtv = (double)gc[t * n + k] + a2 * gv;
+      const double x = X[t * n + k];
+      const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
+      gt[idx] = gtv;
+      fx[idx] = fixed ? 1 : 0;
+      if (!fixed) pgmax = fmax(pgmax, fabs(gtv));
+    }
   }
   pgmax = warp_max(pgmax);
   if (2.0 * pgmax <= p.tol_grad) {
@@ -842,131 +848,130 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   __syncwarp();
 
   // ---------------- damped projected Gauss-Newton step: block Thomas algorithm in float64 ----------------
+  const int r = lane;            // row owned by this lane (rows >= n are identity padding)
+  const bool rin = r < n;
   bool ok = false;
   for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
     ok = true;
+    double prev[NP];  // row r of Sinv_{i-1}
+#pragma unroll
+    for (int c = 0; c < NP; ++c) prev[c] = 0.0;
+    double vprev = 0.0;  // v_{i-1}[r]
     // forward sweep: S_i = D_i - C_i Sinv_{i-1} C_i ; u_i = b_i - C_i v_{i-1} ; v_i = Sinv_i u_i
-    for (int i = 0; i < m && ok; ++i) {
+    for (int i = 0; i < m; ++i) {
       const int t = i + 2;
       const double cnt = (t < T - 1) ? 2.0 : 1.0;
-      double* Sc = p.sinv_in_smem ? Sinv + (size_t)i * nn : S2 + (size_t)(i & 1) * nn;
-      const double* Sp = p.sinv_in_smem ? Sinv + (size_t)(i - 1) * nn : S2 + (size_t)((i + 1) & 1) * nn;
-      for (int e = lane; e < nn; e += 32) {
-        const int r = e / n, c = e - r * n;
-        const bool fr = fx[i * n + r], fc = fx[i * n + c];
-        double v = (double)Hs[i * nn + e];
-        if (r == c) {
-          v += a2 * cnt;
-          v += lam * v;
-        }
-        if (fr || fc) v = (r == c) ? 1.0 : 0.0;
-        if (i > 0) {
-          const double cr = (fr || fx[(i - 1) * n + r]) ? 0.0 : a2;
-          const double cc = (fc || fx[(i - 1) * n + c]) ? 0.0 : a2;
-          v -= cr * cc * Sp[e];
-        }
-        Sc[e] = v;
-      }
-      if (lane < n) {
-        const bool fr = fx[i * n + lane];
-        double u = fr ? 0.0 : -gt[i * n + lane];
-        if (i > 0) {
-          const double cr = (fr || fx[(i - 1) * n + lane]) ? 0.0 : a2;
-          u += cr * V[lane];
-        }
-        U[lane] = u;
-      }
-      __syncwarp();
-      // in-place Gauss-Jordan inverse of the SPD block
-      for (int k = 0; k < n; ++k) {
-        const double piv = Sc[k * n + k];
-        if (!(piv > 0.0)) { ok = false; break; }
-        const double ip = 1.0 / piv;
-        double nv[(GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32];
+      const bool fr = rin ? (fx[i * n + r] != 0) : true;
+      const bool frp = (i > 0 && rin) ? (fx[(i - 1) * n + r] != 0) : true;
+      const double cr = (fr || frp) ? 0.0 : a2;
+      double row[NP];
 #pragma unroll
-        for (int j = 0; j < (GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32; ++j) {
-          const int e = lane + 32 * j;
-          if (e < nn) {
-            const int r = e / n, c = e - r * n;
-            double v;
-            if (r == k && c == k) v = ip;
-            else if (r == k) v = Sc[e] * ip;
-            else if (c == k) v = -Sc[e] * ip;
-            else v = Sc[e] - Sc[r * n + k] * Sc[k * n + c] * ip;
-            nv[j] = v;
+      for (int c = 0; c < NP; ++c) {
+        double v = 0.0;
+        if (c < n) {
+          const bool fc = fx[i * n + c] != 0;
+          if (rin) {
+            v = (double)Hs[i * nn + r * n + c];
+            if (r == c) {
+              v += a2 * cnt;
+              v += lam * v;
+            }
           }
+          if (fr || fc) v = (r == c) ? 1.0 : 0.0;
+          if (i > 0) {
+            const double cc = (fc || fx[(i - 1) * n + c] != 0) ? 0.0 : a2;
+            v -= cr * cc * prev[c];
+          }
+        } else {
+          v = (r == c) ? 1.0 : 0.0;
         }
-        __syncwarp();
+        row[c] = v;
+      }
+      double u = (rin && !fr) ? -gt[i * n + r] : 0.0;
+      if (i > 0) u += cr * vprev;
+      // Gauss-Jordan inverse in registers; the pivot row travels by warp shuffle
 #pragma unroll
-        for (int j = 0; j < (GTO_MAX_OPT * GTO_MAX_OPT + 31) / 32; ++j) {
-          const int e = lane + 32 * j;
-          if (e < nn) Sc[e] = nv[j];
+      for (int k = 0; k < NP; ++k) {
+        const double piv = shfl_d(row[k], k);
+        if (!(piv > 0.0)) ok = false;  // uniform: every lane sees the same pivot
+        double ip = (double)__frcp_rn((float)piv);
+        ip = ip * (2.0 - piv * ip);
+        ip = ip * (2.0 - piv * ip);
+        const double f = row[k];
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          const double pk = shfl_d(row[c], k);
+          double nvv;
+          if (c == k) nvv = (r == k) ? ip : -f * ip;
+          else nvv = (r == k) ? pk * ip : row[c] - f * pk * ip;
+          row[c] = nvv;
         }
-        __syncwarp();
       }
       if (!ok) break;
-      if (!p.sinv_in_smem)
-        for (int e = lane; e < nn; e += 32) Sinv[(size_t)i * nn + e] = Sc[e];
+      // v_i = Sinv_i u_i
       double v = 0.0;
-      if (lane < n) {
-        for (int c = 0; c < n; ++c) v += Sc[lane * n + c] * U[c];
-        vv[i * n + lane] = v;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) v += row[c] * shfl_d(u, c);
+      if (rin) {
+        vv[i * n + r] = v;
+#pragma unroll
+        for (int c = 0; c < NP; ++c)
+          if (c < n) Sinv[(size_t)i * nn + r * n + c] = row[c];
       }
-      __syncwarp();
-      if (lane < n) V[lane] = v;
-      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NP; ++c) prev[c] = row[c];
+      vprev = v;
     }
-    if (!ok) {
-      lam = fmin(p.lambda_max, lam * 10.0);  // not positive definite: add damping and refactor
-      __syncwarp();
-    }
+    if (!ok) lam = fmin(p.lambda_max, lam * 10.0);  // not positive definite: add damping and refactor
+    __syncwarp();
   }
   if (!ok) {
     if (lane == 0) { p.status[b] = GTO_STATUS_NAN; p.iters[b] = it; }
     return;
   }
   // backward sweep: x_i = v_i + Sinv_i (c_{i+1} o x_{i+1}); trial point = clip(X + x)
-  double stepmax = 0.0, gdot = 0.0;
+  double stepmax = 0.0, gdot = 0.0, xnext = 0.0;
   for (int i = m - 1; i >= 0; --i) {
     const int t = i + 2;
-    double x = 0.0;
-    if (lane < n) {
-      x = vv[i * n + lane];
-      if (i < m - 1) {
-        const double* Si = Sinv + (size_t)i * nn;
-        double s = 0.0;
-        for (int c = 0; c < n; ++c) {
+    double x = rin ? vv[i * n + r] : 0.0;
+    if (i < m - 1) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) {
+        const double xc_ = shfl_d(xnext, c);
+        if (c < n && rin) {
           const double cc = (fx[i * n + c] || fx[(i + 1) * n + c]) ? 0.0 : a2;
-          s += Si[lane * n + c] * cc * U[c];
+          s += Sinv[(size_t)i * nn + r * n + c] * cc * xc_;
         }
-        x += s;
       }
+      x += s;
     }
-    __syncwarp();
-    if (lane < n) {
-      U[lane] = x;  // the unclipped solution feeds the recursion
-      const double xc = X[t * n + lane];
-      const double xn = fmin(fmax(xc + x, R.lo[lane]), R.hi[lane]);
+    xnext = x;  // the unclipped solution feeds the recursion
+    if (rin) {
+      const double xc = X[t * n + r];
+      const double xn = fmin(fmax(xc + x, R.lo[r]), R.hi[r]);
       const double d = xn - xc;
-      Xt[t * n + lane] = xn;
-      p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[lane]] = xn;
-      dd[i * n + lane] = d;
+      Xt[t * n + r] = xn;
+      p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[r]] = xn;
+      dd[i * n + r] = d;
       stepmax = fmax(stepmax, fabs(d));
-      gdot += gt[i * n + lane] * d;
+      gdot += gt[i * n + r] * d;
     }
-    __syncwarp();
   }
+  __syncwarp();
   stepmax = warp_max(stepmax);
   gdot = warp_sum(gdot);
-  // predicted reduction with the undamped, unmasked model: -(g.d + 0.5 d^T A d)
+  // predicted reduction with the undamped, unmasked model: -(g.d + 0.5 d^T A d); lane r sums its rows
   double quad = 0.0;
-  for (int idx = lane; idx < m * nn; idx += 32) {
-    const int i = idx / nn, e = idx - i * nn, r = e / n, c = e - r * n, t = i + 2;
-    double h = (double)Hs[idx];
-    if (r == c) h += a2 * ((t < T - 1) ? 2.0 : 1.0);
-    quad += h * dd[i * n + r] * dd[i * n + c];
+  if (rin) {
+    for (int i = 0; i < m; ++i) {
+      const double dg = a2 * ((i + 2 < T - 1) ? 2.0 : 1.0);
+      double hd = dg * dd[i * n + r];
+      for (int c = 0; c < n; ++c) hd += (double)Hs[i * nn + r * n + c] * dd[i * n + c];
+      quad += dd[i * n + r] * hd;
+      if (i < m - 1) quad -= 2.0 * a2 * dd[i * n + r] * dd[(i + 1) * n + r];
+    }
   }
-  for (int idx = lane; idx < (m - 1) * n; idx += 32) quad -= 2.0 * a2 * dd[idx] * dd[idx + n];
   quad = warp_sum(quad);
   if (lane == 0) {
     p.pred[b] = -(gdot + 0.5 * quad);
@@ -1544,7 +1549,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(ctx->Sinv.ensure((size_t)B * (T - 2) * n * n));
   }
   st.Sinv_g = ctx->Sinv.p;
-  CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
+  CK(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
+  CK(cudaFuncSetAttribute(k_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1582,7 +1588,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       CK(cudaEventRecord(bE, ctx->stream));
       st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
       st.iter = it;
-      k_step<<<nb, 32, step_smem, ctx->stream>>>(st);
+      if (n <= 8) k_step<8><<<nb, 32, step_smem, ctx->stream>>>(st);
+      else k_step<16><<<nb, 32, step_smem, ctx->stream>>>(st);
       CK(cudaGetLastError());
       CK(cudaEventRecord(c, ctx->stream));
       ev_kind.push_back(0);
