@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgto_b200.so")
 
 GTO_OK = 0
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN, STATUS_STALLED = 0, 1, 2, 3
-FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK = 1, 2, 4
+FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK, FLAG_V1_KERNEL = 1, 2, 4, 8
 
 SYMBOLS = [
     "gto_abi_version", "gto_create", "gto_destroy", "gto_last_error", "gto_default_options", "gto_set_robot",

@@ -68,6 +68,7 @@ struct FieldDev {
   int nx, ny, nz, nzp;
   float ox, oy, oz, inv_pitch;
   int has_tma;
+  const CUtensorMap* maps2;  // [7*7*7] tile maps with per-axis box sizes 8,12,...,32 (k_linearize_pipe); NULL if unavailable
 };
 
 struct LinParams {
@@ -613,6 +614,8 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
   }
 }
 
+#include "lin_pipe.cuh"
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_init: eliminate the equality constraints (gto/gto_planner.py:59-72): optimised rows of knots 0,1 = qc; clip the seed
 // to the position limits (:138); parameter-joint entries are kept from the seed (optas/solver.py:126-159).
@@ -1087,6 +1090,7 @@ struct DevBuf {
 
 struct FieldHost {
   float* data = nullptr;
+  CUtensorMap* maps2 = nullptr;
   int nx = 0, ny = 0, nz = 0, nzp = 0;
   double origin[3] = {0, 0, 0};
   double pitch = 0;
@@ -1107,6 +1111,7 @@ struct gto_ctx {
   DevBuf<float> px, py, pz;
   DevBuf<int> chunk_start, chunk_count;
   int lin_warps = 8;
+  int pipe_cons = 8;
   double max_link_diag = 0.0;  // largest |half extent|_2 over links
   // fields
   std::vector<FieldHost> fields;
@@ -1200,8 +1205,10 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (auto& f : ctx->fields)
+  for (auto& f : ctx->fields) {
     if (f.data) cudaFree(f.data);
+    if (f.maps2) cudaFree(f.maps2);
+  }
   for (auto e : ctx->ev) cudaEventDestroy(e);
   if (ctx->robot_d) cudaFree(ctx->robot_d);
   if (ctx->fields_d) cudaFree(ctx->fields_d);
@@ -1294,6 +1301,15 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
     if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
   }
   ctx->lin_warps = best;
+  {  // consumer warps of the pipelined kernel: chunks are dealt round-robin over the whole item
+    int bestc = 8;
+    double beff = 0;
+    for (int w = 6; w <= 8; ++w) {
+      const double eff = (double)h.nchunks / ((double)((h.nchunks + w - 1) / w) * w);
+      if (eff > beff + 1e-9) { beff = eff; bestc = w; }
+    }
+    ctx->pipe_cons = bestc;
+  }
   CK(ctx->px.ensure(r->npoints)); CK(ctx->py.ensure(r->npoints)); CK(ctx->pz.ensure(r->npoints));
   CK(ctx->chunk_start.ensure(cs.size())); CK(ctx->chunk_count.ensure(cs.size()));
   CK(cudaMemcpy(ctx->px.p, hx.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
@@ -1343,6 +1359,28 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
     if (ok) {
       CK(cudaMemcpy(ctx->tmaps_d + (size_t)slot * NCLASS, maps, sizeof(maps), cudaMemcpyHostToDevice));
       d.has_tma = 1;
+    }
+  }
+  d.maps2 = nullptr;
+  if (d.has_tma) {  // per-axis box sizes for the pipelined kernel
+    std::vector<CUtensorMap> m2((size_t)PIPE_NAXC * PIPE_NAXC * PIPE_NAXC);
+    bool ok = true;
+    for (int cx = 0; cx < PIPE_NAXC && ok; ++cx)
+      for (int cy = 0; cy < PIPE_NAXC && ok; ++cy)
+        for (int cz = 0; cz < PIPE_NAXC && ok; ++cz) {
+          const cuuint64_t gdim[3] = {(cuuint64_t)f.nz, (cuuint64_t)f.ny, (cuuint64_t)f.nx};
+          const cuuint64_t gstr[2] = {(cuuint64_t)nzp * sizeof(float), (cuuint64_t)f.ny * nzp * sizeof(float)};
+          const cuuint32_t box[3] = {(cuuint32_t)(8 + 4 * cz), (cuuint32_t)(8 + 4 * cy), (cuuint32_t)(8 + 4 * cx)};
+          const cuuint32_t estr[3] = {1, 1, 1};
+          CUresult rc = ctx->encode(&m2[((size_t)cx * PIPE_NAXC + cy) * PIPE_NAXC + cz], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)f.data, gdim,
+                                    gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          ok = (rc == CUDA_SUCCESS);
+        }
+    if (ok) {
+      if (!f.maps2) CK(cudaMalloc((void**)&f.maps2, m2.size() * sizeof(CUtensorMap)));
+      CK(cudaMemcpy(f.maps2, m2.data(), m2.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+      d.maps2 = f.maps2;
     }
   }
   CK(cudaMemcpy(ctx->fields_d + slot, &d, sizeof(d), cudaMemcpyHostToDevice));
@@ -1463,6 +1501,49 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   p.collision = ctx->collision;
   p.sw_obs = (float)sqrt(ctx->w_obs); p.sw_goal = (float)sqrt(ctx->w_goal);
   p.flags = flags;
+  // ---- default: warp-specialised TMA-pipelined kernel ----
+  bool pipe_ok = !(flags & (GTO_FLAG_V1_KERNEL | GTO_FLAG_NO_TMA | GTO_FLAG_NO_BRICK)) && !getenv("GTO_V1_KERNEL");
+  for (auto& ff : ctx->fields)
+    if (ff.set && !ff.maps2) pipe_ok = false;
+  if (pipe_ok) {
+    PipeParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.lin = p;
+    pp.chunk_link = nullptr;
+    const int n3 = ctx->min_pitch > 0 ? (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 5 : 8;
+    int slot_floats = n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
+    if (const char* e = getenv("GTO_SLOT_FLOATS")) slot_floats = std::max(512, atoi(e) & ~127);
+    pp.slot_floats = slot_floats;
+    int nc = ctx->pipe_cons;
+    if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
+    pp.ncons = nc;
+    const int RS = R.nopt + 1;
+    size_t sm = (sizeof(PipeShared) + 127) & ~(size_t)127;
+    sm += (size_t)PIPE_NSLOT * slot_floats * sizeof(float);
+    sm += (size_t)nc * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
+    sm += (size_t)2 * nc * (R.nopt * R.nopt + R.nopt + 2) * sizeof(float);
+    sm = (sm + 127) & ~(size_t)127;
+    const int threads = (nc + 1) * 32;
+    int occ = 0;
+    cudaError_t e;
+    if (R.nopt <= 8) {
+      e = cudaFuncSetAttribute(k_linearize_pipe<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize_pipe<8>, threads, sm);
+    } else {
+      e = cudaFuncSetAttribute(k_linearize_pipe<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize_pipe<16>, threads, sm);
+    }
+    if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("pipelined linearize launch setup: ") + cudaGetErrorString(e));
+    if (occ >= 1) {
+      const long long max_items = (long long)nproblems * (ctx->T - t_lo);
+      const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
+      if (R.nopt <= 8) k_linearize_pipe<8><<<grid, threads, sm, ctx->stream>>>(pp);
+      else k_linearize_pipe<16><<<grid, threads, sm, ctx->stream>>>(pp);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_pipe launch: ") + cudaGetErrorString(e));
+      return GTO_OK;
+    }
+  }
   int bm = pick_brick_max(ctx);
   size_t smem = lin_smem_bytes(ctx, bm, ctx->lin_warps);
   while (smem > (size_t)ctx->max_smem_optin / 2 && bm > kBrickClassDev(0)) {  // keep two CTAs per SM

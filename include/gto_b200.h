@@ -53,6 +53,7 @@ extern "C" {
 #define GTO_FLAG_NO_JROWS 1u      /* do not materialise the Jacobian rows in HBM (assembly still fused) */
 #define GTO_FLAG_NO_TMA 2u        /* stage SDF bricks with plain loads instead of TMA (debug / A-B check) */
 #define GTO_FLAG_NO_BRICK 4u      /* read the SDF straight from global memory (debug / A-B check) */
+#define GTO_FLAG_V1_KERNEL 8u     /* use the non-pipelined linearise kernel (A-B check) */
 
 typedef struct gto_ctx gto_ctx;
 

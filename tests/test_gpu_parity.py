@@ -52,28 +52,47 @@ def _check_eval(ctx, w, frac_bad_rows=2e-4):
     return out
 
 
-def test_eval_parity_panda_tabletop(ctx):
+KERNELS = [pytest.param(0, id="pipelined"), pytest.param(capi.FLAG_V1_KERNEL, id="v1")]
+
+
+@pytest.mark.parametrize("kflag", KERNELS)
+def test_eval_parity_panda_tabletop(ctx, kflag):
     """Rows A1-A9: FK -> points -> trilinear SDF -> residual + Jacobian rows -> J^T J / J^T r, Panda (row stride 8)."""
     w = small_workload("C2", "panda_small", B=4, n_field=64)
+    w.batch.flags = kflag
     out = _check_eval(ctx, w)
     assert np.abs(out["rows"][:, : 30 * w.table.npoints, :7]).max() > 0  # the obstacle term is active in this scene
 
 
-def test_eval_parity_full_point_set(ctx):
+@pytest.mark.parametrize("kflag", KERNELS)
+def test_eval_parity_full_point_set(ctx, kflag):
     w = small_workload("C2", None, B=2, n_field=96)
+    w.batch.flags = kflag
     _check_eval(ctx, w)
 
 
-def test_eval_parity_fetch8_shelf(ctx):
+@pytest.mark.parametrize("kflag", KERNELS)
+def test_eval_parity_fetch8_shelf(ctx, kflag):
     """nopt = 8 -> row stride 9 (unaligned store path), prismatic torso joint in the chain."""
     w = small_workload("C3", None, B=2, n_field=96)
+    w.batch.flags = kflag
     _check_eval(ctx, w)
 
 
-def test_eval_parity_fetch10_mobile(ctx):
+@pytest.mark.parametrize("kflag", KERNELS)
+def test_eval_parity_fetch10_mobile(ctx, kflag):
     """nopt = 10 -> 16-wide tensor-core tile (two n-tiles), virtual planar base joints."""
     w = small_workload("C4", None, B=2, n_field=64)
+    w.batch.flags = kflag
     _check_eval(ctx, w)
+
+
+def test_eval_parity_points_outside_the_field(ctx):
+    """Clamped lookups (gto_models.py:176-183): a base offset pushes part of the robot outside the voxel field, so the
+    pipelined kernel must take its generic path (index clamping, partial bricks) and still match the oracle."""
+    w = small_workload("C2", "panda_small", B=2, n_field=48)
+    w.batch.base_position = np.array([[0.0, 1.9, 0.0], [-0.7, 0.0, -0.6]])
+    _check_eval(ctx, w, frac_bad_rows=1e-3)
 
 
 def test_brick_paths_bit_identical(ctx):
@@ -82,7 +101,7 @@ def test_brick_paths_bit_identical(ctx):
     ctx.set_robot(w.table)
     upload_fields(ctx, w)
     outs = []
-    for flags in (0, capi.FLAG_NO_TMA, capi.FLAG_NO_BRICK):
+    for flags in (capi.FLAG_V1_KERNEL, capi.FLAG_NO_TMA, capi.FLAG_NO_BRICK):
         w.batch.flags = flags
         outs.append(ctx.eval_batch(w.batch))
     w.batch.flags = 0

@@ -43,13 +43,13 @@ def main():
             ctx.set_robot(w.table)
             upload_fields(ctx, w)
             outs = {}
-            for flags, label in [(capi.FLAG_NO_BRICK, "global"), (capi.FLAG_NO_TMA, "coop-brick"), (0, "tma-brick")]:
+            for flags, label in [(capi.FLAG_NO_BRICK, "global"), (capi.FLAG_V1_KERNEL, "tma-brick"), (0, "pipe")]:
                 try:
                     outs[label] = eval_compare(ctx, w, flags, label)
                 except Exception:
                     traceback.print_exc()
             if "global" in outs:
-                for k in ("coop-brick", "tma-brick"):
+                for k in ("tma-brick", "pipe"):
                     if k in outs:
                         print(k, "identical to global:", np.array_equal(outs[k]["rows"], outs["global"]["rows"]),
                               "max diff", np.abs(outs[k]["rows"] - outs["global"]["rows"]).max(), flush=True)
@@ -91,9 +91,9 @@ def main():
         w.batch.flags = capi.FLAG_NO_JROWS
         res = ctx.solve_batch(w.batch)
         print("no-jrows profile", ctx.profile(), flush=True)
-        w.batch.flags = capi.FLAG_NO_TMA
+        w.batch.flags = capi.FLAG_V1_KERNEL
         res = ctx.solve_batch(w.batch)
-        print("no-tma profile", ctx.profile(), flush=True)
+        print("v1-kernel profile", ctx.profile(), flush=True)
         w.batch.flags = capi.FLAG_NO_BRICK
         res = ctx.solve_batch(w.batch)
         print("no-brick profile", ctx.profile(), flush=True)
