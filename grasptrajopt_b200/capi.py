@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgto_b200.so")
 
 GTO_OK = 0
-STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN, STATUS_STALLED = 0, 1, 2, 3
+STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN, STATUS_STALLED, STATUS_SLOW = 0, 1, 2, 3, 4
 FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK, FLAG_V1_KERNEL = 1, 2, 4, 8
 
 SYMBOLS = [
@@ -62,7 +62,7 @@ class Options(C.Structure):
     _fields_ = [
         ("max_iter", C.c_int32), ("tol_step", C.c_double), ("tol_grad", C.c_double), ("lambda0", C.c_double),
         ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("eta", C.c_double), ("noise_rel", C.c_double),
-        ("bound_eps", C.c_double), ("check_every", C.c_int32),
+        ("bound_eps", C.c_double), ("check_every", C.c_int32), ("ftol", C.c_double), ("lambda_slow", C.c_double),
     ]
 
 

@@ -699,7 +699,7 @@ struct StepParams {
   int T;
   double dt, w_vel;
   int max_iter;
-  double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps;
+  double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps, ftol, lambda_slow;
   double* Qc;
   double* Qt;
   double* q_trial;
@@ -714,8 +714,6 @@ struct StepParams {
   const int* nactive_in;
   int* active_out;
   int* nactive_out;
-  double* Sinv_g;  // [B][m][n*n] global scratch, used only when the factor does not fit shared memory
-  int sinv_in_smem;
   int iter;        // number of LM steps already taken by the problems in the active list
 };
 
@@ -733,10 +731,10 @@ __device__ __forceinline__ double warp_max(double v) {
 // One warp (= one CTA) per active problem; the whole block-tridiagonal system of the problem lives in shared memory:
 //   X [T][n] f64 | gt [m][n] f64 | vv [m][n] f64 | dd [m][n] f64 | Sinv [m][n*n] f64 (or global) | S [2][n*n] f64 | U,V [16] f64
 //   | Hs [m][n*n] f32 | fx [m][n] u8
-__host__ __device__ inline size_t step_smem_bytes(int T, int n, bool sinv_in_smem) {
+__host__ __device__ inline size_t step_smem_bytes(int T, int n) {
   const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
-  size_t d = (size_t)T * n + 3 * m * n + (sinv_in_smem ? m * nn : 0) + 2 * nn + 32;
-  size_t bytes = d * sizeof(double) + m * nn * sizeof(float) + m * n;
+  size_t d = (size_t)T * n + 3 * m * n + m * nn;
+  size_t bytes = d * sizeof(double) + (m * nn + 4) * sizeof(float) + m * n;
   return (bytes + 15) & ~(size_t)15;
 }
 
@@ -744,7 +742,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 // NP = padded block order (8 or 16).  Lane r < NP owns row r of the current diagonal block in registers; the
 // Gauss-Jordan inverse runs on warp shuffles (no shared-memory round trips inside the serial recurrence).
-template <int NP>
+template <int NP, bool EXACT>
 __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   extern __shared__ __align__(16) unsigned char step_smem[];
   const RobotDev& R = *p.robot;
@@ -752,15 +750,14 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   const int a_idx = blockIdx.x;
   if (a_idx >= *p.nactive_in) return;
   const int b = p.active_in[a_idx];
-  const int n = R.nopt, T = p.T, m = T - 2, nn = n * n;
+  const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;  // EXACT: block order known at compile time
   const double a2 = p.w_vel / (p.dt * p.dt);
   double* X = reinterpret_cast<double*>(step_smem);
   double* gt = X + (size_t)T * n;
   double* vv = gt + (size_t)m * n;
   double* dd = vv + (size_t)m * n;
-  double* Sinv = p.sinv_in_smem ? dd + (size_t)m * n : p.Sinv_g + (size_t)b * m * nn;
-  double* S2 = (p.sinv_in_smem ? Sinv + (size_t)m * nn : dd + (size_t)m * n);
-  float* Hs = reinterpret_cast<float*>(S2 + 2 * nn + 32);
+  double* Sinv = dd + (size_t)m * n;  // [m][n*n] inverse diagonal blocks of the factor (always in shared memory)
+  float* Hs = reinterpret_cast<float*>(Sinv + (size_t)m * nn);
   unsigned char* fx = reinterpret_cast<unsigned char*>(Hs + (size_t)m * nn);
 
   double* Xc = p.Qc + (long long)b * T * n;
@@ -799,10 +796,12 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
         for (int i = lane; i < T * n; i += 32) Xc[i] = Xt[i];
         cur = tri;
         if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
+        const double lam_used = lam;
         const double w = 2.0 * fmin(rho, 1.0) - 1.0;
         lam = fmax(p.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - w * w * w));
         nu = 2.0;
         if (step <= p.tol_step) done = GTO_STATUS_CONVERGED;
+        else if (lam_used >= p.lambda_slow && ared <= p.ftol * Fcur) done = GTO_STATUS_SLOW;
       } else {
         if (pred <= 0.0 && step <= p.tol_step) {
           done = GTO_STATUS_CONVERGED;
@@ -824,8 +823,11 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   // ---------------- stage the accepted point and its Gauss-Newton blocks in shared memory ----------------
   const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn;
   const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
+  // Gauss-Newton blocks: asynchronous 4-byte copies (cp.async), all in flight at once, no register staging
+  for (int i = lane; i < m * nn; i += 32)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(Hs + i)), "l"(Hc + 2 * nn + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = lane; i < T * n; i += 32) X[i] = Xc[i];
-  for (int i = lane; i < m * nn; i += 32) Hs[i] = Hc[2 * nn + i];
   __syncwarp();
 
   double pgmax = 0.0;
@@ -850,6 +852,8 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   }
   __syncwarp();
 
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
   // ---------------- damped projected Gauss-Newton step: block Thomas algorithm in float64 ----------------
   const int r = lane;            // row owned by this lane (rows >= n are identity padding)
   const bool rin = r < n;
@@ -900,15 +904,16 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
         double ip = (double)__frcp_rn((float)piv);
         ip = ip * (2.0 - piv * ip);
         ip = ip * (2.0 - piv * ip);
-        const double f = row[k];
+        // pivot row: new = old * ip; other rows: new = old - (f*ip) * pivot_row; column k: the multiplier itself
+        const bool isk = (r == k);
+        const double coef = isk ? ip : -row[k] * ip;
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
+          if (c == k) continue;
           const double pk = shfl_d(row[c], k);
-          double nvv;
-          if (c == k) nvv = (r == k) ? ip : -f * ip;
-          else nvv = (r == k) ? pk * ip : row[c] - f * pk * ip;
-          row[c] = nvv;
+          row[c] = fma(coef, pk, isk ? 0.0 : row[c]);
         }
+        row[k] = coef;
       }
       if (!ok) break;
       // v_i = Sinv_i u_i
@@ -1161,6 +1166,8 @@ extern "C" void gto_default_options(gto_options* o) {
   o->noise_rel = 1e-6;
   o->bound_eps = 1e-12;
   o->check_every = 4;
+  o->ftol = 1e-6;
+  o->lambda_slow = 1.0;
 }
 
 extern "C" const char* gto_last_error(gto_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1304,7 +1311,7 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
   {  // consumer warps of the pipelined kernel: chunks are dealt round-robin over the whole item
     int bestc = 8;
     double beff = 0;
-    for (int w = 6; w <= 8; ++w) {
+    for (int w = PIPE_MAX_CONS; w >= 5; --w) {  // prefer more warps on ties (latency hiding)
       const double eff = (double)h.nchunks / ((double)((h.nchunks + w - 1) / w) * w);
       if (eff > beff + 1e-9) { beff = eff; bestc = w; }
     }
@@ -1526,19 +1533,19 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
     const int threads = (nc + 1) * 32;
     int occ = 0;
     cudaError_t e;
-    if (R.nopt <= 8) {
-      e = cudaFuncSetAttribute(k_linearize_pipe<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize_pipe<8>, threads, sm);
-    } else {
-      e = cudaFuncSetAttribute(k_linearize_pipe<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize_pipe<16>, threads, sm);
-    }
+    void (*kern)(const PipeParams) = nullptr;
+    if (R.nopt == 7) kern = k_linearize_pipe<8, 7>;
+    else if (R.nopt == 8) kern = k_linearize_pipe<8, 8>;
+    else if (R.nopt == 10) kern = k_linearize_pipe<16, 10>;
+    else if (R.nopt < 8) kern = k_linearize_pipe<8, 0>;
+    else kern = k_linearize_pipe<16, 0>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, sm);
     if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("pipelined linearize launch setup: ") + cudaGetErrorString(e));
     if (occ >= 1) {
       const long long max_items = (long long)nproblems * (ctx->T - t_lo);
       const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
-      if (R.nopt <= 8) k_linearize_pipe<8><<<grid, threads, sm, ctx->stream>>>(pp);
-      else k_linearize_pipe<16><<<grid, threads, sm, ctx->stream>>>(pp);
+      kern<<<grid, threads, sm, ctx->stream>>>(pp);
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_pipe launch: ") + cudaGetErrorString(e));
       return GTO_OK;
@@ -1616,22 +1623,21 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   memset(&st, 0, sizeof(st));
   st.robot = ctx->robot_d; st.T = T; st.dt = ctx->dt; st.w_vel = ctx->w_vel; st.max_iter = o.max_iter;
   st.tol_step = o.tol_step; st.tol_grad = o.tol_grad; st.lambda_min = o.lambda_min; st.lambda_max = o.lambda_max; st.eta = o.eta;
-  st.noise_rel = o.noise_rel; st.bound_eps = o.bound_eps;
+  st.noise_rel = o.noise_rel; st.bound_eps = o.bound_eps; st.ftol = o.ftol; st.lambda_slow = o.lambda_slow;
   st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;
   st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
   st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;
   st.stepn = ctx->stepn.p; st.iters = ctx->iters.p; st.status = ctx->status.p;
-  size_t step_smem = step_smem_bytes(T, n, true);
-  st.sinv_in_smem = 1;
-  if (step_smem > (size_t)ctx->max_smem_optin) {  // long horizon x many joints: keep the factor in global scratch
-    st.sinv_in_smem = 0;
-    step_smem = step_smem_bytes(T, n, false);
-    if (step_smem > (size_t)ctx->max_smem_optin) return fail(ctx, GTO_ERR_INVALID, "T * nopt^2 too large for the step kernel");
-    CK(ctx->Sinv.ensure((size_t)B * (T - 2) * n * n));
-  }
-  st.Sinv_g = ctx->Sinv.p;
-  CK(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
-  CK(cudaFuncSetAttribute(k_step<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
+  const size_t step_smem = step_smem_bytes(T, n);
+  if (step_smem > (size_t)ctx->max_smem_optin)
+    return fail(ctx, GTO_ERR_INVALID, "(T-2) * nopt^2 too large: the block-tridiagonal factor must fit in shared memory");
+  void (*step_kern)(const StepParams) = nullptr;
+  if (n == 7) step_kern = k_step<7, true>;
+  else if (n == 8) step_kern = k_step<8, true>;
+  else if (n == 10) step_kern = k_step<10, true>;
+  else if (n < 8) step_kern = k_step<8, false>;
+  else step_kern = k_step<16, false>;
+  CK(cudaFuncSetAttribute(step_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1669,8 +1675,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       CK(cudaEventRecord(bE, ctx->stream));
       st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
       st.iter = it;
-      if (n <= 8) k_step<8><<<nb, 32, step_smem, ctx->stream>>>(st);
-      else k_step<16><<<nb, 32, step_smem, ctx->stream>>>(st);
+      step_kern<<<nb, 32, step_smem, ctx->stream>>>(st);
       CK(cudaGetLastError());
       CK(cudaEventRecord(c, ctx->stream));
       ev_kind.push_back(0);

@@ -30,12 +30,35 @@ struct ItemCtx {
   int b, t, fid, obuf;
 };
 
+struct LinkMeta {
+  int c0, c1, pt_start, pt_end;
+  unsigned mask;
+};
+
 struct PipeShared {
   double Tm[GTO_MAX_MOV][12];
   double A[GTO_MAX_MOV][12];
   ItemCtx ctx[2];
+  LinkMeta links[GTO_MAX_LINKS];
   unsigned long long slot_full[PIPE_NSLOT], slot_empty[PIPE_NSLOT], ctx_full[2], ctx_empty[2];
 };
+
+// try_wait with a suspend-time hint: the hardware parks the thread instead of burning issue slots on polling
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int tries = 0; tries < (1 << 20); ++tries) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();  // a lost transaction must abort the launch, never hang the device
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -84,13 +107,14 @@ struct PipeParams {
   int ncons;              // consumer warps
 };
 
-template <int NP>
+// NP: padded tensor-core tile width (8 or 16); NOPT_CT: number of optimised joints when known at compile time (0: runtime)
+template <int NP, int NOPT_CT>
 __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(const __grid_constant__ PipeParams pp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LinParams& p = pp.lin;
   PipeShared& S = *reinterpret_cast<PipeShared*>(smem_raw);
   const RobotDev& R = *p.robot;
-  const int nopt = R.nopt, RS = nopt + 1, NC = pp.ncons;
+  const int nopt = NOPT_CT ? NOPT_CT : R.nopt, RS = nopt + 1, NC = pp.ncons;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   size_t off = (sizeof(PipeShared) + 127) & ~(size_t)127;
   float* ring = reinterpret_cast<float*>(smem_raw + off);
@@ -116,6 +140,15 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
     }
     mbar_fence_init();
   }
+  if ((int)threadIdx.x < R.nlinks) {
+    LinkMeta m;
+    m.c0 = R.link_chunk0[threadIdx.x];
+    m.c1 = R.link_chunk0[threadIdx.x + 1];
+    m.pt_start = R.link_pt_start[threadIdx.x];
+    m.pt_end = m.pt_start + R.link_pt_count[threadIdx.x];
+    m.mask = R.link_optmask[threadIdx.x];
+    S.links[threadIdx.x] = m;
+  }
   __syncthreads();
 
   const int nknots = p.T - p.t_lo;
@@ -128,7 +161,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
     unsigned ic = 0, bc = 0;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
       const int ci = ic & 1;
-      if (ic >= 2) mbar_wait(ctx_empty + ci, ((ic >> 1) - 1) & 1);
+      if (ic >= 2) mbar_wait_sleep(ctx_empty + ci, ((ic >> 1) - 1) & 1);
       ItemCtx& C = S.ctx[ci];
       const int a = (int)(item / nknots);
       const int t = p.t_lo + (int)(item - (long long)a * nknots);
@@ -272,7 +305,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
           const CUtensorMap* maps = p.fields[fid].maps2;
           for (int l = 0; l < nlinks; ++l) {
             const unsigned idx = bc + l, s = idx % PIPE_NSLOT;
-            if (idx >= PIPE_NSLOT) mbar_wait(slot_empty + s, ((idx / PIPE_NSLOT) - 1) & 1);
+            if (idx >= PIPE_NSLOT) mbar_wait_sleep(slot_empty + s, ((idx / PIPE_NSLOT) - 1) & 1);
             const int sx = C.bdim[l][0], sy = C.bdim[l][1], sz = C.bdim[l][2];
             const int mi = ((sx / 4 - 2) * PIPE_NAXC + (sy / 4 - 2)) * PIPE_NAXC + (sz / 4 - 2);
             mbar_expect_tx(slot_full + s, (uint32_t)(sx * sy * sz * sizeof(float)));
@@ -289,11 +322,10 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
   // =============================== CONSUMER WARPS ===============================
   float* stage = stage_base + warp * st_floats;
   const int gq = lane >> 2, tq = lane & 3;
-  const int nchunks = R.nchunks;
   unsigned ic = 0, bc = 0;
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
     const int ci = ic & 1;
-    mbar_wait(ctx_full + ci, (ic >> 1) & 1);
+    mbar_wait_sleep(ctx_full + ci, (ic >> 1) & 1);
     const ItemCtx& C = S.ctx[ci];
     const int b = C.b, t = C.t, fid = C.fid;
     const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
@@ -305,6 +337,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
     float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
 
     if (p.collision) {
+      int ch = warp;  // chunks are dealt round-robin over the whole item: this warp owns ch = warp, warp+NC, ...
       for (int l = 0; l < nlinks; ++l) {
         // every consumer warp observes every brick (full) before it releases it (empty), chunks or not: an early release
         // of a later use of the same slot could otherwise complete the empty barrier of the current use
@@ -313,21 +346,21 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
         int dxm2 = 0, dym2 = 0, dzm2 = 0, dy = 0, dz = 0, fast = 0;
         if (fid >= 0) {
           const unsigned idx = bc + l;
-          mbar_wait(slot_full + (idx % PIPE_NSLOT), (idx / PIPE_NSLOT) & 1);
+          mbar_wait_sleep(slot_full + (idx % PIPE_NSLOT), (idx / PIPE_NSLOT) & 1);
           brick = ring + (size_t)(idx % PIPE_NSLOT) * pp.slot_floats;
           clx = C.cl[l][0]; cly = C.cl[l][1]; clz = C.cl[l][2]; ipitch = C.cl[l][3];
           dxm2 = C.bdim[l][0] - 2; dy = C.bdim[l][1]; dz = C.bdim[l][2]; fast = C.bdim[l][3];
           dym2 = dy - 2; dzm2 = dz - 2;
         }
-        const int c0 = R.link_chunk0[l], c1 = R.link_chunk0[l + 1];
-        int ch = c0 + ((warp - c0 % NC) + NC) % NC;
+        const LinkMeta lm = S.links[l];
+        const int c0 = lm.c0, c1 = lm.c1;
         if (ch < c1) {
-          const unsigned mask = R.link_optmask[l];
+          const unsigned mask = lm.mask;
           float F[12];
 #pragma unroll
           for (int e = 0; e < 12; ++e) F[e] = C.frames[l][e];
           for (; ch < c1; ch += NC) {
-            const int p0 = p.chunk_start[ch], cnt = p.chunk_count[ch];
+            const int p0 = lm.pt_start + 32 * (ch - c0), cnt = min(32, lm.pt_end - p0);
             const bool act = lane < cnt;
             float J[NP];
 #pragma unroll
@@ -374,16 +407,32 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
             }
             cacc = fmaf(r, r, cacc);
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              if (k < nopt) {
-                gacc[k] = fmaf(J[k], r, gacc[k]);
-                stage[lane * RS + k] = J[k];
-              }
+            for (int k = 0; k < NP; ++k)
+              if (k < nopt) gacc[k] = fmaf(J[k], r, gacc[k]);
+            if (NOPT_CT == 7) {  // row = [J0..J6 | r] = 32 bytes: two 128-bit shared stores
+              float4* s4 = reinterpret_cast<float4*>(stage + lane * 8);
+              s4[0] = make_float4(J[0], J[1], J[2], J[3]);
+              s4[1] = make_float4(J[4], J[5], J[6], r);
+            } else {
+#pragma unroll
+              for (int k = 0; k < NP; ++k)
+                if (k < nopt) stage[lane * RS + k] = J[k];
+              stage[lane * RS + nopt] = r;
             }
-            stage[lane * RS + nopt] = r;
             __syncwarp();
             mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
-            if (rows_b) store_rows(rows_b + ((long long)t * R.npoints + p0) * RS, stage, cnt * RS, lane);
+            if (rows_b) {
+              float* dst = rows_b + ((long long)t * R.npoints + p0) * RS;
+              if (NOPT_CT == 7 && cnt == 32) {  // 1 KB tile, 16-byte aligned by construction
+                const float4* s4 = reinterpret_cast<const float4*>(stage);
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                const float4 v0 = s4[lane], v1 = s4[lane + 32];
+                __stcs(d4 + lane, v0);
+                __stcs(d4 + lane + 32, v1);
+              } else {
+                store_rows(dst, stage, cnt * RS, lane);
+              }
+            }
             __syncwarp();
           }
         }

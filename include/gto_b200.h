@@ -40,6 +40,8 @@ extern "C" {
 #define GTO_STATUS_MAX_ITER 1
 #define GTO_STATUS_NAN 2
 #define GTO_STATUS_STALLED 3  /* damping hit lambda_max without an acceptable step */
+#define GTO_STATUS_SLOW 4     /* heavily damped accepted steps no longer reduce the cost (iterate sits at a kink of the
+                                 piecewise-trilinear field); the trajectory is returned but not counted as converged */
 
 /* joint types in the robot table */
 #define GTO_JOINT_REVOLUTE 1
@@ -106,6 +108,8 @@ typedef struct gto_options {
   double noise_rel;    /* cost reductions below noise_rel*point-cost count as fp32 noise (1e-6) */
   double bound_eps;    /* 1e-12 */
   int32_t check_every; /* host polls the device convergence counter every this many iterations (4) */
+  double ftol;         /* GTO_STATUS_SLOW: accepted step with cost reduction <= ftol*f ...          (1e-6) */
+  double lambda_slow;  /* ... while the damping that produced it was >= lambda_slow                  (1.0)  */
 } gto_options;
 
 /*

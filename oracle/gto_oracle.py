@@ -472,12 +472,15 @@ class SolverOptions:
     eta: float = 1e-4  # acceptance ratio
     noise_rel: float = 1e-6  # reductions below noise_rel * point-cost are inside fp32 noise
     bound_eps: float = 1e-12
+    ftol: float = 1e-6  # STATUS_SLOW: an accepted step reduced the cost by <= ftol*f ...
+    lambda_slow: float = 1.0  # ... while the damping that produced it was >= lambda_slow
 
 
 STATUS_CONVERGED = 0
 STATUS_MAX_ITER = 1
 STATUS_NAN = 2
 STATUS_STALLED = 3
+STATUS_SLOW = 4
 
 
 def _system(p: Problem, Qx: np.ndarray, lin: Linearization):
@@ -651,12 +654,16 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
         step = float(np.max(np.abs(d))) if d.size else 0.0
         if pred > 0 and ared + noise >= opts.eta * pred:
             rho = ared / pred if pred > 0 else 1.0
+            F_before, lam_used = F, lam
             Q, lin, F = Qt, lin_t, Ft
             lam = max(opts.lambda_min, lam * max(1.0 / 3.0, 1.0 - (2.0 * min(rho, 1.0) - 1.0) ** 3))
             nu = 2.0
             hist.append(F)
             if step <= opts.tol_step:
                 status = STATUS_CONVERGED
+                break
+            if lam_used >= opts.lambda_slow and ared <= opts.ftol * F_before:
+                status = STATUS_SLOW  # heavily damped and no longer reducing the cost: a kink of the trilinear field
                 break
         else:
             if pred <= 0 and step <= opts.tol_step:

@@ -32,7 +32,7 @@ def test_default_options_match_oracle():
 
     o = capi.default_options()
     ref = O.SolverOptions()
-    for k in ("max_iter", "tol_step", "tol_grad", "lambda0", "lambda_min", "lambda_max", "eta", "noise_rel", "bound_eps"):
+    for k in ("max_iter", "tol_step", "tol_grad", "lambda0", "lambda_min", "lambda_max", "eta", "noise_rel", "bound_eps", "ftol", "lambda_slow"):
         assert getattr(o, k) == getattr(ref, k), k
 
 
@@ -62,7 +62,7 @@ def test_struct_layouts_follow_header_field_order():
 def test_status_and_flag_constants_match_header():
     hdr = _header()
     for name, val in (("GTO_STATUS_CONVERGED", capi.STATUS_CONVERGED), ("GTO_STATUS_MAX_ITER", capi.STATUS_MAX_ITER),
-                      ("GTO_STATUS_NAN", capi.STATUS_NAN), ("GTO_STATUS_STALLED", capi.STATUS_STALLED)):
+                      ("GTO_STATUS_NAN", capi.STATUS_NAN), ("GTO_STATUS_STALLED", capi.STATUS_STALLED), ("GTO_STATUS_SLOW", capi.STATUS_SLOW)):
         assert int(re.search(r"#define %s (\d+)" % name, hdr).group(1)) == val
     for name, val in (("GTO_FLAG_NO_JROWS", capi.FLAG_NO_JROWS), ("GTO_FLAG_NO_TMA", capi.FLAG_NO_TMA), ("GTO_FLAG_NO_BRICK", capi.FLAG_NO_BRICK)):
         assert int(re.search(r"#define %s (\d+)u" % name, hdr).group(1)) == val

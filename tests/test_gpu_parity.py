@@ -169,7 +169,9 @@ def test_solve_properties_full_c2(ctx):
     t, b = w.table, w.batch
     Q = res["Q"]
     oi = t.opt_qidx
-    assert np.mean(res["status"] == capi.STATUS_CONVERGED) > 0.95
+    st = res["status"]
+    assert np.mean(st == capi.STATUS_CONVERGED) > 0.9  # step / gradient criterion
+    assert np.mean((st == capi.STATUS_CONVERGED) | (st == capi.STATUS_SLOW)) > 0.98  # + stopped at a kink of the field
     np.testing.assert_array_equal(Q[:, 0, oi], b.qc[:, oi])  # initial configuration
     np.testing.assert_array_equal(Q[:, 1, oi], b.qc[:, oi])  # zero initial velocity
     assert np.all(Q[:, :, oi] >= t.lo - 1e-12) and np.all(Q[:, :, oi] <= t.hi + 1e-12)
