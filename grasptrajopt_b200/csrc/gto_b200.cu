@@ -699,7 +699,9 @@ struct StepParams {
   int T;
   double dt, w_vel;
   int max_iter;
-  double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps, ftol, lambda_slow;
+  double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps, ftol, lambda_slow, slow_ftol;
+  int slow_window;
+  double* Fhist;  // [B][16] accepted cost per iteration (ring)
   double* Qc;
   double* Qt;
   double* q_trial;
@@ -811,6 +813,16 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
           if (lam >= p.lambda_max) done = GTO_STATUS_STALLED;
         }
       }
+    }
+    if (done < 0 && isfinite(Ft) && p.slow_window > 0) {  // windowed progress test on the accepted cost
+      const double Fnow = (cur == tri) ? Ft : p.F[b];
+      double* hist = p.Fhist + (long long)b * 16;
+      if (it >= p.slow_window) {
+        const double Fold = hist[(it - p.slow_window) & 15];
+        if (Fold - Fnow <= p.slow_ftol * Fnow) done = GTO_STATUS_SLOW;
+      }
+      __syncwarp();
+      if (lane == 0) hist[it & 15] = Fnow;
     }
     if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
     if (done >= 0) {
@@ -1130,7 +1142,7 @@ struct gto_ctx {
   double dt = 0, w_goal = 1, w_obs = 10, w_vel = 0.01;
   int standoff_offset = -10, use_standoff = 1, collision = 1;
   unsigned flags = 0;
-  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, outQ, outdQ, outcost;
+  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, Fhist, outQ, outdQ, outcost;
   DevBuf<double> q_trial, goal_tf;
   DevBuf<float> base, H, g, costp, rows, result;
   DevBuf<int> field_ids, bufsel, iters, status, active, nactive;
@@ -1168,6 +1180,8 @@ extern "C" void gto_default_options(gto_options* o) {
   o->check_every = 4;
   o->ftol = 1e-6;
   o->lambda_slow = 1.0;
+  o->slow_window = 0;
+  o->slow_ftol = 1e-3;
 }
 
 extern "C" const char* gto_last_error(gto_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1223,7 +1237,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   ctx->px.release(); ctx->py.release(); ctx->pz.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
   ctx->qc.release(); ctx->q_seed.release(); ctx->Qc.release(); ctx->Qt.release(); ctx->F.release(); ctx->Fp.release();
-  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release();
+  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release(); ctx->Fhist.release();
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
@@ -1624,6 +1638,9 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   st.robot = ctx->robot_d; st.T = T; st.dt = ctx->dt; st.w_vel = ctx->w_vel; st.max_iter = o.max_iter;
   st.tol_step = o.tol_step; st.tol_grad = o.tol_grad; st.lambda_min = o.lambda_min; st.lambda_max = o.lambda_max; st.eta = o.eta;
   st.noise_rel = o.noise_rel; st.bound_eps = o.bound_eps; st.ftol = o.ftol; st.lambda_slow = o.lambda_slow;
+  st.slow_ftol = o.slow_ftol; st.slow_window = std::min(16, std::max(0, (int)o.slow_window));
+  CK(ctx->Fhist.ensure((size_t)B * 16));
+  st.Fhist = ctx->Fhist.p;
   st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;
   st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
   st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;

@@ -110,6 +110,9 @@ typedef struct gto_options {
   int32_t check_every; /* host polls the device convergence counter every this many iterations (4) */
   double ftol;         /* GTO_STATUS_SLOW: accepted step with cost reduction <= ftol*f ...          (1e-6) */
   double lambda_slow;  /* ... while the damping that produced it was >= lambda_slow                  (1.0)  */
+  int32_t slow_window; /* GTO_STATUS_SLOW as well when the cost fell by <= slow_ftol*f over the last slow_window
+                          iterations (default 0 = disabled: it also fires during slow but healthy linear convergence; at most 16) */
+  double slow_ftol;    /* (1e-3) */
 } gto_options;
 
 /*

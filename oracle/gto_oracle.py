@@ -474,6 +474,8 @@ class SolverOptions:
     bound_eps: float = 1e-12
     ftol: float = 1e-6  # STATUS_SLOW: an accepted step reduced the cost by <= ftol*f ...
     lambda_slow: float = 1.0  # ... while the damping that produced it was >= lambda_slow
+    slow_window: int = 0  # >0: STATUS_SLOW as well when the cost fell by <= slow_ftol*f over the last slow_window iterations (off)
+    slow_ftol: float = 1e-3
 
 
 STATUS_CONVERGED = 0
@@ -634,6 +636,8 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
     lam, nu = opts.lambda0, 2.0
     status = STATUS_MAX_ITER
     hist = [F]
+    fhist = [0.0] * 16
+    fhist[0] = F
     it = 0
     while it < opts.max_iter:
         Qx_trial, d, pred, pgnorm = lm_step(p, Q[:, oi], lin, lam, opts)
@@ -674,6 +678,11 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
             if lam >= opts.lambda_max:
                 status = STATUS_STALLED
                 break
+        if opts.slow_window > 0:  # windowed progress test on the accepted cost (same bookkeeping as k_step)
+            if it >= opts.slow_window and fhist[(it - opts.slow_window) % 16] - F <= opts.slow_ftol * F:
+                status = STATUS_SLOW
+                break
+            fhist[it % 16] = F
     Qf, dQ = unpack_solution(p, Q)
     return SolveResult(Qf, dQ, F, it, status, hist)
 

@@ -32,7 +32,7 @@ def test_default_options_match_oracle():
 
     o = capi.default_options()
     ref = O.SolverOptions()
-    for k in ("max_iter", "tol_step", "tol_grad", "lambda0", "lambda_min", "lambda_max", "eta", "noise_rel", "bound_eps", "ftol", "lambda_slow"):
+    for k in ("max_iter", "tol_step", "tol_grad", "lambda0", "lambda_min", "lambda_max", "eta", "noise_rel", "bound_eps", "ftol", "lambda_slow", "slow_window", "slow_ftol"):
         assert getattr(o, k) == getattr(ref, k), k
 
 
