@@ -116,48 +116,23 @@ def algorithmic_bytes(w, prof, n_fields_per_launch=2):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def cpu_oracle_sample(w, idx):
+def time_cpu(w, nsample, nthreads):
+    """C restatement of the oracle (oracle/gto_oracle.c, float64, one pthread per core) on a bounded sample of the workload."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
-    sys.path.insert(0, os.path.join(REPO, "tests"))
-    import gto_oracle as O
-    from helpers import problems_from_workload
+    import c_oracle
 
-    out = []
-    for p in problems_from_workload(w, idx):
-        r = O.solve_lm(p)
-        out.append((r.status, r.iters, r.cost))
-    return out
-
-
-def _cpu_worker(args):
-    config, scale, idx = args
-    from grasptrajopt_b200 import workloads as W
-
-    w = W.make_workload(config, scale=scale)
-    return cpu_oracle_sample(w, idx)
-
-
-def time_cpu(config, scale, nsample, B, nproc):
-    """Oracle port on `nproc` host processes over a bounded sample of the same workload."""
-    import multiprocessing as mp
-
-    idx = list(np.linspace(0, B - 1, nsample).astype(int))
-    chunks = [idx[i::nproc] for i in range(nproc) if idx[i::nproc]]
+    B = w.batch.B
+    idx = np.unique(np.linspace(0, B - 1, min(nsample, B)).astype(int))
+    c_oracle.load()
     t0 = time.perf_counter()
-    if len(chunks) == 1:
-        res = [_cpu_worker((config, scale, chunks[0]))]
-    else:
-        with mp.get_context("spawn").Pool(len(chunks)) as pool:
-            res = pool.map(_cpu_worker, [(config, scale, c) for c in chunks])
+    res = c_oracle.solve_workload(w, indices=idx, nthreads=nthreads)
     dt = time.perf_counter() - t0
-    flat = [r for c in res for r in c]
-    conv = sum(1 for r in flat if r[0] == 0)
-    return dt, conv, len(flat), len(chunks)
+    return dt, int(np.sum(res["status"] == 0)), len(idx), int(res["threads"])
 
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU path.  CasADi/IPOPT are not installable offline, so this is the oracle port
-    (same reduced problem, projected LM, float64 NumPy) on all host cores; each step is a bounded sample of the workload."""
+    (same reduced problem, projected LM, float64 C) on all host cores; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,25 +141,25 @@ def run_reference(args):
     ncpu = os.cpu_count() or 1
     w = W.make_workload(args.config, scale=args.scale)
     B = w.batch.B
-    nsample = max(1, min(B, ncpu))
+    nsample = max(1, min(B, 8 * ncpu))
     for _ in range(max(0, min(args.warmup, 1))):
-        time_cpu(args.config, args.scale, nsample, B, min(ncpu, nsample))
-    tot_t, tot_conv = 0.0, 0
+        time_cpu(w, nsample, ncpu)
+    tot_t, tot_conv, threads = 0.0, 0, ncpu
     steps = max(1, args.steps)
     for _ in range(steps):
-        dt, conv, n, nproc = time_cpu(args.config, args.scale, nsample, B, min(ncpu, nsample))
+        dt, conv, n, threads = time_cpu(w, nsample, ncpu)
         tot_t += dt
         tot_conv += conv
     value = tot_conv / tot_t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": w.description, "config": args.config},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(ncpu, nsample), "kind": "port",
-                         "sample": f"{nsample} of {B} problems per step, oracle/gto_oracle.py solve_lm, one process per core (wall clock incl. workload regeneration per process)"},
+        "data": "synthetic", "config": {"workload": w.description, "config": args.config.upper()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{nsample} of {B} problems per step, oracle/gto_oracle.c (projected LM, float64), {threads} pthreads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference CasADi/IPOPT path not installable offline; published wall-clock is ~0.1 trajectories/s (BASELINE.md)",
+        "note": "reference CasADi/IPOPT path not installable offline; its published wall-clock is ~0.1 trajectories/s (BASELINE.md)",
     }
     print(json.dumps(line))
 
@@ -336,10 +311,11 @@ def run_b200(args):
         }
         # CPU baseline on rank 0 at N=1 only: bounded sample of the same workload
         if world == 1 and args.cpu_sample != 0:
-            ns = args.cpu_sample if args.cpu_sample > 0 else 2
-            dt, cconv, n, nproc = time_cpu(args.config, scale, ns, B, 1)
-            line["cpu_baseline"] = {"value": cconv / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{ns} of {B} problems of the same workload, oracle/gto_oracle.py solve_lm (float64 NumPy), 1 process"}
+            ncpu = os.cpu_count() or 1
+            ns = args.cpu_sample if args.cpu_sample > 0 else min(B, 16 * ncpu)
+            dt, cconv, n, threads = time_cpu(w, ns, ncpu)
+            line["cpu_baseline"] = {"value": cconv / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n} of {B} problems of the same workload, oracle/gto_oracle.c (projected LM, float64), {threads} pthreads, {dt:.1f} s"}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
