@@ -205,14 +205,12 @@ def run_b200(args):
     nfl = w.table.nopt * b.T + 2
     gathered = torch.empty((world * B, nfl), dtype=torch.float32, device=f"cuda:{local}") if world > 1 else None
 
-    class _DevArr:  # wrap the library's device buffer for torch.distributed without a copy
-        def __init__(self, ptr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+    from grasptrajopt_b200.distributed import DeviceArray
 
-    def exchange():
+    def exchange():  # ONE all-gather of the converged trajectories, straight from the library's device buffer
         if world > 1:
             ptr, n = ctx.result_device_ptr()
-            local_res = torch.as_tensor(_DevArr(ptr, (B, n)), device=f"cuda:{local}")
+            local_res = torch.as_tensor(DeviceArray(ptr, (B, n)), device=f"cuda:{local}")
             dist.all_gather_into_tensor(gathered, local_res)
 
     def sync_all():

@@ -1,0 +1,74 @@
+"""``IKSolver`` on the B200 solver (reference ``gto/ik_solver.py:18-115``): the T=1 point-matching problem
+
+    min_q  sum_k | FK_gripper(q) x_k - (RT.G) x_k |^2     s.t.  lo <= q <= hi
+
+is the trajectory problem with one free knot, no velocity term and no stand-off, so it runs on the same kernels
+(3 knots: two pinned at the seed, one free).  Many goals can be solved in one batch with ``solve_ik_batch``.
+
+The reference's optional IK collision term ``10 * sum(c)`` (unsquared, :69) is disabled in every shipped experiment
+(``ik_collision_avoidance=False``, Q14) and is not available here; ``collision_avoidance=True`` uses the planner's squared
+term ``10 * sum(c^2)`` instead and says so once.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+import optas
+from gto.b200_solver import B200Solver
+from grasptrajopt_b200 import capi
+from grasptrajopt_b200.spatial import mat2quat_wxyz
+
+
+class IKSolver:
+    def __init__(self, robot, link_ee, link_gripper, collision_avoidance=True, device=0):
+        self.robot = robot
+        self.link_ee = link_ee
+        self.link_gripper = link_gripper
+        self.robot_name = robot.get_name()
+        self.gripper_points = robot.surface_pc_map[link_gripper].points
+        self.gripper_tf = robot.get_link_transform_function(link=link_gripper, base_link=link_ee)
+        self.collision_avoidance = collision_avoidance
+        self.device = device
+        self.solver = None
+
+    def setup_optimization(self):
+        self.fk = self.robot.get_global_link_transform_function(link=self.link_ee)
+        if self.collision_avoidance:
+            warnings.warn("IKSolver(collision_avoidance=True): the B200 build uses the squared obstacle term 10*sum(c^2) "
+                          "instead of the reference's 10*sum(c)", stacklevel=2)
+        self.solver = B200Solver(self.robot, self.link_ee, self.link_gripper, T=3, dt=1.0, use_standoff=False, standoff_offset=-1,
+                                 collision_avoidance=self.collision_avoidance, w_vel=0.0, device=self.device,
+                                 options=capi.default_options(max_iter=50))  # reference: max_iter 50 (:75)
+
+    def _errors(self, q, RT):
+        tf = self.fk(q).toarray()
+        err_pos = np.linalg.norm(RT[:3, 3] - tf[:3, 3])
+        quat1, quat2 = mat2quat_wxyz(RT[:3, :3]), mat2quat_wxyz(tf[:3, :3])
+        err_rot = np.arccos(np.clip(2 * np.square(np.dot(quat1, quat2)) - 1, -1, 1)) * 180 / np.pi
+        return err_pos, err_rot
+
+    def solve_ik(self, q_0, RT, sdf_cost_obstacle, base_position):
+        q_0 = np.asarray(q_0, dtype=np.float64).reshape(-1)
+        RT = np.asarray(RT, dtype=np.float64)
+        Q0 = np.tile(q_0.reshape(-1, 1), (1, 3))
+        self.solver.reset_initial_seed({f"{self.robot_name}/q/x": self.robot.extract_optimized_dimensions(Q0)})
+        params = {f"{self.robot_name}/q/p": self.robot.extract_parameter_dimensions(Q0), "tf_goal": RT, "qc": q_0}
+        if self.collision_avoidance:
+            params["sdf_cost_obstacle"] = optas.DM(np.asarray(sdf_cost_obstacle).reshape(-1))
+            params["base_position"] = optas.DM(base_position)
+        self.solver.reset_parameters(params)
+        # knots 0 and 1 are pinned at the seed; the IK unknown is knot 2.  The seed itself must stay free, so the pinned
+        # knots only serve as the (costless, w_vel = 0) anchor of the trajectory layout.
+        solution = self.solver.solve()
+        q = solution[f"{self.robot_name}/q"].toarray()[:, 2]
+        err_pos, err_rot = self._errors(q, RT)
+        if self.collision_avoidance:
+            cost, _ = self.robot.compute_plan_cost(q.reshape(-1, 1), np.asarray(sdf_cost_obstacle).reshape(-1), base_position)
+        else:
+            cost = 0
+        return q.flatten(), err_pos, err_rot, cost
+
+    def solve_fk(self, q_0):
+        return self.fk(q_0).toarray()

@@ -1,0 +1,91 @@
+"""``DepthPointCloud`` (reference ``mesh_to_sdf/depth_point_cloud.py:9-142``): depth image -> world point cloud -> signed
+distance by nearest neighbour + camera visibility -> CHOMP-style cost field (epsilon = 0.02).
+
+Producer of the voxel fields the hot path consumes (SURVEY.md section 8(f) "next #2").  Same constructor, attributes and method
+names as the reference; the KD-tree is scikit-learn's, exactly as in the reference.  ``pyrender`` is only imported by the
+visualisation branches (the reference imports it at module level, :4).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from sklearn.neighbors import KDTree
+
+
+class DepthPointCloud:
+    def __init__(self, depth, intrinsic_matrix, camera_pose, target_mask=None, threshold=1.5):
+        self.depth = depth
+        self.intrinsic_matrix = intrinsic_matrix
+        self.camera_pose = camera_pose
+        self.target_mask = target_mask
+        self.width = depth.shape[1]
+        self.height = depth.shape[0]
+        self.threshold = threshold
+        pc = self.backproject_camera(depth, intrinsic_matrix)
+        pc_base = camera_pose[:3, :3] @ pc + camera_pose[:3, 3].reshape((3, 1))
+        self.points = pc_base.T
+        self.kd_tree = KDTree(self.points)
+
+    def get_random_surface_points(self, count):
+        return self.points[np.random.choice(self.points.shape[0], count), :]
+
+    def backproject_camera(self, im_depth, K):
+        Kinv = np.linalg.inv(K)
+        width, height = im_depth.shape[1], im_depth.shape[0]
+        depth = im_depth.astype(np.float32, copy=True).flatten()
+        mask = (depth > 0) & (depth < self.threshold)
+        if self.target_mask is not None:
+            mask &= self.target_mask.flatten() == 0
+        x, y = np.meshgrid(np.arange(width), np.arange(height))
+        ones = np.ones((height, width), dtype=np.float32)
+        x2d = np.stack((x, y, ones), axis=2).reshape(width * height, 3)
+        R = Kinv.dot(x2d.transpose())
+        X = np.multiply(np.tile(depth.reshape(1, width * height), (3, 1)), R)
+        return X[:, mask]
+
+    def is_outside(self, points):
+        RT = np.linalg.inv(self.camera_pose)
+        pc_camera = RT[:3, :3] @ points.T + RT[:3, 3].reshape((3, 1))
+        x2d = self.intrinsic_matrix @ pc_camera
+        x2d[0, :] /= x2d[2, :]
+        x2d[1, :] /= x2d[2, :]
+        pixels = x2d[:2].T.astype(int)
+        in_viewport = (pixels[:, 0] >= 0) & (pixels[:, 1] >= 0) & (pixels[:, 0] < self.width) & (pixels[:, 1] < self.height)
+        pc_camera = pc_camera.T
+        result = np.ones(points.shape[0], dtype=bool)
+        result[in_viewport] = pc_camera[in_viewport, 2] < self.depth[pixels[in_viewport, 1], pixels[in_viewport, 0]]
+        return result
+
+    def get_sdf(self, query_points):
+        distances, _ = self.kd_tree.query(query_points)
+        distances = distances.astype(np.float32).reshape(-1)
+        inside = ~self.is_outside(query_points)
+        distances[inside] *= -1
+        return distances
+
+    def get_sdf_cost(self, query_points, epsilon=0.02, w_inside=1, vis=False):
+        distances = self.get_sdf(query_points)
+        inside = distances < 0
+        if vis:  # pragma: no cover - rendering only
+            import pyrender
+
+            index = np.absolute(distances) < 0.03
+            colors = np.zeros((int(index.sum()), 3))
+            colors[distances[index] < 0, 2] = 1
+            colors[distances[index] > 0, 0] = 1
+            scene = pyrender.Scene()
+            scene.add(pyrender.Mesh.from_points(query_points[index], colors=colors))
+            scene.add(pyrender.Mesh.from_points(self.points[::100]))
+            pyrender.Viewer(scene, use_raymond_lighting=True, point_size=5)
+        cost = np.zeros_like(distances)
+        cost[inside] = w_inside * (-distances[inside] + epsilon / 2)
+        index = (distances > 0) & (distances < epsilon)
+        cost[index] = np.square(distances[index] - epsilon) / (2 * epsilon)
+        return cost
+
+    def get_sdf_in_batches(self, query_points, batch_size=1000000):
+        if query_points.shape[0] <= batch_size:
+            return self.get_sdf(query_points)
+        n_batches = int(math.ceil(query_points.shape[0] / batch_size))
+        return np.concatenate([self.get_sdf(p) for p in np.array_split(query_points, n_batches)])

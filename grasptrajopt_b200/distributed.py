@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing: problems are independent, so a batch is split into contiguous shards (one process per GPU,
+``torch.distributed``), each rank solves its shard with no communication, and the converged trajectories are exchanged
+with ONE all-gather of the packed float32 results ``[B_local, nopt*T + 2]`` = (optimised rows of Q knot-major, cost,
+status) -- SURVEY.md section 8(e).  On GPUs the payload is the library's own device buffer (``gto_result_device_ptr``) and the
+backend is NCCL over NVLink; the same code runs with ``gloo`` on CPU tensors in the tests."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(B: int, rank: int, world: int):
+    """Contiguous equal split of [0, B) (remainder to the first ranks)."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_result(Q: np.ndarray, cost: np.ndarray, status: np.ndarray, opt_qidx) -> np.ndarray:
+    """Host-side twin of the packing k_finalize does on the device."""
+    B, T = Q.shape[0], Q.shape[1]
+    out = np.zeros((B, len(opt_qidx) * T + 2), dtype=np.float32)
+    out[:, : len(opt_qidx) * T] = Q[:, :, opt_qidx].reshape(B, -1)
+    out[:, -2] = cost
+    out[:, -1] = status
+    return out
+
+
+def unpack_result(packed: np.ndarray, T: int, nopt: int):
+    packed = np.asarray(packed)
+    B = packed.shape[0]
+    return packed[:, : nopt * T].reshape(B, T, nopt), packed[:, -2], packed[:, -1].astype(np.int32)
+
+
+class DeviceArray:
+    """Zero-copy view of a raw device pointer for ``torch.as_tensor`` (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def all_gather_results(local, world: int, counts=None):
+    """All-gather of per-rank packed results (torch tensors, equal or ragged shard sizes).  Returns [sum(B_r), nfl]."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    if counts is None or len(set(counts)) == 1:
+        out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    mx = max(counts)
+    pad = torch.zeros((mx, local.shape[1]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * mx, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    return torch.cat([out[r * mx : r * mx + counts[r]] for r in range(world)], dim=0)

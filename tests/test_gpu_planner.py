@@ -1,0 +1,90 @@
+"""The reference-facing planner classes (gto.GTOPlanner / gto.IKSolver on B200Solver) end to end on the GPU, checked against
+the oracle on the same inputs.  Uses a small synthetic URDF + box meshes written at test time (the GPU box has no
+reference checkout).  Run with -m gpu."""
+import numpy as np
+import pytest
+
+import gto_oracle as O
+from gto.gto_models import GTORobotModel
+from gto.gto_planner import GTOPlanner
+from gto.ik_solver import IKSolver
+from grasptrajopt_b200 import scenes as S
+
+from test_compat_api import _write_box
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def robot(tmp_path_factory):
+    d = tmp_path_factory.mktemp("arm3")
+    _write_box(d)
+    r = GTORobotModel(str(d), urdf_filename=str(d / "arm3.urdf"), time_derivs=[0, 1], param_joints=["slide"],
+                      collision_link_names=["base", "l1", "l2", "tool"], sample_point_count=64, seed=1)
+    r.setup_workspace_field(arm_len=0.6, arm_height=0.2)
+    return r
+
+
+def _problem(robot, planner, qc, RT, seed, field_all, field_obs, use_standoff, axis):
+    t = robot.to_table("tool", "tool")
+    shape = tuple(robot.field_shape)
+    mk = lambda c: None if c is None or not np.any(c) else O.Field(np.asarray(c, np.float32).reshape(shape), robot.origin.reshape(3), robot.grid_resolution)
+    return O.Problem(table=t, T=planner.T, dt=planner.dt, qc=qc, RT=RT, q_seed=seed.T, base_position=np.zeros(3), field_all=mk(field_all),
+                     field_obs=mk(field_obs), standoff_offset=planner.standoff_offset, standoff_distance=planner.standoff_distance,
+                     axis_standoff=axis, use_standoff=use_standoff, collision_avoidance=True)
+
+
+def test_plan_matches_oracle(robot):
+    planner = GTOPlanner(robot, "tool", "tool", standoff_distance=-0.05)
+    planner.T = 30
+    assert planner.dt == pytest.approx(10.0 / 29)
+    qc = np.array([0.2, -0.3, 0.01])
+    q_star = np.array([1.1, 0.6, 0.01])
+    RT = robot.get_global_link_transform("tool", q_star).toarray()
+    sdf = np.zeros(robot.field_size)
+    Q, dQ, cost = planner.plan(qc, RT, sdf, [0, 0, 0], q_solution=q_star + 0.05, use_standoff=True, axis_standoff="x")
+    assert Q.shape == (3, 30) and dQ.shape == (3, 29) and cost.shape == (1,)
+    seed = planner._seed_from(qc, q_star + 0.05)
+    r = O.solve_lm(_problem(robot, planner, qc, RT, seed, None, None, True, "x"))
+    assert np.abs(Q.T - r.Q).max() < 1e-4
+    assert cost[0] == pytest.approx(r.cost, rel=1e-5)
+    np.testing.assert_array_equal(Q[2], qc[2])  # parameter joint row constant
+    assert planner.solver.did_solve() and planner.solver.number_of_iterations() == r.iters
+
+
+def test_plan_goalset_returns_cheapest_goal(robot):
+    planner = GTOPlanner(robot, "tool", "tool", standoff_distance=-0.05)
+    planner.T = 30
+    qc = np.array([0.2, -0.3, 0.01])
+    q_goals = np.array([[1.1, 0.6, 0.01], [-1.4, 1.3, 0.01], [0.4, -0.9, 0.01]])
+    RTs = np.stack([robot.get_global_link_transform("tool", q).toarray() for q in q_goals])
+    # obstacle field: a box near the second goal makes it expensive
+    boxes = [((float(RTs[1][0, 3]), float(RTs[1][1, 3]), float(RTs[1][2, 3])), (0.15, 0.15, 0.15))]
+    cost = S.sdf_cost(S.box_sdf(robot.workspace_points, boxes)).astype(np.float64)
+    Q, dQ, f = planner.plan_goalset(qc, RTs, cost, cost, [0, 0, 0], q_solutions=q_goals.T, use_standoff=True, axis_standoff="x")
+    res = planner.solver.batch_result
+    assert res["cost"].shape == (3,) and f[0] == pytest.approx(res["cost"].min())
+    best = int(np.argmin(res["cost"]))
+    assert best != 1
+    np.testing.assert_allclose(Q.T, res["Q"][best])
+    # the seed chosen by the GPU ranking pass equals the reference's NumPy ranking
+    plans = np.stack([planner._seed_from(qc, q) for q in q_goals])
+    c_gpu, d_gpu = planner._rank_seeds(plans, cost, [0, 0, 0])
+    for i in range(3):
+        c_ref, d_ref = robot.compute_plan_cost(plans[i], cost, [0, 0, 0])
+        assert c_gpu[i] == pytest.approx(c_ref, rel=1e-4, abs=1e-6) and d_gpu[i] == pytest.approx(d_ref)
+    # per-goal solutions agree with the oracle
+    seed = plans[np.lexsort((d_gpu, c_gpu))[0]]
+    for i in (0, 2):
+        r = O.solve_lm(_problem(robot, planner, qc, RTs[i], seed, cost, cost, True, "x"))
+        assert res["cost"][i] == pytest.approx(r.cost, rel=1e-3)
+
+
+def test_ik_solver_reaches_pose(robot):
+    ik = IKSolver(robot, "tool", "tool", collision_avoidance=False)
+    ik.setup_optimization()
+    q_star = np.array([0.9, 0.5, 0.02])
+    RT = robot.get_global_link_transform("tool", q_star).toarray()
+    q, err_pos, err_rot, cost = ik.solve_ik(np.array([0.5, 0.1, 0.02]).reshape(-1, 1), RT, np.zeros(robot.field_size), [0, 0, 0])
+    assert q.shape == (3,) and err_pos < 1e-4 and err_rot < 0.05 and cost == 0
+    assert q[2] == 0.02
