@@ -55,6 +55,7 @@ struct RobotDev {
   float link_center[GTO_MAX_LINKS][4];  // AABB of the link's points in its visual frame
   float link_half[GTO_MAX_LINKS][4];
   int link_chunk0[GTO_MAX_LINKS + 1];   // chunk range per link
+  int part_link0[3][5];                 // link ranges when an item is split in 1 / 2 / 4 parts (tail launches)
   int grip_mov;
   float grip_tf[12];
   int grip_pt_start, grip_pt_count;
@@ -92,13 +93,15 @@ struct LinParams {
   float* H;                // [2][Bcap][T][nopt*nopt]
   float* g;                // [2][Bcap][T][nopt]
   float* costp;            // [2][Bcap][T]
-  long long buf_stride_H, buf_stride_g, buf_stride_c;
+  long long buf_stride_H, buf_stride_g, buf_stride_c;     // accepted / trial buffer
+  long long part_stride_H, part_stride_g, part_stride_c;  // item part (an item may be split over several CTAs)
   float* rows;             // [Bchunk][nrows][RS] or NULL
   long long rows_per_problem;
   int T, t_lo, knot_standoff, use_standoff, collision;
   float sw_obs, sw_goal;
   unsigned flags;
   int brick_max;           // largest brick edge that fits the shared memory carve-out
+  int allow_split;         // solver launches: split items over several CTAs when few are left (see split_factor)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -143,6 +146,15 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+#define GTO_SPLIT_MAX 4
+// Tail launches: when few (problem, knot) items are left, each item is split over 2 or 4 CTAs (contiguous link ranges).
+// Both kernels derive the factor from the same device counter, so no host round trip is needed.
+__host__ __device__ __forceinline__ int split_factor(long long nitems, int grid) {
+  if (nitems * 4 <= grid) return 4;
+  if (nitems * 2 <= grid) return 2;
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -709,6 +721,10 @@ struct StepParams {
   const float* g;
   float* costp;
   long long buf_stride_H, buf_stride_g, buf_stride_c;
+  long long part_stride_H, part_stride_g, part_stride_c;
+  int lin_grid;  // grid of the linearise launch (decides the item split, see split_factor)
+  int Bcap;
+  int* bufsplit;  // [2][Bcap] split factor each buffer was written with
   int* bufsel;
   double *F, *Fp, *lam, *nu, *pred, *stepn;
   int *iters, *status;
@@ -736,7 +752,7 @@ __device__ __forceinline__ double warp_max(double v) {
 __host__ __device__ inline size_t step_smem_bytes(int T, int n) {
   const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
   size_t d = (size_t)T * n + 3 * m * n + m * nn;
-  size_t bytes = d * sizeof(double) + (m * nn + 4) * sizeof(float) + m * n;
+  size_t bytes = d * sizeof(double) + (m * nn + 4) * sizeof(float) + ((m * n + 3) & ~(size_t)3) + (m + 1) * sizeof(unsigned);
   return (bytes + 15) & ~(size_t)15;
 }
 
@@ -761,19 +777,29 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   double* Sinv = dd + (size_t)m * n;  // [m][n*n] inverse diagonal blocks of the factor (always in shared memory)
   float* Hs = reinterpret_cast<float*>(Sinv + (size_t)m * nn);
   unsigned char* fx = reinterpret_cast<unsigned char*>(Hs + (size_t)m * nn);
+  unsigned* fm = reinterpret_cast<unsigned*>(fx + (((size_t)m * n + 3) & ~(size_t)3));  // per-block bit-mask of fixed variables
 
   double* Xc = p.Qc + (long long)b * T * n;
   double* Xt = p.Qt + (long long)b * T * n;
   int cur = p.bufsel[b];
   const int it = p.iter;
   double lam = p.lam[b], nu = p.nu[b];
+  // the linearise launch that produced the trial buffers split every item in `nsplit` parts
+  const int nsplit = split_factor((long long)(*p.nactive_in) * (it == 0 ? T : T - 2), p.lin_grid);
+  const int tri_buf = 1 - cur;
+  if (lane == 0) p.bufsplit[tri_buf * p.Bcap + b] = nsplit;
 
   // ---------------- evaluate the trial point produced by the previous call ----------------
   {
     const int tri = 1 - cur;
     float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
     double s = 0.0;
-    for (int t = lane; t < T; t += 32) s += (double)ct[t];
+    for (int t = lane; t < T; t += 32) {
+      double c = (double)ct[t];
+      if (t >= 2 || it == 0)  // knots 0,1 live in part 0 only (see below)
+        for (int part = 1; part < nsplit; ++part) c += (double)ct[part * p.part_stride_c + t];
+      s += c;
+    }
     const double Fp_t = warp_sum(s);
     s = 0.0;
     for (int i = lane; i < (T - 1) * n; i += 32) {
@@ -785,8 +811,12 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
     if (!isfinite(Ft)) {
       done = GTO_STATUS_NAN;
     } else if (it == 0) {  // initial point: accept unconditionally
-      // knots 0 and 1 never move and are linearised only once: mirror their cost into the other buffer
-      if (lane < 2) p.costp[cur * p.buf_stride_c + (long long)b * T + lane] = ct[lane];
+      // knots 0 and 1 never move and are linearised only once: keep their summed cost in part 0 of both buffers
+      if (lane < 2) {
+        float c01 = ct[lane];
+        for (int part = 1; part < nsplit; ++part) c01 += ct[part * p.part_stride_c + lane];
+        for (int buf = 0; buf < 2; ++buf) p.costp[buf * p.buf_stride_c + (long long)b * T + lane] = c01;
+      }
       cur = tri;
       if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
     } else {
@@ -836,8 +866,18 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn;
   const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
   // Gauss-Newton blocks: asynchronous 4-byte copies (cp.async), all in flight at once, no register staging
-  for (int i = lane; i < m * nn; i += 32)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(Hs + i)), "l"(Hc + 2 * nn + i) : "memory");
+  // split factor the accepted buffer was written with (it may stem from an earlier launch if trials were rejected since)
+  const int hsplit = (cur == tri_buf) ? nsplit : p.bufsplit[cur * p.Bcap + b];
+  if (hsplit == 1) {
+    for (int i = lane; i < m * nn; i += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(Hs + i)), "l"(Hc + 2 * nn + i) : "memory");
+  } else {
+    for (int i = lane; i < m * nn; i += 32) {
+      float h = Hc[2 * nn + i];
+      for (int part = 1; part < hsplit; ++part) h += Hc[part * p.part_stride_H + 2 * nn + i];
+      Hs[i] = h;
+    }
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = lane; i < T * n; i += 32) X[i] = Xc[i];
   __syncwarp();
@@ -849,7 +889,9 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
       const int k = krow, t = i + 2, idx = i * n + k;
       double gv = X[t * n + k] - X[(t - 1) * n + k];
       if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
-      const double gtv = (double)gc[t * n + k] + a2 * gv;
+      double gsum = (double)gc[t * n + k];
+      for (int part = 1; part < hsplit; ++part) gsum += (double)gc[part * p.part_stride_g + t * n + k];
+      const double gtv = gsum + a2 * gv;
       const double x = X[t * n + k];
       const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
       gt[idx] = gtv;
@@ -864,6 +906,11 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   }
   __syncwarp();
 
+  for (int i = lane; i < m; i += 32) {
+    unsigned mk = 0;
+    for (int k = 0; k < n; ++k) mk |= (unsigned)fx[i * n + k] << k;
+    fm[i] = mk;
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   // ---------------- damped projected Gauss-Newton step: block Thomas algorithm in float64 ----------------
@@ -880,15 +927,17 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
     for (int i = 0; i < m; ++i) {
       const int t = i + 2;
       const double cnt = (t < T - 1) ? 2.0 : 1.0;
-      const bool fr = rin ? (fx[i * n + r] != 0) : true;
-      const bool frp = (i > 0 && rin) ? (fx[(i - 1) * n + r] != 0) : true;
-      const double cr = (fr || frp) ? 0.0 : a2;
+      const unsigned mi = fm[i], mp = (i > 0) ? fm[i - 1] : 0u;  // fixed-variable masks of this and the previous knot
+      const bool fr = rin ? ((mi >> r) & 1u) != 0 : true;
+      const bool frp = rin ? ((mp >> r) & 1u) != 0 : true;
+      const double cr = (i == 0 || fr || frp) ? 0.0 : a2;
+      const unsigned coupled = ~(mi | mp);  // bit c set: variable c is free at both knots
       double row[NP];
 #pragma unroll
       for (int c = 0; c < NP; ++c) {
         double v = 0.0;
         if (c < n) {
-          const bool fc = fx[i * n + c] != 0;
+          const bool fc = ((mi >> c) & 1u) != 0;
           if (rin) {
             v = (double)Hs[i * nn + r * n + c];
             if (r == c) {
@@ -897,10 +946,7 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
             }
           }
           if (fr || fc) v = (r == c) ? 1.0 : 0.0;
-          if (i > 0) {
-            const double cc = (fc || fx[(i - 1) * n + c] != 0) ? 0.0 : a2;
-            v -= cr * cc * prev[c];
-          }
+          if (i > 0 && ((coupled >> c) & 1u)) v -= cr * a2 * prev[c];
         } else {
           v = (r == c) ? 1.0 : 0.0;
         }
@@ -916,16 +962,17 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
         double ip = (double)__frcp_rn((float)piv);
         ip = ip * (2.0 - piv * ip);
         ip = ip * (2.0 - piv * ip);
-        // pivot row: new = old * ip; other rows: new = old - (f*ip) * pivot_row; column k: the multiplier itself
+        // one fused form for every lane: row[c] += coef * pivot_row[c] with coef = ip - 1 on the pivot lane (-> row*ip) and
+        // -f*ip elsewhere; column k becomes the multiplier itself (ip on the pivot lane)
         const bool isk = (r == k);
-        const double coef = isk ? ip : -row[k] * ip;
+        const double mult = -row[k] * ip;
+        const double coef = isk ? ip - 1.0 : mult;
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
           if (c == k) continue;
-          const double pk = shfl_d(row[c], k);
-          row[c] = fma(coef, pk, isk ? 0.0 : row[c]);
+          row[c] = fma(coef, shfl_d(row[c], k), row[c]);
         }
-        row[k] = coef;
+        row[k] = isk ? ip : mult;
       }
       if (!ok) break;
       // v_i = Sinv_i u_i
@@ -955,16 +1002,14 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
     const int t = i + 2;
     double x = rin ? vv[i * n + r] : 0.0;
     if (i < m - 1) {
+      const unsigned coupled = ~(fm[i] | fm[i + 1]);
       double s = 0.0;
 #pragma unroll
       for (int c = 0; c < NP; ++c) {
         const double xc_ = shfl_d(xnext, c);
-        if (c < n && rin) {
-          const double cc = (fx[i * n + c] || fx[(i + 1) * n + c]) ? 0.0 : a2;
-          s += Sinv[(size_t)i * nn + r * n + c] * cc * xc_;
-        }
+        if (c < n && rin && ((coupled >> c) & 1u)) s += Sinv[(size_t)i * nn + r * n + c] * xc_;
       }
-      x += s;
+      x += a2 * s;
     }
     xnext = x;  // the unclipped solution feeds the recursion
     if (rin) {
@@ -1128,6 +1173,7 @@ struct gto_ctx {
   DevBuf<float> px, py, pz;
   DevBuf<int> chunk_start, chunk_count;
   int lin_warps = 8;
+  int last_lin_grid = 0;
   int pipe_cons = 8;
   double max_link_diag = 0.0;  // largest |half extent|_2 over links
   // fields
@@ -1145,7 +1191,7 @@ struct gto_ctx {
   DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, Fhist, outQ, outdQ, outcost;
   DevBuf<double> q_trial, goal_tf;
   DevBuf<float> base, H, g, costp, rows, result;
-  DevBuf<int> field_ids, bufsel, iters, status, active, nactive;
+  DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive;
   int* h_counter = nullptr;  // pinned
   long long rows_per_problem = 0;
   int Bchunk = 0;
@@ -1240,7 +1286,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release(); ctx->Fhist.release();
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
-  ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
+  ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
   ctx->status.release(); ctx->active.release(); ctx->nactive.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1303,6 +1349,18 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
   }
   h.link_chunk0[r->nlinks] = (int)cs.size();
   h.nchunks = (int)cs.size();
+  for (int si = 0; si < 3; ++si) {  // contiguous link ranges with balanced chunk counts for 1 / 2 / 4 parts
+    const int S = 1 << si;
+    h.part_link0[si][0] = 0;
+    int l = 0;
+    for (int part = 1; part <= S; ++part) {
+      const int target = (int)((long long)h.nchunks * part / S);
+      while (l < r->nlinks && h.link_chunk0[l + 1] <= target) ++l;
+      if (part == S) l = r->nlinks;
+      h.part_link0[si][part] = std::max(l, h.part_link0[si][part - 1]);
+    }
+    for (int part = S + 1; part < 5; ++part) h.part_link0[si][part] = r->nlinks;
+  }
   if (h.nchunks > MAX_CHUNKS * 64) return fail(ctx, GTO_ERR_INVALID, "too many surface points");
   h.grip_mov = r->grip_mov; h.grip_pt_start = r->grip_pt_start; h.grip_pt_count = r->grip_pt_count; h.grip_optmask = r->grip_optmask;
   if (r->grip_pt_start < 0 || r->grip_pt_count < 1 || r->grip_pt_start + r->grip_pt_count > r->npoints || r->grip_mov >= r->nmov)
@@ -1453,7 +1511,8 @@ extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
   CK(ctx->Qc.ensure((size_t)B * T * n)); CK(ctx->Qt.ensure((size_t)B * T * n)); CK(ctx->q_trial.ensure((size_t)B * T * nd));
   CK(ctx->F.ensure(B)); CK(ctx->Fp.ensure(B)); CK(ctx->lam.ensure(B)); CK(ctx->nu.ensure(B)); CK(ctx->pred.ensure(B)); CK(ctx->stepn.ensure(B));
   CK(ctx->bufsel.ensure(B)); CK(ctx->iters.ensure(B)); CK(ctx->status.ensure(B)); CK(ctx->active.ensure((size_t)2 * B));
-  CK(ctx->H.ensure((size_t)2 * B * T * n * n)); CK(ctx->g.ensure((size_t)2 * B * T * n)); CK(ctx->costp.ensure((size_t)2 * B * T));
+  CK(ctx->H.ensure((size_t)2 * GTO_SPLIT_MAX * B * T * n * n)); CK(ctx->g.ensure((size_t)2 * GTO_SPLIT_MAX * B * T * n));
+  CK(ctx->costp.ensure((size_t)2 * GTO_SPLIT_MAX * B * T));
   (void)m;
   CK(ctx->outQ.ensure((size_t)B * T * nd)); CK(ctx->outdQ.ensure((size_t)B * (T - 1) * nd)); CK(ctx->outcost.ensure(B));
   CK(ctx->result.ensure((size_t)B * (n * T + 2)));
@@ -1514,9 +1573,13 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   p.fields = ctx->fields_d; p.tmaps = ctx->tmaps_d;
   p.active = active; p.nactive = nactive; p.nproblems = nproblems; p.b0 = b0; p.bufsel = bufsel;
   p.H = ctx->H.p; p.g = ctx->g.p; p.costp = ctx->costp.p;
-  p.buf_stride_H = (long long)ctx->B * ctx->T * R.nopt * R.nopt;
-  p.buf_stride_g = (long long)ctx->B * ctx->T * R.nopt;
-  p.buf_stride_c = (long long)ctx->B * ctx->T;
+  p.part_stride_H = (long long)ctx->B * ctx->T * R.nopt * R.nopt;
+  p.part_stride_g = (long long)ctx->B * ctx->T * R.nopt;
+  p.part_stride_c = (long long)ctx->B * ctx->T;
+  p.buf_stride_H = GTO_SPLIT_MAX * p.part_stride_H;
+  p.buf_stride_g = GTO_SPLIT_MAX * p.part_stride_g;
+  p.buf_stride_c = GTO_SPLIT_MAX * p.part_stride_c;
+  p.allow_split = (nactive != nullptr) && getenv("GTO_SPLIT_TAIL") != nullptr;  // measured on C2: no gain (tail launches are fixed-latency bound), off by default
   p.rows = rows; p.rows_per_problem = ctx->rows_per_problem;
   p.T = ctx->T; p.t_lo = t_lo; p.knot_standoff = ctx->T + ctx->standoff_offset; p.use_standoff = ctx->use_standoff;
   p.collision = ctx->collision;
@@ -1558,13 +1621,17 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
     if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("pipelined linearize launch setup: ") + cudaGetErrorString(e));
     if (occ >= 1) {
       const long long max_items = (long long)nproblems * (ctx->T - t_lo);
-      const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
+      // solver launches use the full persistent grid: the device decides how many parts an item is split into
+      const int grid = p.allow_split ? ctx->sm_count * occ : (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
+      ctx->last_lin_grid = p.allow_split ? grid : 0;
       kern<<<grid, threads, sm, ctx->stream>>>(pp);
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_pipe launch: ") + cudaGetErrorString(e));
       return GTO_OK;
     }
   }
+  ctx->last_lin_grid = 0;  // the v1 kernel never splits items
+  p.allow_split = 0;
   int bm = pick_brick_max(ctx);
   size_t smem = lin_smem_bytes(ctx, bm, ctx->lin_warps);
   while (smem > (size_t)ctx->max_smem_optin / 2 && bm > kBrickClassDev(0)) {  // keep two CTAs per SM
@@ -1642,7 +1709,12 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   CK(ctx->Fhist.ensure((size_t)B * 16));
   st.Fhist = ctx->Fhist.p;
   st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;
-  st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
+  st.part_stride_H = (long long)B * T * n * n; st.part_stride_g = (long long)B * T * n; st.part_stride_c = (long long)B * T;
+  st.buf_stride_H = GTO_SPLIT_MAX * st.part_stride_H; st.buf_stride_g = GTO_SPLIT_MAX * st.part_stride_g;
+  st.buf_stride_c = GTO_SPLIT_MAX * st.part_stride_c;
+  st.Bcap = B;
+  CK(ctx->bufsplit.ensure((size_t)2 * B));
+  st.bufsplit = ctx->bufsplit.p;
   st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;
   st.stepn = ctx->stepn.p; st.iters = ctx->iters.p; st.status = ctx->status.p;
   const size_t step_smem = step_smem_bytes(T, n);
@@ -1692,6 +1764,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       CK(cudaEventRecord(bE, ctx->stream));
       st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
       st.iter = it;
+      st.lin_grid = ctx->last_lin_grid;
       step_kern<<<nb, 32, step_smem, ctx->stream>>>(st);
       CK(cudaGetLastError());
       CK(cudaEventRecord(c, ctx->stream));

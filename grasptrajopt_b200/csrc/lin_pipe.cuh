@@ -28,6 +28,7 @@ struct ItemCtx {
   int bdim[GTO_MAX_LINKS][4];       // brick dims (x, y, z) and fast flag
   float basep[4];
   int b, t, fid, obuf;
+  int part, l0, l1, last_part;
 };
 
 struct LinkMeta {
@@ -153,8 +154,10 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
 
   const int nknots = p.T - p.t_lo;
   const int nprob = p.nactive ? *p.nactive : p.nproblems;
-  const long long nitems = (long long)nprob * nknots;
-  const int nlinks = R.nlinks;
+  // tail launches: split every (problem, knot) item into link ranges so that the whole chip works on the few problems left
+  const int nsplit = p.allow_split ? split_factor((long long)nprob * nknots, (int)gridDim.x) : 1;
+  const int sidx = nsplit == 4 ? 2 : (nsplit == 2 ? 1 : 0);
+  const long long nitems = (long long)nprob * nknots * nsplit;
 
   if (warp == NC) {
     // =============================== PRODUCER WARP ===============================
@@ -163,9 +166,12 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
       const int ci = ic & 1;
       if (ic >= 2) mbar_wait_sleep(ctx_empty + ci, ((ic >> 1) - 1) & 1);
       ItemCtx& C = S.ctx[ci];
-      const int a = (int)(item / nknots);
-      const int t = p.t_lo + (int)(item - (long long)a * nknots);
+      const int part = (int)(item % nsplit);
+      const long long it2 = item / nsplit;
+      const int a = (int)(it2 / nknots);
+      const int t = p.t_lo + (int)(it2 - (long long)a * nknots);
       const int b = p.active ? p.active[a] : a;
+      const int L0 = R.part_link0[sidx][part], L1 = R.part_link0[sidx][part + 1];
       const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
       const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
       // ---- chain FK in float64 ----
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
         }
         __syncwarp();
       }
-      if (lane < nlinks) {  // visual frames + brick placement
+      if (lane >= L0 && lane < L1) {  // visual frames + brick placement (links of this part only)
         const int mj = R.link_mov[lane];
         double Fd[12];
         if (mj < 0) {
@@ -295,6 +301,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
         }
         C.b = b; C.t = t; C.fid = fid;
         C.obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
+        C.part = part; C.l0 = L0; C.l1 = L1; C.last_part = (part == nsplit - 1);
       }
       if (lane >= 24 && lane < 27) C.basep[lane - 24] = p.base[4 * b + (lane - 24)];
       __syncwarp();
@@ -303,8 +310,8 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
       if (fid >= 0) {
         if (lane == 0) {
           const CUtensorMap* maps = p.fields[fid].maps2;
-          for (int l = 0; l < nlinks; ++l) {
-            const unsigned idx = bc + l, s = idx % PIPE_NSLOT;
+          for (int l = L0; l < L1; ++l) {
+            const unsigned idx = bc + (l - L0), s = idx % PIPE_NSLOT;
             if (idx >= PIPE_NSLOT) mbar_wait_sleep(slot_empty + s, ((idx / PIPE_NSLOT) - 1) & 1);
             const int sx = C.bdim[l][0], sy = C.bdim[l][1], sz = C.bdim[l][2];
             const int mi = ((sx / 4 - 2) * PIPE_NAXC + (sy / 4 - 2)) * PIPE_NAXC + (sz / 4 - 2);
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
             tma_load_3d(ring + (size_t)s * pp.slot_floats, maps + mi, C.blo[l][2], C.blo[l][1], C.blo[l][0], slot_full + s);
           }
         }
-        bc += nlinks;
+        bc += L1 - L0;
         __syncwarp();
       }
     }
@@ -327,8 +334,8 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
     const int ci = ic & 1;
     mbar_wait_sleep(ctx_full + ci, (ic >> 1) & 1);
     const ItemCtx& C = S.ctx[ci];
-    const int b = C.b, t = C.t, fid = C.fid;
-    const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
+    const int b = C.b, t = C.t, fid = C.fid, L0 = C.l0, L1 = C.l1;
+    const bool is_goal = C.last_part && (t == p.T - 1), is_stand = C.last_part && (p.use_standoff && t == p.knot_standoff);
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
     float gacc[NP];
 #pragma unroll
@@ -337,15 +344,15 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
     float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
 
     if (p.collision) {
-      int ch = warp;  // chunks are dealt round-robin over the whole item: this warp owns ch = warp, warp+NC, ...
-      for (int l = 0; l < nlinks; ++l) {
+      int ch = S.links[L0].c0 + warp;  // chunks are dealt round-robin over the item's links: first, first+NC, ...
+      for (int l = L0; l < L1; ++l) {
         // every consumer warp observes every brick (full) before it releases it (empty), chunks or not: an early release
         // of a later use of the same slot could otherwise complete the empty barrier of the current use
         const float* brick = ring;
         float clx = 0.f, cly = 0.f, clz = 0.f, ipitch = 0.f;
         int dxm2 = 0, dym2 = 0, dzm2 = 0, dy = 0, dz = 0, fast = 0;
         if (fid >= 0) {
-          const unsigned idx = bc + l;
+          const unsigned idx = bc + (l - L0);
           mbar_wait_sleep(slot_full + (idx % PIPE_NSLOT), (idx / PIPE_NSLOT) & 1);
           brick = ring + (size_t)(idx % PIPE_NSLOT) * pp.slot_floats;
           clx = C.cl[l][0]; cly = C.cl[l][1]; clz = C.cl[l][2]; ipitch = C.cl[l][3];
@@ -438,10 +445,10 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
         }
         if (fid >= 0) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(slot_empty + ((bc + l) % PIPE_NSLOT));
+          if (lane == 0) mbar_arrive(slot_empty + ((bc + (l - L0)) % PIPE_NSLOT));
         }
       }
-      if (fid >= 0) bc += nlinks;
+      if (fid >= 0) bc += L1 - L0;
     }
 
     // ---- goal / stand-off rows ----
@@ -548,9 +555,9 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
         float s = 0.f;
         for (int w = 0; w < NC; ++w) s += red_base[((size_t)ci * NC + w) * red_floats + i];
         const long long bt = (long long)b * p.T + t;
-        if (i < nH) p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
-        else if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
-        else p.costp[obuf * p.buf_stride_c + bt] = s;
+        if (i < nH) p.H[obuf * p.buf_stride_H + C.part * p.part_stride_H + bt * nH + i] = s;
+        else if (i < nH + nopt) p.g[obuf * p.buf_stride_g + C.part * p.part_stride_g + bt * nopt + (i - nH)] = s;
+        else p.costp[obuf * p.buf_stride_c + C.part * p.part_stride_c + bt] = s;
       }
     }
     __syncwarp();
