@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgto_b200.so")
 
 GTO_OK = 0
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN, STATUS_STALLED, STATUS_SLOW = 0, 1, 2, 3, 4
-FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK, FLAG_V1_KERNEL = 1, 2, 4, 8
+FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK, FLAG_V1_KERNEL, FLAG_PIPE_KERNEL, FLAG_NO_CULL = 1, 2, 4, 8, 16, 32
 
 SYMBOLS = [
     "gto_abi_version", "gto_create", "gto_destroy", "gto_last_error", "gto_default_options", "gto_set_robot",
@@ -91,6 +91,7 @@ class Profile(C.Structure):
         ("knot_items", C.c_int64), ("jrow_bytes", C.c_int64),
         ("problem_iterations", C.c_int64), ("linearize_launches_with_work", C.c_int32), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("links_tested", C.c_int64), ("links_active", C.c_int64),
     ]
 
     def as_dict(self):

@@ -70,6 +70,7 @@ struct FieldDev {
   float ox, oy, oz, inv_pitch;
   int has_tma;
   const CUtensorMap* maps2;  // [7*7*7] tile maps with per-axis box sizes 8,12,...,32 (k_linearize_pipe); NULL if unavailable
+  const unsigned* svt;       // [(nx+1)][(ny+1)][(nz+1)] summed-volume table of the non-zero nodes (culling test); NULL if unavailable
 };
 
 struct LinParams {
@@ -627,6 +628,7 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
 }
 
 #include "lin_pipe.cuh"
+#include "lin_cull.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_init: eliminate the equality constraints (gto/gto_planner.py:59-72): optimised rows of knots 0,1 = qc; clip the seed
@@ -1153,6 +1155,9 @@ struct DevBuf {
 struct FieldHost {
   float* data = nullptr;
   CUtensorMap* maps2 = nullptr;
+  unsigned* svt = nullptr;
+  size_t svt_n = 0;
+  unsigned nonzero = 0;
   int nx = 0, ny = 0, nz = 0, nzp = 0;
   double origin[3] = {0, 0, 0};
   double pitch = 0;
@@ -1191,7 +1196,8 @@ struct gto_ctx {
   DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, Fhist, outQ, outdQ, outcost;
   DevBuf<double> q_trial, goal_tf;
   DevBuf<float> base, H, g, costp, rows, result;
-  DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive;
+  DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive, work_ctr;
+  DevBuf<unsigned long long> stats;
   int* h_counter = nullptr;  // pinned
   long long rows_per_problem = 0;
   int Bchunk = 0;
@@ -1275,6 +1281,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   for (auto& f : ctx->fields) {
     if (f.data) cudaFree(f.data);
     if (f.maps2) cudaFree(f.maps2);
+    if (f.svt) cudaFree(f.svt);
   }
   for (auto e : ctx->ev) cudaEventDestroy(e);
   if (ctx->robot_d) cudaFree(ctx->robot_d);
@@ -1287,7 +1294,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
-  ctx->status.release(); ctx->active.release(); ctx->nactive.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1462,6 +1469,29 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
       d.maps2 = f.maps2;
     }
   }
+  {  // summed-volume table of the non-zero nodes: S[i][j][k] = #{cost != 0 in [0,i) x [0,j) x [0,k)} (culling test of k_linearize_cull)
+    const size_t ex = (size_t)f.nx + 1, ey = (size_t)f.ny + 1, ez = (size_t)f.nz + 1, ns = ex * ey * ez;
+    std::vector<unsigned> S(ns, 0u);
+    for (size_t i = 1; i < ex; ++i)
+      for (size_t j = 1; j < ey; ++j) {
+        const float* src = cost + ((i - 1) * f.ny + (j - 1)) * f.nz;
+        unsigned* row = S.data() + (i * ey + j) * ez;
+        const unsigned* up = S.data() + (i * ey + (j - 1)) * ez;             // S[i][j-1][.]
+        const unsigned* back = S.data() + ((i - 1) * ey + j) * ez;           // S[i-1][j][.]
+        const unsigned* diag = S.data() + ((i - 1) * ey + (j - 1)) * ez;     // S[i-1][j-1][.]
+        unsigned run = 0;  // non-zero nodes of this z-line so far
+        for (size_t k = 1; k < ez; ++k) {
+          run += (src[k - 1] != 0.0f) ? 1u : 0u;
+          row[k] = run + up[k] + back[k] - diag[k];
+        }
+      }
+    if (f.svt && f.svt_n != ns) { cudaFree(f.svt); f.svt = nullptr; }
+    if (!f.svt) CK(cudaMalloc((void**)&f.svt, ns * sizeof(unsigned)));
+    f.svt_n = ns;
+    CK(cudaMemcpy(f.svt, S.data(), ns * sizeof(unsigned), cudaMemcpyHostToDevice));
+    d.svt = f.svt;
+    f.nonzero = S[ns - 1];
+  }
   CK(cudaMemcpy(ctx->fields_d + slot, &d, sizeof(d), cudaMemcpyHostToDevice));
   ctx->min_pitch = 0.0;
   for (auto& ff : ctx->fields)
@@ -1563,7 +1593,7 @@ static size_t lin_smem_bytes(const gto_ctx* ctx, int brick_max, int warps) {
 
 // launches one linearisation on ctx->stream
 static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
-                            float* rows, int t_lo, unsigned flags) {
+                            float* rows, int t_lo, unsigned flags, int* work_counter) {
   const RobotDev& R = ctx->robot_h;
   LinParams p;
   memset(&p, 0, sizeof(p));
@@ -1585,10 +1615,53 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   p.collision = ctx->collision;
   p.sw_obs = (float)sqrt(ctx->w_obs); p.sw_goal = (float)sqrt(ctx->w_goal);
   p.flags = flags;
-  // ---- default: warp-specialised TMA-pipelined kernel ----
   bool pipe_ok = !(flags & (GTO_FLAG_V1_KERNEL | GTO_FLAG_NO_TMA | GTO_FLAG_NO_BRICK)) && !getenv("GTO_V1_KERNEL");
   for (auto& ff : ctx->fields)
     if (ff.set && !ff.maps2) pipe_ok = false;
+  // ---- default: culling + TMA-pipelined kernel with dynamic item scheduling ----
+  if (pipe_ok && work_counter && !(flags & GTO_FLAG_PIPE_KERNEL) && !getenv("GTO_PIPE_KERNEL")) {
+    CullParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.lin = p;
+    cp.lin.allow_split = 0;
+    const int n3 = ctx->min_pitch > 0 ? (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 5 : 8;
+    int slot_floats = n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
+    if (const char* e = getenv("GTO_SLOT_FLOATS")) slot_floats = std::max(512, atoi(e) & ~127);
+    cp.slot_floats = slot_floats;
+    int nc = ctx->pipe_cons;
+    if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
+    cp.ncons = nc;
+    cp.work_counter = work_counter;
+    cp.stats = ctx->stats.p;
+    const int RS = R.nopt + 1;
+    size_t sm = (sizeof(CullShared) + 127) & ~(size_t)127;
+    sm += CULL_ZERO_BYTES;
+    sm += (size_t)CULL_NSLOT * slot_floats * sizeof(float);
+    sm += (size_t)nc * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
+    sm += (size_t)2 * nc * (R.nopt * R.nopt + R.nopt + 2) * sizeof(float);
+    sm = (sm + 127) & ~(size_t)127;
+    const int threads = (nc + 1) * 32;
+    int occ = 0;
+    void (*kern)(const CullParams) = nullptr;
+    if (R.nopt == 7) kern = k_linearize_cull<8, 7>;
+    else if (R.nopt == 8) kern = k_linearize_cull<8, 8>;
+    else if (R.nopt == 10) kern = k_linearize_cull<16, 10>;
+    else if (R.nopt < 8) kern = k_linearize_cull<8, 0>;
+    else kern = k_linearize_cull<16, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, sm);
+    if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("culling linearize launch setup: ") + cudaGetErrorString(e));
+    if (occ >= 1) {
+      const long long max_items = (long long)nproblems * (ctx->T - t_lo);
+      const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
+      ctx->last_lin_grid = 0;
+      kern<<<grid, threads, sm, ctx->stream>>>(cp);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
+      return GTO_OK;
+    }
+  }
+  // ---- warp-specialised TMA-pipelined kernel without culling (A/B reference) ----
   if (pipe_ok) {
     PipeParams pp;
     memset(&pp, 0, sizeof(pp));
@@ -1691,6 +1764,9 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   }
   ctx->Bchunk = Bchunk;
   CK(ctx->nactive.ensure((size_t)o.max_iter + 3));
+  CK(ctx->work_ctr.ensure((size_t)o.max_iter + 3));
+  CK(ctx->stats.ensure(4));
+  CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
 
   StateParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -1732,6 +1808,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
   pf.linearize_launches = pf.step_launches = pf.iterations = 0;
   pf.knot_items = 0; pf.jrow_bytes = 0; pf.problem_iterations = 0; pf.linearize_launches_with_work = 0;
+  pf.links_tested = pf.links_active = 0;
   std::vector<int> h_nact((size_t)o.max_iter + 3);
   size_t nev = 0;
   std::vector<int> ev_kind;  // per recorded interval: 0 linearize, 1 step
@@ -1750,6 +1827,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     int* act0 = ctx->active.p;
     int* act1 = ctx->active.p + B;
     CK(cudaMemsetAsync(ctx->nactive.p, 0, sizeof(int) * ((size_t)o.max_iter + 3), ctx->stream));
+    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, sizeof(int) * ((size_t)o.max_iter + 3), ctx->stream));
     CK(cudaMemcpyAsync(act0, ident.data() + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->nactive.p, &nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     int host_active = nb;
@@ -1759,7 +1837,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       cudaEvent_t a = get_event(ctx, nev++), bE = get_event(ctx, nev++), c = get_event(ctx, nev++);
       CK(cudaEventRecord(a, ctx->stream));
       int rc = launch_linearize(ctx, ctx->q_trial.p, ain, ctx->nactive.p + it, nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
-                                it == 0 ? 0 : 2, ctx->flags);
+                                it == 0 ? 0 : 2, ctx->flags, ctx->work_ctr.p + it);
       if (rc) return rc;
       CK(cudaEventRecord(bE, ctx->stream));
       st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
@@ -1800,6 +1878,12 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   cudaEvent_t ev_end = get_event(ctx, nev++);
   CK(cudaEventRecord(ev_end, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  {
+    unsigned long long hs[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(hs, ctx->stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    pf.links_tested = (long long)hs[1];
+    pf.links_active = (long long)hs[2];
+  }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   pf.solve_ms = ms;
@@ -1868,7 +1952,11 @@ extern "C" int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out
   const long long tot = (long long)B * T;
   k_init<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(sp);
   CK(cudaGetLastError());
-  rc = launch_linearize(ctx, ctx->q_trial.p, nullptr, nullptr, B, 0, nullptr, out->rows ? ctx->rows.p : nullptr, 0, ctx->flags);
+  CK(ctx->work_ctr.ensure(4));
+  CK(ctx->stats.ensure(4));
+  CK(cudaMemsetAsync(ctx->work_ctr.p, 0, sizeof(int) * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
+  rc = launch_linearize(ctx, ctx->q_trial.p, nullptr, nullptr, B, 0, nullptr, out->rows ? ctx->rows.p : nullptr, 0, ctx->flags, ctx->work_ctr.p);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   if (out->rows) CK(cudaMemcpy(out->rows, ctx->rows.p, nrows * sizeof(float), cudaMemcpyDeviceToHost));

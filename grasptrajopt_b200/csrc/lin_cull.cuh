@@ -1,0 +1,586 @@
+// lin_cull.cuh -- k_linearize_cull: the default fused linearisation kernel.
+// Included by gto_b200.cu after lin_pipe.cuh (shares its PTX helpers, LinkMeta and the generic trilinear lookup).
+//
+// Same warp-specialised structure as k_linearize_pipe (1 producer warp + NC consumer warps per persistent CTA, SDF bricks
+// staged by TMA into a shared-memory ring), plus three things:
+//   * exact culling   the cost field is identically zero away from obstacles (DepthPointCloud.get_sdf_cost is 0 for
+//                     d >= epsilon, mesh_to_sdf/depth_point_cloud.py:65-91).  The producer tests, per link, whether the
+//                     box of grid nodes its points can touch holds any non-zero node -- 8 reads of a summed-volume table
+//                     built at gto_set_field -- and only links that do are handed to the consumer warps.  The Jacobian
+//                     rows, J^T J, J^T r and the cost of a culled link are exactly zero, so results are bit-identical.
+//   * zero rows by TMA the dense row block of a culled link is still materialised in HBM (it is part of the Jacobian):
+//                     one cp.async.bulk shared->global copy from a zeroed shared buffer per link (SASS UBLKCP), issued
+//                     by the producer; no consumer instruction is spent on it.
+//   * dynamic items   (problem, knot) items are handed out through a global atomic counter, because their cost now
+//                     varies with the number of surviving links.
+#pragma once
+
+#define CULL_NSLOT 4
+#define CULL_ZERO_BYTES 8192
+
+struct __align__(16) CullCtx {
+  float frames[GTO_MAX_LINKS][12];  // visual frame of each collision link (robot base frame)
+  float tw[GTO_MAX_OPT][8];         // (omega.xyz, -, m.xyz, -) per optimised joint
+  float gripf[12];
+  float goal[2][12];                // gripper frame minus goal / stand-off frame
+  float cl[GTO_MAX_LINKS][4];       // brick-local voxel coordinate = Wb * inv_pitch + cl
+  int blo[GTO_MAX_LINKS][4];        // brick lower corner (grid index) per link
+  int bdim[GTO_MAX_LINKS][4];       // brick dims (x, y, z) and fast flag
+  float basep[4];
+  int b, t, fid, obuf;
+  int nact, kind;                   // surviving links; kind bit 0: goal rows, bit 1: stand-off rows
+  int act[GTO_MAX_LINKS];           // surviving link ids, ascending
+};
+
+struct CullShared {
+  double Tm[GTO_MAX_MOV][12];
+  double A[GTO_MAX_MOV][12];
+  CullCtx ctx[2];
+  LinkMeta links[GTO_MAX_LINKS];
+  unsigned long long slot_full[CULL_NSLOT], slot_empty[CULL_NSLOT], ctx_full[2], ctx_empty[2];
+};
+
+struct CullParams {
+  LinParams lin;
+  int slot_floats;     // capacity of one brick slot
+  int ncons;           // consumer warps
+  int* work_counter;   // zero before the launch: next (problem, knot) item
+  unsigned long long* stats;  // [0] items, [1] links tested, [2] links that survived the culling test (NULL: off)
+};
+
+__device__ __forceinline__ void bulk_store_zero(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+// number of non-zero nodes in the inclusive box [x0,x1] x [y0,y1] x [z0,z1] of the field (summed-volume table lookup)
+__device__ __forceinline__ unsigned svt_count(const FieldDev& f, int x0, int x1, int y0, int y1, int z0, int z1) {
+  const unsigned sy = (unsigned)(f.nz + 1), sx = (unsigned)(f.ny + 1) * sy;
+  const unsigned* S = f.svt;
+  const unsigned X0 = x0 * sx, X1 = (x1 + 1) * sx, Y0 = y0 * sy, Y1 = (y1 + 1) * sy, Z0 = z0, Z1 = z1 + 1;
+  return __ldg(S + X1 + Y1 + Z1) - __ldg(S + X0 + Y1 + Z1) - __ldg(S + X1 + Y0 + Z1) - __ldg(S + X1 + Y1 + Z0) +
+         __ldg(S + X0 + Y0 + Z1) + __ldg(S + X0 + Y1 + Z0) + __ldg(S + X1 + Y0 + Z0) - __ldg(S + X0 + Y0 + Z0);
+}
+
+// NP: padded tensor-core tile width (8 or 16); NOPT_CT: number of optimised joints when known at compile time (0: runtime)
+template <int NP, int NOPT_CT>
+__global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const LinParams& p = pp.lin;
+  CullShared& S = *reinterpret_cast<CullShared*>(smem_raw);
+  const RobotDev& R = *p.robot;
+  const int nopt = NOPT_CT ? NOPT_CT : R.nopt, RS = nopt + 1, NC = pp.ncons;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  size_t off = (sizeof(CullShared) + 127) & ~(size_t)127;
+  float* zero_buf = reinterpret_cast<float*>(smem_raw + off);
+  off += CULL_ZERO_BYTES;
+  float* ring = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)CULL_NSLOT * pp.slot_floats * sizeof(float);
+  const int st_floats = ((32 * RS + 16 + 31) / 32) * 32;
+  float* stage_base = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)NC * st_floats * sizeof(float);
+  const int red_floats = nopt * nopt + nopt + 2;
+  float* red_base = reinterpret_cast<float*>(smem_raw + off);  // [2][NC][red_floats]
+  uint64_t* slot_full = reinterpret_cast<uint64_t*>(S.slot_full);
+  uint64_t* slot_empty = reinterpret_cast<uint64_t*>(S.slot_empty);
+  uint64_t* ctx_full = reinterpret_cast<uint64_t*>(S.ctx_full);
+  uint64_t* ctx_empty = reinterpret_cast<uint64_t*>(S.ctx_empty);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CULL_NSLOT; ++s) {
+      mbar_init(slot_full + s, 1);
+      mbar_init(slot_empty + s, NC);
+    }
+    for (int c = 0; c < 2; ++c) {
+      mbar_init(ctx_full + c, 1);
+      mbar_init(ctx_empty + c, NC);
+    }
+    mbar_fence_init();
+  }
+  if ((int)threadIdx.x < R.nlinks) {
+    LinkMeta m;
+    m.c0 = R.link_chunk0[threadIdx.x];
+    m.c1 = R.link_chunk0[threadIdx.x + 1];
+    m.pt_start = R.link_pt_start[threadIdx.x];
+    m.pt_end = m.pt_start + R.link_pt_count[threadIdx.x];
+    m.mask = R.link_optmask[threadIdx.x];
+    S.links[threadIdx.x] = m;
+  }
+  for (int i = threadIdx.x; i < CULL_ZERO_BYTES / 4; i += blockDim.x) zero_buf[i] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zeros are read by the async proxy (bulk stores)
+  __syncthreads();
+
+  const int nknots = p.T - p.t_lo;
+  const int nprob = p.nactive ? *p.nactive : p.nproblems;
+  const int nitems = nprob * nknots;
+  const int nH = nopt * nopt;
+
+  if (warp == NC) {
+    // =============================== PRODUCER WARP ===============================
+    unsigned pub = 0, bc = 0;
+    unsigned long long st_items = 0, st_links = 0, st_act = 0;
+    const bool cull = !(p.flags & GTO_FLAG_NO_CULL);
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(pp.work_counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= nitems) break;
+      const int ci = pub & 1;
+      if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
+      CullCtx& C = S.ctx[ci];
+      const int a = item / nknots;
+      const int t = p.t_lo + (item - a * nknots);
+      const int b = p.active ? p.active[a] : a;
+      const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
+      const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
+      const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
+      // ---- chain FK in float64 ----
+      if (lane < R.nmov) {
+        const double qj = q[R.mov_qidx[lane]];
+        const double ax = R.mov_axis_d[lane][0], ay = R.mov_axis_d[lane][1], az = R.mov_axis_d[lane][2];
+        double M[12];
+        if (R.mov_type[lane] == GTO_JOINT_REVOLUTE) {
+          double s, c;
+          sincos(qj, &s, &c);
+          const double v = 1.0 - c;
+          M[0] = 1.0 - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.0;
+          M[4] = s * az + v * ax * ay;          M[5] = 1.0 - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.0;
+          M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
+        } else {
+          M[0] = 1.0; M[1] = 0.0; M[2] = 0.0; M[3] = qj * ax;
+          M[4] = 0.0; M[5] = 1.0; M[6] = 0.0; M[7] = qj * ay;
+          M[8] = 0.0; M[9] = 0.0; M[10] = 1.0; M[11] = qj * az;
+        }
+        double Cm[12];
+        mul34(R.mov_origin_d[lane], M, Cm);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) S.A[lane][e] = Cm[e];
+      }
+      __syncwarp();
+      for (int j = 0; j < R.nmov; ++j) {
+        if (lane < 12) {
+          const int r = lane >> 2, c = lane & 3;
+          const int pj = R.mov_parent[j];
+          double s;
+          if (pj < 0) {
+            s = S.A[j][lane];
+          } else {
+            const double* P = S.Tm[pj];
+            s = P[r * 4 + 0] * S.A[j][c] + P[r * 4 + 1] * S.A[j][4 + c] + P[r * 4 + 2] * S.A[j][8 + c];
+            if (c == 3) s += P[r * 4 + 3];
+          }
+          S.Tm[j][lane] = s;
+        }
+        __syncwarp();
+      }
+      // ---- visual frames, brick placement and the culling test (one lane per link) ----
+      bool survives = false;
+      if (lane < R.nlinks) {
+        const int mj = R.link_mov[lane];
+        double Fd[12];
+        if (mj < 0) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) Fd[e] = R.link_tf_d[lane][e];
+        } else {
+          mul34(S.Tm[mj], R.link_tf_d[lane], Fd);
+        }
+        float F[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+          F[e] = (float)Fd[e];
+          C.frames[lane][e] = F[e];
+        }
+        if (fid >= 0) {
+          const FieldDev& f = p.fields[fid];
+          const float* cc = R.link_center[lane];
+          const float* hh = R.link_half[lane];
+          const float bp[3] = {p.base[4 * b + 0], p.base[4 * b + 1], p.base[4 * b + 2]};
+          const float org[3] = {f.ox, f.oy, f.oz};
+          const int N3[3] = {f.nx, f.ny, f.nz};
+          int lo3[3], sz3[3], c0[3], c1[3];
+          bool fast = true;
+#pragma unroll
+          for (int a3 = 0; a3 < 3; ++a3) {
+            const float cw = F[a3 * 4 + 0] * cc[0] + F[a3 * 4 + 1] * cc[1] + F[a3 * 4 + 2] * cc[2] + F[a3 * 4 + 3] + bp[a3];
+            const float hw = fabsf(F[a3 * 4 + 0]) * hh[0] + fabsf(F[a3 * 4 + 1]) * hh[1] + fabsf(F[a3 * 4 + 2]) * hh[2] + 1e-4f;
+            int lo = (int)floorf((cw - hw - org[a3]) * f.inv_pitch);
+            const int hi = (int)floorf((cw + hw - org[a3]) * f.inv_pitch) + 1;  // highest node touched
+            // nodes a (possibly index-clamped) lookup of this link can read, for the culling test
+            c0[a3] = min(max(lo, 0), N3[a3] - 1);
+            c1[a3] = min(max(hi, 0), N3[a3] - 1);
+            if (lo < 0 || hi > N3[a3] - 1) fast = false;  // a point may need index clamping
+            if (a3 == 2) lo &= ~3;
+            const int need = hi - lo + 1;
+            int sz = min(32, max(8, (need + 3) & ~3));
+            if (need > sz) fast = false;
+            lo3[a3] = lo;
+            sz3[a3] = sz;
+          }
+          while (sz3[0] * sz3[1] * sz3[2] > pp.slot_floats) {  // does not fit a slot: shrink the longest axis
+            int am = 0;
+            if (sz3[1] > sz3[am]) am = 1;
+            if (sz3[2] > sz3[am]) am = 2;
+            sz3[am] -= 4;
+            fast = false;
+          }
+          C.blo[lane][0] = lo3[0]; C.blo[lane][1] = lo3[1]; C.blo[lane][2] = lo3[2]; C.blo[lane][3] = 0;
+          C.bdim[lane][0] = sz3[0]; C.bdim[lane][1] = sz3[1]; C.bdim[lane][2] = sz3[2]; C.bdim[lane][3] = fast ? 1 : 0;
+#pragma unroll
+          for (int a3 = 0; a3 < 3; ++a3) C.cl[lane][a3] = (bp[a3] - org[a3]) * f.inv_pitch - (float)lo3[a3];
+          C.cl[lane][3] = f.inv_pitch;
+          survives = (R.link_pt_count[lane] > 0) &&
+                     (!cull || f.svt == nullptr || svt_count(f, c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]) != 0u);
+        }
+      }
+      const unsigned amask = __ballot_sync(0xffffffffu, survives);
+      const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
+      const bool publish = (amask != 0u) || is_goal || is_stand;
+      st_items += 1;
+      if (p.collision) st_links += R.nlinks;
+      st_act += __popc(amask);
+      // ---- rows of the culled links: zeros, straight from shared memory by bulk copy ----
+      if (p.collision && p.rows) {
+        float* rows_b = p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS;
+        bool slow_zero = false;
+        if (lane < R.nlinks && !survives) {
+          const int cnt = R.link_pt_count[lane];
+          char* dst = reinterpret_cast<char*>(rows_b + ((long long)t * R.npoints + R.link_pt_start[lane]) * RS);
+          const unsigned bytes = (unsigned)cnt * RS * 4u;
+          if ((((uintptr_t)dst | bytes) & 15u) == 0u) {
+            for (unsigned o = 0; o < bytes; o += CULL_ZERO_BYTES) bulk_store_zero(dst + o, zero_buf, min((unsigned)CULL_ZERO_BYTES, bytes - o));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          } else {
+            slow_zero = cnt > 0;
+          }
+        }
+        unsigned zm = __ballot_sync(0xffffffffu, slow_zero);  // row blocks that are not 16-byte aligned: plain stores
+        while (zm) {
+          const int l = __ffs(zm) - 1;
+          zm &= zm - 1;
+          float* dst = rows_b + ((long long)t * R.npoints + R.link_pt_start[l]) * RS;
+          const int nfl = R.link_pt_count[l] * RS;
+          for (int i = lane; i < nfl; i += 32) __stcs(dst + i, 0.f);
+        }
+      }
+      if (!publish) {
+        // nothing for the consumers: this knot's Gauss-Newton block is zero
+        const long long bt = (long long)b * p.T + t;
+        for (int i = lane; i < nH; i += 32) p.H[obuf * p.buf_stride_H + bt * nH + i] = 0.f;
+        if (lane < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + lane] = 0.f;
+        if (lane == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.f;
+        continue;
+      }
+      if (lane < nopt) {
+        const int j = R.opt_mov[lane];
+        double om[3] = {0.0, 0.0, 0.0}, mm[3] = {0.0, 0.0, 0.0};
+        if (j >= 0) {
+          const double* Tj = S.Tm[j];
+          const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
+          const double zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
+          const double zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
+          const double zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
+          if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
+            const double ox = Tj[3], oy = Tj[7], oz = Tj[11];
+            om[0] = zx; om[1] = zy; om[2] = zz;
+            mm[0] = oy * zz - oz * zy; mm[1] = oz * zx - ox * zz; mm[2] = ox * zy - oy * zx;
+          } else {
+            mm[0] = zx; mm[1] = zy; mm[2] = zz;
+          }
+        }
+        C.tw[lane][0] = (float)om[0]; C.tw[lane][1] = (float)om[1]; C.tw[lane][2] = (float)om[2]; C.tw[lane][3] = 0.f;
+        C.tw[lane][4] = (float)mm[0]; C.tw[lane][5] = (float)mm[1]; C.tw[lane][6] = (float)mm[2]; C.tw[lane][7] = 0.f;
+      }
+      if (lane == 31) {
+        double F[12];
+        if (R.grip_mov < 0) {
+#pragma unroll
+          for (int e = 0; e < 12; ++e) F[e] = R.grip_tf_d[e];
+        } else {
+          mul34(S.Tm[R.grip_mov], R.grip_tf_d, F);
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+          C.gripf[e] = (float)F[e];
+          C.goal[0][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + e]);
+          C.goal[1][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + 12 + e]);
+        }
+        C.b = b; C.t = t; C.fid = fid; C.obuf = obuf;
+        C.nact = __popc(amask);
+        C.kind = (is_goal ? 1 : 0) | (is_stand ? 2 : 0);
+      }
+      if (survives) C.act[__popc(amask & ((1u << lane) - 1u))] = lane;
+      if (lane >= 24 && lane < 27) C.basep[lane - 24] = p.base[4 * b + (lane - 24)];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ctx_full + ci);  // release: the context is visible to the consumers
+      ++pub;
+      // ---- one TMA brick per surviving link into the ring ----
+      if (amask) {
+        if (lane == 0) {
+          const CUtensorMap* maps = p.fields[fid].maps2;
+          unsigned m = amask, idx = bc;
+          while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned s = idx % CULL_NSLOT;
+            if (idx >= CULL_NSLOT) mbar_wait_sleep(slot_empty + s, ((idx / CULL_NSLOT) - 1) & 1);
+            const int sx = C.bdim[l][0], sy = C.bdim[l][1], sz = C.bdim[l][2];
+            const int mi = ((sx / 4 - 2) * PIPE_NAXC + (sy / 4 - 2)) * PIPE_NAXC + (sz / 4 - 2);
+            mbar_expect_tx(slot_full + s, (uint32_t)(sx * sy * sz * sizeof(float)));
+            tma_load_3d(ring + (size_t)s * pp.slot_floats, maps + mi, C.blo[l][2], C.blo[l][1], C.blo[l][0], slot_full + s);
+            ++idx;
+          }
+        }
+        bc += __popc(amask);
+        __syncwarp();
+      }
+    }
+    // ---- tell the consumers to stop, account, drain the bulk stores ----
+    {
+      const int ci = pub & 1;
+      if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
+      if (lane == 0) {
+        S.ctx[ci].b = -1;
+        mbar_arrive(ctx_full + ci);
+        if (pp.stats) {
+          atomicAdd(pp.stats + 0, st_items);
+          atomicAdd(pp.stats + 1, st_links);
+          atomicAdd(pp.stats + 2, st_act);
+        }
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return;
+  }
+
+  // =============================== CONSUMER WARPS ===============================
+  float* stage = stage_base + warp * st_floats;
+  const int gq = lane >> 2, tq = lane & 3;
+  unsigned ic = 0, bc = 0;
+  for (;; ++ic) {
+    const int ci = ic & 1;
+    mbar_wait_sleep(ctx_full + ci, (ic >> 1) & 1);
+    const CullCtx& C = S.ctx[ci];
+    const int b = C.b;
+    if (b < 0) break;
+    const int t = C.t, fid = C.fid, nact = C.nact;
+    const bool is_goal = (C.kind & 1) != 0, is_stand = (C.kind & 2) != 0;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    float gacc[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) gacc[k] = 0.f;
+    float cacc = 0.f;
+    float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
+
+    int next = warp, cb = 0;  // chunks of the surviving links are dealt round-robin: warp, warp+NC, ... of the concatenation
+    for (int ai = 0; ai < nact; ++ai) {
+      const int l = C.act[ai];
+      // every consumer warp observes every brick (full) before it releases it (empty), chunks or not: an early release
+      // of a later use of the same slot could otherwise complete the empty barrier of the current use
+      const unsigned idx = bc + ai;
+      mbar_wait_sleep(slot_full + (idx % CULL_NSLOT), (idx / CULL_NSLOT) & 1);
+      const float* brick = ring + (size_t)(idx % CULL_NSLOT) * pp.slot_floats;
+      const float clx = C.cl[l][0], cly = C.cl[l][1], clz = C.cl[l][2], ipitch = C.cl[l][3];
+      const int dy = C.bdim[l][1], dz = C.bdim[l][2], fast = C.bdim[l][3];
+      const int dxm2 = C.bdim[l][0] - 2, dym2 = dy - 2, dzm2 = dz - 2;
+      const LinkMeta lm = S.links[l];
+      const int nch = lm.c1 - lm.c0;
+      if (next < cb + nch) {
+        const unsigned mask = lm.mask;
+        float F[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) F[e] = C.frames[l][e];
+        for (; next < cb + nch; next += NC) {
+          const int p0 = lm.pt_start + 32 * (next - cb), cnt = min(32, lm.pt_end - p0);
+          const bool act = lane < cnt;
+          float J[NP];
+#pragma unroll
+          for (int k = 0; k < NP; ++k) J[k] = 0.f;
+          float r = 0.f;
+          if (act) {
+            const float x = __ldg(p.px + p0 + lane), y = __ldg(p.py + p0 + lane), z = __ldg(p.pz + p0 + lane);
+            const float wbx = F[0] * x + F[1] * y + F[2] * z + F[3];
+            const float wby = F[4] * x + F[5] * y + F[6] * z + F[7];
+            const float wbz = F[8] * x + F[9] * y + F[10] * z + F[11];
+            float val, gx, gy, gz;
+            if (fast) {
+              // the brick encloses every point of this link and lies inside the grid: no grid clamping can occur
+              const float ux = fmaf(wbx, ipitch, clx), uy = fmaf(wby, ipitch, cly), uz = fmaf(wbz, ipitch, clz);
+              const int ix = min(max((int)floorf(ux), 0), dxm2), iy = min(max((int)floorf(uy), 0), dym2), iz = min(max((int)floorf(uz), 0), dzm2);
+              const float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
+              const float* q8 = brick + (ix * dy + iy) * dz + iz;
+              const int sx = dy * dz;
+              const float c000 = q8[0], c001 = q8[1], c010 = q8[dz], c011 = q8[dz + 1];
+              const float c100 = q8[sx], c101 = q8[sx + 1], c110 = q8[sx + dz], c111 = q8[sx + dz + 1];
+              const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+              const float z00 = fmaf(fz, d00, c000), z01 = fmaf(fz, d01, c010), z10 = fmaf(fz, d10, c100), z11 = fmaf(fz, d11, c110);
+              const float y0 = fmaf(fy, z01 - z00, z00), y1 = fmaf(fy, z11 - z10, z10);
+              val = fmaf(fx, y1 - y0, y0);
+              const float dy0 = z01 - z00, dy1 = z11 - z10;
+              const float dz0 = fmaf(fy, d01 - d00, d00), dz1 = fmaf(fy, d11 - d10, d10);
+              gx = (y1 - y0) * ipitch;
+              gy = fmaf(fx, dy1 - dy0, dy0) * ipitch;
+              gz = fmaf(fx, dz1 - dz0, dz0) * ipitch;
+            } else {
+              sdf_trilinear_box(p.fields[fid], brick, C.bdim[l], C.blo[l], wbx + C.basep[0], wby + C.basep[1], wbz + C.basep[2], val, gx, gy, gz);
+            }
+            r = p.sw_obs * val;
+            gx *= p.sw_obs; gy *= p.sw_obs; gz *= p.sw_obs;
+            const float nx = wby * gz - wbz * gy, ny = wbz * gx - wbx * gz, nz = wbx * gy - wby * gx;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              if (k < nopt && ((mask >> k) & 1u)) {
+                const float4 o4 = *reinterpret_cast<const float4*>(&C.tw[k][0]);
+                const float4 m4 = *reinterpret_cast<const float4*>(&C.tw[k][4]);
+                J[k] = o4.x * nx + o4.y * ny + o4.z * nz + m4.x * gx + m4.y * gy + m4.z * gz;
+              }
+            }
+          }
+          cacc = fmaf(r, r, cacc);
+#pragma unroll
+          for (int k = 0; k < NP; ++k)
+            if (k < nopt) gacc[k] = fmaf(J[k], r, gacc[k]);
+          if (NOPT_CT == 7) {  // row = [J0..J6 | r] = 32 bytes: two 128-bit shared stores
+            float4* s4 = reinterpret_cast<float4*>(stage + lane * 8);
+            s4[0] = make_float4(J[0], J[1], J[2], J[3]);
+            s4[1] = make_float4(J[4], J[5], J[6], r);
+          } else {
+#pragma unroll
+            for (int k = 0; k < NP; ++k)
+              if (k < nopt) stage[lane * RS + k] = J[k];
+            stage[lane * RS + nopt] = r;
+          }
+          __syncwarp();
+          mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
+          if (rows_b) {
+            float* dst = rows_b + ((long long)t * R.npoints + p0) * RS;
+            if (NOPT_CT == 7 && cnt == 32) {  // 1 KB tile, 16-byte aligned by construction
+              const float4* s4 = reinterpret_cast<const float4*>(stage);
+              float4* d4 = reinterpret_cast<float4*>(dst);
+              const float4 v0 = s4[lane], v1 = s4[lane + 32];
+              __stcs(d4 + lane, v0);
+              __stcs(d4 + lane + 32, v1);
+            } else {
+              store_rows(dst, stage, cnt * RS, lane);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      cb += nch;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(slot_empty + (idx % CULL_NSLOT));
+    }
+    bc += nact;
+
+    // ---- goal / stand-off rows ----
+    if (is_goal || is_stand) {
+      const int Pg = R.grip_pt_count;
+      const long long obs_rows = p.collision ? (long long)p.T * R.npoints : 0;
+      const float* Fg = C.gripf;
+      const unsigned mask = R.grip_optmask;
+      for (int which = 0; which < 2; ++which) {
+        if (which == 0 && !is_goal) continue;
+        if (which == 1 && !is_stand) continue;
+        const float* Dg = C.goal[which];
+        const long long rbase = obs_rows + (which == 1 ? 3LL * Pg : 0);
+        const int nch = (Pg + 31) / 32;
+        for (int ch = warp; ch < nch; ch += NC) {
+          const int k0 = ch * 32, cnt = min(32, Pg - k0);
+          const bool act = lane < cnt;
+          float w3[3] = {0.f, 0.f, 0.f}, r3[3] = {0.f, 0.f, 0.f};
+          if (act) {
+            const int pi = R.grip_pt_start + k0 + lane;
+            const float x = __ldg(p.px + pi), y = __ldg(p.py + pi), z = __ldg(p.pz + pi);
+#pragma unroll
+            for (int a3 = 0; a3 < 3; ++a3) {
+              w3[a3] = Fg[a3 * 4 + 0] * x + Fg[a3 * 4 + 1] * y + Fg[a3 * 4 + 2] * z + Fg[a3 * 4 + 3];
+              r3[a3] = p.sw_goal * (Dg[a3 * 4 + 0] * x + Dg[a3 * 4 + 1] * y + Dg[a3 * 4 + 2] * z + Dg[a3 * 4 + 3]);
+            }
+          }
+#pragma unroll
+          for (int a3 = 0; a3 < 3; ++a3) {
+            float J[NP];
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              J[k] = 0.f;
+              if (act && k < nopt && ((mask >> k) & 1u)) {
+                const float4 o4 = *reinterpret_cast<const float4*>(&C.tw[k][0]);
+                const float4 m4 = *reinterpret_cast<const float4*>(&C.tw[k][4]);
+                float v;
+                if (a3 == 0) v = o4.y * w3[2] - o4.z * w3[1] + m4.x;
+                else if (a3 == 1) v = o4.z * w3[0] - o4.x * w3[2] + m4.y;
+                else v = o4.x * w3[1] - o4.y * w3[0] + m4.z;
+                J[k] = p.sw_goal * v;
+              }
+            }
+            const float r = r3[a3];
+            cacc = fmaf(r, r, cacc);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              if (k < nopt) {
+                gacc[k] = fmaf(J[k], r, gacc[k]);
+                stage[lane * RS + k] = J[k];
+              }
+            }
+            stage[lane * RS + nopt] = r;
+            __syncwarp();
+            mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
+            if (rows_b) store_rows(rows_b + (rbase + (long long)a3 * Pg + k0) * RS, stage, cnt * RS, lane);
+            __syncwarp();
+          }
+        }
+      }
+    }
+
+    // ---- reduce over lanes / consumer warps, write the per-knot Gauss-Newton block ----
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cacc += __shfl_xor_sync(0xffffffffu, cacc, o);
+    {
+      float* red = red_base + ((size_t)ci * NC + warp) * red_floats;
+      const int c0 = 2 * tq;
+      if (gq < nopt) {
+        if (c0 < nopt) red[gq * nopt + c0] = acc0[0];
+        if (c0 + 1 < nopt) red[gq * nopt + c0 + 1] = acc0[1];
+      }
+      if (NP == 16) {
+        if (gq + 8 < nopt) {
+          if (c0 < nopt) red[(gq + 8) * nopt + c0] = acc0[2];
+          if (c0 + 1 < nopt) red[(gq + 8) * nopt + c0 + 1] = acc0[3];
+        }
+        if (gq < nopt) {
+          if (c0 + 8 < nopt) red[gq * nopt + c0 + 8] = acc1[0];
+          if (c0 + 9 < nopt) red[gq * nopt + c0 + 9] = acc1[1];
+        }
+        if (gq + 8 < nopt) {
+          if (c0 + 8 < nopt) red[(gq + 8) * nopt + c0 + 8] = acc1[2];
+          if (c0 + 9 < nopt) red[(gq + 8) * nopt + c0 + 9] = acc1[3];
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          if (k < nopt) red[nopt * nopt + k] = gacc[k];
+        red[nopt * nopt + nopt] = cacc;
+      }
+    }
+    const int obuf = C.obuf;
+    asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");  // consumers only; the producer keeps running ahead
+    {
+      const int ntot = nH + nopt + 1;
+      for (int i = threadIdx.x; i < ntot; i += NC * 32) {
+        float s = 0.f;
+        for (int w = 0; w < NC; ++w) s += red_base[((size_t)ci * NC + w) * red_floats + i];
+        const long long bt = (long long)b * p.T + t;
+        if (i < nH) p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
+        else if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
+        else p.costp[obuf * p.buf_stride_c + bt] = s;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ctx_empty + ci);  // this warp no longer reads ctx[ci] / red[ci]
+  }
+}

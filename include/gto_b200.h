@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GTO_ABI_VERSION 1
+#define GTO_ABI_VERSION 2
 
 /* error codes */
 #define GTO_OK 0
@@ -56,6 +56,8 @@ extern "C" {
 #define GTO_FLAG_NO_TMA 2u        /* stage SDF bricks with plain loads instead of TMA (debug / A-B check) */
 #define GTO_FLAG_NO_BRICK 4u      /* read the SDF straight from global memory (debug / A-B check) */
 #define GTO_FLAG_V1_KERNEL 8u     /* use the non-pipelined linearise kernel (A-B check) */
+#define GTO_FLAG_PIPE_KERNEL 16u  /* use the pipelined kernel without culling / dynamic scheduling (A-B check) */
+#define GTO_FLAG_NO_CULL 32u      /* default kernel, but every link is treated as touching a non-zero node (A-B check) */
 
 typedef struct gto_ctx gto_ctx;
 
@@ -174,6 +176,8 @@ typedef struct gto_profile {
   int32_t linearize_launches_with_work;  /* launches that had at least one active problem */
   double h2d_ms, d2h_ms;     /* last upload / download */
   int64_t h2d_bytes, d2h_bytes;
+  int64_t links_tested;      /* (problem, knot, link) triples whose node box was tested against the field's summed-volume table */
+  int64_t links_active;      /* ... of which touched a non-zero node and went through the point kernel (the rest: zero rows) */
 } gto_profile;
 
 int gto_abi_version(void);

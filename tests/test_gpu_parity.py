@@ -52,7 +52,7 @@ def _check_eval(ctx, w, frac_bad_rows=2e-4):
     return out
 
 
-KERNELS = [pytest.param(0, id="pipelined"), pytest.param(capi.FLAG_V1_KERNEL, id="v1")]
+KERNELS = [pytest.param(0, id="cull"), pytest.param(capi.FLAG_PIPE_KERNEL, id="pipelined"), pytest.param(capi.FLAG_V1_KERNEL, id="v1")]
 
 
 @pytest.mark.parametrize("kflag", KERNELS)
@@ -109,6 +109,33 @@ def test_brick_paths_bit_identical(ctx):
         np.testing.assert_array_equal(o["rows"], outs[0]["rows"])
         np.testing.assert_array_equal(o["g"], outs[0]["g"])
         np.testing.assert_array_equal(o["cost"], outs[0]["cost"])
+
+
+def test_culling_is_exact(ctx):
+    """Links whose node box holds only zero cost nodes are culled (zero rows written by bulk copies): the result must be
+    identical to the same kernel with the test disabled (rows bit for bit, the per-knot sums up to summation order), and to the kernel without culling, and links must actually
+    be culled in this scene."""
+    for cfg, tab, nf in (("C2", "panda_small", 64), ("C3", None, 96), ("C4", None, 64)):
+        w = small_workload(cfg, tab, B=3, n_field=nf)
+        ctx.set_robot(w.table)
+        upload_fields(ctx, w)
+        outs = []
+        for flags in (0, capi.FLAG_NO_CULL, capi.FLAG_PIPE_KERNEL):
+            w.batch.flags = flags
+            outs.append(ctx.eval_batch(w.batch))
+        w.batch.flags = 0
+        for o in outs[1:]:
+            np.testing.assert_array_equal(o["rows"], outs[0]["rows"], err_msg=cfg)
+            for k in ("H", "g", "cost"):  # same terms, summed in a different order over the warps
+                np.testing.assert_allclose(o[k], outs[0][k], rtol=2e-5, atol=1e-7, err_msg=f"{cfg} {k}")
+        assert np.abs(outs[0]["rows"]).max() > 0
+    # the solver reports how many (problem, knot, link) triples survived the test
+    w = small_workload("C2", "panda_small", B=4, n_field=64)
+    ctx.set_robot(w.table)
+    upload_fields(ctx, w)
+    ctx.solve_batch(w.batch)
+    pf = ctx.profile()
+    assert 0 < pf["links_active"] < 0.6 * pf["links_tested"]
 
 
 def test_eval_options_no_collision_no_standoff(ctx):
