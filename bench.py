@@ -244,7 +244,7 @@ def run_b200(args):
         dev_ms += p["solve_ms"]
         lin_ms += p["linearize_ms"]
         step_ms += p["step_ms"]
-        launches += p["linearize_launches"] + p["step_launches"] + 2
+        launches += p["kernel_launches"]
         for k in prof_acc:
             prof_acc[k] += p[k]
     sync_all()

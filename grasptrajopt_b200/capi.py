@@ -91,7 +91,7 @@ class Profile(C.Structure):
         ("knot_items", C.c_int64), ("jrow_bytes", C.c_int64),
         ("problem_iterations", C.c_int64), ("linearize_launches_with_work", C.c_int32), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-        ("links_tested", C.c_int64), ("links_active", C.c_int64),
+        ("links_tested", C.c_int64), ("links_active", C.c_int64), ("kernel_launches", C.c_int64),
     ]
 
     def as_dict(self):

@@ -1198,6 +1198,7 @@ struct gto_ctx {
   DevBuf<float> base, H, g, costp, rows, result;
   DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive, work_ctr;
   DevBuf<unsigned long long> stats;
+  DevBuf<CullCtx> recs;
   int* h_counter = nullptr;  // pinned
   long long rows_per_problem = 0;
   int Bchunk = 0;
@@ -1294,7 +1295,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
-  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->recs.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1655,6 +1656,14 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       const long long max_items = (long long)nproblems * (ctx->T - t_lo);
       const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
       ctx->last_lin_grid = 0;
+      e = ctx->recs.ensure((size_t)max_items);
+      if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
+      cp.recs = ctx->recs.p;
+      const size_t fk_smem = (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
+      k_item_fk<<<(unsigned)((max_items + 7) / 8), 128, fk_smem, ctx->stream>>>(cp);
+      ctx->prof.kernel_launches += 2;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
       kern<<<grid, threads, sm, ctx->stream>>>(cp);
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
@@ -1698,6 +1707,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       const int grid = p.allow_split ? ctx->sm_count * occ : (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
       ctx->last_lin_grid = p.allow_split ? grid : 0;
       kern<<<grid, threads, sm, ctx->stream>>>(pp);
+      ctx->prof.kernel_launches += 1;
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_pipe launch: ") + cudaGetErrorString(e));
       return GTO_OK;
@@ -1728,6 +1738,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
   if (R.nopt <= 8) k_linearize<8><<<grid, threads, smem, ctx->stream>>>(p);
   else k_linearize<16><<<grid, threads, smem, ctx->stream>>>(p);
+  ctx->prof.kernel_launches += 1;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize launch: ") + cudaGetErrorString(e));
   return GTO_OK;
@@ -1809,6 +1820,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   pf.linearize_launches = pf.step_launches = pf.iterations = 0;
   pf.knot_items = 0; pf.jrow_bytes = 0; pf.problem_iterations = 0; pf.linearize_launches_with_work = 0;
   pf.links_tested = pf.links_active = 0;
+  pf.kernel_launches = 2;  // k_init + k_finalize; the linearise / step launches are added where they happen
   std::vector<int> h_nact((size_t)o.max_iter + 3);
   size_t nev = 0;
   std::vector<int> ev_kind;  // per recorded interval: 0 linearize, 1 step
@@ -1844,6 +1856,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       st.iter = it;
       st.lin_grid = ctx->last_lin_grid;
       step_kern<<<nb, 32, step_smem, ctx->stream>>>(st);
+      pf.kernel_launches += 1;
       CK(cudaGetLastError());
       CK(cudaEventRecord(c, ctx->stream));
       ev_kind.push_back(0);

@@ -29,12 +29,12 @@ struct __align__(16) CullCtx {
   float basep[4];
   int b, t, fid, obuf;
   int nact, kind;                   // surviving links; kind bit 0: goal rows, bit 1: stand-off rows
+  unsigned amask;                   // bit l: link l survived the culling test
+  int pad_;
   int act[GTO_MAX_LINKS];           // surviving link ids, ascending
 };
 
 struct CullShared {
-  double Tm[GTO_MAX_MOV][12];
-  double A[GTO_MAX_MOV][12];
   CullCtx ctx[2];
   LinkMeta links[GTO_MAX_LINKS];
   unsigned long long slot_full[CULL_NSLOT], slot_empty[CULL_NSLOT], ctx_full[2], ctx_empty[2];
@@ -45,6 +45,7 @@ struct CullParams {
   int slot_floats;     // capacity of one brick slot
   int ncons;           // consumer warps
   int* work_counter;   // zero before the launch: next (problem, knot) item
+  CullCtx* recs;       // [items] per-item records written by k_item_fk, read by the producer warps (bulk copy)
   unsigned long long* stats;  // [0] items, [1] links tested, [2] links that survived the culling test (NULL: off)
 };
 
@@ -59,6 +60,201 @@ __device__ __forceinline__ unsigned svt_count(const FieldDev& f, int x0, int x1,
   const unsigned X0 = x0 * sx, X1 = (x1 + 1) * sx, Y0 = y0 * sy, Y1 = (y1 + 1) * sy, Z0 = z0, Z1 = z1 + 1;
   return __ldg(S + X1 + Y1 + Z1) - __ldg(S + X0 + Y1 + Z1) - __ldg(S + X1 + Y0 + Z1) - __ldg(S + X1 + Y1 + Z0) +
          __ldg(S + X0 + Y0 + Z1) + __ldg(S + X0 + Y1 + Z0) + __ldg(S + X1 + Y0 + Z0) - __ldg(S + X0 + Y0 + Z0);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_item_fk: everything of a (problem, knot) item that does not depend on the surface points, 16 lanes per item:
+// float64 chain FK (optas/models.py:826-868) -> visual frames of the collision links (gto/gto_models.py:83-101), joint
+// twists, gripper-minus-goal frames, SDF brick placement per link and the culling test.  One record per item in HBM;
+// the linearise kernel's producer warp pulls it into shared memory with one bulk copy.  Items whose Gauss-Newton
+// block is identically zero (no surviving link, no goal rows) get their zeros written here.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullParams pp) {
+  extern __shared__ __align__(16) unsigned char fk_smem[];
+  const LinParams& p = pp.lin;
+  const RobotDev& R = *p.robot;
+  const int nopt = R.nopt, nmov = R.nmov, nlinks = R.nlinks;
+  const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  double* A = reinterpret_cast<double*>(fk_smem) + (size_t)grp * 2 * nmov * 12;
+  double* Tm = A + (size_t)nmov * 12;
+  const int nknots = p.T - p.t_lo;
+  const int nprob = p.nactive ? *p.nactive : p.nproblems;
+  const int nitems = nprob * nknots;
+  const int item = blockIdx.x * (blockDim.x >> 4) + grp;
+  if (item >= nitems) return;  // whole 16-lane group leaves together
+  const int a = item / nknots;
+  const int t = p.t_lo + (item - a * nknots);
+  const int b = p.active ? p.active[a] : a;
+  const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
+  const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
+  const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
+  const bool cull = !(p.flags & GTO_FLAG_NO_CULL);
+  CullCtx& C = pp.recs[item];
+
+  for (int j = hl; j < nmov; j += 16) {  // A_j = origin_j * motion_j(q_j)
+    const double qj = q[R.mov_qidx[j]];
+    const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
+    double M[12];
+    if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
+      double s, c;
+      sincos(qj, &s, &c);
+      const double v = 1.0 - c;
+      M[0] = 1.0 - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.0;
+      M[4] = s * az + v * ax * ay;          M[5] = 1.0 - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.0;
+      M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
+    } else {
+      M[0] = 1.0; M[1] = 0.0; M[2] = 0.0; M[3] = qj * ax;
+      M[4] = 0.0; M[5] = 1.0; M[6] = 0.0; M[7] = qj * ay;
+      M[8] = 0.0; M[9] = 0.0; M[10] = 1.0; M[11] = qj * az;
+    }
+    double Cm[12];
+    mul34(R.mov_origin_d[j], M, Cm);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) A[j * 12 + e] = Cm[e];
+  }
+  __syncwarp(hmask);
+  for (int j = 0; j < nmov; ++j) {  // sequential along the tree, 12 lanes per product
+    if (hl < 12) {
+      const int r = hl >> 2, c = hl & 3;
+      const int pj = R.mov_parent[j];
+      double s;
+      if (pj < 0) {
+        s = A[j * 12 + hl];
+      } else {
+        const double* P = Tm + pj * 12;
+        s = P[r * 4 + 0] * A[j * 12 + c] + P[r * 4 + 1] * A[j * 12 + 4 + c] + P[r * 4 + 2] * A[j * 12 + 8 + c];
+        if (c == 3) s += P[r * 4 + 3];
+      }
+      Tm[j * 12 + hl] = s;
+    }
+    __syncwarp(hmask);
+  }
+  // ---- visual frames, brick placement and the culling test (one lane per link) ----
+  unsigned amask = 0u;
+  for (int l0 = 0; l0 < nlinks; l0 += 16) {
+    const int l = l0 + hl;
+    bool survives = false;
+    if (l < nlinks) {
+      const int mj = R.link_mov[l];
+      double Fd[12];
+      if (mj < 0) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Fd[e] = R.link_tf_d[l][e];
+      } else {
+        mul34(Tm + mj * 12, R.link_tf_d[l], Fd);
+      }
+      float F[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) F[e] = (float)Fd[e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) reinterpret_cast<float4*>(C.frames[l])[e] = make_float4(F[4 * e], F[4 * e + 1], F[4 * e + 2], F[4 * e + 3]);
+      if (fid >= 0) {
+        const FieldDev& f = p.fields[fid];
+        const float* cc = R.link_center[l];
+        const float* hh = R.link_half[l];
+        const float bp[3] = {p.base[4 * b + 0], p.base[4 * b + 1], p.base[4 * b + 2]};
+        const float org[3] = {f.ox, f.oy, f.oz};
+        const int N3[3] = {f.nx, f.ny, f.nz};
+        int lo3[3], sz3[3], c0[3], c1[3];
+        bool fast = true;
+#pragma unroll
+        for (int a3 = 0; a3 < 3; ++a3) {
+          const float cw = F[a3 * 4 + 0] * cc[0] + F[a3 * 4 + 1] * cc[1] + F[a3 * 4 + 2] * cc[2] + F[a3 * 4 + 3] + bp[a3];
+          const float hw = fabsf(F[a3 * 4 + 0]) * hh[0] + fabsf(F[a3 * 4 + 1]) * hh[1] + fabsf(F[a3 * 4 + 2]) * hh[2] + 1e-4f;
+          int lo = (int)floorf((cw - hw - org[a3]) * f.inv_pitch);
+          const int hi = (int)floorf((cw + hw - org[a3]) * f.inv_pitch) + 1;  // highest node touched
+          // nodes a (possibly index-clamped) lookup of this link can read, for the culling test
+          c0[a3] = min(max(lo, 0), N3[a3] - 1);
+          c1[a3] = min(max(hi, 0), N3[a3] - 1);
+          if (lo < 0 || hi > N3[a3] - 1) fast = false;  // a point may need index clamping
+          if (a3 == 2) lo &= ~3;
+          const int need = hi - lo + 1;
+          int sz = min(32, max(8, (need + 3) & ~3));
+          if (need > sz) fast = false;
+          lo3[a3] = lo;
+          sz3[a3] = sz;
+        }
+        while (sz3[0] * sz3[1] * sz3[2] > pp.slot_floats) {  // does not fit a slot: shrink the longest axis
+          int am = 0;
+          if (sz3[1] > sz3[am]) am = 1;
+          if (sz3[2] > sz3[am]) am = 2;
+          sz3[am] -= 4;
+          fast = false;
+        }
+        *reinterpret_cast<int4*>(C.blo[l]) = make_int4(lo3[0], lo3[1], lo3[2], 0);
+        *reinterpret_cast<int4*>(C.bdim[l]) = make_int4(sz3[0], sz3[1], sz3[2], fast ? 1 : 0);
+        *reinterpret_cast<float4*>(C.cl[l]) = make_float4((bp[0] - org[0]) * f.inv_pitch - (float)lo3[0], (bp[1] - org[1]) * f.inv_pitch - (float)lo3[1],
+                                                          (bp[2] - org[2]) * f.inv_pitch - (float)lo3[2], f.inv_pitch);
+        survives = (R.link_pt_count[l] > 0) &&
+                   (!cull || f.svt == nullptr || svt_count(f, c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]) != 0u);
+      }
+    }
+    const unsigned bal = (__ballot_sync(hmask, survives) >> (threadIdx.x & 16)) & 0xffffu;
+    if (survives) C.act[__popc(amask) + __popc(bal & ((1u << hl) - 1u))] = l;
+    amask |= bal << l0;
+  }
+  for (int k = hl; k < nopt; k += 16) {  // joint twists: v(W) = omega x W + m
+    const int j = R.opt_mov[k];
+    double om[3] = {0.0, 0.0, 0.0}, mm[3] = {0.0, 0.0, 0.0};
+    if (j >= 0) {
+      const double* Tj = Tm + j * 12;
+      const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
+      const double zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
+      const double zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
+      const double zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
+      if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
+        const double ox = Tj[3], oy = Tj[7], oz = Tj[11];
+        om[0] = zx; om[1] = zy; om[2] = zz;
+        mm[0] = oy * zz - oz * zy; mm[1] = oz * zx - ox * zz; mm[2] = ox * zy - oy * zx;  // o x z
+      } else {
+        mm[0] = zx; mm[1] = zy; mm[2] = zz;
+      }
+    }
+    reinterpret_cast<float4*>(C.tw[k])[0] = make_float4((float)om[0], (float)om[1], (float)om[2], 0.f);
+    reinterpret_cast<float4*>(C.tw[k])[1] = make_float4((float)mm[0], (float)mm[1], (float)mm[2], 0.f);
+  }
+  const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
+  if (hl == 15) {  // gripper link frame and its difference to the two goal frames, formed in float64
+    double F[12];
+    if (R.grip_mov < 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) F[e] = R.grip_tf_d[e];
+    } else {
+      mul34(Tm + R.grip_mov * 12, R.grip_tf_d, F);
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      C.gripf[e] = (float)F[e];
+      C.goal[0][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + e]);
+      C.goal[1][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + 12 + e]);
+    }
+    C.b = b; C.t = t; C.fid = fid; C.obuf = obuf;
+    C.nact = __popc(amask);
+    C.kind = (is_goal ? 1 : 0) | (is_stand ? 2 : 0);
+    C.amask = amask;
+    C.pad_ = 0;
+  }
+  if (hl < 3) C.basep[hl] = p.base[4 * b + hl];
+  if (amask == 0u && !is_goal && !is_stand) {  // nothing for the point kernel: this knot's Gauss-Newton block is zero
+    const int nH = nopt * nopt;
+    const long long bt = (long long)b * p.T + t;
+    for (int i = hl; i < nH; i += 16) p.H[obuf * p.buf_stride_H + bt * nH + i] = 0.f;
+    if (hl < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + hl] = 0.f;
+    if (hl == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.f;
+  }
+  if (pp.stats && hl == 0) {
+    atomicAdd(pp.stats + 0, 1ull);
+    if (p.collision) atomicAdd(pp.stats + 1, (unsigned long long)nlinks);
+    atomicAdd(pp.stats + 2, (unsigned long long)__popc(amask));
+  }
+}
+
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // NP: padded tensor-core tile width (8 or 16); NOPT_CT: number of optimised joints when known at compile time (0: runtime)
@@ -116,235 +312,90 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
 
   if (warp == NC) {
     // =============================== PRODUCER WARP ===============================
+    // per item: read the header of its record, write the zero rows of the culled links (bulk stores), and -- if anything
+    // is left for the point kernel -- pull the record into shared memory (one bulk copy) and the surviving links' bricks
+    // into the ring (one TMA tile each).  The next item index is fetched one item ahead.
     unsigned pub = 0, bc = 0;
-    unsigned long long st_items = 0, st_links = 0, st_act = 0;
-    const bool cull = !(p.flags & GTO_FLAG_NO_CULL);
+    const int nlinks = R.nlinks;
+    int my_start = 0, my_cnt = 0;
+    if (lane < nlinks) { my_start = S.links[lane].pt_start; my_cnt = S.links[lane].pt_end - my_start; }
+    int next_item = 0;
+    if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
     for (;;) {
-      int item = 0;
-      if (lane == 0) item = atomicAdd(pp.work_counter, 1);
-      item = __shfl_sync(0xffffffffu, item, 0);
+      const int item = __shfl_sync(0xffffffffu, next_item, 0);
       if (item >= nitems) break;
-      const int ci = pub & 1;
-      if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
-      CullCtx& C = S.ctx[ci];
-      const int a = item / nknots;
-      const int t = p.t_lo + (item - a * nknots);
-      const int b = p.active ? p.active[a] : a;
-      const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
-      const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
-      const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
-      // ---- chain FK in float64 ----
-      if (lane < R.nmov) {
-        const double qj = q[R.mov_qidx[lane]];
-        const double ax = R.mov_axis_d[lane][0], ay = R.mov_axis_d[lane][1], az = R.mov_axis_d[lane][2];
-        double M[12];
-        if (R.mov_type[lane] == GTO_JOINT_REVOLUTE) {
-          double s, c;
-          sincos(qj, &s, &c);
-          const double v = 1.0 - c;
-          M[0] = 1.0 - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.0;
-          M[4] = s * az + v * ax * ay;          M[5] = 1.0 - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.0;
-          M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
-        } else {
-          M[0] = 1.0; M[1] = 0.0; M[2] = 0.0; M[3] = qj * ax;
-          M[4] = 0.0; M[5] = 1.0; M[6] = 0.0; M[7] = qj * ay;
-          M[8] = 0.0; M[9] = 0.0; M[10] = 1.0; M[11] = qj * az;
-        }
-        double Cm[12];
-        mul34(R.mov_origin_d[lane], M, Cm);
-#pragma unroll
-        for (int e = 0; e < 12; ++e) S.A[lane][e] = Cm[e];
+      if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
+      const CullCtx* G = pp.recs + item;
+      const int4 h0 = __ldg(reinterpret_cast<const int4*>(&G->b));     // b, t, fid, obuf
+      const int4 h1 = __ldg(reinterpret_cast<const int4*>(&G->nact));  // nact, kind, amask, -
+      int4 mydim = make_int4(0, 0, 0, 0), mylo = make_int4(0, 0, 0, 0);
+      const int b = h0.x, t = h0.y, fid = h0.z;
+      const unsigned amask = (unsigned)h1.z;
+      const bool survives = (amask >> lane) & 1u;
+      if (survives) {
+        mydim = __ldg(reinterpret_cast<const int4*>(G->bdim[lane]));
+        mylo = __ldg(reinterpret_cast<const int4*>(G->blo[lane]));
       }
-      __syncwarp();
-      for (int j = 0; j < R.nmov; ++j) {
-        if (lane < 12) {
-          const int r = lane >> 2, c = lane & 3;
-          const int pj = R.mov_parent[j];
-          double s;
-          if (pj < 0) {
-            s = S.A[j][lane];
-          } else {
-            const double* P = S.Tm[pj];
-            s = P[r * 4 + 0] * S.A[j][c] + P[r * 4 + 1] * S.A[j][4 + c] + P[r * 4 + 2] * S.A[j][8 + c];
-            if (c == 3) s += P[r * 4 + 3];
-          }
-          S.Tm[j][lane] = s;
-        }
-        __syncwarp();
-      }
-      // ---- visual frames, brick placement and the culling test (one lane per link) ----
-      bool survives = false;
-      if (lane < R.nlinks) {
-        const int mj = R.link_mov[lane];
-        double Fd[12];
-        if (mj < 0) {
-#pragma unroll
-          for (int e = 0; e < 12; ++e) Fd[e] = R.link_tf_d[lane][e];
-        } else {
-          mul34(S.Tm[mj], R.link_tf_d[lane], Fd);
-        }
-        float F[12];
-#pragma unroll
-        for (int e = 0; e < 12; ++e) {
-          F[e] = (float)Fd[e];
-          C.frames[lane][e] = F[e];
-        }
-        if (fid >= 0) {
-          const FieldDev& f = p.fields[fid];
-          const float* cc = R.link_center[lane];
-          const float* hh = R.link_half[lane];
-          const float bp[3] = {p.base[4 * b + 0], p.base[4 * b + 1], p.base[4 * b + 2]};
-          const float org[3] = {f.ox, f.oy, f.oz};
-          const int N3[3] = {f.nx, f.ny, f.nz};
-          int lo3[3], sz3[3], c0[3], c1[3];
-          bool fast = true;
-#pragma unroll
-          for (int a3 = 0; a3 < 3; ++a3) {
-            const float cw = F[a3 * 4 + 0] * cc[0] + F[a3 * 4 + 1] * cc[1] + F[a3 * 4 + 2] * cc[2] + F[a3 * 4 + 3] + bp[a3];
-            const float hw = fabsf(F[a3 * 4 + 0]) * hh[0] + fabsf(F[a3 * 4 + 1]) * hh[1] + fabsf(F[a3 * 4 + 2]) * hh[2] + 1e-4f;
-            int lo = (int)floorf((cw - hw - org[a3]) * f.inv_pitch);
-            const int hi = (int)floorf((cw + hw - org[a3]) * f.inv_pitch) + 1;  // highest node touched
-            // nodes a (possibly index-clamped) lookup of this link can read, for the culling test
-            c0[a3] = min(max(lo, 0), N3[a3] - 1);
-            c1[a3] = min(max(hi, 0), N3[a3] - 1);
-            if (lo < 0 || hi > N3[a3] - 1) fast = false;  // a point may need index clamping
-            if (a3 == 2) lo &= ~3;
-            const int need = hi - lo + 1;
-            int sz = min(32, max(8, (need + 3) & ~3));
-            if (need > sz) fast = false;
-            lo3[a3] = lo;
-            sz3[a3] = sz;
-          }
-          while (sz3[0] * sz3[1] * sz3[2] > pp.slot_floats) {  // does not fit a slot: shrink the longest axis
-            int am = 0;
-            if (sz3[1] > sz3[am]) am = 1;
-            if (sz3[2] > sz3[am]) am = 2;
-            sz3[am] -= 4;
-            fast = false;
-          }
-          C.blo[lane][0] = lo3[0]; C.blo[lane][1] = lo3[1]; C.blo[lane][2] = lo3[2]; C.blo[lane][3] = 0;
-          C.bdim[lane][0] = sz3[0]; C.bdim[lane][1] = sz3[1]; C.bdim[lane][2] = sz3[2]; C.bdim[lane][3] = fast ? 1 : 0;
-#pragma unroll
-          for (int a3 = 0; a3 < 3; ++a3) C.cl[lane][a3] = (bp[a3] - org[a3]) * f.inv_pitch - (float)lo3[a3];
-          C.cl[lane][3] = f.inv_pitch;
-          survives = (R.link_pt_count[lane] > 0) &&
-                     (!cull || f.svt == nullptr || svt_count(f, c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]) != 0u);
-        }
-      }
-      const unsigned amask = __ballot_sync(0xffffffffu, survives);
-      const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
-      const bool publish = (amask != 0u) || is_goal || is_stand;
-      st_items += 1;
-      if (p.collision) st_links += R.nlinks;
-      st_act += __popc(amask);
       // ---- rows of the culled links: zeros, straight from shared memory by bulk copy ----
       if (p.collision && p.rows) {
         float* rows_b = p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS;
         bool slow_zero = false;
-        if (lane < R.nlinks && !survives) {
-          const int cnt = R.link_pt_count[lane];
-          char* dst = reinterpret_cast<char*>(rows_b + ((long long)t * R.npoints + R.link_pt_start[lane]) * RS);
-          const unsigned bytes = (unsigned)cnt * RS * 4u;
+        if (lane < nlinks && !survives) {
+          char* dst = reinterpret_cast<char*>(rows_b + ((long long)t * R.npoints + my_start) * RS);
+          const unsigned bytes = (unsigned)my_cnt * RS * 4u;
           if ((((uintptr_t)dst | bytes) & 15u) == 0u) {
             for (unsigned o = 0; o < bytes; o += CULL_ZERO_BYTES) bulk_store_zero(dst + o, zero_buf, min((unsigned)CULL_ZERO_BYTES, bytes - o));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           } else {
-            slow_zero = cnt > 0;
+            slow_zero = my_cnt > 0;
           }
         }
         unsigned zm = __ballot_sync(0xffffffffu, slow_zero);  // row blocks that are not 16-byte aligned: plain stores
         while (zm) {
           const int l = __ffs(zm) - 1;
           zm &= zm - 1;
-          float* dst = rows_b + ((long long)t * R.npoints + R.link_pt_start[l]) * RS;
-          const int nfl = R.link_pt_count[l] * RS;
+          float* dst = rows_b + ((long long)t * R.npoints + S.links[l].pt_start) * RS;
+          const int nfl = (S.links[l].pt_end - S.links[l].pt_start) * RS;
           for (int i = lane; i < nfl; i += 32) __stcs(dst + i, 0.f);
         }
       }
-      if (!publish) {
-        // nothing for the consumers: this knot's Gauss-Newton block is zero
-        const long long bt = (long long)b * p.T + t;
-        for (int i = lane; i < nH; i += 32) p.H[obuf * p.buf_stride_H + bt * nH + i] = 0.f;
-        if (lane < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + lane] = 0.f;
-        if (lane == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.f;
-        continue;
+      if (amask == 0u && h1.y == 0) continue;  // k_item_fk wrote the zero Gauss-Newton block
+      const int ci = pub & 1;
+      if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
+      if (lane == 0) {
+        mbar_expect_tx(ctx_full + ci, (uint32_t)sizeof(CullCtx));
+        bulk_load(&S.ctx[ci], G, (uint32_t)sizeof(CullCtx), ctx_full + ci);
       }
-      if (lane < nopt) {
-        const int j = R.opt_mov[lane];
-        double om[3] = {0.0, 0.0, 0.0}, mm[3] = {0.0, 0.0, 0.0};
-        if (j >= 0) {
-          const double* Tj = S.Tm[j];
-          const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
-          const double zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
-          const double zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
-          const double zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
-          if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
-            const double ox = Tj[3], oy = Tj[7], oz = Tj[11];
-            om[0] = zx; om[1] = zy; om[2] = zz;
-            mm[0] = oy * zz - oz * zy; mm[1] = oz * zx - ox * zz; mm[2] = ox * zy - oy * zx;
-          } else {
-            mm[0] = zx; mm[1] = zy; mm[2] = zz;
-          }
-        }
-        C.tw[lane][0] = (float)om[0]; C.tw[lane][1] = (float)om[1]; C.tw[lane][2] = (float)om[2]; C.tw[lane][3] = 0.f;
-        C.tw[lane][4] = (float)mm[0]; C.tw[lane][5] = (float)mm[1]; C.tw[lane][6] = (float)mm[2]; C.tw[lane][7] = 0.f;
-      }
-      if (lane == 31) {
-        double F[12];
-        if (R.grip_mov < 0) {
-#pragma unroll
-          for (int e = 0; e < 12; ++e) F[e] = R.grip_tf_d[e];
-        } else {
-          mul34(S.Tm[R.grip_mov], R.grip_tf_d, F);
-        }
-#pragma unroll
-        for (int e = 0; e < 12; ++e) {
-          C.gripf[e] = (float)F[e];
-          C.goal[0][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + e]);
-          C.goal[1][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + 12 + e]);
-        }
-        C.b = b; C.t = t; C.fid = fid; C.obuf = obuf;
-        C.nact = __popc(amask);
-        C.kind = (is_goal ? 1 : 0) | (is_stand ? 2 : 0);
-      }
-      if (survives) C.act[__popc(amask & ((1u << lane) - 1u))] = lane;
-      if (lane >= 24 && lane < 27) C.basep[lane - 24] = p.base[4 * b + (lane - 24)];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ctx_full + ci);  // release: the context is visible to the consumers
       ++pub;
       // ---- one TMA brick per surviving link into the ring ----
       if (amask) {
-        if (lane == 0) {
-          const CUtensorMap* maps = p.fields[fid].maps2;
-          unsigned m = amask, idx = bc;
-          while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
+        const CUtensorMap* maps = p.fields[fid].maps2;
+        unsigned m = amask, idx = bc;
+        while (m) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const int sx = __shfl_sync(0xffffffffu, mydim.x, l), sy = __shfl_sync(0xffffffffu, mydim.y, l), sz = __shfl_sync(0xffffffffu, mydim.z, l);
+          const int lx = __shfl_sync(0xffffffffu, mylo.x, l), ly = __shfl_sync(0xffffffffu, mylo.y, l), lz = __shfl_sync(0xffffffffu, mylo.z, l);
+          if (lane == 0) {
             const unsigned s = idx % CULL_NSLOT;
             if (idx >= CULL_NSLOT) mbar_wait_sleep(slot_empty + s, ((idx / CULL_NSLOT) - 1) & 1);
-            const int sx = C.bdim[l][0], sy = C.bdim[l][1], sz = C.bdim[l][2];
             const int mi = ((sx / 4 - 2) * PIPE_NAXC + (sy / 4 - 2)) * PIPE_NAXC + (sz / 4 - 2);
             mbar_expect_tx(slot_full + s, (uint32_t)(sx * sy * sz * sizeof(float)));
-            tma_load_3d(ring + (size_t)s * pp.slot_floats, maps + mi, C.blo[l][2], C.blo[l][1], C.blo[l][0], slot_full + s);
-            ++idx;
+            tma_load_3d(ring + (size_t)s * pp.slot_floats, maps + mi, lz, ly, lx, slot_full + s);
           }
+          ++idx;
         }
         bc += __popc(amask);
         __syncwarp();
       }
     }
-    // ---- tell the consumers to stop, account, drain the bulk stores ----
+    // ---- tell the consumers to stop, drain the bulk stores ----
     {
       const int ci = pub & 1;
       if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
       if (lane == 0) {
         S.ctx[ci].b = -1;
         mbar_arrive(ctx_full + ci);
-        if (pp.stats) {
-          atomicAdd(pp.stats + 0, st_items);
-          atomicAdd(pp.stats + 1, st_links);
-          atomicAdd(pp.stats + 2, st_act);
-        }
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -178,6 +178,7 @@ typedef struct gto_profile {
   int64_t h2d_bytes, d2h_bytes;
   int64_t links_tested;      /* (problem, knot, link) triples whose node box was tested against the field's summed-volume table */
   int64_t links_active;      /* ... of which touched a non-zero node and went through the point kernel (the rest: zero rows) */
+  int64_t kernel_launches;   /* kernels launched by the last gto_solve_* */
 } gto_profile;
 
 int gto_abi_version(void);
