@@ -1051,6 +1051,8 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
   }
 }
 
+#include "step_cr.cuh"
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_plan_cost: nearest-node cost of whole plans (seed ranking, gto/gto_models.py:204-215; clip-then-truncate indexing of
 // points_to_offsets_numpy :190-201).  One block per (plan, knot).
@@ -1814,6 +1816,16 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   else if (n < 8) step_kern = k_step<8, false>;
   else step_kern = k_step<16, false>;
   CK(cudaFuncSetAttribute(step_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
+  // default: block cyclic reduction, one CTA per problem (k_step_cr); the sequential block Thomas kernel is the A/B reference
+  void (*step_cr_kern)(const StepParams) = nullptr;
+  if (n == 7) step_cr_kern = k_step_cr<7, true>;
+  else if (n == 8) step_cr_kern = k_step_cr<8, true>;
+  else if (n == 10) step_cr_kern = k_step_cr<10, true>;
+  else if (n < 8) step_cr_kern = k_step_cr<8, false>;
+  else step_cr_kern = k_step_cr<16, false>;
+  const size_t cr_smem = step_cr_smem_bytes(T, n);
+  bool use_cr = !getenv("GTO_STEP_V1") && !getenv("GTO_SPLIT_TAIL") && cr_smem <= (size_t)ctx->max_smem_optin;
+  if (use_cr) CK(cudaFuncSetAttribute(step_cr_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_smem));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1855,7 +1867,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
       st.iter = it;
       st.lin_grid = ctx->last_lin_grid;
-      step_kern<<<nb, 32, step_smem, ctx->stream>>>(st);
+      if (use_cr) step_cr_kern<<<nb, STEP_CR_THREADS, cr_smem, ctx->stream>>>(st);
+      else step_kern<<<nb, 32, step_smem, ctx->stream>>>(st);
       pf.kernel_launches += 1;
       CK(cudaGetLastError());
       CK(cudaEventRecord(c, ctx->stream));

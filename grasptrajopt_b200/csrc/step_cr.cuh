@@ -1,0 +1,429 @@
+// step_cr.cuh -- k_step_cr: Levenberg-Marquardt bookkeeping + damped projected Gauss-Newton step, one CTA per problem.
+// Included by gto_b200.cu after k_step (shares StepParams, warp_sum / warp_max / shfl_d).
+//
+// Same mathematics as k_step (mirrors oracle/gto_oracle.py solve_lm / lm_step, float64), but the SPD block-tridiagonal
+// system  (H_t + a2 c_t I)(1 + lambda) on the diagonal, -a2 I off it  (the velocity term gto/gto_planner.py:134-135
+// couples neighbouring knots) is solved by *block cyclic reduction* instead of the sequential block Thomas sweep:
+// at stride s every block i = s (mod 2s) is eliminated at once -- one warp per block: Gauss-Jordan inverse of the 7x7..16x16
+// diagonal block in registers (pivot rows travel by warp shuffle), W_L = D^-1 L, W_U = D^-1 U, w = D^-1 b -- and its two
+// neighbours i -+ s absorb the Schur complement.  log2(T) levels instead of T-2 dependent block steps: the launch is
+// latency bound (a few thousand flops per problem), so the depth of the dependency chain is what sets its duration.
+// Elimination in any symmetric order is stable for an SPD matrix; a non-positive pivot means the damped matrix is not
+// positive definite and the factorisation is retried with more damping, exactly as in k_step.
+#pragma once
+
+#define STEP_CR_THREADS 256
+
+__host__ __device__ inline size_t step_cr_smem_bytes(int T, int n) {
+  const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
+  const size_t d = (size_t)T * n + 4 * m * n + 3 * m * nn + 40;
+  return ((d * sizeof(double) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
+}
+
+// deterministic block reductions (fixed tree): every thread of the CTA must call them
+__device__ __forceinline__ double cta_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  return s;
+}
+__device__ __forceinline__ double cta_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = red[0];
+  for (int w = 1; w < nw; ++w) s = fmax(s, red[w]);
+  return s;
+}
+
+// In-register Gauss-Jordan inverse of an SPD block: lane r < NP owns row r.  Returns false (uniformly) on a
+// non-positive pivot.
+template <int NP>
+__device__ __forceinline__ bool gj_inverse(double (&row)[NP], int r) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const double piv = shfl_d(row[k], k);
+    if (!(piv > 0.0)) ok = false;  // uniform: every lane sees the same pivot
+    double ip = (double)__frcp_rn((float)piv);
+    ip = ip * (2.0 - piv * ip);
+    ip = ip * (2.0 - piv * ip);
+    const bool isk = (r == k);
+    const double mult = -row[k] * ip;
+    const double coef = isk ? ip - 1.0 : mult;
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+      if (c == k) continue;
+      row[c] = fma(coef, shfl_d(row[c], k), row[c]);
+    }
+    row[k] = isk ? ip : mult;
+  }
+  return ok;
+}
+
+template <int NP, bool EXACT>
+__global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char step_smem[];
+  const RobotDev& R = *p.robot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
+  const int a_idx = blockIdx.x;
+  if (a_idx >= *p.nactive_in) return;
+  const int b = p.active_in[a_idx];
+  const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;
+  const double a2 = p.w_vel / (p.dt * p.dt);
+  double* X = reinterpret_cast<double*>(step_smem);  // [T][n] accepted point
+  double* gt = X + (size_t)T * n;                    // [m][n] gradient
+  double* dd = gt + (size_t)m * n;                   // [m][n] clipped step
+  double* xs = dd + (size_t)m * n;                   // [m][n] solution of the linear system
+  double* bb = xs + (size_t)m * n;                   // [m][n] right-hand side -> D^-1 b of eliminated blocks
+  double* Dm = bb + (size_t)m * n;                   // [m][n*n] diagonal blocks -> their inverses
+  double* Lm = Dm + (size_t)m * nn;                  // [m][n*n] coupling to block i - s -> D^-1 L
+  double* Um = Lm + (size_t)m * nn;                  // [m][n*n] coupling to block i + s -> D^-1 U
+  double* red = Um + (size_t)m * nn;                 // [40] reduction scratch
+  unsigned* fm = reinterpret_cast<unsigned*>(red + 40);  // [m] bit k: variable k of knot i+2 is held at a bound
+  int* sflag = reinterpret_cast<int*>(fm + m);           // [0] factorisation failed
+
+  double* Xc = p.Qc + (long long)b * T * n;
+  double* Xt = p.Qt + (long long)b * T * n;
+  int cur = p.bufsel[b];
+  const int it = p.iter;
+  double lam = p.lam[b], nu = p.nu[b];
+  const int tri = 1 - cur;
+  if (tid == 0) p.bufsplit[tri * p.Bcap + b] = 1;
+  bool accepted = false;
+
+  // ---------------- evaluate the trial point produced by the previous call ----------------
+  {
+    float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
+    double s = 0.0;
+    for (int t = tid; t < T; t += NT) s += (double)ct[t];
+    const double Fp_t = cta_sum(s, red);
+    s = 0.0;
+    for (int i = tid; i < (T - 1) * n; i += NT) {
+      const double d = Xt[i + n] - Xt[i];
+      s += d * d;
+    }
+    const double Ft = Fp_t + a2 * cta_sum(s, red);
+    int done = -1;  // -1: keep running, otherwise final status
+    if (!isfinite(Ft)) {
+      done = GTO_STATUS_NAN;
+    } else if (it == 0) {  // initial point: accept unconditionally
+      // knots 0 and 1 never move and are linearised only once: keep their cost in both buffers
+      if (tid < 2) {
+        const float c01 = ct[tid];
+        for (int buf = 0; buf < 2; ++buf) p.costp[buf * p.buf_stride_c + (long long)b * T + tid] = c01;
+      }
+      cur = tri;
+      accepted = true;
+      if (tid == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
+    } else {
+      const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
+      const double ared = 0.5 * (Fcur - Ft);
+      const double noise = p.noise_rel * fmax(Fpcur, Fp_t);
+      __syncthreads();  // everyone has read F / Fp before thread 0 overwrites them
+      if (pred > 0.0 && ared + noise >= p.eta * pred) {
+        const double rho = ared / pred;
+        cur = tri;
+        accepted = true;
+        if (tid == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
+        const double lam_used = lam;
+        const double w = 2.0 * fmin(rho, 1.0) - 1.0;
+        lam = fmax(p.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - w * w * w));
+        nu = 2.0;
+        if (step <= p.tol_step) done = GTO_STATUS_CONVERGED;
+        else if (lam_used >= p.lambda_slow && ared <= p.ftol * Fcur) done = GTO_STATUS_SLOW;
+      } else {
+        if (pred <= 0.0 && step <= p.tol_step) {
+          done = GTO_STATUS_CONVERGED;
+        } else {
+          lam = fmin(p.lambda_max, lam * nu);
+          nu *= 2.0;
+          if (lam >= p.lambda_max) done = GTO_STATUS_STALLED;
+        }
+      }
+      if (done < 0 && p.slow_window > 0) {  // windowed progress test on the accepted cost
+        const double Fnow = accepted ? Ft : Fcur;
+        double* hist = p.Fhist + (long long)b * 16;
+        if (it >= p.slow_window) {
+          const double Fold = hist[(it - p.slow_window) & 15];
+          if (Fold - Fnow <= p.slow_ftol * Fnow) done = GTO_STATUS_SLOW;
+        }
+        __syncthreads();
+        if (tid == 0) hist[it & 15] = Fnow;
+      }
+    }
+    if (it == 0 && done < 0 && p.slow_window > 0 && tid == 0) p.Fhist[(long long)b * 16] = Ft;
+    if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
+    // the accepted point (the trial point becomes the accepted one)
+    for (int i = tid; i < T * n; i += NT) {
+      double v;
+      if (accepted) {
+        v = Xt[i];
+        if (it > 0) Xc[i] = v;
+      } else {
+        v = Xc[i];
+      }
+      X[i] = v;
+    }
+    if (done >= 0) {
+      if (tid == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
+      return;
+    }
+  }
+  for (int i = tid; i < m; i += NT) fm[i] = 0u;
+  __syncthreads();
+
+  // ---------------- gradient with the analytic velocity terms, active set, projected-gradient test ----------------
+  const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn + 2 * nn;  // knots 2..T-1
+  const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
+  {
+    double pgmax = 0.0;
+    for (int idx = tid; idx < m * n; idx += NT) {
+      const int i = idx / n, k = idx - i * n, t = i + 2;
+      const double x = X[t * n + k];
+      double gv = x - X[(t - 1) * n + k];
+      if (t < T - 1) gv -= X[(t + 1) * n + k] - x;
+      const double gtv = (double)gc[t * n + k] + a2 * gv;
+      const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
+      gt[idx] = gtv;
+      if (fixed) atomicOr(fm + i, 1u << k);
+      else pgmax = fmax(pgmax, fabs(gtv));
+    }
+    pgmax = cta_max(pgmax, red);
+    if (2.0 * pgmax <= p.tol_grad) {
+      if (tid == 0) { p.status[b] = GTO_STATUS_CONVERGED; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
+      return;
+    }
+  }
+  __syncthreads();
+
+  // ---------------- damped projected Gauss-Newton step: block cyclic reduction in float64 ----------------
+  constexpr int OUT_A = (2 * NP * NP + NP + 31) / 32;  // results a lane holds in phase A / B before they are written back
+  constexpr int OUT_B = (3 * NP * NP + NP + 31) / 32;
+  bool ok = false;
+  for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
+    // build the masked, damped system
+    for (int idx = tid; idx < m * nn; idx += NT) {
+      const int i = idx / nn, rc = idx - i * nn, r = rc / n, c = rc - r * n;
+      const unsigned mi = fm[i];
+      const bool fr = (mi >> r) & 1u, fc = (mi >> c) & 1u;
+      double v = (double)Hc[idx];
+      if (r == c) {
+        v += a2 * ((i + 2 < T - 1) ? 2.0 : 1.0);
+        v += lam * v;
+      }
+      if (fr || fc) v = (r == c) ? 1.0 : 0.0;
+      Dm[idx] = v;
+      double l = 0.0, u = 0.0;
+      if (r == c && !fr) {
+        if (i > 0 && !((fm[i - 1] >> r) & 1u)) l = -a2;
+        if (i < m - 1 && !((fm[i + 1] >> r) & 1u)) u = -a2;
+      }
+      Lm[idx] = l;
+      Um[idx] = u;
+    }
+    for (int idx = tid; idx < m * n; idx += NT) {
+      const int i = idx / n, k = idx - i * n;
+      bb[idx] = ((fm[i] >> k) & 1u) ? 0.0 : -gt[idx];
+    }
+    if (tid == 0) sflag[0] = 0;
+    __syncthreads();
+
+    // forward: strides 1, 2, 4, ...; the last pass (s >= m) eliminates block 0, which has no neighbour left
+    int s = 1;
+    for (;; s <<= 1) {
+      const bool last = (s >= m);
+      // ---- phase A: one warp per eliminated block i = s (mod 2s) ----
+      const int nel = last ? 1 : (m - s + 2 * s - 1) / (2 * s);
+      for (int e = warp; e < nel; e += NW) {
+        const int i = last ? 0 : s + 2 * s * e;
+        double* Di = Dm + (size_t)i * nn;
+        double* Li = Lm + (size_t)i * nn;
+        double* Ui = Um + (size_t)i * nn;
+        double* bi = bb + (size_t)i * n;
+        const bool hasL = !last;                 // i - s >= 0 always holds for an eliminated block
+        const bool hasU = !last && (i + s < m);
+        double row[NP];
+#pragma unroll
+        for (int c = 0; c < NP; ++c) row[c] = (lane < n && c < n) ? Di[lane * n + c] : ((lane == c) ? 1.0 : 0.0);
+        const bool good = gj_inverse<NP>(row, lane);
+        if (!good && lane == 0) sflag[0] = 1;
+        __syncwarp();
+        if (lane < n) {
+#pragma unroll
+          for (int c = 0; c < NP; ++c)
+            if (c < n) Di[lane * n + c] = row[c];
+        }
+        __syncwarp();
+        // W_L = D^-1 L, W_U = D^-1 U, w = D^-1 b : outputs dealt over the 32 lanes, written back in place afterwards
+        double outv[OUT_A];
+        const int nout = 2 * nn + n;
+#pragma unroll
+        for (int o = 0; o < OUT_A; ++o) {
+          const int id = lane + 32 * o;
+          double acc = 0.0;
+          if (id < nout) {
+            if (id < 2 * nn) {
+              const bool isU = id >= nn;
+              const int rc = isU ? id - nn : id, r = rc / n, c = rc - r * n;
+              const double* M = isU ? Ui : Li;
+              if (isU ? hasU : hasL)
+                for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], M[k * n + c], acc);
+            } else {
+              const int r = id - 2 * nn;
+              for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], bi[k], acc);
+            }
+          }
+          outv[o] = acc;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 0; o < OUT_A; ++o) {
+          const int id = lane + 32 * o;
+          if (id < nn) Li[id] = outv[o];
+          else if (id < 2 * nn) Ui[id - nn] = outv[o];
+          else if (id < nout) bi[id - 2 * nn] = outv[o];
+        }
+      }
+      __syncthreads();
+      if (last) break;
+      // ---- phase B: one warp per kept block j = 0 (mod 2s): absorb the Schur complements of j - s and j + s ----
+      const int nkeep = (m + 2 * s - 1) / (2 * s);
+      for (int e = warp; e < nkeep; e += NW) {
+        const int j = 2 * s * e;
+        const int i1 = j - s, i2 = j + s;
+        const bool has1 = (i1 >= 0), has2 = (i2 < m);
+        if (!has1 && !has2) continue;
+        double* Dj = Dm + (size_t)j * nn;
+        double* Lj = Lm + (size_t)j * nn;
+        double* Uj = Um + (size_t)j * nn;
+        double* bj = bb + (size_t)j * n;
+        const double* WL1 = Lm + (size_t)(has1 ? i1 : 0) * nn;
+        const double* WU1 = Um + (size_t)(has1 ? i1 : 0) * nn;
+        const double* w1 = bb + (size_t)(has1 ? i1 : 0) * n;
+        const double* WL2 = Lm + (size_t)(has2 ? i2 : 0) * nn;
+        const double* WU2 = Um + (size_t)(has2 ? i2 : 0) * nn;
+        const double* w2 = bb + (size_t)(has2 ? i2 : 0) * n;
+        const bool has1L = has1 && (i1 - s >= 0);  // j - 2s exists
+        const bool has2U = has2 && (i2 + s < m);   // j + 2s exists
+        double outv[OUT_B];
+        const int nout = 3 * nn + n;
+#pragma unroll
+        for (int o = 0; o < OUT_B; ++o) {
+          const int id = lane + 32 * o;
+          double acc = 0.0;
+          if (id < nout) {
+            if (id < nn) {  // D_j - U_j W_L(j+s) - L_j W_U(j-s)
+              const int r = id / n, c = id - r * n;
+              acc = Dj[id];
+              if (has2)
+                for (int k = 0; k < n; ++k) acc = fma(-Uj[r * n + k], WL2[k * n + c], acc);
+              if (has1)
+                for (int k = 0; k < n; ++k) acc = fma(-Lj[r * n + k], WU1[k * n + c], acc);
+            } else if (id < 2 * nn) {  // new L_j = -L_j W_L(j-s)
+              const int rc = id - nn, r = rc / n, c = rc - r * n;
+              if (has1L)
+                for (int k = 0; k < n; ++k) acc = fma(-Lj[r * n + k], WL1[k * n + c], acc);
+            } else if (id < 3 * nn) {  // new U_j = -U_j W_U(j+s)
+              const int rc = id - 2 * nn, r = rc / n, c = rc - r * n;
+              if (has2U)
+                for (int k = 0; k < n; ++k) acc = fma(-Uj[r * n + k], WU2[k * n + c], acc);
+            } else {  // b_j - U_j w(j+s) - L_j w(j-s)
+              const int r = id - 3 * nn;
+              acc = bj[r];
+              if (has2)
+                for (int k = 0; k < n; ++k) acc = fma(-Uj[r * n + k], w2[k], acc);
+              if (has1)
+                for (int k = 0; k < n; ++k) acc = fma(-Lj[r * n + k], w1[k], acc);
+            }
+          }
+          outv[o] = acc;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 0; o < OUT_B; ++o) {
+          const int id = lane + 32 * o;
+          if (id < nn) Dj[id] = outv[o];
+          else if (id < 2 * nn) Lj[id - nn] = outv[o];
+          else if (id < 3 * nn) Uj[id - 2 * nn] = outv[o];
+          else if (id < nout) bj[id - 3 * nn] = outv[o];
+        }
+      }
+      __syncthreads();
+    }
+    ok = (sflag[0] == 0);
+    __syncthreads();
+    if (!ok) {
+      lam = fmin(p.lambda_max, lam * 10.0);  // not positive definite: add damping and refactor
+      continue;
+    }
+    // back substitution: x_0 = w_0, then the eliminated blocks level by level, coarsest first
+    if (tid < n) xs[tid] = bb[tid];
+    __syncthreads();
+    for (s >>= 1; s >= 1; s >>= 1) {
+      const int nel = (m - s + 2 * s - 1) / (2 * s);
+      for (int idx = tid; idx < nel * n; idx += NT) {
+        const int e = idx / n, r = idx - e * n;
+        const int i = s + 2 * s * e;
+        const double* WL = Lm + (size_t)i * nn + r * n;
+        const double* WU = Um + (size_t)i * nn + r * n;
+        double acc = bb[i * n + r];
+        const double* xl = xs + (size_t)(i - s) * n;
+        for (int k = 0; k < n; ++k) acc = fma(-WL[k], xl[k], acc);
+        if (i + s < m) {
+          const double* xu = xs + (size_t)(i + s) * n;
+          for (int k = 0; k < n; ++k) acc = fma(-WU[k], xu[k], acc);
+        }
+        xs[i * n + r] = acc;
+      }
+      __syncthreads();
+    }
+  }
+  if (!ok) {
+    if (tid == 0) { p.status[b] = GTO_STATUS_NAN; p.iters[b] = it; }
+    return;
+  }
+
+  // ---------------- trial point = clip(X + x); predicted reduction with the undamped, unmasked model ----------------
+  double stepmax = 0.0, gdot = 0.0;
+  for (int idx = tid; idx < m * n; idx += NT) {
+    const int i = idx / n, r = idx - i * n, t = i + 2;
+    const double xc = X[t * n + r];
+    const double xn = fmin(fmax(xc + xs[idx], R.lo[r]), R.hi[r]);
+    const double d = xn - xc;
+    Xt[t * n + r] = xn;
+    p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[r]] = xn;
+    dd[idx] = d;
+    stepmax = fmax(stepmax, fabs(d));
+    gdot += gt[idx] * d;
+  }
+  stepmax = cta_max(stepmax, red);
+  gdot = cta_sum(gdot, red);  // (the barriers inside also publish dd)
+  double quad = 0.0;
+  for (int idx = tid; idx < m * n; idx += NT) {
+    const int i = idx / n, r = idx - i * n;
+    const double dg = a2 * ((i + 2 < T - 1) ? 2.0 : 1.0);
+    const double dr = dd[idx];
+    double hd = dg * dr;
+    const float* Hr = Hc + (size_t)i * nn + r * n;
+    for (int c = 0; c < n; ++c) hd += (double)Hr[c] * dd[i * n + c];
+    quad += dr * hd;
+    if (i < m - 1) quad -= 2.0 * a2 * dr * dd[idx + n];
+  }
+  quad = cta_sum(quad, red);
+  if (tid == 0) {
+    p.pred[b] = -(gdot + 0.5 * quad);
+    p.stepn[b] = stepmax;
+    p.lam[b] = lam;
+    p.nu[b] = nu;
+    p.iters[b] = it + 1;
+    const int slot = atomicAdd(p.nactive_out, 1);
+    p.active_out[slot] = b;
+  }
+}
