@@ -735,6 +735,9 @@ struct StepParams {
   int* active_out;
   int* nactive_out;
   int iter;        // number of LM steps already taken by the problems in the active list
+  long long* dbg;  // k_step_cr: clock64() at phase boundaries of CTA 0 (diagnostics, NULL: off)
+  int do_fk;       // k_step_cr: also write the item records (FK, brick placement, culling test) of the new trial point
+  CullParams fk;   // what item_fk_body needs (robot, fields, records, Gauss-Newton buffers)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -1200,8 +1203,12 @@ struct gto_ctx {
   DevBuf<float> base, H, g, costp, rows, result;
   DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive, work_ctr;
   DevBuf<unsigned long long> stats;
-  DevBuf<CullCtx> recs;
-  int* h_counter = nullptr;  // pinned
+  DevBuf<long long> dbg;
+  DevBuf<CullCtx> recs, rec_dummy;
+  int* h_counter = nullptr;  // pinned, 16 ints
+  std::vector<cudaStream_t> gstreams;  // one stream per problem group (see gto_solve_resident)
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
   long long rows_per_problem = 0;
   int Bchunk = 0;
   // profiling
@@ -1268,7 +1275,7 @@ extern "C" int gto_create(gto_ctx** out, int device) {
   if (cudaMalloc((void**)&ctx->robot_d, sizeof(RobotDev)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->fields_d, sizeof(FieldDev) * MAX_FIELDS) != cudaSuccess ||
       cudaMalloc((void**)&ctx->tmaps_d, sizeof(CUtensorMap) * MAX_FIELDS * NCLASS) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_counter, sizeof(int) * 4) != cudaSuccess) {
+      cudaMallocHost((void**)&ctx->h_counter, sizeof(int) * 16) != cudaSuccess) {
     gto_destroy(ctx);
     return GTO_ERR_NOMEM;
   }
@@ -1287,6 +1294,9 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
     if (f.svt) cudaFree(f.svt);
   }
   for (auto e : ctx->ev) cudaEventDestroy(e);
+  for (auto e : ctx->ev_join) cudaEventDestroy(e);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (auto st_ : ctx->gstreams) cudaStreamDestroy(st_);
   if (ctx->robot_d) cudaFree(ctx->robot_d);
   if (ctx->fields_d) cudaFree(ctx->fields_d);
   if (ctx->tmaps_d) cudaFree(ctx->tmaps_d);
@@ -1297,7 +1307,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
-  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->recs.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->recs.release(); ctx->rec_dummy.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1595,10 +1605,9 @@ static size_t lin_smem_bytes(const gto_ctx* ctx, int brick_max, int warps) {
 }
 
 // launches one linearisation on ctx->stream
-static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
-                            float* rows, int t_lo, unsigned flags, int* work_counter) {
+static void fill_lin_params(gto_ctx* ctx, LinParams& p, const double* q, const int* active, const int* nactive, int nproblems, int b0,
+                            const int* bufsel, float* rows, int t_lo, unsigned flags) {
   const RobotDev& R = ctx->robot_h;
-  LinParams p;
   memset(&p, 0, sizeof(p));
   p.robot = ctx->robot_d; p.chunk_start = ctx->chunk_start.p; p.chunk_count = ctx->chunk_count.p;
   p.px = ctx->px.p; p.py = ctx->py.p; p.pz = ctx->pz.p;
@@ -1618,18 +1627,42 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   p.collision = ctx->collision;
   p.sw_obs = (float)sqrt(ctx->w_obs); p.sw_goal = (float)sqrt(ctx->w_goal);
   p.flags = flags;
-  bool pipe_ok = !(flags & (GTO_FLAG_V1_KERNEL | GTO_FLAG_NO_TMA | GTO_FLAG_NO_BRICK)) && !getenv("GTO_V1_KERNEL");
+}
+
+// the kernels with TMA-staged bricks need a tile map for every field
+static bool pipe_path_ok(const gto_ctx* ctx, unsigned flags) {
+  bool ok = !(flags & (GTO_FLAG_V1_KERNEL | GTO_FLAG_NO_TMA | GTO_FLAG_NO_BRICK)) && !getenv("GTO_V1_KERNEL");
   for (auto& ff : ctx->fields)
-    if (ff.set && !ff.maps2) pipe_ok = false;
+    if (ff.set && !ff.maps2) ok = false;
+  return ok;
+}
+static bool cull_path_ok(const gto_ctx* ctx, unsigned flags) {
+  return pipe_path_ok(ctx, flags) && !(flags & GTO_FLAG_PIPE_KERNEL) && !getenv("GTO_PIPE_KERNEL");
+}
+static int brick_slot_floats(const gto_ctx* ctx) {
+  const int n3 = ctx->min_pitch > 0 ? (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 5 : 8;
+  int slot_floats = n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
+  if (const char* e = getenv("GTO_SLOT_FLOATS")) slot_floats = std::max(512, atoi(e) & ~127);
+  return slot_floats;
+}
+
+// launches one linearisation on ctx->stream; `have_recs`: the item records of this launch were already written (by the
+// step kernel that produced the trial point), so k_item_fk is skipped
+static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
+                            float* rows, int t_lo, unsigned flags, int* work_counter, bool have_recs = false, cudaStream_t stream = nullptr,
+                            CullCtx* recs = nullptr) {
+  if (!stream) stream = ctx->stream;
+  const RobotDev& R = ctx->robot_h;
+  LinParams p;
+  fill_lin_params(ctx, p, q, active, nactive, nproblems, b0, bufsel, rows, t_lo, flags);
+  const bool pipe_ok = pipe_path_ok(ctx, flags);
   // ---- default: culling + TMA-pipelined kernel with dynamic item scheduling ----
-  if (pipe_ok && work_counter && !(flags & GTO_FLAG_PIPE_KERNEL) && !getenv("GTO_PIPE_KERNEL")) {
+  if (work_counter && cull_path_ok(ctx, flags)) {
     CullParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.lin = p;
     cp.lin.allow_split = 0;
-    const int n3 = ctx->min_pitch > 0 ? (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 5 : 8;
-    int slot_floats = n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
-    if (const char* e = getenv("GTO_SLOT_FLOATS")) slot_floats = std::max(512, atoi(e) & ~127);
+    const int slot_floats = brick_slot_floats(ctx);
     cp.slot_floats = slot_floats;
     int nc = ctx->pipe_cons;
     if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
@@ -1658,15 +1691,24 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       const long long max_items = (long long)nproblems * (ctx->T - t_lo);
       const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
       ctx->last_lin_grid = 0;
-      e = ctx->recs.ensure((size_t)max_items);
+      if (!recs) {
+        e = ctx->recs.ensure((size_t)max_items);
+        if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
+        recs = ctx->recs.p;
+      }
+      cp.recs = recs;
+      e = ctx->rec_dummy.ensure(1);
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
-      cp.recs = ctx->recs.p;
-      const size_t fk_smem = (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
-      k_item_fk<<<(unsigned)((max_items + 7) / 8), 128, fk_smem, ctx->stream>>>(cp);
-      ctx->prof.kernel_launches += 2;
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
-      kern<<<grid, threads, sm, ctx->stream>>>(cp);
+      cp.rec_dummy = ctx->rec_dummy.p;
+      ctx->prof.kernel_launches += 1;
+      if (!have_recs) {
+        const size_t fk_smem = ((sizeof(RobotDev) + 15) & ~(size_t)15) + (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
+        k_item_fk<<<(unsigned)((max_items + 7) / 8), 128, fk_smem, stream>>>(cp);
+        ctx->prof.kernel_launches += 1;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
+      }
+      kern<<<grid, threads, sm, stream>>>(cp);
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
       return GTO_OK;
@@ -1678,9 +1720,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
     memset(&pp, 0, sizeof(pp));
     pp.lin = p;
     pp.chunk_link = nullptr;
-    const int n3 = ctx->min_pitch > 0 ? (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 5 : 8;
-    int slot_floats = n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
-    if (const char* e = getenv("GTO_SLOT_FLOATS")) slot_floats = std::max(512, atoi(e) & ~127);
+    const int slot_floats = brick_slot_floats(ctx);
     pp.slot_floats = slot_floats;
     int nc = ctx->pipe_cons;
     if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
@@ -1708,7 +1748,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       // solver launches use the full persistent grid: the device decides how many parts an item is split into
       const int grid = p.allow_split ? ctx->sm_count * occ : (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
       ctx->last_lin_grid = p.allow_split ? grid : 0;
-      kern<<<grid, threads, sm, ctx->stream>>>(pp);
+      kern<<<grid, threads, sm, stream>>>(pp);
       ctx->prof.kernel_launches += 1;
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_pipe launch: ") + cudaGetErrorString(e));
@@ -1738,8 +1778,8 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   if (occ < 1) return fail(ctx, GTO_ERR_CUDA, "linearize kernel does not fit on an SM");
   const long long max_items = (long long)nproblems * (ctx->T - t_lo);
   const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
-  if (R.nopt <= 8) k_linearize<8><<<grid, threads, smem, ctx->stream>>>(p);
-  else k_linearize<16><<<grid, threads, smem, ctx->stream>>>(p);
+  if (R.nopt <= 8) k_linearize<8><<<grid, threads, smem, stream>>>(p);
+  else k_linearize<16><<<grid, threads, smem, stream>>>(p);
   ctx->prof.kernel_launches += 1;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize launch: ") + cudaGetErrorString(e));
@@ -1776,8 +1816,6 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(ctx->rows.ensure((size_t)Bchunk * ctx->rows_per_problem * (n + 1)));
   }
   ctx->Bchunk = Bchunk;
-  CK(ctx->nactive.ensure((size_t)o.max_iter + 3));
-  CK(ctx->work_ctr.ensure((size_t)o.max_iter + 3));
   CK(ctx->stats.ensure(4));
   CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
 
@@ -1826,6 +1864,11 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   const size_t cr_smem = step_cr_smem_bytes(T, n);
   bool use_cr = !getenv("GTO_STEP_V1") && !getenv("GTO_SPLIT_TAIL") && cr_smem <= (size_t)ctx->max_smem_optin;
   if (use_cr) CK(cudaFuncSetAttribute(step_cr_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_smem));
+  // the step kernel also writes the item records of its new trial point when the culling kernel will consume them and
+  // its FK scratch fits into the (by then free) factorisation storage
+  const bool step_fk = use_cr && cull_path_ok(ctx, ctx->flags) && getenv("GTO_STEP_FK") &&  // measured on C2: slower than a k_item_fk launch of its own (two serial rounds per CTA), off by default
+                       (size_t)(STEP_CR_THREADS / 16) * 2 * R.nmov * 12 <= (size_t)3 * (T - 2) * n * n;
+  if (step_fk) CK(ctx->recs.ensure((size_t)Bchunk * T));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1833,7 +1876,6 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   pf.knot_items = 0; pf.jrow_bytes = 0; pf.problem_iterations = 0; pf.linearize_launches_with_work = 0;
   pf.links_tested = pf.links_active = 0;
   pf.kernel_launches = 2;  // k_init + k_finalize; the linearise / step launches are added where they happen
-  std::vector<int> h_nact((size_t)o.max_iter + 3);
   size_t nev = 0;
   std::vector<int> ev_kind;  // per recorded interval: 0 linearize, 1 step
   cudaEvent_t ev_begin = get_event(ctx, nev++);
@@ -1846,55 +1888,133 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   std::vector<int> ident(B);
   for (int b = 0; b < B; ++b) ident[b] = b;
 
+  // Problem groups: the problems of a chunk are split into G contiguous groups, each iterating on a stream of its own.
+  // Once most problems have converged the launches are latency bound (a handful of CTAs); the groups' dependency chains
+  // (linearise -> step -> linearise ...) then overlap on the otherwise idle SMs.  Results do not depend on the grouping.
+  int G = 1;  // measured on C2: no gain from G > 1 (the chain of the slowest problem sets the time), kept as an option
+  if (const char* e = getenv("GTO_GROUPS")) G = atoi(e);
+  if (getenv("GTO_SPLIT_TAIL")) G = 1;
+  G = std::max(1, std::min(G, 8));
+  while ((int)ctx->gstreams.size() < G) {
+    cudaStream_t s_;
+    CK(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+    ctx->gstreams.push_back(s_);
+    cudaEvent_t ej;
+    CK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
+    ctx->ev_join.push_back(ej);
+  }
+  if (!ctx->ev_fork) CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  const size_t cstride = (size_t)o.max_iter + 3;  // per-group counter arrays
+  CK(ctx->nactive.ensure(cstride * G));
+  CK(ctx->work_ctr.ensure(cstride * G));
+  const bool cull_ok = cull_path_ok(ctx, ctx->flags);
+  if (getenv("GTO_STEP_DBG")) {
+    CK(ctx->dbg.ensure(64));
+    CK(cudaMemsetAsync(ctx->dbg.p, 0, 64 * sizeof(long long), ctx->stream));
+    st.dbg = ctx->dbg.p;
+  }
+  if (cull_ok) CK(ctx->recs.ensure((size_t)Bchunk * T));
+  struct Grp {
+    int b0, nb;
+    cudaStream_t s;
+    int *act0, *act1, *nact, *wctr;
+    CullCtx* recs;
+    bool done;
+  };
+  std::vector<int> h_nact(cstride * G);
+
   for (int b0 = 0; b0 < B; b0 += Bchunk) {
     const int nb = std::min(Bchunk, B - b0);
-    int* act0 = ctx->active.p;
-    int* act1 = ctx->active.p + B;
-    CK(cudaMemsetAsync(ctx->nactive.p, 0, sizeof(int) * ((size_t)o.max_iter + 3), ctx->stream));
-    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, sizeof(int) * ((size_t)o.max_iter + 3), ctx->stream));
-    CK(cudaMemcpyAsync(act0, ident.data() + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->nactive.p, &nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    int host_active = nb;
+    const int ng = std::min(G, nb);
+    std::vector<Grp> grp(ng);
+    CK(cudaMemsetAsync(ctx->nactive.p, 0, sizeof(int) * cstride * G, ctx->stream));
+    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, sizeof(int) * cstride * G, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->active.p + b0, ident.data() + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    for (int g = 0; g < ng; ++g) {
+      Grp& r = grp[g];
+      r.b0 = b0 + (int)((long long)nb * g / ng);
+      r.nb = b0 + (int)((long long)nb * (g + 1) / ng) - r.b0;
+      r.s = (ng == 1) ? ctx->stream : ctx->gstreams[g];
+      r.act0 = ctx->active.p + r.b0;
+      r.act1 = ctx->active.p + B + r.b0;
+      r.nact = ctx->nactive.p + cstride * g;
+      r.wctr = ctx->work_ctr.p + cstride * g;
+      r.recs = cull_ok ? ctx->recs.p + (size_t)(r.b0 - b0) * T : nullptr;
+      r.done = false;
+      CK(cudaMemcpyAsync(r.nact, &r.nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ng > 1) {
+      CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      for (int g = 0; g < ng; ++g) CK(cudaStreamWaitEvent(grp[g].s, ctx->ev_fork, 0));
+    }
     for (int it = 0; it <= o.max_iter; ++it) {
-      int* ain = (it & 1) ? act1 : act0;
-      int* aout = (it & 1) ? act0 : act1;
-      cudaEvent_t a = get_event(ctx, nev++), bE = get_event(ctx, nev++), c = get_event(ctx, nev++);
-      CK(cudaEventRecord(a, ctx->stream));
-      int rc = launch_linearize(ctx, ctx->q_trial.p, ain, ctx->nactive.p + it, nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
-                                it == 0 ? 0 : 2, ctx->flags, ctx->work_ctr.p + it);
-      if (rc) return rc;
-      CK(cudaEventRecord(bE, ctx->stream));
-      st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
-      st.iter = it;
-      st.lin_grid = ctx->last_lin_grid;
-      if (use_cr) step_cr_kern<<<nb, STEP_CR_THREADS, cr_smem, ctx->stream>>>(st);
-      else step_kern<<<nb, 32, step_smem, ctx->stream>>>(st);
-      pf.kernel_launches += 1;
-      CK(cudaGetLastError());
-      CK(cudaEventRecord(c, ctx->stream));
-      ev_kind.push_back(0);
-      pf.linearize_launches++;
-      pf.step_launches++;
-      pf.iterations = std::max(pf.iterations, it);
+      bool any = false;
+      for (int g = 0; g < ng; ++g) {
+        Grp& r = grp[g];
+        if (r.done) continue;
+        any = true;
+        int* ain = (it & 1) ? r.act1 : r.act0;
+        int* aout = (it & 1) ? r.act0 : r.act1;
+        cudaEvent_t a = get_event(ctx, nev++), bE = get_event(ctx, nev++), c = get_event(ctx, nev++);
+        CK(cudaEventRecord(a, r.s));
+        int rc = launch_linearize(ctx, ctx->q_trial.p, ain, r.nact + it, r.nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
+                                  it == 0 ? 0 : 2, ctx->flags, r.wctr + it, step_fk && it > 0, r.s, r.recs);
+        if (rc) return rc;
+        CK(cudaEventRecord(bE, r.s));
+        st.active_in = ain; st.nactive_in = r.nact + it; st.active_out = aout; st.nactive_out = r.nact + it + 1;
+        st.iter = it;
+        st.lin_grid = ctx->last_lin_grid;
+        st.do_fk = step_fk ? 1 : 0;
+        if (step_fk) {
+          memset(&st.fk, 0, sizeof(st.fk));
+          fill_lin_params(ctx, st.fk.lin, ctx->q_trial.p, nullptr, nullptr, r.nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr, 2, ctx->flags);
+          st.fk.lin.allow_split = 0;
+          st.fk.slot_floats = brick_slot_floats(ctx);
+          st.fk.recs = r.recs;
+          CK(ctx->rec_dummy.ensure(1));
+          st.fk.rec_dummy = ctx->rec_dummy.p;
+          st.fk.stats = ctx->stats.p;
+        }
+        if (use_cr) step_cr_kern<<<r.nb, STEP_CR_THREADS, cr_smem, r.s>>>(st);
+        else step_kern<<<r.nb, 32, step_smem, r.s>>>(st);
+        pf.kernel_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c, r.s));
+        ev_kind.push_back(0);
+        pf.linearize_launches++;
+        pf.step_launches++;
+        pf.iterations = std::max(pf.iterations, it);
+      }
+      if (!any) break;
       if (((it + 1) % o.check_every) == 0 || it == o.max_iter) {
-        CK(cudaMemcpyAsync(ctx->h_counter, ctx->nactive.p + it + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        host_active = ctx->h_counter[0];
-        if (host_active == 0) break;
+        for (int g = 0; g < ng; ++g)
+          if (!grp[g].done) CK(cudaMemcpyAsync(ctx->h_counter + g, grp[g].nact + it + 1, sizeof(int), cudaMemcpyDeviceToHost, grp[g].s));
+        for (int g = 0; g < ng; ++g) {
+          if (grp[g].done) continue;
+          CK(cudaStreamSynchronize(grp[g].s));
+          if (ctx->h_counter[g] == 0) grp[g].done = true;
+        }
+      }
+    }
+    if (ng > 1) {  // join: the chunk's groups are finished before the next chunk reuses the row buffer / k_finalize runs
+      for (int g = 0; g < ng; ++g) {
+        CK(cudaEventRecord(ctx->ev_join[g], grp[g].s));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
       }
     }
     // exact work accounting for the roofline: problems active in every linearise launch of this chunk
-    CK(cudaMemcpyAsync(h_nact.data(), ctx->nactive.p, sizeof(int) * h_nact.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_nact.data(), ctx->nactive.p, sizeof(int) * cstride * G, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int it = 0; it <= o.max_iter; ++it) {
-      const long long na = h_nact[it];
-      if (na <= 0) break;
-      pf.problem_iterations += na;
-      pf.linearize_launches_with_work++;
-      pf.knot_items += na * (it == 0 ? T : T - 2);
-      if (want_rows)
-        pf.jrow_bytes += na * (it == 0 ? ctx->rows_per_problem : ctx->rows_per_problem - 2LL * (ctx->collision ? R.npoints : 0)) * (n + 1) * 4;
-    }
+    for (int g = 0; g < ng; ++g)
+      for (int it = 0; it <= o.max_iter; ++it) {
+        const long long na = h_nact[cstride * g + it];
+        if (na <= 0) break;
+        pf.problem_iterations += na;
+        pf.linearize_launches_with_work++;
+        pf.knot_items += na * (it == 0 ? T : T - 2);
+        if (want_rows)
+          pf.jrow_bytes += na * (it == 0 ? ctx->rows_per_problem : ctx->rows_per_problem - 2LL * (ctx->collision ? R.npoints : 0)) * (n + 1) * 4;
+      }
   }
   {
     const long long tot = (long long)B * T;
@@ -1909,6 +2029,13 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(cudaMemcpy(hs, ctx->stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
     pf.links_tested = (long long)hs[1];
     pf.links_active = (long long)hs[2];
+  }
+  if (st.dbg) {
+    long long hd[64];
+    CK(cudaMemcpy(hd, ctx->dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[gto] k_step_cr phase clocks (cycles since kernel start, last launch with work, CTA 0):");
+    for (int i = 1; i < 64 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[0]);
+    fprintf(stderr, "\n");
   }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));

@@ -46,6 +46,7 @@ struct CullParams {
   int ncons;           // consumer warps
   int* work_counter;   // zero before the launch: next (problem, knot) item
   CullCtx* recs;       // [items] per-item records written by k_item_fk, read by the producer warps (bulk copy)
+  CullCtx* rec_dummy;  // one record nobody reads
   unsigned long long* stats;  // [0] items, [1] links tested, [2] links that survived the culling test (NULL: off)
 };
 
@@ -70,28 +71,23 @@ __device__ __forceinline__ unsigned svt_count(const FieldDev& f, int x0, int x1,
 // the linearise kernel's producer warp pulls it into shared memory with one bulk copy.  Items whose Gauss-Newton
 // block is identically zero (no surviving link, no goal rows) get their zeros written here.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullParams pp) {
-  extern __shared__ __align__(16) unsigned char fk_smem[];
+// 16 lanes (`hl` = lane within the group, `hshift` = 0 / 16: which half of the warp) compute the record of item `item` =
+// (problem b, knot t) at configuration q; A / Tm: 2 x nmov x 12 doubles of shared scratch owned by the group.  The two
+// halves of a warp run in lock step (full-warp barriers, one instruction stream for two items): a half without an item
+// of its own (`valid` false) recomputes a neighbour's item into the dummy record.
+__device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDev& R, int item, bool valid, int b, int t, int obuf, const double* q,
+                                             double* A, double* Tm, int hl, int hshift) {
   const LinParams& p = pp.lin;
-  const RobotDev& R = *p.robot;
   const int nopt = R.nopt, nmov = R.nmov, nlinks = R.nlinks;
-  const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
-  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
-  double* A = reinterpret_cast<double*>(fk_smem) + (size_t)grp * 2 * nmov * 12;
-  double* Tm = A + (size_t)nmov * 12;
-  const int nknots = p.T - p.t_lo;
-  const int nprob = p.nactive ? *p.nactive : p.nproblems;
-  const int nitems = nprob * nknots;
-  const int item = blockIdx.x * (blockDim.x >> 4) + grp;
-  if (item >= nitems) return;  // whole 16-lane group leaves together
-  const int a = item / nknots;
-  const int t = p.t_lo + (item - a * nknots);
-  const int b = p.active ? p.active[a] : a;
-  const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
   const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
-  const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
   const bool cull = !(p.flags & GTO_FLAG_NO_CULL);
-  CullCtx& C = pp.recs[item];
+  CullCtx& C = valid ? pp.recs[item] : *pp.rec_dummy;
+  // issued before the FK chain, consumed after it: field geometry, base offset
+  FieldDev fld;
+  fld.data = nullptr; fld.nx = fld.ny = fld.nz = fld.nzp = 2; fld.ox = fld.oy = fld.oz = 0.f; fld.inv_pitch = 1.f; fld.has_tma = 0;
+  fld.maps2 = nullptr; fld.svt = nullptr;
+  if (fid >= 0) fld = p.fields[fid];
+  const float bpx = p.base[4 * b + 0], bpy = p.base[4 * b + 1], bpz = p.base[4 * b + 2];
 
   for (int j = hl; j < nmov; j += 16) {  // A_j = origin_j * motion_j(q_j)
     const double qj = q[R.mov_qidx[j]];
@@ -114,7 +110,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
 #pragma unroll
     for (int e = 0; e < 12; ++e) A[j * 12 + e] = Cm[e];
   }
-  __syncwarp(hmask);
+  __syncwarp();
   for (int j = 0; j < nmov; ++j) {  // sequential along the tree, 12 lanes per product
     if (hl < 12) {
       const int r = hl >> 2, c = hl & 3;
@@ -129,7 +125,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
       }
       Tm[j * 12 + hl] = s;
     }
-    __syncwarp(hmask);
+    __syncwarp();
   }
   // ---- visual frames, brick placement and the culling test (one lane per link) ----
   unsigned amask = 0u;
@@ -151,10 +147,10 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
 #pragma unroll
       for (int e = 0; e < 3; ++e) reinterpret_cast<float4*>(C.frames[l])[e] = make_float4(F[4 * e], F[4 * e + 1], F[4 * e + 2], F[4 * e + 3]);
       if (fid >= 0) {
-        const FieldDev& f = p.fields[fid];
+        const FieldDev& f = fld;
         const float* cc = R.link_center[l];
         const float* hh = R.link_half[l];
-        const float bp[3] = {p.base[4 * b + 0], p.base[4 * b + 1], p.base[4 * b + 2]};
+        const float bp[3] = {bpx, bpy, bpz};
         const float org[3] = {f.ox, f.oy, f.oz};
         const int N3[3] = {f.nx, f.ny, f.nz};
         int lo3[3], sz3[3], c0[3], c1[3];
@@ -191,7 +187,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
                    (!cull || f.svt == nullptr || svt_count(f, c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]) != 0u);
       }
     }
-    const unsigned bal = (__ballot_sync(hmask, survives) >> (threadIdx.x & 16)) & 0xffffu;
+    const unsigned bal = (__ballot_sync(0xffffffffu, survives) >> hshift) & 0xffffu;
     if (survives) C.act[__popc(amask) + __popc(bal & ((1u << hl) - 1u))] = l;
     amask |= bal << l0;
   }
@@ -236,19 +232,49 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
     C.amask = amask;
     C.pad_ = 0;
   }
-  if (hl < 3) C.basep[hl] = p.base[4 * b + hl];
-  if (amask == 0u && !is_goal && !is_stand) {  // nothing for the point kernel: this knot's Gauss-Newton block is zero
+  if (hl < 3) C.basep[hl] = (hl == 0) ? bpx : (hl == 1 ? bpy : bpz);
+  if (valid && amask == 0u && !is_goal && !is_stand) {  // nothing for the point kernel: this knot's Gauss-Newton block is zero
     const int nH = nopt * nopt;
     const long long bt = (long long)b * p.T + t;
     for (int i = hl; i < nH; i += 16) p.H[obuf * p.buf_stride_H + bt * nH + i] = 0.f;
     if (hl < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + hl] = 0.f;
     if (hl == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.f;
   }
-  if (pp.stats && hl == 0) {
+  if (pp.stats && valid && hl == 0) {
     atomicAdd(pp.stats + 0, 1ull);
     if (p.collision) atomicAdd(pp.stats + 1, (unsigned long long)nlinks);
     atomicAdd(pp.stats + 2, (unsigned long long)__popc(amask));
   }
+}
+
+__global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullParams pp) {
+  extern __shared__ __align__(16) unsigned char fk_smem[];
+  const LinParams& p = pp.lin;
+  // the robot table is staged in shared memory with one batch of loads: the serial FK chain then never waits on L2
+  RobotDev& R = *reinterpret_cast<RobotDev*>(fk_smem);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.robot);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(fk_smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(RobotDev) / 8); i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  const int nprob = p.nactive ? *p.nactive : p.nproblems;
+  __syncthreads();
+  const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const int hshift = threadIdx.x & 16;
+  double* A = reinterpret_cast<double*>(fk_smem + ((sizeof(RobotDev) + 15) & ~(size_t)15)) + (size_t)grp * 2 * R.nmov * 12;
+  double* Tm = A + (size_t)R.nmov * 12;
+  const int nknots = p.T - p.t_lo;
+  const int nitems = nprob * nknots;
+  int item = blockIdx.x * (blockDim.x >> 4) + grp;
+  if ((item & ~1) >= nitems) return;  // the whole warp (two items) leaves together
+  const bool valid = item < nitems;
+  if (!valid) item = nitems - 1;
+  const int a = item / nknots;
+  const int t = p.t_lo + (item - a * nknots);
+  const int b = p.active ? p.active[a] : a;
+  const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
+  const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
+  item_fk_body(pp, R, item, valid, b, t, obuf, q, A, Tm, hl, hshift);
 }
 
 __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

@@ -16,8 +16,8 @@
 
 __host__ __device__ inline size_t step_cr_smem_bytes(int T, int n) {
   const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
-  const size_t d = (size_t)T * n + 4 * m * n + 3 * m * nn + 40;
-  return ((d * sizeof(double) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
+  const size_t d = (size_t)2 * T * n + 4 * m * n + 3 * m * nn + 64;
+  return ((d * sizeof(double) + 2 * (m * nn + m * n) * sizeof(float) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
 }
 
 // deterministic block reductions (fixed tree): every thread of the CTA must call them
@@ -30,6 +30,15 @@ __device__ __forceinline__ double cta_sum(double v, double* red) {
   double s = 0.0;
   for (int w = 0; w < nw; ++w) s += red[w];
   return s;
+}
+__device__ __forceinline__ void cta_sum3(double& a, double& b, double& c, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  __syncthreads();
+  if (lane == 0) { red[warp] = a; red[16 + warp] = b; red[32 + warp] = c; }
+  __syncthreads();
+  a = 0.0; b = 0.0; c = 0.0;
+  for (int w = 0; w < nw; ++w) { a += red[w]; b += red[16 + w]; c += red[32 + w]; }
 }
 __device__ __forceinline__ double cta_max(double v, double* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -51,7 +60,9 @@ __device__ __forceinline__ bool gj_inverse(double (&row)[NP], int r) {
   for (int k = 0; k < NP; ++k) {
     const double piv = shfl_d(row[k], k);
     if (!(piv > 0.0)) ok = false;  // uniform: every lane sees the same pivot
-    double ip = (double)__frcp_rn((float)piv);
+    float ipf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ipf) : "f"((float)piv));  // seed; two Newton steps in float64 follow
+    double ip = (double)ipf;
     ip = ip * (2.0 - piv * ip);
     ip = ip * (2.0 - piv * ip);
     const bool isk = (r == k);
@@ -73,6 +84,9 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   const RobotDev& R = *p.robot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
   const int a_idx = blockIdx.x;
+  int dbg_i = 0;
+#define STEP_MARK() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
+  STEP_MARK();
   if (a_idx >= *p.nactive_in) return;
   const int b = p.active_in[a_idx];
   const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;
@@ -85,31 +99,56 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   double* Dm = bb + (size_t)m * n;                   // [m][n*n] diagonal blocks -> their inverses
   double* Lm = Dm + (size_t)m * nn;                  // [m][n*n] coupling to block i - s -> D^-1 L
   double* Um = Lm + (size_t)m * nn;                  // [m][n*n] coupling to block i + s -> D^-1 U
-  double* red = Um + (size_t)m * nn;                 // [40] reduction scratch
-  unsigned* fm = reinterpret_cast<unsigned*>(red + 40);  // [m] bit k: variable k of knot i+2 is held at a bound
-  int* sflag = reinterpret_cast<int*>(fm + m);           // [0] factorisation failed
+  double* red = Um + (size_t)m * nn;                 // [64] reduction scratch
+  double* X2 = red + 64;                             // [T][n] the other of (accepted, trial) point while the decision is open
+  float* HS = reinterpret_cast<float*>(X2 + (size_t)T * n);  // [2][m][n*n] Gauss-Newton blocks of both buffers (knots 2..T-1)
+  float* gS = HS + (size_t)2 * m * nn;                       // [2][m][n]
+  unsigned* fm = reinterpret_cast<unsigned*>(gS + (size_t)2 * m * n);  // [m] bit k: variable k of knot i+2 is held at a bound
+  int* sflag = reinterpret_cast<int*>(fm + m);           // [0] factorisation failed, [1] slot in the next active list
 
   double* Xc = p.Qc + (long long)b * T * n;
   double* Xt = p.Qt + (long long)b * T * n;
-  int cur = p.bufsel[b];
   const int it = p.iter;
+  // ---- everything that only depends on b is requested in one batch: the launch is latency bound, and every dependent
+  //      round trip to L2 / HBM costs about a microsecond ----
+  for (int buf = 0; buf < 2; ++buf) {  // Gauss-Newton blocks of both buffers (which one is "accepted" is decided below)
+    const float* Hg = p.H + buf * p.buf_stride_H + (long long)b * T * nn + 2 * nn;
+    const float* gg = p.g + buf * p.buf_stride_g + (long long)b * T * n + 2 * n;
+    for (int i = tid; i < m * nn; i += NT)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(HS + (size_t)buf * m * nn + i)), "l"(Hg + i) : "memory");
+    for (int i = tid; i < m * n; i += NT)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(gS + (size_t)buf * m * n + i)), "l"(gg + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int cur = p.bufsel[b];
   double lam = p.lam[b], nu = p.nu[b];
+  const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
   const int tri = 1 - cur;
   if (tid == 0) p.bufsplit[tri * p.Bcap + b] = 1;
   bool accepted = false;
 
   // ---------------- evaluate the trial point produced by the previous call ----------------
   {
-    float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
-    double s = 0.0;
-    for (int t = tid; t < T; t += NT) s += (double)ct[t];
-    const double Fp_t = cta_sum(s, red);
-    s = 0.0;
-    for (int i = tid; i < (T - 1) * n; i += NT) {
-      const double d = Xt[i + n] - Xt[i];
-      s += d * d;
+    double s0 = 0.0, s1 = 0.0, sv = 0.0;
+    for (int t = tid; t < T; t += NT) {
+      s0 += (double)p.costp[(long long)b * T + t];
+      s1 += (double)p.costp[p.buf_stride_c + (long long)b * T + t];
     }
-    const double Ft = Fp_t + a2 * cta_sum(s, red);
+    for (int i = tid; i < T * n; i += NT) {
+      const double xt = Xt[i];
+      X[i] = xt;         // trial point
+      X2[i] = Xc[i];     // accepted point
+      if (i >= n) {
+        const double d = xt - Xt[i - n];
+        sv += d * d;
+      }
+    }
+    STEP_MARK();  // 1: loads issued
+    cta_sum3(s0, s1, sv, red);
+    STEP_MARK();  // 2: trial cost known
+    float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
+    const double Fp_t = tri ? s1 : s0;
+    const double Ft = Fp_t + a2 * sv;
     int done = -1;  // -1: keep running, otherwise final status
     if (!isfinite(Ft)) {
       done = GTO_STATUS_NAN;
@@ -123,10 +162,8 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       accepted = true;
       if (tid == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
     } else {
-      const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
       const double ared = 0.5 * (Fcur - Ft);
       const double noise = p.noise_rel * fmax(Fpcur, Fp_t);
-      __syncthreads();  // everyone has read F / Fp before thread 0 overwrites them
       if (pred > 0.0 && ared + noise >= p.eta * pred) {
         const double rho = ared / pred;
         cur = tri;
@@ -161,27 +198,28 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     if (it == 0 && done < 0 && p.slow_window > 0 && tid == 0) p.Fhist[(long long)b * 16] = Ft;
     if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
     // the accepted point (the trial point becomes the accepted one)
-    for (int i = tid; i < T * n; i += NT) {
-      double v;
+    for (int i = tid; i < T * n; i += NT) {  // same thread -> same entries as in the staging loop above
       if (accepted) {
-        v = Xt[i];
-        if (it > 0) Xc[i] = v;
+        if (it > 0) Xc[i] = X[i];
       } else {
-        v = Xc[i];
+        X[i] = X2[i];
       }
-      X[i] = v;
     }
     if (done >= 0) {
       if (tid == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       return;
     }
   }
   for (int i = tid; i < m; i += NT) fm[i] = 0u;
   __syncthreads();
+  STEP_MARK();  // 3: accept / reject done
 
   // ---------------- gradient with the analytic velocity terms, active set, projected-gradient test ----------------
-  const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn + 2 * nn;  // knots 2..T-1
-  const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const float* Hc = HS + (size_t)cur * m * nn;  // knots 2..T-1 of the accepted buffer
+  const float* gc = gS + (size_t)cur * m * n;
   {
     double pgmax = 0.0;
     for (int idx = tid; idx < m * n; idx += NT) {
@@ -189,7 +227,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       const double x = X[t * n + k];
       double gv = x - X[(t - 1) * n + k];
       if (t < T - 1) gv -= X[(t + 1) * n + k] - x;
-      const double gtv = (double)gc[t * n + k] + a2 * gv;
+      const double gtv = (double)gc[idx] + a2 * gv;
       const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
       gt[idx] = gtv;
       if (fixed) atomicOr(fm + i, 1u << k);
@@ -202,6 +240,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     }
   }
   __syncthreads();
+  STEP_MARK();  // 4: gradient, active set
 
   // ---------------- damped projected Gauss-Newton step: block cyclic reduction in float64 ----------------
   constexpr int OUT_A = (2 * NP * NP + NP + 31) / 32;  // results a lane holds in phase A / B before they are written back
@@ -234,6 +273,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     }
     if (tid == 0) sflag[0] = 0;
     __syncthreads();
+    STEP_MARK();  // 5: system built
 
     // forward: strides 1, 2, 4, ...; the last pass (s >= m) eliminates block 0, which has no neighbour left
     int s = 1;
@@ -292,6 +332,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
         }
       }
       __syncthreads();
+      STEP_MARK();  // phase A of this level
       if (last) break;
       // ---- phase B: one warp per kept block j = 0 (mod 2s): absorb the Schur complements of j - s and j + s ----
       const int nkeep = (m + 2 * s - 1) / (2 * s);
@@ -356,6 +397,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
         }
       }
       __syncthreads();
+      STEP_MARK();  // phase B of this level
     }
     ok = (sflag[0] == 0);
     __syncthreads();
@@ -390,6 +432,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     return;
   }
 
+  STEP_MARK();  // back substitution done
   // ---------------- trial point = clip(X + x); predicted reduction with the undamped, unmasked model ----------------
   double stepmax = 0.0, gdot = 0.0;
   for (int idx = tid; idx < m * n; idx += NT) {
@@ -417,6 +460,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     if (i < m - 1) quad -= 2.0 * a2 * dr * dd[idx + n];
   }
   quad = cta_sum(quad, red);
+  STEP_MARK();  // trial point, predicted reduction
   if (tid == 0) {
     p.pred[b] = -(gdot + 0.5 * quad);
     p.stepn[b] = stepmax;
@@ -425,5 +469,22 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     p.iters[b] = it + 1;
     const int slot = atomicAdd(p.nactive_out, 1);
     p.active_out[slot] = b;
+    sflag[1] = slot;
+  }
+  if (!p.do_fk) return;
+  // ---------------- item records of the trial point (what k_item_fk would compute in a launch of its own) ----------------
+  __syncthreads();  // q_trial of this problem and the slot are visible to the whole CTA
+  {
+    const int slot = sflag[1];
+    const int hl = tid & 15, grp = tid >> 4, ngrp = NT >> 4, hshift = tid & 16;
+    double* A = Dm + (size_t)grp * 2 * R.nmov * 12;  // the factorisation is done: its storage is free
+    double* Tm = A + (size_t)R.nmov * 12;
+    for (int i0 = 0; i0 < m; i0 += ngrp) {
+      const bool valid = (i0 + grp) < m;
+      const int i = valid ? i0 + grp : m - 1;
+      const int t = i + 2;
+      item_fk_body(p.fk, R, slot * m + i, valid, b, t, 1 - cur, p.q_trial + ((long long)b * T + t) * R.ndof, A, Tm, hl, hshift);
+      __syncwarp();
+    }
   }
 }
