@@ -97,6 +97,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one full k_linearize_cull launch (256 problems x 28 knots, C2), from the
+# ncu --set full capture summarised in profiles/ (bytes per launch; algorithmic bytes of that launch: 413.4 MB)
+TRAFFIC_NCU = None
+
+
 def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -249,6 +254,18 @@ def run_b200(args):
             prof_acc[k] += p[k]
     sync_all()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    last_prof = ctx.profile()
+    # cross-check pass (not part of `value`): the same steps with CUDA events recorded around every launch on the library's
+    # stream.  The timed region above measures the kernels with in-kernel %globaltimer stamps instead, because an event
+    # record between two launches costs ~3 us of stream serialisation (x ~300 launches per solve).
+    ev = {"lin_ms": 0.0, "step_ms": 0.0, "solve_ms": 0.0}
+    os.environ["GTO_LAUNCH_EVENTS"] = "1"
+    for _ in range(args.steps):
+        ctx.solve_resident(opts)
+        p = ctx.profile()
+        ev["lin_ms"] += p["linearize_ms"]; ev["step_ms"] += p["step_ms"]; ev["solve_ms"] += p["solve_ms"]
+    os.environ.pop("GTO_LAUNCH_EVENTS", None)
+    sync_all()
     res = ctx.download_batch()
     conv = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
     iters_hist = np.bincount(res["iters"], minlength=1).tolist()
@@ -301,10 +318,18 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "wall clock between device synchronisations around gto_solve_batch with pinned host buffers"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "k_linearize_cull (+ k_item_fk, its per-item pre-pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": TRAFFIC_NCU,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": alg / args.steps, "kernel_ms_per_step": lin_ms / args.steps,
                          "kernel_share_of_step": lin_ms / dev_ms if dev_ms else None, "step_kernel_ms_per_step": step_ms / args.steps,
-                         "launches_per_step": prof_acc["linearize_launches"] / args.steps},
+                         "launches_per_step": prof_acc["linearize_launches"] / args.steps,
+                         "timing": "sum over the linearise launches of (last warp end - first CTA start), %globaltimer stamps written by the kernels "
+                                   "on the library's stream, inside the timed region",
+                         "cuda_events_cross_check": {"achieved": alg / (ev["lin_ms"] * 1e-3) / 1e9 if ev["lin_ms"] > 0 else None,
+                                                     "kernel_ms_per_step": ev["lin_ms"] / args.steps, "step_kernel_ms_per_step": ev["step_ms"] / args.steps,
+                                                     "ms_per_step": ev["solve_ms"] / args.steps,
+                                                     "note": "separate pass of the same steps with a CUDA event before/after every launch"},
+                         "links_culled_frac": 1.0 - last_prof["links_active"] / max(1, last_prof["links_tested"])},
             "clocks": clocks,
         }
         # CPU baseline on rank 0 at N=1 only: bounded sample of the same workload

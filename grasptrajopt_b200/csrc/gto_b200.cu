@@ -149,6 +149,20 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// In-kernel launch timing: ts[0] = max over CTAs of ~start, ts[1] = max over warps of end (ns, %globaltimer); both zeroed
+// before the solve.  Replaces CUDA events between the launches, which cost ~3 us of stream serialisation each.
+__device__ __forceinline__ unsigned long long gto_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp_begin(unsigned long long* ts) {
+  if (ts && threadIdx.x == 0) atomicMax(ts, ~gto_globaltimer());
+}
+__device__ __forceinline__ void stamp_end(unsigned long long* ts) {
+  if (ts && (threadIdx.x & 31) == 0) atomicMax(ts + 1, gto_globaltimer());
+}
+
 #define GTO_SPLIT_MAX 4
 // Tail launches: when few (problem, knot) items are left, each item is split over 2 or 4 CTAs (contiguous link ranges).
 // Both kernels derive the factor from the same device counter, so no host round trip is needed.
@@ -736,6 +750,7 @@ struct StepParams {
   int* nactive_out;
   int iter;        // number of LM steps already taken by the problems in the active list
   long long* dbg;  // k_step_cr: clock64() at phase boundaries of CTA 0 (diagnostics, NULL: off)
+  unsigned long long* ts;  // k_step_cr: launch time stamps (NULL: off)
   int do_fk;       // k_step_cr: also write the item records (FK, brick placement, culling test) of the new trial point
   CullParams fk;   // what item_fk_body needs (robot, fields, records, Gauss-Newton buffers)
 };
@@ -1204,6 +1219,7 @@ struct gto_ctx {
   DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive, work_ctr;
   DevBuf<unsigned long long> stats;
   DevBuf<long long> dbg;
+  DevBuf<unsigned long long> tstamps;
   DevBuf<CullCtx> recs, rec_dummy;
   int* h_counter = nullptr;  // pinned, 16 ints
   std::vector<cudaStream_t> gstreams;  // one stream per problem group (see gto_solve_resident)
@@ -1307,7 +1323,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
-  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->recs.release(); ctx->rec_dummy.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release(); ctx->recs.release(); ctx->rec_dummy.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1650,7 +1666,7 @@ static int brick_slot_floats(const gto_ctx* ctx) {
 // step kernel that produced the trial point), so k_item_fk is skipped
 static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
                             float* rows, int t_lo, unsigned flags, int* work_counter, bool have_recs = false, cudaStream_t stream = nullptr,
-                            CullCtx* recs = nullptr) {
+                            CullCtx* recs = nullptr, unsigned long long* ts = nullptr) {
   if (!stream) stream = ctx->stream;
   const RobotDev& R = ctx->robot_h;
   LinParams p;
@@ -1700,6 +1716,8 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       e = ctx->rec_dummy.ensure(1);
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
       cp.rec_dummy = ctx->rec_dummy.p;
+      cp.ts_fk = ts;
+      cp.ts_lin = ts ? ts + 2 : nullptr;
       ctx->prof.kernel_launches += 1;
       if (!have_recs) {
         const size_t fk_smem = ((sizeof(RobotDev) + 15) & ~(size_t)15) + (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
@@ -1922,6 +1940,15 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     bool done;
   };
   std::vector<int> h_nact(cstride * G);
+  // per-launch durations for the profile (linearize_ms / step_ms): in-kernel %globaltimer stamps by default; CUDA events
+  // between the launches on request or when a kernel without stamps is selected (they cost ~3 us of serialisation each)
+  const bool launch_events = getenv("GTO_LAUNCH_EVENTS") != nullptr || !cull_ok || !use_cr;
+  const bool launch_stamps = !launch_events;
+  const size_t ts_n = cstride * G * 6;
+  if (launch_stamps) {
+    CK(ctx->tstamps.ensure(ts_n));
+    CK(cudaMemsetAsync(ctx->tstamps.p, 0, ts_n * sizeof(unsigned long long), ctx->stream));
+  }
 
   for (int b0 = 0; b0 < B; b0 += Bchunk) {
     const int nb = std::min(Bchunk, B - b0);
@@ -1955,14 +1982,19 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
         any = true;
         int* ain = (it & 1) ? r.act1 : r.act0;
         int* aout = (it & 1) ? r.act0 : r.act1;
-        cudaEvent_t a = get_event(ctx, nev++), bE = get_event(ctx, nev++), c = get_event(ctx, nev++);
-        CK(cudaEventRecord(a, r.s));
+        cudaEvent_t a = nullptr, bE = nullptr, c = nullptr;
+        if (launch_events) {
+          a = get_event(ctx, nev++); bE = get_event(ctx, nev++); c = get_event(ctx, nev++);
+          CK(cudaEventRecord(a, r.s));
+        }
         int rc = launch_linearize(ctx, ctx->q_trial.p, ain, r.nact + it, r.nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
-                                  it == 0 ? 0 : 2, ctx->flags, r.wctr + it, step_fk && it > 0, r.s, r.recs);
+                                  it == 0 ? 0 : 2, ctx->flags, r.wctr + it, step_fk && it > 0, r.s, r.recs,
+                                  launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 : nullptr);
         if (rc) return rc;
-        CK(cudaEventRecord(bE, r.s));
+        if (launch_events) CK(cudaEventRecord(bE, r.s));
         st.active_in = ain; st.nactive_in = r.nact + it; st.active_out = aout; st.nactive_out = r.nact + it + 1;
         st.iter = it;
+        st.ts = launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 + 4 : nullptr;
         st.lin_grid = ctx->last_lin_grid;
         st.do_fk = step_fk ? 1 : 0;
         if (step_fk) {
@@ -1979,8 +2011,10 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
         else step_kern<<<r.nb, 32, step_smem, r.s>>>(st);
         pf.kernel_launches += 1;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(c, r.s));
-        ev_kind.push_back(0);
+        if (launch_events) {
+          CK(cudaEventRecord(c, r.s));
+          ev_kind.push_back(0);
+        }
         pf.linearize_launches++;
         pf.step_launches++;
         pf.iterations = std::max(pf.iterations, it);
@@ -2040,6 +2074,18 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   pf.solve_ms = ms;
+  if (launch_stamps) {
+    std::vector<unsigned long long> hts(ts_n);
+    CK(cudaMemcpy(hts.data(), ctx->tstamps.p, ts_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i + 1 < ts_n; i += 2) {
+      if (!hts[i + 1] || !hts[i]) continue;
+      const unsigned long long t0 = ~hts[i], t1 = hts[i + 1];
+      if (t1 <= t0) continue;
+      const double msd = (double)(t1 - t0) * 1e-6;
+      if ((i / 2) % 3 == 2) pf.step_ms += msd;
+      else pf.linearize_ms += msd;
+    }
+  }
   for (size_t i = 0; i < ev_kind.size(); ++i) {
     float m1 = 0, m2 = 0;
     cudaEventElapsedTime(&m1, ctx->ev[1 + 3 * i], ctx->ev[2 + 3 * i]);

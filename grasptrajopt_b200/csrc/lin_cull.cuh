@@ -47,6 +47,8 @@ struct CullParams {
   int* work_counter;   // zero before the launch: next (problem, knot) item
   CullCtx* recs;       // [items] per-item records written by k_item_fk, read by the producer warps (bulk copy)
   CullCtx* rec_dummy;  // one record nobody reads
+  unsigned long long* ts_fk;   // launch time stamps of k_item_fk / k_linearize_cull (NULL: off), see stamp_begin
+  unsigned long long* ts_lin;
   unsigned long long* stats;  // [0] items, [1] links tested, [2] links that survived the culling test (NULL: off)
 };
 
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
   const LinParams& p = pp.lin;
   // the robot table is staged in shared memory with one batch of loads: the serial FK chain then never waits on L2
   RobotDev& R = *reinterpret_cast<RobotDev*>(fk_smem);
+  stamp_begin(pp.ts_fk);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.robot);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(fk_smem);
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
   const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
   const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
   item_fk_body(pp, R, item, valid, b, t, obuf, q, A, Tm, hl, hshift);
+  stamp_end(pp.ts_fk);
 }
 
 __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   uint64_t* ctx_full = reinterpret_cast<uint64_t*>(S.ctx_full);
   uint64_t* ctx_empty = reinterpret_cast<uint64_t*>(S.ctx_empty);
 
+  stamp_begin(pp.ts_lin);
   if (threadIdx.x == 0) {
     for (int s = 0; s < CULL_NSLOT; ++s) {
       mbar_init(slot_full + s, 1);
@@ -425,6 +430,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    stamp_end(pp.ts_lin);
     return;
   }
 
@@ -660,4 +666,5 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
     __syncwarp();
     if (lane == 0) mbar_arrive(ctx_empty + ci);  // this warp no longer reads ctx[ci] / red[ci]
   }
+  stamp_end(pp.ts_lin);
 }

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
 #define STEP_MARK() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
   STEP_MARK();
   if (a_idx >= *p.nactive_in) return;
+  stamp_begin(p.ts);
   const int b = p.active_in[a_idx];
   const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;
   const double a2 = p.w_vel / (p.dt * p.dt);
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     if (done >= 0) {
       if (tid == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      stamp_end(p.ts);
       return;
     }
   }
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     pgmax = cta_max(pgmax, red);
     if (2.0 * pgmax <= p.tol_grad) {
       if (tid == 0) { p.status[b] = GTO_STATUS_CONVERGED; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
+      stamp_end(p.ts);
       return;
     }
   }
@@ -429,6 +432,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   }
   if (!ok) {
     if (tid == 0) { p.status[b] = GTO_STATUS_NAN; p.iters[b] = it; }
+    stamp_end(p.ts);
     return;
   }
 
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     p.active_out[slot] = b;
     sflag[1] = slot;
   }
-  if (!p.do_fk) return;
+  if (!p.do_fk) { stamp_end(p.ts); return; }
   // ---------------- item records of the trial point (what k_item_fk would compute in a launch of its own) ----------------
   __syncthreads();  // q_trial of this problem and the slot are visible to the whole CTA
   {
@@ -487,4 +491,5 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       __syncwarp();
     }
   }
+  stamp_end(p.ts);
 }
