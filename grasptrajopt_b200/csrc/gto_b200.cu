@@ -163,6 +163,13 @@ __device__ __forceinline__ void stamp_end(unsigned long long* ts) {
   if (ts && (threadIdx.x & 31) == 0) atomicMax(ts + 1, gto_globaltimer());
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in the stream is
+// still running; pdl_wait() blocks until the predecessor has completed and its writes are visible, pdl_trigger() lets the
+// successor start.  Everything a kernel does before pdl_wait() (shared-memory set-up, static tables) overlaps the tail of
+// the previous kernel; the ~300 dependent launches of a solve otherwise pay ~5 us each.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #define GTO_SPLIT_MAX 4
 // Tail launches: when few (problem, knot) items are left, each item is split over 2 or 4 CTAs (contiguous link ranges).
 // Both kernels derive the factor from the same device counter, so no host round trip is needed.
@@ -1221,10 +1228,12 @@ struct gto_ctx {
   DevBuf<long long> dbg;
   DevBuf<unsigned long long> tstamps;
   DevBuf<CullCtx> recs, rec_dummy;
+  bool use_pdl = true;       // programmatic dependent launch of the solver kernels (GTO_NO_PDL=1 turns it off)
   int* h_counter = nullptr;  // pinned, 16 ints
   std::vector<cudaStream_t> gstreams;  // one stream per problem group (see gto_solve_resident)
   cudaEvent_t ev_fork = nullptr;
   std::vector<cudaEvent_t> ev_join;
+  cudaEvent_t ev_poll[16] = {nullptr};  // convergence polls in flight: [group][parity]
   long long rows_per_problem = 0;
   int Bchunk = 0;
   // profiling
@@ -1287,6 +1296,7 @@ extern "C" int gto_create(gto_ctx** out, int device) {
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     ctx->encode = (PFN_encodeTiled)fn;
+  ctx->use_pdl = getenv("GTO_NO_PDL") == nullptr;
   ctx->fields.resize(MAX_FIELDS);
   if (cudaMalloc((void**)&ctx->robot_d, sizeof(RobotDev)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->fields_d, sizeof(FieldDev) * MAX_FIELDS) != cudaSuccess ||
@@ -1312,6 +1322,8 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   for (auto e : ctx->ev) cudaEventDestroy(e);
   for (auto e : ctx->ev_join) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 16; ++i)
+    if (ctx->ev_poll[i]) cudaEventDestroy(ctx->ev_poll[i]);
   for (auto st_ : ctx->gstreams) cudaStreamDestroy(st_);
   if (ctx->robot_d) cudaFree(ctx->robot_d);
   if (ctx->fields_d) cudaFree(ctx->fields_d);
@@ -1621,6 +1633,22 @@ static size_t lin_smem_bytes(const gto_ctx* ctx, int brick_max, int warps) {
 }
 
 // launches one linearisation on ctx->stream
+template <typename P>
+static cudaError_t launch_pdl(void (*kern)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool pdl, const P& params) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, params);
+}
+
 static void fill_lin_params(gto_ctx* ctx, LinParams& p, const double* q, const int* active, const int* nactive, int nproblems, int b0,
                             const int* bufsel, float* rows, int t_lo, unsigned flags) {
   const RobotDev& R = ctx->robot_h;
@@ -1721,12 +1749,14 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       ctx->prof.kernel_launches += 1;
       if (!have_recs) {
         const size_t fk_smem = ((sizeof(RobotDev) + 15) & ~(size_t)15) + (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
-        k_item_fk<<<(unsigned)((max_items + 7) / 8), 128, fk_smem, stream>>>(cp);
+        e = launch_pdl<CullParams>(k_item_fk, (unsigned)((max_items + 7) / 8), 128, fk_smem, stream, ctx->use_pdl, cp);
+        if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
         ctx->prof.kernel_launches += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
       }
-      kern<<<grid, threads, sm, stream>>>(cp);
+      e = launch_pdl<CullParams>(kern, (unsigned)grid, (unsigned)threads, sm, stream, ctx->use_pdl, cp);
+      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
       return GTO_OK;
@@ -1922,6 +1952,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     ctx->ev_join.push_back(ej);
   }
   if (!ctx->ev_fork) CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 16; ++i)
+    if (!ctx->ev_poll[i]) CK(cudaEventCreateWithFlags(&ctx->ev_poll[i], cudaEventDisableTiming));
   const size_t cstride = (size_t)o.max_iter + 3;  // per-group counter arrays
   CK(ctx->nactive.ensure(cstride * G));
   CK(ctx->work_ctr.ensure(cstride * G));
@@ -1974,6 +2006,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
       for (int g = 0; g < ng; ++g) CK(cudaStreamWaitEvent(grp[g].s, ctx->ev_fork, 0));
     }
+    size_t nblk = 0;
     for (int it = 0; it <= o.max_iter; ++it) {
       bool any = false;
       for (int g = 0; g < ng; ++g) {
@@ -2007,7 +2040,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
           st.fk.rec_dummy = ctx->rec_dummy.p;
           st.fk.stats = ctx->stats.p;
         }
-        if (use_cr) step_cr_kern<<<r.nb, STEP_CR_THREADS, cr_smem, r.s>>>(st);
+        if (use_cr) CK(launch_pdl<StepParams>(step_cr_kern, (unsigned)r.nb, STEP_CR_THREADS, cr_smem, r.s, ctx->use_pdl, st));
         else step_kern<<<r.nb, 32, step_smem, r.s>>>(st);
         pf.kernel_launches += 1;
         CK(cudaGetLastError());
@@ -2021,13 +2054,25 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       }
       if (!any) break;
       if (((it + 1) % o.check_every) == 0 || it == o.max_iter) {
-        for (int g = 0; g < ng; ++g)
-          if (!grp[g].done) CK(cudaMemcpyAsync(ctx->h_counter + g, grp[g].nact + it + 1, sizeof(int), cudaMemcpyDeviceToHost, grp[g].s));
+        // convergence poll, one block behind: the counter of this block is requested now and looked at after the NEXT block
+        // has been enqueued, so the GPU never waits for the host (cost: up to check_every empty iterations at the end)
+        const int par = (int)(nblk & 1);
         for (int g = 0; g < ng; ++g) {
           if (grp[g].done) continue;
-          CK(cudaStreamSynchronize(grp[g].s));
-          if (ctx->h_counter[g] == 0) grp[g].done = true;
+          CK(cudaMemcpyAsync(ctx->h_counter + 2 * g + par, grp[g].nact + it + 1, sizeof(int), cudaMemcpyDeviceToHost, grp[g].s));
+          CK(cudaEventRecord(ctx->ev_poll[2 * g + par], grp[g].s));
         }
+        for (int g = 0; g < ng; ++g) {
+          if (grp[g].done) continue;
+          if (it == o.max_iter) {
+            CK(cudaStreamSynchronize(grp[g].s));
+            grp[g].done = true;
+          } else if (nblk > 0) {
+            CK(cudaEventSynchronize(ctx->ev_poll[2 * g + (par ^ 1)]));
+            if (ctx->h_counter[2 * g + (par ^ 1)] == 0) grp[g].done = true;
+          }
+        }
+        ++nblk;
       }
     }
     if (ng > 1) {  // join: the chunk's groups are finished before the next chunk reuses the row buffer / k_finalize runs

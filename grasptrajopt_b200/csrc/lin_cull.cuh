@@ -254,12 +254,14 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
   const LinParams& p = pp.lin;
   // the robot table is staged in shared memory with one batch of loads: the serial FK chain then never waits on L2
   RobotDev& R = *reinterpret_cast<RobotDev*>(fk_smem);
-  stamp_begin(pp.ts_fk);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.robot);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(fk_smem);
     for (int i = threadIdx.x; i < (int)(sizeof(RobotDev) / 8); i += blockDim.x) dst[i] = __ldg(src + i);
   }
+  pdl_wait();  // the trial point / active list of the step kernel before us
+  pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
+  stamp_begin(pp.ts_fk);
   const int nprob = p.nactive ? *p.nactive : p.nproblems;
   __syncthreads();
   const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
@@ -311,7 +313,6 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   uint64_t* ctx_full = reinterpret_cast<uint64_t*>(S.ctx_full);
   uint64_t* ctx_empty = reinterpret_cast<uint64_t*>(S.ctx_empty);
 
-  stamp_begin(pp.ts_lin);
   if (threadIdx.x == 0) {
     for (int s = 0; s < CULL_NSLOT; ++s) {
       mbar_init(slot_full + s, 1);
@@ -335,6 +336,9 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   for (int i = threadIdx.x; i < CULL_ZERO_BYTES / 4; i += blockDim.x) zero_buf[i] = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zeros are read by the async proxy (bulk stores)
   __syncthreads();
+  pdl_wait();  // the item records (k_item_fk) and everything before them
+  pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
+  stamp_begin(pp.ts_lin);
 
   const int nknots = p.T - p.t_lo;
   const int nprob = p.nactive ? *p.nactive : p.nproblems;

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   const int a_idx = blockIdx.x;
   int dbg_i = 0;
 #define STEP_MARK() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
+  pdl_wait();  // the Gauss-Newton blocks of the linearise kernel before us
+  pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
   STEP_MARK();
   if (a_idx >= *p.nactive_in) return;
   stamp_begin(p.ts);
