@@ -235,13 +235,19 @@ __device__ __forceinline__ void sdf_trilinear(const FieldDev& f, const float* __
 }
 
 // 3x4 product C = A * B (both [R|t] row-major, implicit last row 0 0 0 1)
+// a0*b0 + a1*b1 + a2*b2 with a fixed association (explicit fused multiply-adds): every code shape that forms a frame
+// entry -- unrolled 3x4 product, one entry per lane -- gives the same bits
+template <typename T>
+__device__ __forceinline__ T dot3(T a0, T b0, T a1, T b1, T a2, T b2) {
+  return fma(a2, b2, fma(a1, b1, a0 * b0));
+}
 template <typename TA, typename TB, typename TC>
 __device__ __forceinline__ void mul34(const TA* A, const TB* B, TC* C) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      TC s = A[r * 4 + 0] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c];
+      TC s = dot3<TC>((TC)A[r * 4 + 0], (TC)B[c], (TC)A[r * 4 + 1], (TC)B[4 + c], (TC)A[r * 4 + 2], (TC)B[8 + c]);
       if (c == 3) s += A[r * 4 + 3];
       C[r * 4 + c] = s;
     }
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __gri
             s = S.A[j][lane];
           } else {
             const double* P = S.Tm[pj];
-            s = P[r * 4 + 0] * S.A[j][c] + P[r * 4 + 1] * S.A[j][4 + c] + P[r * 4 + 2] * S.A[j][8 + c];
+            s = dot3<double>(P[r * 4 + 0], S.A[j][c], P[r * 4 + 1], S.A[j][4 + c], P[r * 4 + 2], S.A[j][8 + c]);
             if (c == 3) s += P[r * 4 + 3];
           }
           S.Tm[j][lane] = s;
@@ -1744,6 +1750,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
       e = ctx->rec_dummy.ensure(1);
       if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
       cp.rec_dummy = ctx->rec_dummy.p;
+      cp.dbg = getenv("GTO_STEP_DBG") ? ctx->dbg.p : nullptr;
       cp.ts_fk = ts;
       cp.ts_lin = ts ? ts + 2 : nullptr;
       ctx->prof.kernel_launches += 1;
@@ -2114,6 +2121,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(cudaMemcpy(hd, ctx->dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[gto] k_step_cr phase clocks (cycles since kernel start, last launch with work, CTA 0):");
     for (int i = 1; i < 64 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[0]);
+    fprintf(stderr, "\n[gto] k_item_fk phase clocks (cycles since pdl_wait):");
+    for (int i = 33; i < 40 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[32]);
     fprintf(stderr, "\n");
   }
   float ms = 0;

@@ -47,6 +47,7 @@ struct CullParams {
   int* work_counter;   // zero before the launch: next (problem, knot) item
   CullCtx* recs;       // [items] per-item records written by k_item_fk, read by the producer warps (bulk copy)
   CullCtx* rec_dummy;  // one record nobody reads
+  long long* dbg;              // k_item_fk: clock64() at phase boundaries of CTA 0 (diagnostics, NULL: off)
   unsigned long long* ts_fk;   // launch time stamps of k_item_fk / k_linearize_cull (NULL: off), see stamp_begin
   unsigned long long* ts_lin;
   unsigned long long* stats;  // [0] items, [1] links tested, [2] links that survived the culling test (NULL: off)
@@ -77,6 +78,7 @@ __device__ __forceinline__ unsigned svt_count(const FieldDev& f, int x0, int x1,
 // (problem b, knot t) at configuration q; A / Tm: 2 x nmov x 12 doubles of shared scratch owned by the group.  The two
 // halves of a warp run in lock step (full-warp barriers, one instruction stream for two items): a half without an item
 // of its own (`valid` false) recomputes a neighbour's item into the dummy record.
+#define FK_MARK(k) do { if (pp.dbg && blockIdx.x == 0 && threadIdx.x == 0) pp.dbg[32 + (k)] = clock64(); } while (0)
 __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDev& R, int item, bool valid, int b, int t, int obuf, const double* q,
                                              double* A, double* Tm, int hl, int hshift) {
   const LinParams& p = pp.lin;
@@ -91,6 +93,7 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
   if (fid >= 0) fld = p.fields[fid];
   const float bpx = p.base[4 * b + 0], bpy = p.base[4 * b + 1], bpz = p.base[4 * b + 2];
 
+  FK_MARK(1);
   for (int j = hl; j < nmov; j += 16) {  // A_j = origin_j * motion_j(q_j)
     const double qj = q[R.mov_qidx[j]];
     const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
@@ -113,6 +116,7 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
     for (int e = 0; e < 12; ++e) A[j * 12 + e] = Cm[e];
   }
   __syncwarp();
+  FK_MARK(2);
   for (int j = 0; j < nmov; ++j) {  // sequential along the tree, 12 lanes per product
     if (hl < 12) {
       const int r = hl >> 2, c = hl & 3;
@@ -122,13 +126,14 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
         s = A[j * 12 + hl];
       } else {
         const double* P = Tm + pj * 12;
-        s = P[r * 4 + 0] * A[j * 12 + c] + P[r * 4 + 1] * A[j * 12 + 4 + c] + P[r * 4 + 2] * A[j * 12 + 8 + c];
+        s = dot3<double>(P[r * 4 + 0], A[j * 12 + c], P[r * 4 + 1], A[j * 12 + 4 + c], P[r * 4 + 2], A[j * 12 + 8 + c]);
         if (c == 3) s += P[r * 4 + 3];
       }
       Tm[j * 12 + hl] = s;
     }
     __syncwarp();
   }
+  FK_MARK(3);
   // ---- visual frames, brick placement and the culling test (one lane per link) ----
   unsigned amask = 0u;
   for (int l0 = 0; l0 < nlinks; l0 += 16) {
@@ -193,6 +198,7 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
     if (survives) C.act[__popc(amask) + __popc(bal & ((1u << hl) - 1u))] = l;
     amask |= bal << l0;
   }
+  FK_MARK(4);
   for (int k = hl; k < nopt; k += 16) {  // joint twists: v(W) = omega x W + m
     const int j = R.opt_mov[k];
     double om[3] = {0.0, 0.0, 0.0}, mm[3] = {0.0, 0.0, 0.0};
@@ -213,21 +219,23 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
     reinterpret_cast<float4*>(C.tw[k])[0] = make_float4((float)om[0], (float)om[1], (float)om[2], 0.f);
     reinterpret_cast<float4*>(C.tw[k])[1] = make_float4((float)mm[0], (float)mm[1], (float)mm[2], 0.f);
   }
+  FK_MARK(5);
   const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
-  if (hl == 15) {  // gripper link frame and its difference to the two goal frames, formed in float64
-    double F[12];
+  if (hl < 12) {  // gripper link frame and its difference to the two goal frames, formed in float64: one entry per lane
+    const int r = hl >> 2, c = hl & 3;
+    double F;
     if (R.grip_mov < 0) {
-#pragma unroll
-      for (int e = 0; e < 12; ++e) F[e] = R.grip_tf_d[e];
+      F = R.grip_tf_d[hl];
     } else {
-      mul34(Tm + R.grip_mov * 12, R.grip_tf_d, F);
+      const double* P = Tm + R.grip_mov * 12;
+      F = dot3<double>(P[r * 4 + 0], R.grip_tf_d[c], P[r * 4 + 1], R.grip_tf_d[4 + c], P[r * 4 + 2], R.grip_tf_d[8 + c]);
+      if (c == 3) F += P[r * 4 + 3];
     }
-#pragma unroll
-    for (int e = 0; e < 12; ++e) {
-      C.gripf[e] = (float)F[e];
-      C.goal[0][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + e]);
-      C.goal[1][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + 12 + e]);
-    }
+    C.gripf[hl] = (float)F;
+    C.goal[0][hl] = (float)(F - p.goal_tf[(long long)b * 24 + hl]);
+    C.goal[1][hl] = (float)(F - p.goal_tf[(long long)b * 24 + 12 + hl]);
+  }
+  if (hl == 15) {
     C.b = b; C.t = t; C.fid = fid; C.obuf = obuf;
     C.nact = __popc(amask);
     C.kind = (is_goal ? 1 : 0) | (is_stand ? 2 : 0);
@@ -242,6 +250,7 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
     if (hl < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + hl] = 0.f;
     if (hl == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.f;
   }
+  FK_MARK(6);
   if (pp.stats && valid && hl == 0) {
     atomicAdd(pp.stats + 0, 1ull);
     if (p.collision) atomicAdd(pp.stats + 1, (unsigned long long)nlinks);
@@ -261,6 +270,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
   }
   pdl_wait();  // the trial point / active list of the step kernel before us
   pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
+  FK_MARK(0);
   stamp_begin(pp.ts_fk);
   const int nprob = p.nactive ? *p.nactive : p.nproblems;
   __syncthreads();
@@ -280,6 +290,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
   const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
   const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
   item_fk_body(pp, R, item, valid, b, t, obuf, q, A, Tm, hl, hshift);
+  FK_MARK(7);
   stamp_end(pp.ts_fk);
 }
 

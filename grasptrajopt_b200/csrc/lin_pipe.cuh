@@ -206,7 +206,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_pipe(
             s = S.A[j][lane];
           } else {
             const double* P = S.Tm[pj];
-            s = P[r * 4 + 0] * S.A[j][c] + P[r * 4 + 1] * S.A[j][4 + c] + P[r * 4 + 2] * S.A[j][8 + c];
+            s = dot3<double>(P[r * 4 + 0], S.A[j][c], P[r * 4 + 1], S.A[j][4 + c], P[r * 4 + 2], S.A[j][8 + c]);
             if (c == 3) s += P[r * 4 + 3];
           }
           S.Tm[j][lane] = s;
