@@ -99,7 +99,7 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full k_linearize_cull launch (256 problems x 28 knots, C2), from the
 # ncu --set full capture summarised in profiles/ (bytes per launch; algorithmic bytes of that launch: 413.4 MB)
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 445.6e6
 
 
 def measured_peaks():
