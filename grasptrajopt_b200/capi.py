@@ -25,7 +25,7 @@ FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK, FLAG_V1_KERNEL, FLAG_PIPE_KERNEL, FLA
 SYMBOLS = [
     "gto_abi_version", "gto_create", "gto_destroy", "gto_last_error", "gto_default_options", "gto_set_robot",
     "gto_set_field", "gto_solve_batch", "gto_upload_batch", "gto_solve_resident", "gto_download_batch",
-    "gto_result_device_ptr", "gto_eval_batch", "gto_get_profile", "gto_plan_cost",
+    "gto_result_device_ptr", "gto_eval_batch", "gto_get_profile", "gto_plan_cost", "gto_cloud_set", "gto_cloud_query",
 ]
 
 
@@ -129,6 +129,8 @@ def load_library(path: Optional[str] = None):
     lib.gto_result_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.gto_eval_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(EvalOut)]
     lib.gto_get_profile.argtypes = [C.c_void_p, C.POINTER(Profile)]
+    lib.gto_cloud_set.argtypes = [C.c_void_p, _dp, C.c_int64]
+    lib.gto_cloud_query.argtypes = [C.c_void_p, _dp, C.c_int64, _fp, C.c_int32, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_double, _fp, _dp]
     lib.gto_plan_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp]
     if path == os.environ.get("GTO_B200_LIB", LIB_PATH):
         _lib = lib
@@ -325,6 +327,22 @@ class GtoContext:
         p = Profile()
         self._check(self._lib.gto_get_profile(self._h, C.byref(p)))
         return p.as_dict()
+
+    def cloud_set(self, points: np.ndarray):
+        """World-frame points of a depth image (reference ``DepthPointCloud.points``, the KD-tree's data)."""
+        pts = _d(points).reshape(-1, 3)
+        self._check(self._lib.gto_cloud_set(self._h, _ptr(pts, _dp), pts.shape[0]))
+
+    def cloud_query(self, query: np.ndarray, depth: np.ndarray, K: np.ndarray, cam_inv: np.ndarray, mode: int, epsilon=0.02, w_inside=1.0):
+        """Signed distance (mode 0) or cost (mode 1) of ``query`` [N,3] w.r.t. the cloud; returns (float32 [N], kernel ms)."""
+        q = _d(query).reshape(-1, 3)
+        dep = np.ascontiguousarray(depth, dtype=np.float32)
+        Km, Ri = _d(np.asarray(K).reshape(9)), _d(np.asarray(cam_inv).reshape(16))
+        out = np.zeros(q.shape[0], np.float32)
+        ms = np.zeros(1)
+        self._check(self._lib.gto_cloud_query(self._h, _ptr(q, _dp), q.shape[0], _ptr(dep, _fp), dep.shape[0], dep.shape[1], _ptr(Km, _dp),
+                                              _ptr(Ri, _dp), int(mode), float(epsilon), float(w_inside), _ptr(out, _fp), _ptr(ms, _dp)))
+        return out, float(ms[0])
 
     def plan_cost(self, plans: np.ndarray, field_slot: int, base_position=(0.0, 0.0, 0.0)):
         """plans [n,T,ndof] -> (cost [n], dist [n]) (reference ``GTORobotModel.compute_plan_cost``)."""

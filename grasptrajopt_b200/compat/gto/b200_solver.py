@@ -127,6 +127,28 @@ class B200Solver:
         return {f"{name}/q": DM(Q), f"{name}/dq": DM(dQ), f"{name}/q/x": DM(Q[t.opt_qidx]), f"{name}/dq/x": DM(dQ[t.opt_qidx]),
                 "f": DM(np.array([[res["cost"][best]]]))}
 
+    def solve_many(self, qc, q_seed, RT, base_position=None, field_all=-1, field_obs=-1) -> dict:
+        """B independent problems in ONE batch (no arg-min): ``qc`` [B,ndof], ``q_seed`` [B,T,ndof], ``RT`` [B,4,4], optional
+        ``base_position`` [B,3] or [3]; ``field_all`` / ``field_obs``: field slots already uploaded with ``ctx.set_field`` (or -1).
+        Returns the raw per-problem result of ``GtoContext.solve_batch`` (Q [B,T,ndof], dQ, cost, iters, status)."""
+        t = self.table
+        ctx = get_context(self.device)
+        if ctx.table is not t:
+            ctx.set_robot(t)
+        RT = np.asarray(RT, dtype=np.float64).reshape(-1, 4, 4)
+        n = RT.shape[0]
+        base = np.zeros((n, 3)) if base_position is None else np.broadcast_to(np.asarray(base_position, dtype=np.float64).reshape(-1, 3), (n, 3))
+        collide = self.collision_avoidance and (field_all >= 0 or field_obs >= 0)
+        batch = capi.Batch(
+            T=self.T, dt=self.dt, qc=np.asarray(qc, dtype=np.float64).reshape(n, t.ndof), q_seed=np.asarray(q_seed, dtype=np.float64).reshape(n, self.T, t.ndof),
+            goal_tf=capi.goal_transforms(t, RT, self.standoff_distance, self.axis_standoff), base_position=np.ascontiguousarray(base),
+            field_all=np.full(n, field_all, np.int32), field_obs=np.full(n, field_obs, np.int32), standoff_offset=self.standoff_offset,
+            use_standoff=self.use_standoff, collision_avoidance=collide, w_goal=self.w_goal, w_obs=self.w_obs, w_vel=self.w_vel)
+        res = ctx.solve_batch(batch, self.options)
+        self.batch_result = res
+        res["profile"] = ctx.profile()
+        return res
+
     def stats(self) -> dict:
         return self._stats
 

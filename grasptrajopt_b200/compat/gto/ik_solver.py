@@ -70,5 +70,34 @@ class IKSolver:
             cost = 0
         return q.flatten(), err_pos, err_rot, cost
 
+    def solve_ik_batch(self, q_0, RTs, sdf_cost_obstacle=None, base_position=None):
+        """All candidate grasps of an object in ONE batch (the reference loops ``solve_ik`` over the grasps,
+        ``examples/pybullet_gto_planning.py:243-273``).  ``q_0`` [ndof] (shared seed) or [B,ndof], ``RTs`` [B,4,4].
+        Returns ``(q [B,ndof], err_pos [B], err_rot_deg [B], cost [B], status [B])`` -- per goal the same values as ``solve_ik``."""
+        from grasptrajopt_b200 import kinematics as K
+
+        t = self.solver.table
+        RTs = np.asarray(RTs, dtype=np.float64).reshape(-1, 4, 4)
+        B = RTs.shape[0]
+        q0 = np.broadcast_to(np.asarray(q_0, dtype=np.float64).reshape(-1, t.ndof), (B, t.ndof))
+        seeds = np.repeat(q0[:, None, :], 3, axis=1)
+        fo = -1
+        if self.collision_avoidance and sdf_cost_obstacle is not None and np.any(sdf_cost_obstacle):
+            self.solver.p = {"sdf_cost_obstacle": np.asarray(sdf_cost_obstacle, dtype=np.float64).reshape(-1, 1)}
+            from gto.b200_solver import get_context
+            fo = self.solver._field(get_context(self.device), self.solver.FIELD_OBS, "sdf_cost_obstacle")
+        res = self.solver.solve_many(q0, seeds, RTs, base_position=base_position, field_all=fo, field_obs=fo)
+        q = res["Q"][:, 2, :]
+        tf = K.ee_frames(t, q)
+        err_pos = np.linalg.norm(RTs[:, :3, 3] - tf[:, :3, 3], axis=1)
+        err_rot = np.array([np.arccos(np.clip(2 * np.square(np.dot(mat2quat_wxyz(RTs[i, :3, :3]), mat2quat_wxyz(tf[i, :3, :3]))) - 1, -1, 1)) * 180 / np.pi
+                            for i in range(B)])
+        if fo >= 0:
+            cost = np.array([self.robot.compute_plan_cost(q[i].reshape(-1, 1), np.asarray(sdf_cost_obstacle).reshape(-1),
+                                                          [0, 0, 0] if base_position is None else base_position)[0] for i in range(B)])
+        else:
+            cost = np.zeros(B)
+        return q, err_pos, err_rot, cost, res["status"]
+
     def solve_fk(self, q_0):
         return self.fk(q_0).toarray()

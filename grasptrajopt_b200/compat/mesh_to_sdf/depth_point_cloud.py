@@ -2,19 +2,22 @@
 distance by nearest neighbour + camera visibility -> CHOMP-style cost field (epsilon = 0.02).
 
 Producer of the voxel fields the hot path consumes (SURVEY.md section 8(f) "next #2").  Same constructor, attributes and method
-names as the reference; the KD-tree is scikit-learn's, exactly as in the reference.  ``pyrender`` is only imported by the
-visualisation branches (the reference imports it at module level, :4).
+names as the reference.  ``backend="b200"`` (default): the nearest-neighbour queries, the visibility sign and the cost transform
+run in ``libgto_b200.so`` (``k_cloud_query``: exact tiled brute force on the GPU; fails loudly without a device).
+``backend="kdtree"``: the reference's own algorithm (scikit-learn KD-tree on the CPU), kept to validate the GPU path against.
+``pyrender`` is only imported by the visualisation branches (the reference imports it at module level, :4).
 """
 from __future__ import annotations
 
 import math
 
+import os
+
 import numpy as np
-from sklearn.neighbors import KDTree
 
 
 class DepthPointCloud:
-    def __init__(self, depth, intrinsic_matrix, camera_pose, target_mask=None, threshold=1.5):
+    def __init__(self, depth, intrinsic_matrix, camera_pose, target_mask=None, threshold=1.5, backend=None, device=0):
         self.depth = depth
         self.intrinsic_matrix = intrinsic_matrix
         self.camera_pose = camera_pose
@@ -25,7 +28,32 @@ class DepthPointCloud:
         pc = self.backproject_camera(depth, intrinsic_matrix)
         pc_base = camera_pose[:3, :3] @ pc + camera_pose[:3, 3].reshape((3, 1))
         self.points = pc_base.T
-        self.kd_tree = KDTree(self.points)
+        self.backend = backend or os.environ.get("GTO_DPC_BACKEND", "b200")
+        self.device = device
+        self.kd_tree = None
+        self.last_kernel_ms = None
+        if self.backend == "kdtree":
+            from sklearn.neighbors import KDTree
+
+            self.kd_tree = KDTree(self.points)
+        elif self.backend == "b200":
+            from gto.b200_solver import get_context
+
+            self._ctx = get_context(device)
+            self._ctx.cloud_set(self.points)
+            self._ctx._cloud_obj = self
+        else:
+            raise ValueError(f"unknown DepthPointCloud backend {self.backend!r}")
+
+    def _gpu_query(self, query_points, mode, epsilon=0.02, w_inside=1):
+        # one cloud is resident per context: re-upload if another DepthPointCloud used the context since
+        if getattr(self._ctx, "_cloud_obj", None) is not self:
+            self._ctx.cloud_set(self.points)
+            self._ctx._cloud_obj = self
+        out, ms = self._ctx.cloud_query(np.asarray(query_points, dtype=np.float64), np.asarray(self.depth, dtype=np.float32), self.intrinsic_matrix,
+                                        np.linalg.inv(self.camera_pose), mode, epsilon, w_inside)
+        self.last_kernel_ms = ms
+        return out
 
     def get_random_surface_points(self, count):
         return self.points[np.random.choice(self.points.shape[0], count), :]
@@ -58,6 +86,8 @@ class DepthPointCloud:
         return result
 
     def get_sdf(self, query_points):
+        if self.backend == "b200":
+            return self._gpu_query(query_points, 0)
         distances, _ = self.kd_tree.query(query_points)
         distances = distances.astype(np.float32).reshape(-1)
         inside = ~self.is_outside(query_points)
@@ -65,6 +95,8 @@ class DepthPointCloud:
         return distances
 
     def get_sdf_cost(self, query_points, epsilon=0.02, w_inside=1, vis=False):
+        if self.backend == "b200" and not vis:
+            return self._gpu_query(query_points, 1, epsilon, w_inside)
         distances = self.get_sdf(query_points)
         inside = distances < 0
         if vis:  # pragma: no cover - rendering only

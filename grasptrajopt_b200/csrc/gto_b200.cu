@@ -1083,6 +1083,7 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
 }
 
 #include "step_cr.cuh"
+#include "cloud_sdf.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_plan_cost: nearest-node cost of whole plans (seed ranking, gto/gto_models.py:204-215; clip-then-truncate indexing of
@@ -1232,6 +1233,10 @@ struct gto_ctx {
   DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive, work_ctr;
   DevBuf<unsigned long long> stats;
   DevBuf<long long> dbg;
+  DevBuf<float4> cloud;      // depth point cloud (gto_cloud_set), padded to a multiple of CLOUD_TILE
+  long long cloud_n = 0;
+  DevBuf<double> cloud_q;
+  DevBuf<float> cloud_depth, cloud_out;
   DevBuf<unsigned long long> tstamps;
   DevBuf<CullCtx> recs, rec_dummy;
   bool use_pdl = true;       // programmatic dependent launch of the solver kernels (GTO_NO_PDL=1 turns it off)
@@ -1341,7 +1346,8 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
-  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release(); ctx->recs.release(); ctx->rec_dummy.release();
+  ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release();
+  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->recs.release(); ctx->rec_dummy.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -2262,5 +2268,57 @@ extern "C" int gto_plan_cost(gto_ctx* ctx, int32_t nplans, int32_t T, const doub
       }
       dist[i] = sqrt(s);
     }
+  return GTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Scene side: depth point cloud -> signed distance / cost at query points (DepthPointCloud)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M) {
+  if (!ctx || !points || M < 1) return GTO_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const size_t Mpad = ((size_t)M + CLOUD_TILE - 1) / CLOUD_TILE * CLOUD_TILE;
+  std::vector<float4> h(Mpad);
+  for (size_t i = 0; i < (size_t)M; ++i) h[i] = make_float4((float)points[3 * i], (float)points[3 * i + 1], (float)points[3 * i + 2], 0.f);
+  for (size_t i = (size_t)M; i < Mpad; ++i) h[i] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);  // never the nearest
+  CK(ctx->cloud.ensure(Mpad));
+  CK(cudaMemcpy(ctx->cloud.p, h.data(), Mpad * sizeof(float4), cudaMemcpyHostToDevice));
+  ctx->cloud_n = M;
+  return GTO_OK;
+}
+
+extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, const float* depth, int32_t H, int32_t W, const double K[9],
+                               const double cam_inv[16], int32_t mode, double epsilon, double w_inside, float* out, double* kernel_ms) {
+  if (!ctx || !query || !depth || !K || !cam_inv || !out || N < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return GTO_ERR_INVALID;
+  if (ctx->cloud_n < 1) return fail(ctx, GTO_ERR_STATE, "gto_cloud_set has not been called");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->cloud_q.ensure((size_t)N * 3));
+  CK(ctx->cloud_out.ensure((size_t)N));
+  CK(ctx->cloud_depth.ensure((size_t)H * W));
+  CK(cudaMemcpyAsync(ctx->cloud_q.p, query, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->cloud_depth.p, depth, sizeof(float) * H * W, cudaMemcpyHostToDevice, ctx->stream));
+  CloudParams p;
+  memset(&p, 0, sizeof(p));
+  p.pts = ctx->cloud.p;
+  p.Mpad = (int)(((size_t)ctx->cloud_n + CLOUD_TILE - 1) / CLOUD_TILE * CLOUD_TILE);
+  p.query = ctx->cloud_q.p; p.N = N; p.depth = ctx->cloud_depth.p; p.H = H; p.W = W;
+  for (int i = 0; i < 9; ++i) p.K[i] = K[i];
+  for (int i = 0; i < 12; ++i) p.RT[i] = cam_inv[i];
+  p.mode = mode;
+  p.eps = (float)epsilon; p.half_eps = (float)(epsilon / 2); p.two_eps = (float)(2 * epsilon); p.w_inside = (float)w_inside;
+  p.out = ctx->cloud_out.p;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, ctx->stream));
+  const long long per = (long long)CLOUD_THREADS * CLOUD_QPT;
+  k_cloud_query<<<(unsigned)((N + per - 1) / per), CLOUD_THREADS, 0, ctx->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->cloud_out.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (kernel_ms) *kernel_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return GTO_OK;
 }

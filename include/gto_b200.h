@@ -217,6 +217,18 @@ int gto_get_profile(gto_ctx* ctx, gto_profile* prof);
 int gto_plan_cost(gto_ctx* ctx, int32_t n, int32_t T, const double* plans, int32_t field_slot, const double base_position[3],
                   double* cost, double* dist);
 
+/*
+ * Scene side: the reference's DepthPointCloud (mesh_to_sdf/depth_point_cloud.py:9-91,127-142).
+ * gto_cloud_set uploads the world-frame point cloud of a depth image (what the reference puts into a scikit-learn KD-tree, :20-25);
+ * gto_cloud_query returns, for N query points, the distance to the nearest cloud point, negative where the query is hidden behind
+ * the visible surface (is_outside, :127-142: projection with the intrinsics K into the depth image through cam_inv, the inverse
+ * camera pose, row-major 4x4) -- mode 0, get_sdf :57-62 -- or the CHOMP-style cost of that distance -- mode 1, get_sdf_cost :65-91.
+ * kernel_ms (may be NULL) receives the device time of the query kernel.
+ */
+int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M);
+int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, const float* depth, int32_t H, int32_t W, const double K[9],
+                    const double cam_inv[16], int32_t mode, double epsilon, double w_inside, float* out, double* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,7 +119,7 @@ def test_field_geometry_matches_reference_run(model):
 
 def test_depth_point_cloud_matches_reference_run():
     z = np.load(os.path.join(GOLDEN, "ref_field.npz"))
-    dpc = DepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5)
+    dpc = DepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5, backend="kdtree")
     np.testing.assert_allclose(dpc.points, z["dpc_points"], atol=1e-12)
     np.testing.assert_array_equal(dpc.get_sdf(z["dpc_query"]), z["dpc_sdf"])
     np.testing.assert_array_equal(dpc.get_sdf_cost(z["dpc_query"], epsilon=0.02), z["dpc_cost"])

@@ -1,0 +1,60 @@
+"""SURVEY.md section 8(f) row 2 on the GPU: DepthPointCloud.get_sdf / get_sdf_cost through libgto_b200 (k_cloud_query) against
+(1) the outputs of the reference's own DepthPointCloud stored in tests/golden/ref_field.npz and (2) the reference algorithm
+(scikit-learn KD-tree backend) on a larger synthetic depth image.  Run with -m gpu."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from mesh_to_sdf.depth_point_cloud import DepthPointCloud
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_cloud_query_matches_reference_run():
+    z = np.load(os.path.join(GOLDEN, "ref_field.npz"))
+    dpc = DepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5, backend="b200")
+    sdf = dpc.get_sdf(z["dpc_query"])
+    assert sdf.dtype == np.float32 and sdf.shape == z["dpc_sdf"].shape
+    np.testing.assert_array_equal(np.sign(sdf), np.sign(z["dpc_sdf"]))
+    np.testing.assert_allclose(sdf, z["dpc_sdf"], rtol=0, atol=2e-6)  # float32 search vs float64 KD-tree cast to float32
+    np.testing.assert_allclose(dpc.get_sdf_cost(z["dpc_query"], epsilon=0.02), z["dpc_cost"], rtol=0, atol=2e-6)
+    assert (z["dpc_sdf"] < 0).any() and (z["dpc_cost"] > 0).any()
+
+
+def _scene_depth(H=120, W=160):
+    """Camera 1 m above a table looking straight down; a box and a slanted plane segment on the table."""
+    f = 140.0
+    K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1.0]])
+    cam = np.eye(4)
+    cam[:3, :3] = np.array([[1.0, 0, 0], [0, -1, 0], [0, 0, -1]])  # optical axis = -z world
+    cam[:3, 3] = [0.5, 0.0, 1.0]
+    v, u = np.mgrid[0:H, 0:W]
+    depth = np.full((H, W), 1.0, np.float32)
+    depth[40:80, 50:100] = 0.85  # box top
+    depth[10:30, 20:140] = (0.95 - 0.001 * (u[10:30, 20:140] - 20)).astype(np.float32)  # ramp
+    depth[100:, :10] = 0.0  # invalid pixels
+    return depth, K, cam
+
+
+def test_cloud_query_matches_kdtree_backend_on_a_grid():
+    depth, K, cam = _scene_depth()
+    gpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="b200")
+    cpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
+    np.testing.assert_array_equal(gpu.points, cpu.points)
+    n = 56
+    g = np.stack(np.meshgrid(np.linspace(0.0, 1.0, n), np.linspace(-0.5, 0.5, n), np.linspace(-0.2, 0.8, n), indexing="ij"), axis=-1).reshape(-1, 3)
+    t0 = time.time(); s_gpu = gpu.get_sdf(g); t1 = time.time(); s_cpu = cpu.get_sdf(g); t2 = time.time()
+    print(f"cloud {gpu.points.shape[0]} points x {g.shape[0]} queries: GPU kernel {gpu.last_kernel_ms:.2f} ms (call {1e3*(t1-t0):.1f} ms), KD-tree {1e3*(t2-t1):.1f} ms")
+    flip = np.sign(s_gpu) != np.sign(s_cpu)
+    assert flip.mean() < 1e-4  # a query projecting exactly onto a pixel border may fall on either side
+    np.testing.assert_allclose(np.abs(s_gpu), np.abs(s_cpu), rtol=0, atol=2e-6)
+    c_gpu, c_cpu = gpu.get_sdf_cost(g, epsilon=0.02), cpu.get_sdf_cost(g, epsilon=0.02)
+    ok = ~flip
+    np.testing.assert_allclose(c_gpu[ok], c_cpu[ok], rtol=0, atol=2e-6)
+    assert (c_cpu > 0).mean() > 0.05 and (s_cpu < 0).any()
+    # ragged sizes: fewer queries than one block, a non-multiple of the tile
+    for m in (1, 7, 1500):
+        np.testing.assert_allclose(np.abs(gpu.get_sdf(g[:m])), np.abs(s_cpu[:m]), rtol=0, atol=2e-6)

@@ -88,3 +88,20 @@ def test_ik_solver_reaches_pose(robot):
     q, err_pos, err_rot, cost = ik.solve_ik(np.array([0.5, 0.1, 0.02]).reshape(-1, 1), RT, np.zeros(robot.field_size), [0, 0, 0])
     assert q.shape == (3,) and err_pos < 1e-4 and err_rot < 0.05 and cost == 0
     assert q[2] == 0.02
+
+
+def test_ik_batch_equals_single_solves(robot):
+    """all candidate grasps in one batch == one ``solve_ik`` per grasp (reference loop,
+    examples/pybullet_gto_planning.py:243-273), and each reaches its pose."""
+    ik = IKSolver(robot, "tool", "tool", collision_avoidance=False)
+    ik.setup_optimization()
+    rng = np.random.default_rng(5)
+    q_stars = np.stack([rng.uniform([-1.2, -1.0, 0.02], [1.2, 1.0, 0.02]) for _ in range(16)])
+    RTs = np.stack([robot.get_global_link_transform("tool", q).toarray() for q in q_stars])
+    q0 = np.array([0.3, 0.2, 0.02])
+    qb, ep, er, cost, status = ik.solve_ik_batch(q0, RTs)
+    assert qb.shape == (16, 3) and np.all(status == 0) and np.all(ep < 1e-4) and np.all(er < 0.05) and np.all(cost == 0)
+    for i in (0, 7, 15):
+        q1, ep1, er1, _ = ik.solve_ik(q0.reshape(-1, 1), RTs[i], np.zeros(robot.field_size), [0, 0, 0])
+        np.testing.assert_array_equal(q1, qb[i])
+        assert ep1 == pytest.approx(ep[i], abs=1e-12)
