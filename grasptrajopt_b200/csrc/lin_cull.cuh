@@ -347,12 +347,13 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   for (int i = threadIdx.x; i < CULL_ZERO_BYTES / 4; i += blockDim.x) zero_buf[i] = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zeros are read by the async proxy (bulk stores)
   __syncthreads();
+  // (the active count was written by the step kernel two launches back, long complete: read it ahead of the wait)
+  const int nprob = p.nactive ? *p.nactive : p.nproblems;
   pdl_wait();  // the item records (k_item_fk) and everything before them
   pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
   stamp_begin(pp.ts_lin);
 
   const int nknots = p.T - p.t_lo;
-  const int nprob = p.nactive ? *p.nactive : p.nproblems;
   const int nitems = nprob * nknots;
   const int nH = nopt * nopt;
 

@@ -86,11 +86,11 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   const int a_idx = blockIdx.x;
   int dbg_i = 0;
 #define STEP_MARK() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
-  pdl_wait();  // the Gauss-Newton blocks of the linearise kernel before us
-  pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
+  // Programmatic dependent launch: the per-problem solver state read below (active list, damping, accepted / trial point) was
+  // written by the PREVIOUS step kernel, which completed before the linearise kernel ahead of us even started -- only the
+  // Gauss-Newton blocks and costs need pdl_wait(), so the dependent round trips for the state overlap the linearise kernel.
   STEP_MARK();
   if (a_idx >= *p.nactive_in) return;
-  stamp_begin(p.ts);
   const int b = p.active_in[a_idx];
   const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;
   const double a2 = p.w_vel / (p.dt * p.dt);
@@ -113,7 +113,26 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   double* Xt = p.Qt + (long long)b * T * n;
   const int it = p.iter;
   // ---- everything that only depends on b is requested in one batch: the launch is latency bound, and every dependent
-  //      round trip to L2 / HBM costs about a microsecond ----
+  //      round trip to L2 / HBM costs the better part of a microsecond ----
+  int cur = p.bufsel[b];
+  double lam = p.lam[b], nu = p.nu[b];
+  const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
+  const int tri = 1 - cur;
+  if (tid == 0) p.bufsplit[tri * p.Bcap + b] = 1;
+  bool accepted = false;
+  double s0 = 0.0, s1 = 0.0, sv = 0.0;
+  for (int i = tid; i < T * n; i += NT) {
+    const double xt = Xt[i];
+    X[i] = xt;         // trial point
+    X2[i] = Xc[i];     // accepted point
+    if (i >= n) {
+      const double d = xt - Xt[i - n];
+      sv += d * d;
+    }
+  }
+  pdl_wait();     // from here on: results of the linearise kernel before us
+  pdl_trigger();  // the successor may be scheduled (it blocks in its own pdl_wait until we are done)
+  stamp_begin(p.ts);
   for (int buf = 0; buf < 2; ++buf) {  // Gauss-Newton blocks of both buffers (which one is "accepted" is decided below)
     const float* Hg = p.H + buf * p.buf_stride_H + (long long)b * T * nn + 2 * nn;
     const float* gg = p.g + buf * p.buf_stride_g + (long long)b * T * n + 2 * n;
@@ -123,28 +142,12 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(gS + (size_t)buf * m * n + i)), "l"(gg + i) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  int cur = p.bufsel[b];
-  double lam = p.lam[b], nu = p.nu[b];
-  const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
-  const int tri = 1 - cur;
-  if (tid == 0) p.bufsplit[tri * p.Bcap + b] = 1;
-  bool accepted = false;
 
   // ---------------- evaluate the trial point produced by the previous call ----------------
   {
-    double s0 = 0.0, s1 = 0.0, sv = 0.0;
     for (int t = tid; t < T; t += NT) {
       s0 += (double)p.costp[(long long)b * T + t];
       s1 += (double)p.costp[p.buf_stride_c + (long long)b * T + t];
-    }
-    for (int i = tid; i < T * n; i += NT) {
-      const double xt = Xt[i];
-      X[i] = xt;         // trial point
-      X2[i] = Xc[i];     // accepted point
-      if (i >= n) {
-        const double d = xt - Xt[i - n];
-        sv += d * d;
-      }
     }
     STEP_MARK();  // 1: loads issued
     cta_sum3(s0, s1, sv, red);
