@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
               const bool isU = id >= nn;
               const int rc = isU ? id - nn : id, r = rc / n, c = rc - r * n;
               const double* M = isU ? Ui : Li;
-              if (isU ? hasU : hasL)
-                for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], M[k * n + c], acc);
+              if (isU ? hasU : hasL) {
+                if (s == 1) acc = Di[r * n + c] * M[c * n + c];  // first level: the couplings are still diagonal (-a2 I, masked)
+                else
+                  for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], M[k * n + c], acc);
+              }
             } else {
               const int r = id - 2 * nn;
               for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], bi[k], acc);
@@ -368,7 +371,25 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
           const int id = lane + 32 * o;
           double acc = 0.0;
           if (id < nout) {
-            if (id < nn) {  // D_j - U_j W_L(j+s) - L_j W_U(j-s)
+            if (s == 1) {  // first level: L_j, U_j are diagonal, the products are row scalings
+              if (id < nn) {
+                const int r = id / n, c = id - r * n;
+                acc = Dj[id];
+                if (has2) acc = fma(-Uj[r * n + r], WL2[r * n + c], acc);
+                if (has1) acc = fma(-Lj[r * n + r], WU1[r * n + c], acc);
+              } else if (id < 2 * nn) {
+                const int rc = id - nn, r = rc / n, c = rc - r * n;
+                if (has1L) acc = -Lj[r * n + r] * WL1[r * n + c];
+              } else if (id < 3 * nn) {
+                const int rc = id - 2 * nn, r = rc / n, c = rc - r * n;
+                if (has2U) acc = -Uj[r * n + r] * WU2[r * n + c];
+              } else {
+                const int r = id - 3 * nn;
+                acc = bj[r];
+                if (has2) acc = fma(-Uj[r * n + r], w2[r], acc);
+                if (has1) acc = fma(-Lj[r * n + r], w1[r], acc);
+              }
+            } else if (id < nn) {  // D_j - U_j W_L(j+s) - L_j W_U(j-s)
               const int r = id / n, c = id - r * n;
               acc = Dj[id];
               if (has2)
