@@ -2094,6 +2094,20 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
       }
     }
+    if (launch_stamps) {  // per-launch durations of this chunk; the stamp array is reused by the next chunk
+      std::vector<unsigned long long> hts(ts_n);
+      CK(cudaMemcpyAsync(hts.data(), ctx->tstamps.p, ts_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemsetAsync(ctx->tstamps.p, 0, ts_n * sizeof(unsigned long long), ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (size_t i = 0; i + 1 < ts_n; i += 2) {
+        if (!hts[i + 1] || !hts[i]) continue;
+        const unsigned long long t0 = ~hts[i], t1 = hts[i + 1];
+        if (t1 <= t0) continue;
+        const double msd = (double)(t1 - t0) * 1e-6;
+        if ((i / 2) % 3 == 2) pf.step_ms += msd;
+        else pf.linearize_ms += msd;
+      }
+    }
     // exact work accounting for the roofline: problems active in every linearise launch of this chunk
     CK(cudaMemcpyAsync(h_nact.data(), ctx->nactive.p, sizeof(int) * cstride * G, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2134,18 +2148,6 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   pf.solve_ms = ms;
-  if (launch_stamps) {
-    std::vector<unsigned long long> hts(ts_n);
-    CK(cudaMemcpy(hts.data(), ctx->tstamps.p, ts_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i + 1 < ts_n; i += 2) {
-      if (!hts[i + 1] || !hts[i]) continue;
-      const unsigned long long t0 = ~hts[i], t1 = hts[i + 1];
-      if (t1 <= t0) continue;
-      const double msd = (double)(t1 - t0) * 1e-6;
-      if ((i / 2) % 3 == 2) pf.step_ms += msd;
-      else pf.linearize_ms += msd;
-    }
-  }
   for (size_t i = 0; i < ev_kind.size(); ++i) {
     float m1 = 0, m2 = 0;
     cudaEventElapsedTime(&m1, ctx->ev[1 + 3 * i], ctx->ev[2 + 3 * i]);
