@@ -214,3 +214,19 @@ def test_solve_properties_full_c2(ctx):
     np.testing.assert_array_equal(res2["Q"], Q)
     # the packed float32 result that feeds the all-gather matches
     assert ctx.profile()["linearize_launches"] > 0
+
+
+def test_chunked_solve_is_identical(ctx, monkeypatch):
+    """A Jacobian-row budget smaller than the batch splits the solve into chunks (C5 at full size needs two): same bits, and
+    the per-launch time stamps of all chunks add up to less than the solve."""
+    w = small_workload("C2", "panda_small", B=8, n_field=64)
+    ctx.set_robot(w.table)
+    upload_fields(ctx, w)
+    ref = ctx.solve_batch(w.batch)
+    per_problem_mb = (w.batch.T * w.table.npoints + 6 * w.table.grip_pt_count) * (w.table.nopt + 1) * 4 / 2**20
+    monkeypatch.setenv("GTO_JROWS_BUDGET_MB", str(3.5 * per_problem_mb))  # 3 problems per chunk -> chunks of 3, 3, 2
+    res = ctx.solve_batch(w.batch)
+    pf = ctx.profile()
+    for k in ("Q", "dQ", "cost", "iters", "status"):
+        np.testing.assert_array_equal(res[k], ref[k], err_msg=k)
+    assert 0 < pf["linearize_ms"] + pf["step_ms"] <= pf["solve_ms"] * 1.05
