@@ -275,17 +275,25 @@ class GtoContext:
         s.w_goal, s.w_obs, s.w_vel, s.flags = float(b.w_goal), float(b.w_obs), float(b.w_vel), int(b.flags)
         return s, keep
 
-    def _batch_out(self, B: int, T: int):
+    def _batch_out(self, B: int, T: int, out: Optional[dict] = None):
         nd = self.table.ndof
-        res = dict(Q=np.zeros((B, T, nd)), dQ=np.zeros((B, T - 1, nd)), cost=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
+        shapes = dict(Q=((B, T, nd), np.float64), dQ=((B, T - 1, nd), np.float64), cost=((B,), np.float64), iters=((B,), np.int32), status=((B,), np.int32))
+        if out is not None:  # caller-owned (e.g. pinned) result buffers, reused across calls
+            for k, (shp, dt) in shapes.items():
+                a = out.get(k)
+                if a is None or a.shape != shp or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError(f"out[{k!r}] must be a C-contiguous {np.dtype(dt).name} array of shape {shp}")
+            res = out
+        else:
+            res = {k: np.empty(shp, dt) for k, (shp, dt) in shapes.items()}
         o = BatchOut()
         o.Q, o.dQ, o.cost = _ptr(res["Q"], _dp), _ptr(res["dQ"], _dp), _ptr(res["cost"], _dp)
         o.iters, o.status = _ptr(res["iters"], _ip), _ptr(res["status"], _ip)
         return o, res
 
-    def solve_batch(self, b: Batch, options: Optional[Options] = None) -> dict:
+    def solve_batch(self, b: Batch, options: Optional[Options] = None, out: Optional[dict] = None) -> dict:
         s, keep = self._batch_in(b)
-        o, res = self._batch_out(b.B, int(b.T))
+        o, res = self._batch_out(b.B, int(b.T), out)
         self._check(self._lib.gto_solve_batch(self._h, C.byref(s), C.byref(options) if options is not None else None, C.byref(o)))
         return res
 

@@ -1723,12 +1723,15 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
     int nc = ctx->pipe_cons;
     if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
     cp.ncons = nc;
+    int nslot = 4;
+    if (const char* e = getenv("GTO_CULL_NSLOT")) nslot = std::min(CULL_NSLOT_MAX, std::max(2, atoi(e)));
+    cp.nslot = nslot;
     cp.work_counter = work_counter;
     cp.stats = ctx->stats.p;
     const int RS = R.nopt + 1;
     size_t sm = (sizeof(CullShared) + 127) & ~(size_t)127;
     sm += CULL_ZERO_BYTES;
-    sm += (size_t)CULL_NSLOT * slot_floats * sizeof(float);
+    sm += (size_t)nslot * slot_floats * sizeof(float);
     sm += (size_t)nc * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
     sm += (size_t)2 * nc * (R.nopt * R.nopt + R.nopt + 2) * sizeof(float);
     sm = (sm + 127) & ~(size_t)127;

@@ -15,7 +15,7 @@
 //                     varies with the number of surviving links.
 #pragma once
 
-#define CULL_NSLOT 4
+#define CULL_NSLOT_MAX 8  // brick ring slots: run-time (CullParams.nslot), default 4
 #define CULL_ZERO_BYTES 8192
 
 struct __align__(16) CullCtx {
@@ -37,13 +37,14 @@ struct __align__(16) CullCtx {
 struct CullShared {
   CullCtx ctx[2];
   LinkMeta links[GTO_MAX_LINKS];
-  unsigned long long slot_full[CULL_NSLOT], slot_empty[CULL_NSLOT], ctx_full[2], ctx_empty[2];
+  unsigned long long slot_full[CULL_NSLOT_MAX], slot_empty[CULL_NSLOT_MAX], ctx_full[2], ctx_empty[2];
 };
 
 struct CullParams {
   LinParams lin;
   int slot_floats;     // capacity of one brick slot
   int ncons;           // consumer warps
+  int nslot;           // brick ring slots (<= CULL_NSLOT_MAX)
   int* work_counter;   // zero before the launch: next (problem, knot) item
   CullCtx* recs;       // [items] per-item records written by k_item_fk, read by the producer warps (bulk copy)
   CullCtx* rec_dummy;  // one record nobody reads
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   CullShared& S = *reinterpret_cast<CullShared*>(smem_raw);
   const RobotDev& R = *p.robot;
   const int nopt = NOPT_CT ? NOPT_CT : R.nopt, RS = nopt + 1, NC = pp.ncons;
+  const unsigned CULL_NSLOT = (unsigned)pp.nslot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   size_t off = (sizeof(CullShared) + 127) & ~(size_t)127;
   float* zero_buf = reinterpret_cast<float*>(smem_raw + off);
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   uint64_t* ctx_empty = reinterpret_cast<uint64_t*>(S.ctx_empty);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CULL_NSLOT; ++s) {
+    for (int s = 0; s < (int)CULL_NSLOT; ++s) {
       mbar_init(slot_full + s, 1);
       mbar_init(slot_empty + s, NC);
     }
