@@ -1986,6 +1986,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     int *act0, *act1, *nact, *wctr;
     CullCtx* recs;
     bool done;
+    int known;  // upper bound of the problems still active (last polled count; the count only decreases): sizes the grids
   };
   std::vector<int> h_nact(cstride * G);
   // per-launch durations for the profile (linearize_ms / step_ms): in-kernel %globaltimer stamps by default; CUDA events
@@ -2016,6 +2017,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       r.wctr = ctx->work_ctr.p + cstride * g;
       r.recs = cull_ok ? ctx->recs.p + (size_t)(r.b0 - b0) * T : nullptr;
       r.done = false;
+      r.known = r.nb;
       CK(cudaMemcpyAsync(r.nact, &r.nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (ng > 1) {
@@ -2036,7 +2038,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
           a = get_event(ctx, nev++); bE = get_event(ctx, nev++); c = get_event(ctx, nev++);
           CK(cudaEventRecord(a, r.s));
         }
-        int rc = launch_linearize(ctx, ctx->q_trial.p, ain, r.nact + it, r.nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
+        int rc = launch_linearize(ctx, ctx->q_trial.p, ain, r.nact + it, r.known, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
                                   it == 0 ? 0 : 2, ctx->flags, r.wctr + it, step_fk && it > 0, r.s, r.recs,
                                   launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 : nullptr);
         if (rc) return rc;
@@ -2056,8 +2058,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
           st.fk.rec_dummy = ctx->rec_dummy.p;
           st.fk.stats = ctx->stats.p;
         }
-        if (use_cr) CK(launch_pdl<StepParams>(step_cr_kern, (unsigned)r.nb, STEP_CR_THREADS, cr_smem, r.s, ctx->use_pdl, st));
-        else step_kern<<<r.nb, 32, step_smem, r.s>>>(st);
+        if (use_cr) CK(launch_pdl<StepParams>(step_cr_kern, (unsigned)r.known, STEP_CR_THREADS, cr_smem, r.s, ctx->use_pdl, st));
+        else step_kern<<<r.known, 32, step_smem, r.s>>>(st);
         pf.kernel_launches += 1;
         CK(cudaGetLastError());
         if (launch_events) {
@@ -2086,6 +2088,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
           } else if (nblk > 0) {
             CK(cudaEventSynchronize(ctx->ev_poll[2 * g + (par ^ 1)]));
             if (ctx->h_counter[2 * g + (par ^ 1)] == 0) grp[g].done = true;
+            else grp[g].known = std::min(grp[g].known, ctx->h_counter[2 * g + (par ^ 1)]);
           }
         }
         ++nblk;
