@@ -764,6 +764,7 @@ struct StepParams {
   int iter;        // number of LM steps already taken by the problems in the active list
   long long* dbg;  // k_step_cr: clock64() at phase boundaries of CTA 0 (diagnostics, NULL: off)
   unsigned long long* ts;  // k_step_cr: launch time stamps (NULL: off)
+  int fk_robot_smem;  // k_step_cr: the robot table fits into the shared storage that is free during the FK phase
   int do_fk;       // k_step_cr: also write the item records (FK, brick placement, culling test) of the new trial point
   CullParams fk;   // what item_fk_body needs (robot, fields, records, Gauss-Newton buffers)
 };
@@ -1236,7 +1237,7 @@ struct gto_ctx {
   DevBuf<float4> cloud;      // depth point cloud (gto_cloud_set), padded to a multiple of CLOUD_TILE
   long long cloud_n = 0;
   DevBuf<double> cloud_q;
-  DevBuf<float> cloud_depth, cloud_out;
+  DevBuf<float> cloud_depth, cloud_out, cloud_tiles;
   DevBuf<unsigned long long> tstamps;
   DevBuf<CullCtx> recs, rec_dummy;
   bool use_pdl = true;       // programmatic dependent launch of the solver kernels (GTO_NO_PDL=1 turns it off)
@@ -1347,7 +1348,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
   ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release();
-  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->recs.release(); ctx->rec_dummy.release();
+  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->cloud_tiles.release(); ctx->recs.release(); ctx->rec_dummy.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1930,9 +1931,17 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   if (use_cr) CK(cudaFuncSetAttribute(step_cr_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_smem));
   // the step kernel also writes the item records of its new trial point when the culling kernel will consume them and
   // its FK scratch fits into the (by then free) factorisation storage
-  const bool step_fk = use_cr && cull_path_ok(ctx, ctx->flags) && getenv("GTO_STEP_FK") &&  // measured on C2: slower than a k_item_fk launch of its own (two serial rounds per CTA), off by default
-                       (size_t)(STEP_CR_THREADS / 16) * 2 * R.nmov * 12 <= (size_t)3 * (T - 2) * n * n;
-  if (step_fk) CK(ctx->recs.ensure((size_t)Bchunk * T));
+  // GTO_STEP_FK = "all": every step launch; "tail" (or a number): only once at most that many problems (default 16) are left,
+  // where a launch of k_item_fk costs more than two extra FK rounds at the end of the step kernel; unset: never
+  int step_fk_limit = 0;
+  if (const char* e = getenv("GTO_STEP_FK")) {
+    if (!strcmp(e, "all") || !strcmp(e, "1")) step_fk_limit = 1 << 30;
+    else if (!strcmp(e, "tail")) step_fk_limit = 16;
+    else step_fk_limit = atoi(e);
+  }
+  const bool step_fk_ok = use_cr && cull_path_ok(ctx, ctx->flags) && step_fk_limit > 0 &&
+                          (size_t)(STEP_CR_THREADS / 16) * 2 * R.nmov * 12 <= (size_t)3 * (T - 2) * n * n;
+  if (step_fk_ok) CK(ctx->recs.ensure((size_t)Bchunk * T));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1986,6 +1995,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     int *act0, *act1, *nact, *wctr;
     CullCtx* recs;
     bool done;
+    bool recs_ready;  // the last step launch of this group wrote the item records of its trial point
     int known;  // upper bound of the problems still active (last polled count; the count only decreases): sizes the grids
   };
   std::vector<int> h_nact(cstride * G);
@@ -2017,6 +2027,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       r.wctr = ctx->work_ctr.p + cstride * g;
       r.recs = cull_ok ? ctx->recs.p + (size_t)(r.b0 - b0) * T : nullptr;
       r.done = false;
+      r.recs_ready = false;
       r.known = r.nb;
       CK(cudaMemcpyAsync(r.nact, &r.nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
@@ -2039,7 +2050,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
           CK(cudaEventRecord(a, r.s));
         }
         int rc = launch_linearize(ctx, ctx->q_trial.p, ain, r.nact + it, r.known, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
-                                  it == 0 ? 0 : 2, ctx->flags, r.wctr + it, step_fk && it > 0, r.s, r.recs,
+                                  it == 0 ? 0 : 2, ctx->flags, r.wctr + it, r.recs_ready && it > 0, r.s, r.recs,
                                   launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 : nullptr);
         if (rc) return rc;
         if (launch_events) CK(cudaEventRecord(bE, r.s));
@@ -2047,7 +2058,10 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
         st.iter = it;
         st.ts = launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 + 4 : nullptr;
         st.lin_grid = ctx->last_lin_grid;
+        const bool step_fk = step_fk_ok && r.known <= step_fk_limit;
         st.do_fk = step_fk ? 1 : 0;
+        st.fk_robot_smem = sizeof(RobotDev) <= (size_t)T * n * 8 + (size_t)2 * ((T - 2) * n * n + (T - 2) * n) * 4 ? 1 : 0;
+        r.recs_ready = step_fk;
         if (step_fk) {
           memset(&st.fk, 0, sizeof(st.fk));
           fill_lin_params(ctx, st.fk.lin, ctx->q_trial.p, nullptr, nullptr, r.nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr, 2, ctx->flags);
@@ -2282,15 +2296,55 @@ extern "C" int gto_plan_cost(gto_ctx* ctx, int32_t nplans, int32_t T, const doub
 // ------------------------------------------------------------------------------------------------------------------
 // Scene side: depth point cloud -> signed distance / cost at query points (DepthPointCloud)
 // ------------------------------------------------------------------------------------------------------------------
+static inline unsigned morton_spread10(unsigned v) {  // 10 bits -> every third bit
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
 extern "C" int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M) {
   if (!ctx || !points || M < 1) return GTO_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   const size_t Mpad = ((size_t)M + CLOUD_TILE - 1) / CLOUD_TILE * CLOUD_TILE;
+  // order the cloud along a Morton curve (10 bits per axis over its bounding box): consecutive points are neighbours in
+  // space, so the 256-point tiles of the pruned query kernel have small bounding boxes
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int64_t i = 0; i < M; ++i)
+    for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], points[3 * i + a]); hi[a] = std::max(hi[a], points[3 * i + a]); }
+  std::vector<std::pair<unsigned, unsigned>> key((size_t)M);
+  for (int64_t i = 0; i < M; ++i) {
+    unsigned code = 0;
+    for (int a = 0; a < 3; ++a) {
+      const double ext = hi[a] - lo[a];
+      const unsigned q = ext > 0 ? (unsigned)std::min(1023.0, (points[3 * i + a] - lo[a]) / ext * 1024.0) : 0u;
+      code |= morton_spread10(q) << a;
+    }
+    key[(size_t)i] = std::make_pair(code, (unsigned)i);
+  }
+  std::sort(key.begin(), key.end());
   std::vector<float4> h(Mpad);
-  for (size_t i = 0; i < (size_t)M; ++i) h[i] = make_float4((float)points[3 * i], (float)points[3 * i + 1], (float)points[3 * i + 2], 0.f);
+  for (size_t i = 0; i < (size_t)M; ++i) {
+    const size_t j = key[i].second;
+    h[i] = make_float4((float)points[3 * j], (float)points[3 * j + 1], (float)points[3 * j + 2], 0.f);
+  }
   for (size_t i = (size_t)M; i < Mpad; ++i) h[i] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);  // never the nearest
+  const size_t ntiles = ((size_t)M + CLOUD_PTILE - 1) / CLOUD_PTILE;
+  std::vector<float> tb(ntiles * 6);
+  for (size_t t = 0; t < ntiles; ++t) {
+    float l3[3] = {3.0e38f, 3.0e38f, 3.0e38f}, h3[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (size_t i = t * CLOUD_PTILE; i < std::min((size_t)M, (t + 1) * CLOUD_PTILE); ++i) {
+      const float v[3] = {h[i].x, h[i].y, h[i].z};
+      for (int a = 0; a < 3; ++a) { l3[a] = std::min(l3[a], v[a]); h3[a] = std::max(h3[a], v[a]); }
+    }
+    for (int a = 0; a < 3; ++a) { tb[6 * t + a] = l3[a]; tb[6 * t + 3 + a] = h3[a]; }
+  }
   CK(ctx->cloud.ensure(Mpad));
+  CK(ctx->cloud_tiles.ensure(tb.size()));
   CK(cudaMemcpy(ctx->cloud.p, h.data(), Mpad * sizeof(float4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->cloud_tiles.p, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice));
   ctx->cloud_n = M;
   return GTO_OK;
 }
@@ -2318,8 +2372,15 @@ extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, con
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, ctx->stream));
-  const long long per = (long long)CLOUD_THREADS * CLOUD_QPT;
-  k_cloud_query<<<(unsigned)((N + per - 1) / per), CLOUD_THREADS, 0, ctx->stream>>>(p);
+  p.tiles = ctx->cloud_tiles.p;
+  p.ntiles = (int)(((size_t)ctx->cloud_n + CLOUD_PTILE - 1) / CLOUD_PTILE);
+  if (getenv("GTO_CLOUD_BRUTE")) {  // A/B reference: every query against every point
+    const long long per = (long long)CLOUD_THREADS * CLOUD_QPT;
+    k_cloud_query<<<(unsigned)((N + per - 1) / per), CLOUD_THREADS, 0, ctx->stream>>>(p);
+  } else {
+    const long long nwarps = (N + CLOUD_WQ - 1) / CLOUD_WQ;
+    k_cloud_query_pruned<<<(unsigned)((nwarps + 3) / 4), 128, 0, ctx->stream>>>(p);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaMemcpyAsync(out, ctx->cloud_out.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));

@@ -506,6 +506,16 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   __syncthreads();  // q_trial of this problem and the slot are visible to the whole CTA
   {
     const int slot = sflag[1];
+    // the robot table moves into shared memory (the storage of X2 / HS / gS is free by now) when it fits: the serial FK chain
+    // then never waits on L2
+    const RobotDev* Rf = &R;
+    if (p.fk_robot_smem) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.robot);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(X2);
+      for (int i = tid; i < (int)(sizeof(RobotDev) / 8); i += NT) dst[i] = __ldg(src + i);
+      __syncthreads();
+      Rf = reinterpret_cast<const RobotDev*>(X2);
+    }
     const int hl = tid & 15, grp = tid >> 4, ngrp = NT >> 4, hshift = tid & 16;
     double* A = Dm + (size_t)grp * 2 * R.nmov * 12;  // the factorisation is done: its storage is free
     double* Tm = A + (size_t)R.nmov * 12;
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       const bool valid = (i0 + grp) < m;
       const int i = valid ? i0 + grp : m - 1;
       const int t = i + 2;
-      item_fk_body(p.fk, R, slot * m + i, valid, b, t, 1 - cur, p.q_trial + ((long long)b * T + t) * R.ndof, A, Tm, hl, hshift);
+      item_fk_body(p.fk, *Rf, slot * m + i, valid, b, t, 1 - cur, p.q_trial + ((long long)b * T + t) * R.ndof, A, Tm, hl, hshift);
       __syncwarp();
     }
   }

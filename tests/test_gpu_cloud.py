@@ -55,6 +55,15 @@ def test_cloud_query_matches_kdtree_backend_on_a_grid():
     ok = ~flip
     np.testing.assert_allclose(c_gpu[ok], c_cpu[ok], rtol=0, atol=2e-6)
     assert (c_cpu > 0).mean() > 0.05 and (s_cpu < 0).any()
+    # the pruned search visits every tile that could hold a nearer point: bit-identical to the brute-force kernel
+    os.environ["GTO_CLOUD_BRUTE"] = "1"
+    try:
+        s_brute, c_brute = gpu.get_sdf(g), gpu.get_sdf_cost(g, epsilon=0.02)
+        print(f"brute-force kernel {gpu.last_kernel_ms:.2f} ms")
+    finally:
+        os.environ.pop("GTO_CLOUD_BRUTE")
+    np.testing.assert_array_equal(s_gpu, s_brute)
+    np.testing.assert_array_equal(c_gpu, c_brute)
     # ragged sizes: fewer queries than one block, a non-multiple of the tile
     for m in (1, 7, 1500):
         np.testing.assert_allclose(np.abs(gpu.get_sdf(g[:m])), np.abs(s_cpu[:m]), rtol=0, atol=2e-6)

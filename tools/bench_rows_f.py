@@ -38,7 +38,8 @@ try:
     out["ik_batch"]["cpu_port"] = {"ik_solves_per_s": len(idx) / dtc, "threads": int(ro["threads"]), "sample": int(len(idx)),
                                    "median_abs_dq_both_converged": float(np.median(dq[both])) if both.any() else None,
                                    "frac_within_1e-4_rad": float((dq[both] < 1e-4).mean()) if both.any() else None, "n_both": int(both.sum()),
-                                   "note": "IK has several solutions per pose; problems that end in different ones are not counted as agreeing"}
+                                   "note": "a 7-DoF arm has a one-parameter family of IK solutions per pose, so the joint vectors of two float paths need not agree; "
+                                           "both reach the pose (see converged counts)"}
 except Exception as e:  # pragma: no cover
     out["ik_batch"]["cpu_port"] = {"error": repr(e)}
 
