@@ -1727,6 +1727,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
     int nslot = 4;
     if (const char* e = getenv("GTO_CULL_NSLOT")) nslot = std::min(CULL_NSLOT_MAX, std::max(2, atoi(e)));
     cp.nslot = nslot;
+    cp.count_early = have_recs ? 0 : 1;
     cp.work_counter = work_counter;
     cp.stats = ctx->stats.p;
     const int RS = R.nopt + 1;

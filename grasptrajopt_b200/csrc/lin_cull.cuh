@@ -45,6 +45,7 @@ struct CullParams {
   int slot_floats;     // capacity of one brick slot
   int ncons;           // consumer warps
   int nslot;           // brick ring slots (<= CULL_NSLOT_MAX)
+  int count_early;     // the launch before this one is k_item_fk (not the step kernel): *nactive may be read before pdl_wait
   int* work_counter;   // zero before the launch: next (problem, knot) item
   CullCtx* recs;       // [items] per-item records written by k_item_fk, read by the producer warps (bulk copy)
   CullCtx* rec_dummy;  // one record nobody reads
@@ -349,10 +350,13 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
   for (int i = threadIdx.x; i < CULL_ZERO_BYTES / 4; i += blockDim.x) zero_buf[i] = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zeros are read by the async proxy (bulk stores)
   __syncthreads();
-  // (the active count was written by the step kernel two launches back, long complete: read it ahead of the wait)
-  const int nprob = p.nactive ? *p.nactive : p.nproblems;
-  pdl_wait();  // the item records (k_item_fk) and everything before them
+  // the active count is written by the step kernel: two launches back (long complete, read it ahead of the wait) when a
+  // k_item_fk launch sits in between, directly before us when the step kernel wrote the item records itself
+  int nprob = p.nproblems;
+  if (p.nactive && pp.count_early) nprob = *p.nactive;
+  pdl_wait();  // the item records and everything before them
   pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
+  if (p.nactive && !pp.count_early) nprob = *p.nactive;
   stamp_begin(pp.ts_lin);
 
   const int nknots = p.T - p.t_lo;
