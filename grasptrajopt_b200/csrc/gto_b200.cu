@@ -1737,7 +1737,7 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
     sm += (size_t)nc * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
     sm += (size_t)2 * nc * (R.nopt * R.nopt + R.nopt + 2) * sizeof(float);
     sm = (sm + 127) & ~(size_t)127;
-    const int threads = (nc + 1) * 32;
+    const int threads = (nc + 2) * 32;  // consumers + producer + zero-row warp
     int occ = 0;
     void (*kern)(const CullParams) = nullptr;
     if (R.nopt == 7) kern = k_linearize_cull<8, 7>;

@@ -34,10 +34,14 @@ struct __align__(16) CullCtx {
   int act[GTO_MAX_LINKS];           // surviving link ids, ascending
 };
 
+#define CULL_ZQ 16  // entries of the producer -> zero-row warp queue
 struct CullShared {
   CullCtx ctx[2];
   LinkMeta links[GTO_MAX_LINKS];
   unsigned long long slot_full[CULL_NSLOT_MAX], slot_empty[CULL_NSLOT_MAX], ctx_full[2], ctx_empty[2];
+  int4 zq[CULL_ZQ];            // (b, t, amask, -) of the items whose culled links still need their zero rows; b < 0: stop
+  volatile unsigned zq_tail;   // entries written by the producer warp
+  volatile unsigned zq_head;   // entries consumed by the zero-row warp
 };
 
 struct CullParams {
@@ -304,7 +308,7 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
 
 // NP: padded tensor-core tile width (8 or 16); NOPT_CT: number of optimised joints when known at compile time (0: runtime)
 template <int NP, int NOPT_CT>
-__global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
+__global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LinParams& p = pp.lin;
   CullShared& S = *reinterpret_cast<CullShared*>(smem_raw);
@@ -337,6 +341,8 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
       mbar_init(ctx_empty + c, NC);
     }
     mbar_fence_init();
+    S.zq_tail = 0u;
+    S.zq_head = 0u;
   }
   if ((int)threadIdx.x < R.nlinks) {
     LinkMeta m;
@@ -370,8 +376,6 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
     // into the ring (one TMA tile each).  The next item index is fetched one item ahead.
     unsigned pub = 0, bc = 0;
     const int nlinks = R.nlinks;
-    int my_start = 0, my_cnt = 0;
-    if (lane < nlinks) { my_start = S.links[lane].pt_start; my_cnt = S.links[lane].pt_end - my_start; }
     int next_item = 0;
     if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
     for (;;) {
@@ -389,27 +393,17 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
         mydim = __ldg(reinterpret_cast<const int4*>(G->bdim[lane]));
         mylo = __ldg(reinterpret_cast<const int4*>(G->blo[lane]));
       }
-      // ---- rows of the culled links: zeros, straight from shared memory by bulk copy ----
+      // ---- the zero rows of the culled links are handed to the zero-row warp (nobody waits for them) ----
       if (p.collision && p.rows) {
-        float* rows_b = p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS;
-        bool slow_zero = false;
-        if (lane < nlinks && !survives) {
-          char* dst = reinterpret_cast<char*>(rows_b + ((long long)t * R.npoints + my_start) * RS);
-          const unsigned bytes = (unsigned)my_cnt * RS * 4u;
-          if ((((uintptr_t)dst | bytes) & 15u) == 0u) {
-            for (unsigned o = 0; o < bytes; o += CULL_ZERO_BYTES) bulk_store_zero(dst + o, zero_buf, min((unsigned)CULL_ZERO_BYTES, bytes - o));
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          } else {
-            slow_zero = my_cnt > 0;
+        if (lane == 0) {
+          unsigned tail = S.zq_tail;
+          for (int tries = 0; tail - S.zq_head >= CULL_ZQ; ++tries) {  // queue full: the zero-row warp is behind
+            __nanosleep(200);
+            if (tries > (1 << 22)) __trap();
           }
-        }
-        unsigned zm = __ballot_sync(0xffffffffu, slow_zero);  // row blocks that are not 16-byte aligned: plain stores
-        while (zm) {
-          const int l = __ffs(zm) - 1;
-          zm &= zm - 1;
-          float* dst = rows_b + ((long long)t * R.npoints + S.links[l].pt_start) * RS;
-          const int nfl = (S.links[l].pt_end - S.links[l].pt_start) * RS;
-          for (int i = lane; i < nfl; i += 32) __stcs(dst + i, 0.f);
+          S.zq[tail % CULL_ZQ] = make_int4(b, t, (int)amask, 0);
+          __threadfence_block();
+          S.zq_tail = tail + 1;
         }
       }
       if (amask == 0u && h1.y == 0) continue;  // k_item_fk wrote the zero Gauss-Newton block
@@ -449,6 +443,66 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 1) * 32, 2) k_linearize_cull(
       if (lane == 0) {
         S.ctx[ci].b = -1;
         mbar_arrive(ctx_full + ci);
+      }
+    }
+    if (p.collision && p.rows && lane == 0) {  // stop record for the zero-row warp
+      unsigned tail = S.zq_tail;
+      for (int tries = 0; tail - S.zq_head >= CULL_ZQ; ++tries) {
+        __nanosleep(200);
+        if (tries > (1 << 22)) __trap();
+      }
+      S.zq[tail % CULL_ZQ] = make_int4(-1, 0, 0, 0);
+      __threadfence_block();
+      S.zq_tail = tail + 1;
+    }
+    stamp_end(pp.ts_lin);
+    return;
+  }
+  if (warp == NC + 1) {
+    // =============================== ZERO-ROW WARP ===============================
+    // rows of the culled links: zeros, straight from shared memory by bulk copy, decoupled from the producer so that the HBM
+    // write stream keeps running while the producer waits for ring slots / contexts
+    if (!(p.collision && p.rows)) return;
+    const int nlinks = R.nlinks;
+    int my_start = 0, my_cnt = 0;
+    if (lane < nlinks) { my_start = S.links[lane].pt_start; my_cnt = S.links[lane].pt_end - my_start; }
+    for (unsigned head = 0;; ++head) {
+      if (lane == 0) {
+        for (int tries = 0; S.zq_tail == head; ++tries) {
+          __nanosleep(100);
+          if (tries > (1 << 23)) __trap();
+        }
+        __threadfence_block();
+      }
+      __syncwarp();
+      const int4 e = S.zq[head % CULL_ZQ];
+      __syncwarp();
+      if (lane == 0) S.zq_head = head + 1;
+      const int b = e.x, t = e.y;
+      if (b < 0) break;
+      const unsigned amask = (unsigned)e.z;
+      const bool survives = (amask >> lane) & 1u;
+      {
+        float* rows_b = p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS;
+        bool slow_zero = false;
+        if (lane < nlinks && !survives) {
+          char* dst = reinterpret_cast<char*>(rows_b + ((long long)t * R.npoints + my_start) * RS);
+          const unsigned bytes = (unsigned)my_cnt * RS * 4u;
+          if ((((uintptr_t)dst | bytes) & 15u) == 0u) {
+            for (unsigned o = 0; o < bytes; o += CULL_ZERO_BYTES) bulk_store_zero(dst + o, zero_buf, min((unsigned)CULL_ZERO_BYTES, bytes - o));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          } else {
+            slow_zero = my_cnt > 0;
+          }
+        }
+        unsigned zm = __ballot_sync(0xffffffffu, slow_zero);  // row blocks that are not 16-byte aligned: plain stores
+        while (zm) {
+          const int l = __ffs(zm) - 1;
+          zm &= zm - 1;
+          float* dst = rows_b + ((long long)t * R.npoints + S.links[l].pt_start) * RS;
+          const int nfl = (S.links[l].pt_end - S.links[l].pt_start) * RS;
+          for (int i = lane; i < nfl; i += 32) __stcs(dst + i, 0.f);
+        }
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
