@@ -375,7 +375,6 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
     // is left for the point kernel -- pull the record into shared memory (one bulk copy) and the surviving links' bricks
     // into the ring (one TMA tile each).  The next item index is fetched one item ahead.
     unsigned pub = 0, bc = 0;
-    const int nlinks = R.nlinks;
     int next_item = 0;
     if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
     for (;;) {
