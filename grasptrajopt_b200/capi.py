@@ -26,6 +26,7 @@ SYMBOLS = [
     "gto_abi_version", "gto_create", "gto_destroy", "gto_last_error", "gto_default_options", "gto_set_robot",
     "gto_set_field", "gto_solve_batch", "gto_upload_batch", "gto_solve_resident", "gto_download_batch",
     "gto_result_device_ptr", "gto_eval_batch", "gto_get_profile", "gto_plan_cost", "gto_cloud_set", "gto_cloud_query",
+    "gto_base_place",
 ]
 
 
@@ -84,6 +85,17 @@ class EvalOut(C.Structure):
     _fields_ = [("rows", _fp), ("H", _fp), ("g", _fp), ("cost", _fp)]
 
 
+class BaseIn(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("n_goals", C.c_int32), ("qc", _dp), ("goal_tf", _dp), ("w_effort", C.c_double), ("occupancy", _fp),
+        ("occ_dims", C.c_int32 * 2), ("occ_origin", C.c_double * 2), ("occ_resolution", C.c_double),
+    ]
+
+
+class BaseOut(C.Structure):
+    _fields_ = [("Q", _dp), ("y", _dp), ("cost", _dp), ("collision", _dp), ("iters", _ip), ("status", _ip)]
+
+
 class Profile(C.Structure):
     _fields_ = [
         ("solve_ms", C.c_double), ("linearize_ms", C.c_double), ("step_ms", C.c_double),
@@ -132,6 +144,7 @@ def load_library(path: Optional[str] = None):
     lib.gto_cloud_set.argtypes = [C.c_void_p, _dp, C.c_int64]
     lib.gto_cloud_query.argtypes = [C.c_void_p, _dp, C.c_int64, _fp, C.c_int32, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_double, _fp, _dp]
     lib.gto_plan_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp]
+    lib.gto_base_place.argtypes = [C.c_void_p, C.POINTER(BaseIn), C.POINTER(Options), C.POINTER(BaseOut), _dp]
     if path == os.environ.get("GTO_B200_LIB", LIB_PATH):
         _lib = lib
     return lib
@@ -360,3 +373,39 @@ class GtoContext:
         bp = _d(np.asarray(base_position).reshape(3))
         self._check(self._lib.gto_plan_cost(self._h, n, T, _ptr(plans, _dp), int(field_slot), _ptr(bp, _dp), _ptr(cost, _dp), _ptr(dist, _dp)))
         return cost, dist
+
+    def base_place(self, qc: np.ndarray, RTs: np.ndarray, w_effort: float = 0.01, occupancy: Optional[np.ndarray] = None,
+                   occ_origin=(0.0, 0.0), occ_resolution: float = 0.05, options: Optional[Options] = None) -> dict:
+        """Mobile-base placement (reference ``BasePlanner.plan_goalset``, gto/base_planner.py:94-168) for a stack of problems:
+        ``RTs`` [B,n,4,4] goal poses in the current base frame -> Q [B,n,ndof], y [B,3], cost/collision/iters/status [B]."""
+        t = self.table
+        RTs = np.asarray(RTs, dtype=np.float64)
+        if RTs.ndim == 3:
+            RTs = RTs[None]
+        B, n = RTs.shape[0], RTs.shape[1]
+        G = np.eye(4)
+        G[:3] = t.G
+        goal = _d((RTs @ G)[:, :, :3, :])
+        qcv = _d(np.asarray(qc, dtype=np.float64).reshape(-1))
+        if qcv.shape[0] != t.ndof:
+            raise ValueError(f"qc must have {t.ndof} entries")
+        bi = BaseIn()
+        bi.B, bi.n_goals, bi.qc, bi.goal_tf, bi.w_effort = B, n, _ptr(qcv, _dp), _ptr(goal, _dp), float(w_effort)
+        occ = None
+        if occupancy is not None:
+            occ = np.ascontiguousarray(occupancy, dtype=np.float32)
+            if occ.ndim != 2:
+                raise ValueError("occupancy must be [nx,ny]")
+            bi.occupancy = _ptr(occ, _fp)
+            bi.occ_dims[0], bi.occ_dims[1] = occ.shape
+            bi.occ_origin[0], bi.occ_origin[1] = float(occ_origin[0]), float(occ_origin[1])
+            bi.occ_resolution = float(occ_resolution)
+        res = dict(Q=np.zeros((B, n, t.ndof)), y=np.zeros((B, 3)), cost=np.zeros(B), collision=np.zeros(B),
+                   iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
+        bo = BaseOut()
+        bo.Q, bo.y, bo.cost, bo.collision = (_ptr(res[k], _dp) for k in ("Q", "y", "cost", "collision"))
+        bo.iters, bo.status = _ptr(res["iters"], _ip), _ptr(res["status"], _ip)
+        ms = np.zeros(1)
+        self._check(self._lib.gto_base_place(self._h, C.byref(bi), C.byref(options) if options is not None else None, C.byref(bo), _ptr(ms, _dp)))
+        res["kernel_ms"] = float(ms[0])
+        return res

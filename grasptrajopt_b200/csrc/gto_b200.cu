@@ -1085,6 +1085,7 @@ __global__ void __launch_bounds__(32) k_step(const StepParams p) {
 
 #include "step_cr.cuh"
 #include "cloud_sdf.cuh"
+#include "base_place.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_plan_cost: nearest-node cost of whole plans (seed ranking, gto/gto_models.py:204-215; clip-then-truncate indexing of
@@ -1239,6 +1240,10 @@ struct gto_ctx {
   DevBuf<double> cloud_q;
   DevBuf<float> cloud_depth, cloud_out, cloud_tiles;
   DevBuf<unsigned long long> tstamps;
+  double grip_mom[16] = {0};  // sum_k [x_k;1][x_k;1]^T over the gripper point set (base placement)
+  DevBuf<double> base_d;      // base placement: inputs and outputs, one allocation
+  DevBuf<float> base_occ;
+  DevBuf<int> base_i;
   DevBuf<CullCtx> recs, rec_dummy;
   bool use_pdl = true;       // programmatic dependent launch of the solver kernels (GTO_NO_PDL=1 turns it off)
   int* h_counter = nullptr;  // pinned, 16 ints
@@ -1427,6 +1432,12 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
   if (r->grip_pt_start < 0 || r->grip_pt_count < 1 || r->grip_pt_start + r->grip_pt_count > r->npoints || r->grip_mov >= r->nmov)
     return fail(ctx, GTO_ERR_INVALID, "gripper point set out of range");
   for (int e = 0; e < 12; ++e) { h.grip_tf[e] = (float)r->grip_tf[e]; h.grip_tf_d[e] = r->grip_tf[e]; }
+  for (int e = 0; e < 16; ++e) ctx->grip_mom[e] = 0.0;
+  for (int i = r->grip_pt_start; i < r->grip_pt_start + r->grip_pt_count; ++i) {
+    const double v[4] = {(double)hx[i], (double)hy[i], (double)hz[i], 1.0};
+    for (int a = 0; a < 4; ++a)
+      for (int c = 0; c < 4; ++c) ctx->grip_mom[4 * a + c] += v[a] * v[c];
+  }
   // warps per CTA: least idle lanes when a link's chunks are dealt round-robin to the warps
   int best = 8;
   double best_eff = 0;
@@ -2386,6 +2397,84 @@ extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, con
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaMemcpyAsync(out, ctx->cloud_out.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (kernel_ms) *kernel_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return GTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Mobile-base placement (BasePlanner): B problems x n goals in one launch
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_options* user_opts, gto_base_out* out, double* kernel_ms) {
+  if (!ctx || !in || !out || !in->qc || !in->goal_tf || !out->Q || !out->y) return GTO_ERR_INVALID;
+  if (!ctx->has_robot) return fail(ctx, GTO_ERR_STATE, "gto_set_robot has not been called");
+  if (in->B < 1 || in->n_goals < 1 || in->n_goals > 32) return fail(ctx, GTO_ERR_INVALID, "base placement: need B >= 1 and 1 <= n_goals <= 32");
+  if (in->occupancy && (in->occ_dims[0] < 1 || in->occ_dims[1] < 1 || !(in->occ_resolution > 0)))
+    return fail(ctx, GTO_ERR_INVALID, "base placement: bad occupancy grid");
+  CK(cudaSetDevice(ctx->device));
+  gto_options o;
+  if (user_opts) o = *user_opts; else gto_default_options(&o);
+  const RobotDev& h = ctx->robot_h;
+  const int B = in->B, n = in->n_goals, nd = h.ndof, nopt = h.nopt, P = h.npoints;
+  // one float64 allocation: qc | goals | wp | Qx | y | cost | collision
+  const size_t o_qc = 0, o_goal = o_qc + (size_t)nd, o_wp = o_goal + (size_t)B * n * 12, o_Qx = o_wp + (size_t)P * 3,
+               o_y = o_Qx + (size_t)B * n * nopt, o_cost = o_y + (size_t)B * 3, o_coll = o_cost + (size_t)B, total = o_coll + (size_t)B;
+  CK(ctx->base_d.ensure(total));
+  CK(ctx->base_i.ensure((size_t)2 * B));
+  double* d = ctx->base_d.p;
+  CK(cudaMemcpyAsync(d + o_qc, in->qc, sizeof(double) * nd, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + o_goal, in->goal_tf, sizeof(double) * (size_t)B * n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  BaseParams p;
+  memset(&p, 0, sizeof(p));
+  p.robot = ctx->robot_d;
+  p.B = B; p.n = n;
+  p.qc = d + o_qc; p.goal = d + o_goal; p.w_effort = in->w_effort;
+  {  // movable joints from the root to the gripper link
+    int tmp[GTO_MAX_MOV], c = 0;
+    for (int j = h.grip_mov; j >= 0; j = h.mov_parent[j]) tmp[c++] = j;
+    p.nchain = c;
+    for (int i = 0; i < c; ++i) p.chain[i] = tmp[c - 1 - i];
+  }
+  for (int e = 0; e < 16; ++e) p.mom[e] = ctx->grip_mom[e];
+  p.max_iter = o.max_iter; p.tol_step = o.tol_step; p.tol_grad = o.tol_grad; p.lambda0 = o.lambda0; p.lambda_min = o.lambda_min;
+  p.lambda_max = o.lambda_max; p.eta = o.eta; p.bound_eps = o.bound_eps;
+  if (in->occupancy) {
+    const size_t cells = (size_t)in->occ_dims[0] * in->occ_dims[1];
+    CK(ctx->base_occ.ensure(cells));
+    CK(cudaMemcpyAsync(ctx->base_occ.p, in->occupancy, sizeof(float) * cells, cudaMemcpyHostToDevice, ctx->stream));
+    p.occ = ctx->base_occ.p; p.onx = in->occ_dims[0]; p.ony = in->occ_dims[1];
+    p.oox = in->occ_origin[0]; p.ooy = in->occ_origin[1]; p.ores = in->occ_resolution;
+  }
+  p.wp = d + o_wp; p.npoints = P;
+  p.Qx = d + o_Qx; p.y = d + o_y; p.cost = d + o_cost; p.collision = d + o_coll;
+  p.iters = ctx->base_i.p; p.status = ctx->base_i.p + B;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, ctx->stream));
+  if (in->occupancy) k_base_points<<<1, 256, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, p.qc, d + o_wp);
+  k_base_place<<<B, 32, 0, ctx->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, ctx->stream));
+  // results: optimised rows come back packed, the parameter joints are re-inflated from qc on the host (optas/solver.py:126-159)
+  std::vector<double> qx((size_t)B * n * nopt);
+  std::vector<int> is((size_t)2 * B);
+  CK(cudaMemcpyAsync(qx.data(), d + o_Qx, sizeof(double) * qx.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out->y, d + o_y, sizeof(double) * (size_t)B * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out->cost) CK(cudaMemcpyAsync(out->cost, d + o_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out->collision) CK(cudaMemcpyAsync(out->collision, d + o_coll, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(is.data(), ctx->base_i.p, sizeof(int) * is.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t bi = 0; bi < (size_t)B * n; ++bi) {
+    double* q = out->Q + bi * nd;
+    for (int j = 0; j < nd; ++j) q[j] = in->qc[j];
+    for (int k = 0; k < nopt; ++k) q[h.opt_qidx[k]] = qx[bi * nopt + k];
+  }
+  for (int b = 0; b < B; ++b) {
+    if (out->iters) out->iters[b] = is[b];
+    if (out->status) out->status[b] = is[B + b];
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   if (kernel_ms) *kernel_ms = ms;

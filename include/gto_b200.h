@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GTO_ABI_VERSION 2
+#define GTO_ABI_VERSION 3
 
 /* error codes */
 #define GTO_OK 0
@@ -228,6 +228,39 @@ int gto_plan_cost(gto_ctx* ctx, int32_t n, int32_t T, const double* plans, int32
 int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M);
 int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, const float* depth, int32_t H, int32_t W, const double K[9],
                     const double cam_inv[16], int32_t mode, double epsilon, double w_inside, float* out, double* kernel_ms);
+
+/*
+ * Mobile-base placement: the reference's BasePlanner (gto/base_planner.py:35-168).  One problem ==
+ * one BasePlanner.plan_goalset(qc, RTs) call: find the planar base motion y = (x, y, theta) and one arm configuration per goal
+ * minimising  w_effort |y|^2 + sum_i sum_k | F_gripper(q_i) x_k - T_b(y) RT_i G x_k |^2  subject to -pi <= theta <= pi and the
+ * joint limits (:44-89), every arm seeded with qc and y = 0 (:101-118).  B problems (the random grasp subsets of the reference's
+ * rejection loop, examples/pybullet_gto_planning_mobile.py:187-201) are solved to convergence in one kernel launch; `collision`
+ * is the occupancy-grid count of the robot's surface points at qc seen from the new base (:150-165; grid layout and indexing of
+ * GTORobotModel.setup_occupancy_grid / points_to_offsets_occupancy_numpy, gto/gto_models.py:219-271).
+ */
+typedef struct gto_base_in {
+  int32_t B;               /* problems */
+  int32_t n_goals;         /* goals per problem, 1..32 (builder T = goal_size, base_planner.py:38) */
+  const double* qc;        /* [ndof] */
+  const double* goal_tf;   /* [B][n_goals][12]: RT_i . G as row-major 3x4, current base frame */
+  double w_effort;         /* base_effort_weight (0.01) */
+  const float* occupancy;  /* [occ_dims[0]][occ_dims[1]] cell values, or NULL (collision is then 0) */
+  int32_t occ_dims[2];
+  double occ_origin[2];
+  double occ_resolution;
+} gto_base_in;
+
+typedef struct gto_base_out {
+  double* Q;          /* [B][n_goals][ndof] arm configuration per goal (parameter joints = qc) */
+  double* y;          /* [B][3] (x, y, theta): old base in new base (base_planner.py:49-52) */
+  double* cost;       /* [B] objective, may be NULL */
+  double* collision;  /* [B] may be NULL */
+  int32_t* iters;     /* [B] may be NULL */
+  int32_t* status;    /* [B] GTO_STATUS_*, may be NULL */
+} gto_base_out;
+
+/* opts: max_iter, tol_step, tol_grad, lambda0/min/max, eta, bound_eps are used (NULL = defaults). */
+int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_options* opts, gto_base_out* out, double* kernel_ms);
 
 #ifdef __cplusplus
 }

@@ -46,3 +46,31 @@ def small_workload(config="C2", table_name=None, B=4, n_field=64, seed=7):
         assert t.nopt == w.table.nopt and t.ndof == w.table.ndof
         w.table = t
     return w
+
+
+def base_placement_case(table_name="panda_small", B=4, n=4, seed=3, spread=1.5, with_grid=True):
+    """Seeded base-placement problems: goals are gripper poses of random arm configurations seen from a
+    base displaced by a random planar motion, so every problem has a zero-residual placement the effort term pulls on."""
+    import os
+    import base_oracle as BO
+    from grasptrajopt_b200 import workloads as W
+    from grasptrajopt_b200.robot_table import RobotTable
+
+    t = RobotTable.load(os.path.join(W.ASSETS, table_name + ".npz"))
+    qc = (W.PANDA_QC if t.ndof == 9 else W.FETCH_QC).copy()
+    rng = np.random.default_rng(seed)
+    Ginv = np.linalg.inv(O.hom(t.G))
+    RTs = np.zeros((B, n, 4, 4))
+    for b in range(B):
+        ystar = np.array([rng.uniform(-spread, spread), rng.uniform(-spread, spread), rng.uniform(-1.0, 1.0)])
+        Tbi = np.linalg.inv(BO.base_tf(ystar))
+        for i in range(n):
+            q = qc.copy()
+            q[t.opt_qidx] = np.clip(qc[t.opt_qidx] + rng.normal(0, 0.4, t.nopt), t.lo, t.hi)
+            RTs[b, i] = Tbi @ O.gripper_frame(t, q) @ Ginv
+    grid = origin = None
+    res = 0.05
+    if with_grid:
+        grid = (rng.random((60, 70)) < 0.05).astype(np.float32)
+        origin = np.array([-1.0, -1.7])
+    return t, qc, RTs, grid, origin, res

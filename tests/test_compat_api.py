@@ -171,3 +171,21 @@ def test_reference_urdfs_load_and_match_assets():
     np.testing.assert_allclose(t.mov_origin, ref.mov_origin)
     np.testing.assert_allclose(t.lo, ref.lo)
     assert robot.ndof == 9 and robot.optimized_joint_names[0] == "panda_joint1"
+
+
+def test_base_planner_surface(model):
+    """gto.BasePlanner keeps the reference's constructor / setup_optimization / plan_goalset names (gto/base_planner.py:19-94);
+    without a GPU the call fails loudly instead of falling back to anything."""
+    from gto.base_planner import BasePlanner
+    from grasptrajopt_b200 import capi
+
+    bp = BasePlanner(model, "tool", "tool")
+    assert bp.task_name == "base_pose_estimator" and bp.gripper_points.shape[1] == 3
+    bp.setup_optimization(goal_size=2, base_effort_weight=0.02)
+    assert bp.goal_size == 2 and bp.base_effort_weight == 0.02
+    with pytest.raises(ValueError):
+        bp.setup_optimization(goal_size=40)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises((capi.GtoError, capi.GtoLibraryError)):
+            bp.plan_goalset(np.zeros(3), np.tile(np.eye(4), (2, 1, 1)))

@@ -105,3 +105,29 @@ def test_ik_batch_equals_single_solves(robot):
         q1, ep1, er1, _ = ik.solve_ik(q0.reshape(-1, 1), RTs[i], np.zeros(robot.field_size), [0, 0, 0])
         np.testing.assert_array_equal(q1, qb[i])
         assert ep1 == pytest.approx(ep[i], abs=1e-12)
+
+
+def test_base_planner_matches_oracle(robot):
+    """gto.BasePlanner (reference gto/base_planner.py:19-168) through the reference signature, against oracle/base_oracle.py."""
+    import base_oracle as BO
+    from gto.base_planner import BasePlanner
+
+    rng = np.random.default_rng(5)
+    robot.setup_occupancy_grid(np.column_stack([rng.uniform(0, 1.2, 400), rng.uniform(-0.8, 0.8, 400), rng.uniform(0.02, 0.5, 400)]))
+    bp = BasePlanner(robot, "tool", "tool")
+    bp.setup_optimization(goal_size=2, base_effort_weight=0.01)
+    qc = np.array([0.2, -0.3, 0.01])
+    Tb = BO.base_tf(np.array([0.3, -0.2, 0.25]))
+    RTs = np.stack([np.linalg.inv(Tb) @ robot.get_global_link_transform("tool", q).toarray() for q in ([0.9, 0.4, 0.01], [-0.5, 1.0, 0.01])])
+    Q, y, err_pos, err_rot, cost = bp.plan_goalset(qc, RTs)
+    assert Q.shape == (3, 2) and y.shape == (3,) and err_pos.shape == (2,) and err_rot.shape == (2,)
+    t = robot.to_table("tool", "tool")
+    grid = np.asarray(robot.occupancy_grid, np.float32).reshape(robot.occupancy_grid_shape)
+    r = BO.solve_base(BO.BaseProblem(t, qc, RTs, 0.01, grid, np.asarray(robot.occupancy_grid_origin).reshape(2), robot.grid_resolution))
+    tol = 1e-6 if r.status == 0 else 1e-4
+    assert np.abs(y - r.y).max() < tol and np.abs(Q.T - r.Q).max() < tol
+    assert cost == r.collision
+    assert np.allclose(err_pos, r.err_pos, atol=1e-5) and np.allclose(err_rot, r.err_rot, atol=1e-2)
+    # the batched form returns the same bits for the same problem
+    out = bp.plan_goalset_batch(qc, np.stack([RTs, RTs, RTs]))
+    assert np.array_equal(out["y"][0], y) and np.array_equal(out["y"][2], y)

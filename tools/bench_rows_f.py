@@ -1,6 +1,8 @@
 """Measurements for the SURVEY.md section 8(f) rows built so far (not part of bench.py's contract line):
   row 1  batched IK seeding   -- Panda, B goals in one batch (T = 3 layout, goal rows only), vs the C oracle on the host cores
   row 2  cost-field build     -- DepthPointCloud.get_sdf_cost on a 640x480 depth image, 128^3 grid, GPU kernel vs scikit-learn KD-tree
+  row 3  seed ranking         -- gto_plan_cost over 256 candidate plans x 30 knots x 2000 points vs the NumPy oracle
+  row 4  base placement       -- gto_base_place, 4096 problems x 10 goals in one launch vs oracle/base_oracle.py on one host core
 Prints one JSON object."""
 import json, os, sys, time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -66,4 +68,53 @@ for n in (64, 128):
         rec["max_abs_cost_diff"] = float(np.abs(c_gpu - c_cpu).max())
         rec["mismatch_frac_gt_1e-5"] = float((np.abs(c_gpu - c_cpu) > 1e-5).mean())
     out[f"cost_field_{n}"] = rec
+
+# ---- row 3: seed ranking (value-only pass over whole plans) ----
+w2 = W.make_workload("C2")
+t2, b2 = w2.table, w2.batch
+ctx2 = capi.GtoContext(0)
+ctx2.set_robot(t2)
+cf = w2.fields[int(b2.field_obs[0])]
+ctx2.set_field(0, cf.cost, cf.origin, cf.pitch)
+plans = b2.q_seed  # 256 candidate seeds x 30 knots
+ctx2.plan_cost(plans, 0)
+t0 = time.perf_counter()
+for _ in range(5):
+    c_gpu, _ = ctx2.plan_cost(plans, 0)
+dtg = (time.perf_counter() - t0) / 5
+import gto_oracle as O
+fld = O.Field(cf.cost, cf.origin, cf.pitch)
+t0 = time.perf_counter()
+c_cpu = np.array([O.plan_cost_nearest(t2, plans[i], fld, np.zeros(3))[0] for i in range(16)])
+dtc = (time.perf_counter() - t0) / 16
+out["seed_ranking"] = {"plans": int(plans.shape[0]), "knots": int(plans.shape[1]), "points": int(t2.npoints), "gpu_call_ms": 1e3 * dtg,
+                       "plans_per_s_gpu": plans.shape[0] / dtg, "plans_per_s_numpy_1core": 1.0 / dtc, "cpu_sample": 16,
+                       "max_rel_diff_vs_oracle": float(np.abs(c_gpu[:16] - c_cpu).max() / max(1e-12, np.abs(c_cpu).max())),
+                       "note": "float32 FK on the GPU vs float64 in the oracle: a point within rounding of a cell face may read the neighbouring node"}
+ctx2.close()
+
+# ---- row 4: mobile-base placement ----
+import base_oracle as BO
+from helpers import base_placement_case
+for name, Bn, n in (("fetch_small", 4096, 10), ("panda_small", 4096, 10)):
+    tb, qcb, RTb, grid, origin, res = base_placement_case(name, B=Bn, n=n, seed=21, spread=0.5)
+    ctxb = capi.GtoContext(0)
+    ctxb.set_robot(tb)
+    ctxb.base_place(qcb, RTb[:64], 0.01, grid, origin, res)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ob = ctxb.base_place(qcb, RTb, 0.01, grid, origin, res)
+    dtb = (time.perf_counter() - t0) / 3
+    ns = 8
+    t0 = time.perf_counter()
+    ro = [BO.solve_base(BO.BaseProblem(tb, qcb, RTb[i], 0.01, grid, origin, res)) for i in range(ns)]
+    dto = (time.perf_counter() - t0) / ns
+    out[f"base_placement_{name}"] = {
+        "problems": Bn, "goals_per_problem": n, "kernel_ms": ob["kernel_ms"], "call_ms_e2e": 1e3 * dtb, "problems_per_s_e2e": Bn / dtb,
+        "converged": int((ob["status"] == 0).sum()), "at_max_iter": int((ob["status"] == 1).sum()), "iters_mean": float(ob["iters"].mean()),
+        "collision_free": int((ob["collision"] == 0).sum()),
+        "cpu_port": {"problems_per_s": 1.0 / dto, "cores": 1, "kind": "port (oracle/base_oracle.py, NumPy float64)", "sample": ns,
+                     "max_abs_dy_vs_gpu": float(max(np.abs(ro[i].y - ob["y"][i]).max() for i in range(ns))),
+                     "iters_equal": bool(all(ro[i].iters == ob["iters"][i] for i in range(ns)))}}
+    ctxb.close()
 print(json.dumps(out))
