@@ -24,7 +24,7 @@
 // matters is problems per second (tools/bench_rows_f.py).
 #pragma once
 
-#define BASE_NV (GTO_MAX_OPT + 3)  // parameters seen by one goal: its arm joints + (x, y, theta)
+// NP = padded number of optimised joints (8 or 16); a goal sees NP + 3 parameters: its arm joints + (x, y, theta)
 
 struct BaseParams {
   const RobotDev* robot;
@@ -106,14 +106,15 @@ __global__ void k_base_points(const RobotDev* robot, const float* px, const floa
 
 // Linearisation of one goal at (q, y): cost, half gradient g[a] = <E_a, D Mom>, Gram matrix G[a][b] = <E_a Mom, E_b> over the
 // parameters a = arm joints 0..nopt-1, then x, y, theta at nopt..nopt+2.
+template <int NP>
 __device__ __noinline__ void base_goal_linearize(const BaseParams& P, const double* __restrict__ qx, const double* __restrict__ yv,
                                                  const double* __restrict__ A, double& cost, double* __restrict__ g,
-                                                 double (*__restrict__ G)[BASE_NV]) {
+                                                 double (*__restrict__ G)[NP + 3]) {
   const RobotDev& R = *P.robot;
   const int nopt = R.nopt, nv = nopt + 3;
-  double E[BASE_NV][12];
-  double om[GTO_MAX_OPT][3], mm[GTO_MAX_OPT][3];
-  bool on_chain[GTO_MAX_OPT];
+  double E[NP + 3][12];
+  double om[NP][3], mm[NP][3];
+  bool on_chain[NP];
   for (int k = 0; k < nopt; ++k) on_chain[k] = false;
   // chain FK root -> gripper link
   double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -218,8 +219,9 @@ __device__ __noinline__ void base_goal_linearize(const BaseParams& P, const doub
   }
 }
 
-// solve the SPD system M X = R (order n <= GTO_MAX_OPT, 4 right-hand sides) by Cholesky, in place in R
-__device__ __forceinline__ void base_chol_solve4(double (*M)[GTO_MAX_OPT], double (*Rh)[4], int n) {
+// solve the SPD system M X = R (order n <= NP, 4 right-hand sides) by Cholesky, in place in R
+template <int NP>
+__device__ __forceinline__ void base_chol_solve4(double (*M)[NP], double (*Rh)[4], int n) {
   for (int j = 0; j < n; ++j) {
     double d = M[j][j];
     for (int k = 0; k < j; ++k) d -= M[j][k] * M[j][k];
@@ -246,6 +248,7 @@ __device__ __forceinline__ void base_chol_solve4(double (*M)[GTO_MAX_OPT], doubl
   }
 }
 
+template <int NP>
 __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseParams P) {
   const RobotDev& R = *P.robot;
   const int b = blockIdx.x, lane = threadIdx.x;
@@ -255,16 +258,18 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
   const double ylo[3] = {-BIG, -BIG, -PI}, yhi[3] = {BIG, BIG, PI};
   double A[12];
   for (int e = 0; e < 12; ++e) A[e] = act ? P.goal[((long long)b * P.n + lane) * 12 + e] : 0.0;
-  double qx[GTO_MAX_OPT], qn[GTO_MAX_OPT], yv[3] = {0.0, 0.0, 0.0}, yn[3];
+  double qx[NP], qn[NP], yv[3] = {0.0, 0.0, 0.0}, yn[3];
   for (int k = 0; k < nopt; ++k) qx[k] = P.qc[R.opt_qidx[k]];
-  double G[BASE_NV][BASE_NV], g[BASE_NV], Gt[BASE_NV][BASE_NV], gtr[BASE_NV];
+  double Ga[NP + 3][NP + 3], ga[NP + 3], Gb[NP + 3][NP + 3], gb[NP + 3];
+  double(*G)[NP + 3] = Ga, (*Gt)[NP + 3] = Gb;  // current / trial linearisation, swapped on acceptance
+  double *g = ga, *gtr = gb;
   for (int a = 0; a < nv; ++a) {
     g[a] = 0.0;
     gtr[a] = 0.0;
     for (int c = 0; c < nv; ++c) { G[a][c] = 0.0; Gt[a][c] = 0.0; }
   }
   double ci = 0.0;
-  if (act) base_goal_linearize(P, qx, yv, A, ci, g, G);
+  if (act) base_goal_linearize<NP>(P, qx, yv, A, ci, g, G);
   double F = warp_sum(act ? ci : 0.0) + P.w_effort * (yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
   double lam = P.lambda0, nu = 2.0;
   int status = GTO_STATUS_MAX_ITER, it = 0;
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
         S[c][a] = S[a][c];
       }
     }
-    bool fy[3], fq[GTO_MAX_OPT];
+    bool fy[3], fq[NP];
     double pgmax = 0.0;
     for (int a = 0; a < 3; ++a) {
       fy[a] = (yv[a] <= ylo[a] + P.bound_eps && gy[a] > 0.0) || (yv[a] >= yhi[a] - P.bound_eps && gy[a] < 0.0);
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
     pgmax = 2.0 * fmax(pgmax, warp_max(pgq));
     if (pgmax <= P.tol_grad) { status = GTO_STATUS_CONVERGED; break; }
     // ---- per-goal solve H_i Z = [C_i | -g_i], Schur complement on the base block ----
-    double Hd[GTO_MAX_OPT][GTO_MAX_OPT], Z[GTO_MAX_OPT][4], Cm[GTO_MAX_OPT][3];
+    double Hd[NP][NP], Z[NP][4], Cm[NP][3];
     for (int k = 0; k < nopt; ++k) {
       for (int l = 0; l < nopt; ++l) Hd[k][l] = (fq[k] || fq[l]) ? 0.0 : G[k][l];
       Hd[k][k] = fq[k] ? 1.0 : G[k][k] + lam * G[k][k];
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
       }
       Z[k][3] = fq[k] ? 0.0 : -g[k];
     }
-    base_chol_solve4(Hd, Z, nopt);
+    base_chol_solve4<NP>(Hd, Z, nopt);
     double M[3][4];
     for (int a = 0; a < 3; ++a) {
       double v = 0.0;
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
       dy[p] = v / M[p][p];
     }
     // ---- projected trial point ----
-    double dq[GTO_MAX_OPT], stepm = 0.0;
+    double dq[NP], stepm = 0.0;
     for (int k = 0; k < nopt; ++k) {
       const double d = Z[k][3] - (Z[k][0] * dy[0] + Z[k][1] * dy[1] + Z[k][2] * dy[2]);
       qn[k] = fmin(fmax(qx[k] + d, R.lo[k]), R.hi[k]);
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
     ++it;
     // ---- trial linearisation, acceptance ----
     double ct = 0.0;
-    if (act) base_goal_linearize(P, qn, yn, A, ct, gtr, Gt);
+    if (act) base_goal_linearize<NP>(P, qn, yn, A, ct, gtr, Gt);
     const double Ft = warp_sum(act ? ct : 0.0) + P.w_effort * (yn[0] * yn[0] + yn[1] * yn[1] + yn[2] * yn[2]);
     if (!(Ft == Ft) || fabs(Ft) > 1e300) { status = GTO_STATUS_NAN; break; }
     const double ared = 0.5 * (F - Ft);
@@ -369,9 +374,9 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
       const double t = 2.0 * fmin(rho, 1.0) - 1.0;
       for (int k = 0; k < nopt; ++k) qx[k] = qn[k];
       for (int a = 0; a < 3; ++a) yv[a] = yn[a];
-      for (int a = 0; a < nv; ++a) {
-        g[a] = gtr[a];
-        for (int c = 0; c < nv; ++c) G[a][c] = Gt[a][c];
+      {
+        double(*tG)[NP + 3] = G; G = Gt; Gt = tG;
+        double* tg = g; g = gtr; gtr = tg;
       }
       F = Ft;
       lam = fmax(P.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - t * t * t));

@@ -2454,7 +2454,8 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, ctx->stream));
   if (in->occupancy) k_base_points<<<1, 256, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, p.qc, d + o_wp);
-  k_base_place<<<B, 32, 0, ctx->stream>>>(p);
+  if (nopt <= 8) k_base_place<8><<<B, 32, 0, ctx->stream>>>(p);
+  else k_base_place<16><<<B, 32, 0, ctx->stream>>>(p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, ctx->stream));
   // results: optimised rows come back packed, the parameter joints are re-inflated from qc on the host (optas/solver.py:126-159)

@@ -6,7 +6,7 @@
 Prints one JSON object."""
 import json, os, sys, time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (REPO, os.path.join(REPO, "oracle"), os.path.join(REPO, "tests"), os.path.join(REPO, "grasptrajopt_b200", "compat")):
+for p in (REPO, os.path.join(REPO, "oracle"), os.path.join(REPO, "tests"), os.path.join(REPO, "grasptrajopt_b200", "compat"), os.path.join(REPO, "tools")):
     sys.path.insert(0, p)
 import numpy as np
 from grasptrajopt_b200 import capi, workloads as W, scenes as S
@@ -94,27 +94,6 @@ out["seed_ranking"] = {"plans": int(plans.shape[0]), "knots": int(plans.shape[1]
 ctx2.close()
 
 # ---- row 4: mobile-base placement ----
-import base_oracle as BO
-from helpers import base_placement_case
-for name, Bn, n in (("fetch_small", 4096, 10), ("panda_small", 4096, 10)):
-    tb, qcb, RTb, grid, origin, res = base_placement_case(name, B=Bn, n=n, seed=21, spread=0.5)
-    ctxb = capi.GtoContext(0)
-    ctxb.set_robot(tb)
-    ctxb.base_place(qcb, RTb[:64], 0.01, grid, origin, res)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        ob = ctxb.base_place(qcb, RTb, 0.01, grid, origin, res)
-    dtb = (time.perf_counter() - t0) / 3
-    ns = 8
-    t0 = time.perf_counter()
-    ro = [BO.solve_base(BO.BaseProblem(tb, qcb, RTb[i], 0.01, grid, origin, res)) for i in range(ns)]
-    dto = (time.perf_counter() - t0) / ns
-    out[f"base_placement_{name}"] = {
-        "problems": Bn, "goals_per_problem": n, "kernel_ms": ob["kernel_ms"], "call_ms_e2e": 1e3 * dtb, "problems_per_s_e2e": Bn / dtb,
-        "converged": int((ob["status"] == 0).sum()), "at_max_iter": int((ob["status"] == 1).sum()), "iters_mean": float(ob["iters"].mean()),
-        "collision_free": int((ob["collision"] == 0).sum()),
-        "cpu_port": {"problems_per_s": 1.0 / dto, "cores": 1, "kind": "port (oracle/base_oracle.py, NumPy float64)", "sample": ns,
-                     "max_abs_dy_vs_gpu": float(max(np.abs(ro[i].y - ob["y"][i]).max() for i in range(ns))),
-                     "iters_equal": bool(all(ro[i].iters == ob["iters"][i] for i in range(ns)))}}
-    ctxb.close()
+import bench_base
+out.update(bench_base.run())
 print(json.dumps(out))
