@@ -414,3 +414,393 @@ __global__ void __launch_bounds__(32) k_base_place(const __grid_constant__ BaseP
     P.status[b] = status;
   }
 }
+
+// ==================================================================================================================
+// k_base_place_sm: the default kernel.  Same arithmetic as k_base_place above (kept as the A/B reference, GTO_BASE_V1=1),
+// but (1) the per-goal arrays (current and trial Gram matrices, gradients, and one scratch area shared by the linearisation's
+// E / twist tables and the step's H_i / Z / C_i) live in shared memory, element-major with a 32-lane stride, so a lane's
+// accesses are conflict-free and nothing spills to local memory / DRAM; (2) a warp carries floor(32 / n) problems, one per
+// group of n consecutive lanes: the warp sums become group sums (n shuffles, fixed order), and a group that has finished
+// idles (its state is frozen) until the slowest group of the warp is done.
+// ==================================================================================================================
+struct LaneArr {  // element e of this lane's array
+  double* p;
+  __device__ __forceinline__ double& operator[](int e) const { return p[e * 32]; }
+};
+
+template <int NP>
+__host__ __device__ constexpr int base_sm_doubles_per_lane() {
+  constexpr int NV = NP + 3;
+  constexpr int s1 = 12 * NV + 6 * NP, s2 = NP * NP + 7 * NP;
+  return 2 * NV * NV + 2 * NV + (s1 > s2 ? s1 : s2);
+}
+
+__device__ __forceinline__ double group_sum(double v, int gbase, int n) {
+  double s = 0.0;
+  for (int j = 0; j < n; ++j) s += __shfl_sync(0xffffffffu, v, (gbase + j) & 31);
+  return s;
+}
+__device__ __forceinline__ double group_max(double v, int gbase, int n) {
+  double s = 0.0;
+  for (int j = 0; j < n; ++j) s = fmax(s, __shfl_sync(0xffffffffu, v, (gbase + j) & 31));
+  return s;
+}
+
+// linearisation of one goal (see base_goal_linearize); G [NV*NV], g [NV] and the scratch area are the lane's shared-memory arrays
+template <int NP>
+__device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const double* __restrict__ qx, const double* __restrict__ yv,
+                                                    const double* __restrict__ A, double& cost, LaneArr g, LaneArr G, LaneArr scr) {
+  constexpr int NV = NP + 3;
+  const RobotDev& R = *P.robot;
+  const int nopt = R.nopt, nv = nopt + 3;
+  const LaneArr E = scr;                          // [NV][12]
+  const LaneArr om = {scr.p + 12 * NV * 32};      // [NP][3]
+  const LaneArr mm = {scr.p + (12 * NV + 3 * NP) * 32};
+  unsigned on_chain = 0u;
+  double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  for (int c = 0; c < P.nchain; ++c) {
+    const int j = P.chain[c];
+    double U[12];
+    mul34(T, R.mov_origin_d[j], U);
+    const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
+    const double zx = U[0] * ax + U[1] * ay + U[2] * az, zy = U[4] * ax + U[5] * ay + U[6] * az, zz = U[8] * ax + U[9] * ay + U[10] * az;
+    const int k = R.mov_opt[j];
+    const double qj = k >= 0 ? qx[k] : P.qc[R.mov_qidx[j]];
+    if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
+      if (k >= 0) {
+        on_chain |= 1u << k;
+        om[3 * k] = zx; om[3 * k + 1] = zy; om[3 * k + 2] = zz;
+        mm[3 * k] = U[7] * zz - U[11] * zy;  // o x z
+        mm[3 * k + 1] = U[11] * zx - U[3] * zz;
+        mm[3 * k + 2] = U[3] * zy - U[7] * zx;
+      }
+      double s, cs;
+      sincos(qj, &s, &cs);
+      const double v = 1.0 - cs;
+      double M[12];
+      M[0] = 1.0 - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay; M[2] = s * ay + v * ax * az; M[3] = 0.0;
+      M[4] = s * az + v * ax * ay; M[5] = 1.0 - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az; M[7] = 0.0;
+      M[8] = -s * ay + v * ax * az; M[9] = s * ax + v * ay * az; M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
+      mul34(U, M, T);
+    } else {
+      if (k >= 0) {
+        on_chain |= 1u << k;
+        om[3 * k] = 0.0; om[3 * k + 1] = 0.0; om[3 * k + 2] = 0.0;
+        mm[3 * k] = zx; mm[3 * k + 1] = zy; mm[3 * k + 2] = zz;
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) T[e] = U[e];
+      T[3] += qj * zx; T[7] += qj * zy; T[11] += qj * zz;
+    }
+  }
+  double F[12];
+  mul34(T, R.grip_tf_d, F);
+  double s, c;
+  sincos(yv[2], &s, &c);
+  double D[12], RA[12];
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    const double a0 = A[col], a1 = A[4 + col], a2 = A[8 + col];
+    const double m0 = c * a0 - s * a1 + (col == 3 ? yv[0] : 0.0);
+    const double m1 = s * a0 + c * a1 + (col == 3 ? yv[1] : 0.0);
+    D[col] = F[col] - m0;
+    D[4 + col] = F[4 + col] - m1;
+    D[8 + col] = F[8 + col] - a2;
+    RA[col] = -s * a0 - c * a1;
+    RA[4 + col] = c * a0 - s * a1;
+    RA[8 + col] = 0.0;
+  }
+  for (int k = 0; k < nopt; ++k) {
+    if (!((on_chain >> k) & 1u)) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) E[12 * k + e] = 0.0;
+      continue;
+    }
+    const double wx = om[3 * k], wy = om[3 * k + 1], wz = om[3 * k + 2];
+    const double m0 = mm[3 * k], m1 = mm[3 * k + 1], m2 = mm[3 * k + 2];
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+      const double f0 = F[col], f1 = F[4 + col], f2 = F[8 + col];
+      E[12 * k + col] = wy * f2 - wz * f1 + (col == 3 ? m0 : 0.0);
+      E[12 * k + 4 + col] = wz * f0 - wx * f2 + (col == 3 ? m1 : 0.0);
+      E[12 * k + 8 + col] = wx * f1 - wy * f0 + (col == 3 ? m2 : 0.0);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 12; ++e) { E[12 * nopt + e] = 0.0; E[12 * (nopt + 1) + e] = 0.0; E[12 * (nopt + 2) + e] = -RA[e]; }
+  E[12 * nopt + 3] = -1.0;
+  E[12 * (nopt + 1) + 7] = -1.0;
+  double DM[12];
+  double cs = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+      double v = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v += D[4 * r + m] * P.mom[4 * m + col];
+      DM[4 * r + col] = v;
+      cs += v * D[4 * r + col];
+    }
+  cost = cs;
+  for (int a = 0; a < nv; ++a) {
+    double Ea[12], EM[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) Ea[e] = E[12 * a + e];
+    double v = 0.0;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) v += Ea[e] * DM[e];
+    g[a] = v;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int col = 0; col < 4; ++col) {
+        double u = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) u += Ea[4 * r + m] * P.mom[4 * m + col];
+        EM[4 * r + col] = u;
+      }
+    for (int b = a; b < nv; ++b) {
+      double u = 0.0;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) u += EM[e] * E[12 * b + e];
+      G[a * NV + b] = u;
+      G[b * NV + a] = u;
+    }
+  }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ BaseParams P) {
+  constexpr int NV = NP + 3;
+  extern __shared__ double base_sm[];
+  const RobotDev& R = *P.robot;
+  const int lane = threadIdx.x, n = P.n, gpw = 32 / n;
+  const int grp = lane / n, gbase = grp * n, gl = lane - gbase;
+  const int b = blockIdx.x * gpw + grp;
+  const int nopt = R.nopt;
+  const bool act = grp < gpw && b < P.B;
+  const double BIG = 1e30, PI = 3.14159265358979323846;
+  const double ylo[3] = {-BIG, -BIG, -PI}, yhi[3] = {BIG, BIG, PI};
+  LaneArr G = {base_sm + lane}, Gt = {base_sm + NV * NV * 32 + lane};
+  LaneArr g = {base_sm + 2 * NV * NV * 32 + lane}, gtr = {base_sm + (2 * NV * NV + NV) * 32 + lane};
+  const LaneArr scr = {base_sm + (2 * NV * NV + 2 * NV) * 32 + lane};
+  const LaneArr Hd = scr, Z = {scr.p + NP * NP * 32}, Cm = {scr.p + (NP * NP + 4 * NP) * 32};
+  double A[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) A[e] = act ? P.goal[((long long)b * n + gl) * 12 + e] : 0.0;
+  double qx[NP], qn[NP], dq[NP], yv[3] = {0.0, 0.0, 0.0}, yn[3];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) qx[k] = k < nopt ? P.qc[R.opt_qidx[k]] : 0.0;
+  for (int a = 0; a < NV; ++a) {
+    g[a] = 0.0;
+    gtr[a] = 0.0;
+    for (int c = 0; c < NV; ++c) { G[a * NV + c] = 0.0; Gt[a * NV + c] = 0.0; }
+  }
+  double ci = 0.0;
+  if (act) base_goal_linearize_sm<NP>(P, qx, yv, A, ci, g, G, scr);
+  double F = group_sum(act ? ci : 0.0, gbase, n);
+  double lam = P.lambda0, nu = 2.0;
+  int status = GTO_STATUS_MAX_ITER, it = 0;
+  bool done = !act;
+  while (!__all_sync(0xffffffffu, done || it >= P.max_iter)) {
+    bool live = !done && it < P.max_iter;
+    // ---- base block and gradient (group sums), active sets ----
+    double S[3][3], gy[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      gy[a] = group_sum(g[nopt + a], gbase, n) + P.w_effort * yv[a];
+#pragma unroll
+      for (int c = a; c < 3; ++c) {
+        S[a][c] = group_sum(G[(nopt + a) * NV + nopt + c], gbase, n) + (a == c ? P.w_effort : 0.0);
+        S[c][a] = S[a][c];
+      }
+    }
+    bool fy[3];
+    unsigned fq = 0u;
+    double pgmax = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      fy[a] = (yv[a] <= ylo[a] + P.bound_eps && gy[a] > 0.0) || (yv[a] >= yhi[a] - P.bound_eps && gy[a] < 0.0);
+      if (!fy[a]) pgmax = fmax(pgmax, fabs(gy[a]));
+    }
+    double pgq = 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      if (k < nopt) {
+        const double gk = g[k];
+        const bool f = (qx[k] <= R.lo[k] + P.bound_eps && gk > 0.0) || (qx[k] >= R.hi[k] - P.bound_eps && gk < 0.0) ||
+                       !((R.grip_optmask >> k) & 1u) || !act;
+        if (f) fq |= 1u << k;
+        else pgq = fmax(pgq, fabs(gk));
+      }
+    }
+    pgmax = 2.0 * fmax(pgmax, group_max(pgq, gbase, n));
+    if (live && pgmax <= P.tol_grad) { status = GTO_STATUS_CONVERGED; done = true; live = false; }
+    // ---- per-goal solve H_i Z = [C_i | -g_i] (Cholesky in shared memory), Schur complement on the base block ----
+    for (int k = 0; k < nopt; ++k) {
+      const bool fk = (fq >> k) & 1u;
+      for (int l = 0; l < nopt; ++l) Hd[k * NP + l] = (fk || ((fq >> l) & 1u)) ? 0.0 : G[k * NV + l];
+      const double gkk = G[k * NV + k];
+      Hd[k * NP + k] = fk ? 1.0 : gkk + lam * gkk;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double cv = (fk || fy[a]) ? 0.0 : G[k * NV + nopt + a];
+        Cm[3 * k + a] = cv;
+        Z[4 * k + a] = cv;
+      }
+      Z[4 * k + 3] = fk ? 0.0 : -g[k];
+    }
+    for (int j = 0; j < nopt; ++j) {
+      double d = Hd[j * NP + j];
+      for (int k = 0; k < j; ++k) { const double v = Hd[j * NP + k]; d -= v * v; }
+      d = sqrt(d);
+      Hd[j * NP + j] = d;
+      const double inv = 1.0 / d;
+      for (int i = j + 1; i < nopt; ++i) {
+        double v = Hd[i * NP + j];
+        for (int k = 0; k < j; ++k) v -= Hd[i * NP + k] * Hd[j * NP + k];
+        Hd[i * NP + j] = v * inv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      for (int i = 0; i < nopt; ++i) {
+        double v = Z[4 * i + r];
+        for (int k = 0; k < i; ++k) v -= Hd[i * NP + k] * Z[4 * k + r];
+        Z[4 * i + r] = v / Hd[i * NP + i];
+      }
+      for (int i = nopt - 1; i >= 0; --i) {
+        double v = Z[4 * i + r];
+        for (int k = i + 1; k < nopt; ++k) v -= Hd[k * NP + i] * Z[4 * k + r];
+        Z[4 * i + r] = v / Hd[i * NP + i];
+      }
+    }
+    double M[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double v = 0.0;
+      for (int k = 0; k < nopt; ++k) v += Cm[3 * k + a] * Z[4 * k + 3];
+      M[a][3] = (fy[a] ? 0.0 : -gy[a]) - group_sum(v, gbase, n);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double u = 0.0;
+        for (int k = 0; k < nopt; ++k) u += Cm[3 * k + a] * Z[4 * k + c];
+        const double base = (fy[a] || fy[c]) ? (a == c ? 1.0 : 0.0) : S[a][c] + (a == c ? lam * S[a][a] : 0.0);
+        M[a][c] = base - group_sum(u, gbase, n);
+      }
+    }
+    double dy[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const double inv = 1.0 / M[p][p];
+#pragma unroll
+      for (int r = p + 1; r < 3; ++r) {
+        const double f = M[r][p] * inv;
+#pragma unroll
+        for (int c = p; c < 4; ++c) M[r][c] -= f * M[p][c];
+      }
+    }
+#pragma unroll
+    for (int p = 2; p >= 0; --p) {
+      double v = M[p][3];
+#pragma unroll
+      for (int c = p + 1; c < 3; ++c) v -= M[p][c] * dy[c];
+      dy[p] = v / M[p][p];
+    }
+    // ---- projected trial point ----
+    double stepm = 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      if (k < nopt) {
+        const double d = Z[4 * k + 3] - (Z[4 * k] * dy[0] + Z[4 * k + 1] * dy[1] + Z[4 * k + 2] * dy[2]);
+        qn[k] = fmin(fmax(qx[k] + d, R.lo[k]), R.hi[k]);
+        dq[k] = act ? qn[k] - qx[k] : 0.0;
+        stepm = fmax(stepm, fabs(dq[k]));
+      } else {
+        qn[k] = 0.0;
+        dq[k] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      yn[a] = fmin(fmax(yv[a] + dy[a], ylo[a]), yhi[a]);
+      dy[a] = yn[a] - yv[a];
+    }
+    stepm = fmax(group_max(stepm, gbase, n), fmax(fabs(dy[0]), fmax(fabs(dy[1]), fabs(dy[2]))));
+    // ---- predicted reduction with the undamped model ----
+    double pq = 0.0, cd[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      if (k < nopt) {
+        const double c0 = G[k * NV + nopt], c1 = G[k * NV + nopt + 1], c2 = G[k * NV + nopt + 2];
+        double ad = c0 * dy[0] + c1 * dy[1] + c2 * dy[2];
+#pragma unroll
+        for (int l = 0; l < NP; ++l)
+          if (l < nopt) ad += G[k * NV + l] * dq[l];
+        pq += g[k] * dq[k] + 0.5 * dq[k] * ad;
+        cd[0] += c0 * dq[k]; cd[1] += c1 * dq[k]; cd[2] += c2 * dq[k];
+      }
+    }
+    pq = group_sum(pq, gbase, n);
+    double py = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double ady = S[a][0] * dy[0] + S[a][1] * dy[1] + S[a][2] * dy[2] + group_sum(cd[a], gbase, n);
+      py += gy[a] * dy[a] + 0.5 * dy[a] * ady;
+    }
+    const double pred = -(pq + py);
+    if (live) ++it;
+    // ---- trial linearisation, acceptance ----
+    double ct = 0.0;
+    if (act) base_goal_linearize_sm<NP>(P, qn, yn, A, ct, gtr, Gt, scr);
+    const double Ft = group_sum(act ? ct : 0.0, gbase, n) + P.w_effort * (yn[0] * yn[0] + yn[1] * yn[1] + yn[2] * yn[2]);
+    if (live && (!(Ft == Ft) || fabs(Ft) > 1e300)) { status = GTO_STATUS_NAN; done = true; live = false; }
+    if (live) {
+      const double ared = 0.5 * (F - Ft);
+      if (pred > 0.0 && ared >= P.eta * pred) {
+        const double rho = ared / pred;
+        const double t = 2.0 * fmin(rho, 1.0) - 1.0;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) qx[k] = qn[k];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) yv[a] = yn[a];
+        { double* tp = G.p; G.p = Gt.p; Gt.p = tp; tp = g.p; g.p = gtr.p; gtr.p = tp; }
+        F = Ft;
+        lam = fmax(P.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - t * t * t));
+        nu = 2.0;
+        if (stepm <= P.tol_step) { status = GTO_STATUS_CONVERGED; done = true; }
+      } else {
+        if (pred <= 0.0 && stepm <= P.tol_step) { status = GTO_STATUS_CONVERGED; done = true; }
+        else {
+          lam = fmin(P.lambda_max, lam * nu);
+          nu *= 2.0;
+          if (lam >= P.lambda_max) { status = GTO_STATUS_STALLED; done = true; }
+        }
+      }
+    }
+  }
+  // ---- results ----
+  if (act)
+    for (int k = 0; k < nopt; ++k) P.Qx[((long long)b * n + gl) * nopt + k] = qx[k];
+  double coll = 0.0;
+  if (P.occ != nullptr && act) {
+    double s, c;
+    sincos(yv[2], &s, &c);
+    for (int i = gl; i < P.npoints; i += n) {
+      const double px = P.wp[3 * i] - yv[0], py = P.wp[3 * i + 1] - yv[1];
+      const double ux = c * px + s * py, uy = -s * px + c * py;
+      const double fx = floor((ux - P.oox) / P.ores), fyy = floor((uy - P.ooy) / P.ores);
+      const int ix = (int)fmin(fmax(fx, 0.0), (double)(P.onx - 1)), iy = (int)fmin(fmax(fyy, 0.0), (double)(P.ony - 1));
+      coll += (double)P.occ[(long long)ix * P.ony + iy];
+    }
+  }
+  coll = group_sum(coll, gbase, n);
+  if (act && gl == 0) {
+    P.y[3 * b] = yv[0]; P.y[3 * b + 1] = yv[1]; P.y[3 * b + 2] = yv[2];
+    P.cost[b] = F;
+    P.collision[b] = coll;
+    P.iters[b] = it;
+    P.status[b] = status;
+  }
+}

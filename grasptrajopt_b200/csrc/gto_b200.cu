@@ -2454,8 +2454,23 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, ctx->stream));
   if (in->occupancy) k_base_points<<<1, 256, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, p.qc, d + o_wp);
-  if (nopt <= 8) k_base_place<8><<<B, 32, 0, ctx->stream>>>(p);
-  else k_base_place<16><<<B, 32, 0, ctx->stream>>>(p);
+  const bool v1 = getenv("GTO_BASE_V1") != nullptr || nopt > 12;  // local-memory kernel: A/B reference, and robots with > 12 optimised joints
+  if (v1) {
+    if (nopt <= 8) k_base_place<8><<<B, 32, 0, ctx->stream>>>(p);
+    else k_base_place<16><<<B, 32, 0, ctx->stream>>>(p);
+  } else {
+    const int gpw = 32 / n;
+    const unsigned grid = (unsigned)((B + gpw - 1) / gpw);
+    if (nopt <= 8) {
+      const size_t smem = sizeof(double) * 32 * base_sm_doubles_per_lane<8>();
+      CK(cudaFuncSetAttribute(k_base_place_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_base_place_sm<8><<<grid, 32, smem, ctx->stream>>>(p);
+    } else {
+      const size_t smem = sizeof(double) * 32 * base_sm_doubles_per_lane<12>();
+      CK(cudaFuncSetAttribute(k_base_place_sm<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_base_place_sm<12><<<grid, 32, smem, ctx->stream>>>(p);
+    }
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, ctx->stream));
   // results: optimised rows come back packed, the parameter joints are re-inflated from qc on the host (optas/solver.py:126-159)

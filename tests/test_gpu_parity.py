@@ -251,3 +251,51 @@ def test_launch_options_do_not_change_the_result(ctx, monkeypatch, env):
     else:
         for k in ("Q", "dQ", "cost", "iters", "status"):
             np.testing.assert_array_equal(res[k], ref[k], err_msg=f"{env} {k}")
+
+
+def _sub_batch(b, idx):
+    import dataclasses
+    idx = np.asarray(idx, dtype=np.int64)
+    return dataclasses.replace(b, qc=b.qc[idx], q_seed=b.q_seed[idx], goal_tf=b.goal_tf[idx], base_position=b.base_position[idx],
+                               field_all=b.field_all[idx], field_obs=b.field_obs[idx])
+
+
+def test_single_and_ragged_batches_equal_the_full_batch(ctx):
+    """Edge cases of the batch dimension: one problem, and an odd-sized subset in a different order, give the same bits as
+    the same problems inside a larger batch (problems never interact)."""
+    w = small_workload("C2", "panda_small", B=7, n_field=48)
+    ctx.set_robot(w.table)
+    upload_fields(ctx, w)
+    full = ctx.solve_batch(w.batch)
+    one = ctx.solve_batch(_sub_batch(w.batch, [3]))
+    assert np.array_equal(one["Q"][0], full["Q"][3]) and one["iters"][0] == full["iters"][3] and one["cost"][0] == full["cost"][3]
+    idx = [6, 0, 4]
+    rag = ctx.solve_batch(_sub_batch(w.batch, idx))
+    for k, i in enumerate(idx):
+        assert np.array_equal(rag["Q"][k], full["Q"][i]) and rag["status"][k] == full["status"][i]
+
+
+def test_error_behaviour_of_the_boundary(ctx):
+    """Every misuse returns a negative code with a message (raised as GtoError by the binding); nothing crashes or falls back."""
+    import dataclasses
+    w = small_workload("C2", "panda_small", B=2, n_field=48)
+    fresh = capi.GtoContext(0)
+    with pytest.raises(capi.GtoError) as e:  # robot not set
+        fresh.solve_batch(w.batch)
+    assert e.value.code == -4
+    fresh.close()
+    ctx.set_robot(w.table)
+    upload_fields(ctx, w)
+    with pytest.raises(capi.GtoError) as e:  # field slot never uploaded
+        ctx.solve_batch(dataclasses.replace(w.batch, field_obs=np.full(2, 4000, np.int32)))
+    assert e.value.code == -1
+    with pytest.raises(capi.GtoError) as e:  # stand-off knot outside the trajectory
+        ctx.solve_batch(dataclasses.replace(w.batch, standoff_offset=-(w.batch.T + 1)))
+    assert e.value.code == -1
+    with pytest.raises(capi.GtoError) as e:  # too few knots: the first two are pinned to qc
+        ctx.solve_batch(dataclasses.replace(_sub_batch(w.batch, [0, 1]), T=2, q_seed=w.batch.q_seed[:, :2], standoff_offset=-1))
+    assert e.value.code == -1
+    with pytest.raises(capi.GtoError):  # empty batch
+        ctx.solve_batch(_sub_batch(w.batch, []))
+    res = ctx.solve_batch(w.batch)  # the context is still usable afterwards
+    assert res["Q"].shape == (2, w.batch.T, w.table.ndof) and np.all(np.isfinite(res["Q"]))
