@@ -431,8 +431,15 @@ struct LaneArr {  // element e of this lane's array
 template <int NP>
 __host__ __device__ constexpr int base_sm_doubles_per_lane() {
   constexpr int NV = NP + 3;
-  constexpr int s1 = 12 * NV + 6 * NP, s2 = NP * NP + 7 * NP;
-  return 2 * NV * NV + 2 * NV + (s1 > s2 ? s1 : s2);
+  constexpr int s1 = 12 * NV, s2 = NP * NP + 7 * NP;
+  return 2 * (NV * (NV + 1) / 2) + 2 * NV + (s1 > s2 ? s1 : s2);
+}
+
+// packed upper triangle of a symmetric NV x NV matrix
+template <int NV>
+__device__ __forceinline__ int sym_ix(int a, int b) {
+  const int lo = a < b ? a : b, hi = a < b ? b : a;
+  return lo * NV - (lo * (lo - 1)) / 2 + (hi - lo);
 }
 
 __device__ __forceinline__ double group_sum(double v, int gbase, int n) {
@@ -453,9 +460,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
   constexpr int NV = NP + 3;
   const RobotDev& R = *P.robot;
   const int nopt = R.nopt, nv = nopt + 3;
-  const LaneArr E = scr;                          // [NV][12]
-  const LaneArr om = {scr.p + 12 * NV * 32};      // [NP][3]
-  const LaneArr mm = {scr.p + (12 * NV + 3 * NP) * 32};
+  const LaneArr E = scr;  // [NV][12]; until the gripper frame is known, E_k[0..5] holds the joint's twist (omega, m)
   unsigned on_chain = 0u;
   double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   for (int c = 0; c < P.nchain; ++c) {
@@ -469,10 +474,10 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
     if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
       if (k >= 0) {
         on_chain |= 1u << k;
-        om[3 * k] = zx; om[3 * k + 1] = zy; om[3 * k + 2] = zz;
-        mm[3 * k] = U[7] * zz - U[11] * zy;  // o x z
-        mm[3 * k + 1] = U[11] * zx - U[3] * zz;
-        mm[3 * k + 2] = U[3] * zy - U[7] * zx;
+        E[12 * k] = zx; E[12 * k + 1] = zy; E[12 * k + 2] = zz;
+        E[12 * k + 3] = U[7] * zz - U[11] * zy;  // o x z
+        E[12 * k + 4] = U[11] * zx - U[3] * zz;
+        E[12 * k + 5] = U[3] * zy - U[7] * zx;
       }
       double s, cs;
       sincos(qj, &s, &cs);
@@ -485,8 +490,8 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
     } else {
       if (k >= 0) {
         on_chain |= 1u << k;
-        om[3 * k] = 0.0; om[3 * k + 1] = 0.0; om[3 * k + 2] = 0.0;
-        mm[3 * k] = zx; mm[3 * k + 1] = zy; mm[3 * k + 2] = zz;
+        E[12 * k] = 0.0; E[12 * k + 1] = 0.0; E[12 * k + 2] = 0.0;
+        E[12 * k + 3] = zx; E[12 * k + 4] = zy; E[12 * k + 5] = zz;
       }
 #pragma unroll
       for (int e = 0; e < 12; ++e) T[e] = U[e];
@@ -516,8 +521,8 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
       for (int e = 0; e < 12; ++e) E[12 * k + e] = 0.0;
       continue;
     }
-    const double wx = om[3 * k], wy = om[3 * k + 1], wz = om[3 * k + 2];
-    const double m0 = mm[3 * k], m1 = mm[3 * k + 1], m2 = mm[3 * k + 2];
+    const double wx = E[12 * k], wy = E[12 * k + 1], wz = E[12 * k + 2];
+    const double m0 = E[12 * k + 3], m1 = E[12 * k + 4], m2 = E[12 * k + 5];
 #pragma unroll
     for (int col = 0; col < 4; ++col) {
       const double f0 = F[col], f1 = F[4 + col], f2 = F[8 + col];
@@ -564,8 +569,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
       double u = 0.0;
 #pragma unroll
       for (int e = 0; e < 12; ++e) u += EM[e] * E[12 * b + e];
-      G[a * NV + b] = u;
-      G[b * NV + a] = u;
+      G[sym_ix<NV>(a, b)] = u;
     }
   }
 }
@@ -582,9 +586,10 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
   const bool act = grp < gpw && b < P.B;
   const double BIG = 1e30, PI = 3.14159265358979323846;
   const double ylo[3] = {-BIG, -BIG, -PI}, yhi[3] = {BIG, BIG, PI};
-  LaneArr G = {base_sm + lane}, Gt = {base_sm + NV * NV * 32 + lane};
-  LaneArr g = {base_sm + 2 * NV * NV * 32 + lane}, gtr = {base_sm + (2 * NV * NV + NV) * 32 + lane};
-  const LaneArr scr = {base_sm + (2 * NV * NV + 2 * NV) * 32 + lane};
+  constexpr int NG = NV * (NV + 1) / 2;  // packed symmetric Gram matrix
+  LaneArr G = {base_sm + lane}, Gt = {base_sm + NG * 32 + lane};
+  LaneArr g = {base_sm + 2 * NG * 32 + lane}, gtr = {base_sm + (2 * NG + NV) * 32 + lane};
+  const LaneArr scr = {base_sm + (2 * NG + 2 * NV) * 32 + lane};
   const LaneArr Hd = scr, Z = {scr.p + NP * NP * 32}, Cm = {scr.p + (NP * NP + 4 * NP) * 32};
   double A[12];
 #pragma unroll
@@ -592,11 +597,8 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
   double qx[NP], qn[NP], dq[NP], yv[3] = {0.0, 0.0, 0.0}, yn[3];
 #pragma unroll
   for (int k = 0; k < NP; ++k) qx[k] = k < nopt ? P.qc[R.opt_qidx[k]] : 0.0;
-  for (int a = 0; a < NV; ++a) {
-    g[a] = 0.0;
-    gtr[a] = 0.0;
-    for (int c = 0; c < NV; ++c) { G[a * NV + c] = 0.0; Gt[a * NV + c] = 0.0; }
-  }
+  for (int a = 0; a < NV; ++a) { g[a] = 0.0; gtr[a] = 0.0; }
+  for (int e = 0; e < NG; ++e) { G[e] = 0.0; Gt[e] = 0.0; }
   double ci = 0.0;
   if (act) base_goal_linearize_sm<NP>(P, qx, yv, A, ci, g, G, scr);
   double F = group_sum(act ? ci : 0.0, gbase, n);
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
       gy[a] = group_sum(g[nopt + a], gbase, n) + P.w_effort * yv[a];
 #pragma unroll
       for (int c = a; c < 3; ++c) {
-        S[a][c] = group_sum(G[(nopt + a) * NV + nopt + c], gbase, n) + (a == c ? P.w_effort : 0.0);
+        S[a][c] = group_sum(G[sym_ix<NV>(nopt + a, nopt + c)], gbase, n) + (a == c ? P.w_effort : 0.0);
         S[c][a] = S[a][c];
       }
     }
@@ -640,12 +642,12 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
     // ---- per-goal solve H_i Z = [C_i | -g_i] (Cholesky in shared memory), Schur complement on the base block ----
     for (int k = 0; k < nopt; ++k) {
       const bool fk = (fq >> k) & 1u;
-      for (int l = 0; l < nopt; ++l) Hd[k * NP + l] = (fk || ((fq >> l) & 1u)) ? 0.0 : G[k * NV + l];
-      const double gkk = G[k * NV + k];
+      for (int l = 0; l < nopt; ++l) Hd[k * NP + l] = (fk || ((fq >> l) & 1u)) ? 0.0 : G[sym_ix<NV>(k, l)];
+      const double gkk = G[sym_ix<NV>(k, k)];
       Hd[k * NP + k] = fk ? 1.0 : gkk + lam * gkk;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const double cv = (fk || fy[a]) ? 0.0 : G[k * NV + nopt + a];
+        const double cv = (fk || fy[a]) ? 0.0 : G[sym_ix<NV>(k, nopt + a)];
         Cm[3 * k + a] = cv;
         Z[4 * k + a] = cv;
       }
@@ -733,11 +735,11 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
       if (k < nopt) {
-        const double c0 = G[k * NV + nopt], c1 = G[k * NV + nopt + 1], c2 = G[k * NV + nopt + 2];
+        const double c0 = G[sym_ix<NV>(k, nopt)], c1 = G[sym_ix<NV>(k, nopt + 1)], c2 = G[sym_ix<NV>(k, nopt + 2)];
         double ad = c0 * dy[0] + c1 * dy[1] + c2 * dy[2];
 #pragma unroll
         for (int l = 0; l < NP; ++l)
-          if (l < nopt) ad += G[k * NV + l] * dq[l];
+          if (l < nopt) ad += G[sym_ix<NV>(k, l)] * dq[l];
         pq += g[k] * dq[k] + 0.5 * dq[k] * ad;
         cd[0] += c0 * dq[k]; cd[1] += c1 * dq[k]; cd[2] += c2 * dq[k];
       }
