@@ -166,7 +166,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference CasADi/IPOPT path not installable offline; its published wall-clock is ~0.1 trajectories/s (BASELINE.md)",
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -346,14 +346,26 @@ def run_b200(args):
             dt, cconv, n, threads = time_cpu(w, ns, ncpu)
             line["cpu_baseline"] = {"value": cconv / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n} of {B} problems of the same workload, oracle/gto_oracle.c (projected LM, float64), {threads} pthreads, {dt:.1f} s"}
-        print(json.dumps(line))
+        _emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: dict) -> None:
+    """The contract's ONE JSON line goes to the process's real stdout; everything else written to file descriptor 1 while the
+    benchmark runs (e.g. NCCL's version banner when the box exports NCCL_DEBUG) has been diverted to stderr by main()."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # native libraries that print to stdout now land on stderr
     if a.impl == "reference":
         run_reference(a)
     else:
