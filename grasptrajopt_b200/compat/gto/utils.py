@@ -63,3 +63,20 @@ def default_pose(robot_model):
     elif robot_model.name == "panda":
         q = np.array([0.0, -1.285, 0, -2.356, 0.0, 1.571, 0.785, 0.0, 0.0])
     return q
+
+
+def plan_collision_audit(robot, plan, depth_pc, base_position=None, min_points=5):
+    """Collision audit of a stored plan (reference ``examples/pybullet_evaluate_plans.py:219-237``): a knot is in collision when
+    more than ``min_points`` robot surface points lie behind the observed surface (``DepthPointCloud.get_sdf < 0``).
+
+    The reference queries the KD-tree once per knot and stops at the first hit; here the surface points of ALL knots go through
+    one ``get_sdf`` call (one ``k_cloud_query`` launch with the GPU backend).  ``plan`` is ndof-by-T.
+    Returns ``(in_collision, first_knot or -1, counts [T])``."""
+    plan = np.asarray(plan, dtype=np.float64)
+    T = plan.shape[1]
+    off = np.zeros((1, 3)) if base_position is None else np.asarray(base_position, dtype=np.float64).reshape(1, 3)
+    pts = np.concatenate([robot.compute_fk_surface_points(plan[:, i])[0] + off for i in range(T)])
+    sdf = np.asarray(depth_pc.get_sdf(pts)).reshape(T, -1)
+    counts = (sdf < 0).sum(axis=1)
+    hit = np.flatnonzero(counts > min_points)
+    return bool(hit.size), (int(hit[0]) if hit.size else -1), counts

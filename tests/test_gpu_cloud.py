@@ -67,3 +67,29 @@ def test_cloud_query_matches_kdtree_backend_on_a_grid():
     # ragged sizes: fewer queries than one block, a non-multiple of the tile
     for m in (1, 7, 1500):
         np.testing.assert_allclose(np.abs(gpu.get_sdf(g[:m])), np.abs(s_cpu[:m]), rtol=0, atol=2e-6)
+
+
+def test_plan_collision_audit_matches_kdtree_backend(tmp_path):
+    """Plan post-check (examples/pybullet_evaluate_plans.py:219-237): all knots of a plan in one GPU query, same per-knot counts as
+    the reference's per-knot KD-tree loop."""
+    from gto.gto_models import GTORobotModel
+    from gto.utils import plan_collision_audit
+    from test_compat_api import _write_box
+
+    _write_box(tmp_path)
+    robot = GTORobotModel(str(tmp_path), urdf_filename=str(tmp_path / "arm3.urdf"), time_derivs=[0, 1], param_joints=["slide"],
+                          collision_link_names=["base", "l1", "l2", "tool"], sample_point_count=64, seed=2)
+    depth, K, cam = _scene_depth()
+    gpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="b200")
+    cpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
+    T = 12
+    plan = np.stack([np.linspace(-2.0, 2.0, T), np.linspace(0.0, 6.0, T), np.full(T, 0.01)])  # the arm starts inside the box on the table
+    base = np.array([0.2, 0.0, 0.12])
+    hit_g, first_g, cnt_g = plan_collision_audit(robot, plan, gpu, base)
+    # the reference's loop, knot by knot
+    cnt_c = np.array([(cpu.get_sdf(robot.compute_fk_surface_points(plan[:, i])[0] + base) < 0).sum() for i in range(T)])
+    assert np.abs(cnt_g - cnt_c).max() <= 1  # a point projecting exactly onto a pixel border may fall on either side
+    assert 0 < cnt_c[0] <= 5 < cnt_c[1] and cnt_c[2:].max() == 0  # knot 0 touches (4 points), knot 1 collides (6), the rest is free
+    assert hit_g and first_g == int(np.flatnonzero(cnt_c > 5)[0]) == 1
+    hit0, first0, _ = plan_collision_audit(robot, plan[:, :1] * 0, gpu, np.array([0.3, 0.0, 0.6]))
+    assert (cpu.get_sdf(robot.compute_fk_surface_points(plan[:, 0] * 0)[0] + np.array([0.3, 0.0, 0.6])) < 0).sum() <= 5 and not hit0 and first0 == -1
