@@ -57,7 +57,7 @@ def base_placement_case(table_name="panda_small", B=4, n=4, seed=3, spread=1.5, 
     from grasptrajopt_b200.robot_table import RobotTable
 
     t = RobotTable.load(os.path.join(W.ASSETS, table_name + ".npz"))
-    qc = (W.PANDA_QC if t.ndof == 9 else W.FETCH_QC).copy()
+    qc = {9: W.PANDA_QC, 15: W.FETCH_QC, 18: np.concatenate([[0.0, 0.0, 0.0], W.FETCH_QC])}[t.ndof].copy()
     rng = np.random.default_rng(seed)
     Ginv = np.linalg.inv(O.hom(t.G))
     RTs = np.zeros((B, n, 4, 4))

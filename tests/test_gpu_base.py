@@ -9,7 +9,8 @@ from helpers import base_placement_case
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,B,n", [("panda_small", 6, 4), ("fetch_small", 4, 5), ("panda_small", 3, 1)])
+@pytest.mark.parametrize("name,B,n", [("panda_small", 6, 4), ("fetch_small", 4, 5), ("panda_small", 3, 1), ("panda_small", 2, 32),
+                                       ("fetch10_c4", 3, 3)])  # the last one: 10 optimised joints -> k_base_place_sm<12>
 def test_base_place_matches_oracle(name, B, n):
     t, qc, RTs, grid, origin, res = base_placement_case(name, B=B, n=n, spread=0.5)
     ctx = capi.GtoContext(0)
@@ -61,4 +62,23 @@ def test_base_place_rejects_bad_sizes():
     ctx.set_robot(t)
     with pytest.raises(capi.GtoError):
         ctx.base_place(qc, np.tile(np.eye(4), (1, 33, 1, 1)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["panda_small", "fetch10_c4"])
+def test_local_memory_kernel_agrees(name, monkeypatch):
+    """k_base_place (one problem per warp, per-thread arrays; GTO_BASE_V1=1, also the path for > 12 optimised joints) and the
+    default shared-memory kernel run the same iteration; only the order of the warp / group sums differs."""
+    t, qc, RTs, grid, origin, res = base_placement_case(name, B=8, n=4, spread=0.5)
+    ctx = capi.GtoContext(0)
+    ctx.set_robot(t)
+    a = ctx.base_place(qc, RTs, 0.01, grid, origin, res)
+    monkeypatch.setenv("GTO_BASE_V1", "1")
+    b = ctx.base_place(qc, RTs, 0.01, grid, origin, res)
+    monkeypatch.delenv("GTO_BASE_V1")
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
+    conv = a["status"] == 0
+    assert np.abs(a["y"][conv] - b["y"][conv]).max(initial=0.0) < 1e-6 and np.abs(a["y"] - b["y"]).max() < 1e-4
+    assert np.abs(a["Q"] - b["Q"]).max() < 1e-4
+    assert np.allclose(a["cost"], b["cost"], rtol=1e-7, atol=1e-12)
     ctx.close()
