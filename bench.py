@@ -269,6 +269,8 @@ def run_b200(args):
     res = ctx.download_batch()
     conv = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
     iters_hist = np.bincount(res["iters"], minlength=1).tolist()
+    sc = np.bincount(res["status"], minlength=5)
+    status_counts = {"converged": int(sc[0]), "max_iter": int(sc[1]), "nan": int(sc[2]), "stalled": int(sc[3]), "no_progress_at_field_kink": int(sc[4])}
     step_dev_ms = dev_ms + xch_ms  # device time of this rank: solves (library events) + all-gather (torch events)
 
     # ---- e2e: public API with host buffers ----
@@ -320,7 +322,7 @@ def run_b200(args):
                        "field": list(next(iter(w.fields.values())).cost.shape), "materialize_jacobian_rows": not args.no_jrows,
                        "l2": "working set per iteration (Jacobian rows, >=0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "convergence": f"|dq|inf<={opts.tol_step:g} or |proj grad|inf<={opts.tol_grad:g}, max_iter={opts.max_iter}",
-                       "converged": conv_tot, "problems": B * world, "iterations_histogram": iters_hist, "wall_ms_per_step": wall_ms / args.steps,
+                       "converged": conv_tot, "problems": B * world, "iterations_histogram": iters_hist, "status_counts_rank0": status_counts, "wall_ms_per_step": wall_ms / args.steps,
                        "scale": args.scale},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "wall clock between device synchronisations around gto_solve_batch with pinned host buffers"},
