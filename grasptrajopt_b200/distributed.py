@@ -55,3 +55,42 @@ def all_gather_results(local, world: int, counts=None):
     out = torch.empty((world * mx, local.shape[1]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad)
     return torch.cat([out[r * mx : r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+def goalset_argmin(local_cost, lo: int, world: int, local_status=None):
+    """Goal-set semantics across ranks (the reference's ``mmin`` over per-goal costs,
+    ``gto/gto_planner.py:105``, is an arg-min after the solve): every rank reduces its own shard to one ``(cost, global index, flag)``
+    triple, the triples are exchanged with one all-gather of ``[world, 3]`` float64 (cost, index, not-converged flag), and every rank returns the same winner
+    ``(global index, cost, owner rank)``.  ``lo`` is the global index of this rank's first problem (``shard_range``).  Problems
+    whose ``local_status`` is not 0 (converged) only win when no rank has a converged one; ties go to the lowest global index."""
+    import torch
+    import torch.distributed as dist
+
+    cost = torch.as_tensor(local_cost, dtype=torch.float64)
+    dev = cost.device
+    n = cost.shape[0]
+    big = torch.finfo(torch.float64).max
+    if n == 0:
+        pair = torch.tensor([big, -1.0, 1.0], dtype=torch.float64, device=dev)
+    else:
+        if local_status is not None:
+            bad = torch.as_tensor(local_status, device=dev) != 0
+        else:
+            bad = torch.zeros(n, dtype=torch.bool, device=dev)
+        key = torch.where(bad, torch.full_like(cost, big), cost)
+        if bool(bad.all()):
+            i = int(torch.argmin(cost))
+            pair = torch.tensor([float(cost[i]), float(lo + i), 1.0], dtype=torch.float64, device=dev)
+        else:
+            i = int(torch.argmin(key))
+            pair = torch.tensor([float(cost[i]), float(lo + i), 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        allp = torch.empty((world, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allp, pair.reshape(1, 3).contiguous())
+    else:
+        allp = pair.reshape(1, 3)
+    allp = allp.cpu().numpy()
+    # converged candidates first, then cost, then index
+    order = sorted(range(world), key=lambda r: (allp[r, 2], allp[r, 0], allp[r, 1] if allp[r, 1] >= 0 else np.inf))
+    r = order[0]
+    return int(allp[r, 1]), float(allp[r, 0]), int(r)

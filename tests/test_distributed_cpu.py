@@ -66,3 +66,38 @@ def test_sharded_solve_plus_all_gather_equals_full_batch(tmp_path):
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert np.load(tmp_path / "ok.npy")[0]
+
+
+def _argmin_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    from grasptrajopt_b200.distributed import goalset_argmin, shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(4)
+    cost = rng.uniform(1.0, 2.0, 11)
+    status = np.zeros(11, np.int32)
+    cost[7] = 0.25  # global minimum, on rank 1 ...
+    status[7] = 4   # ... but not converged
+    cost[2] = 0.5   # best converged one, on rank 0
+    lo, hi = shard_range(11, rank, world)
+    got = goalset_argmin(torch.from_numpy(cost[lo:hi]), lo, world, torch.from_numpy(status[lo:hi]))
+    got_all = goalset_argmin(torch.from_numpy(cost[lo:hi]), lo, world)  # without statuses: plain arg-min
+    none = goalset_argmin(torch.from_numpy(cost[lo:hi]), lo, world, torch.ones(hi - lo, dtype=torch.int32))  # nobody converged
+    np.save(os.path.join(tmp, f"argmin{rank}.npy"), np.array([got[0], got[2], got_all[0], got_all[2], none[0]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_goalset_argmin_across_ranks(tmp_path):
+    """plan_goalset over a sharded goal set: local arg-min + one all-gather of (cost, index) pairs; every rank gets the same winner."""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_argmin_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "argmin0.npy"), np.load(tmp_path / "argmin1.npy")
+    assert np.array_equal(a, b)
+    assert list(a) == [2, 0, 7, 1, 7]
