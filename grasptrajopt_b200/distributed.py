@@ -85,7 +85,9 @@ def goalset_argmin(local_cost, lo: int, world: int, local_status=None):
             i = int(torch.argmin(key))
             pair = torch.tensor([float(cost[i]), float(lo + i), 0.0], dtype=torch.float64, device=dev)
     if world > 1:
-        allp = torch.empty((world, 3), dtype=torch.float64, device=dev)
+        if dist.get_backend() == "nccl" and not pair.is_cuda:  # host-side costs (the C-ABI returns NumPy arrays): NCCL needs device memory
+            pair = pair.to(torch.device("cuda", torch.cuda.current_device()))
+        allp = torch.empty((world, 3), dtype=torch.float64, device=pair.device)
         dist.all_gather_into_tensor(allp, pair.reshape(1, 3).contiguous())
     else:
         allp = pair.reshape(1, 3)
