@@ -26,12 +26,14 @@ def load(build=True):
     global _lib
     if _lib is None:
         path = os.path.join(HERE, "libgto_oracle.so")
-        if build and not os.path.exists(path):
+        srcs = [os.path.join(HERE, f) for f in ("gto_oracle.c", "base_oracle.c")]
+        if build and (not os.path.exists(path) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in srcs)):
             subprocess.check_call(["make", "-s", "-C", HERE])
         _lib = C.CDLL(path)
         _lib.oracle_solve_batch.argtypes = [C.POINTER(capi.RobotDesc), C.POINTER(OracleField), C.POINTER(capi.BatchIn), C.POINTER(capi.Options),
                                             C.POINTER(capi.BatchOut), C.c_int]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_base_place.argtypes = [C.POINTER(capi.RobotDesc), C.POINTER(capi.BaseIn), C.POINTER(capi.Options), C.POINTER(capi.BaseOut), C.c_int]
     return _lib
 
 
@@ -114,4 +116,38 @@ def solve_workload(w, indices=None, nthreads=0, options=None):
     if rc != 0:
         raise RuntimeError(f"oracle_solve_batch failed ({rc})")
     res["threads"] = lib.oracle_num_threads() if nthreads <= 0 else nthreads
+    return res
+
+
+def base_place(t, qc, RTs, w_effort=0.01, occupancy=None, occ_origin=(0.0, 0.0), occ_resolution=0.05, nthreads=0, options=None):
+    """C restatement of oracle/base_oracle.py (oracle/base_oracle.c), same result layout as GtoContext.base_place."""
+    lib = load()
+    RTs = np.asarray(RTs, dtype=np.float64)
+    if RTs.ndim == 3:
+        RTs = RTs[None]
+    B, n = RTs.shape[:2]
+    G = np.eye(4)
+    G[:3] = t.G
+    goal = np.ascontiguousarray((RTs @ G)[:, :, :3, :], np.float64)
+    qcv = np.ascontiguousarray(np.asarray(qc, np.float64).reshape(-1))
+    d, keep_r = _robot_desc(t)
+    bi = capi.BaseIn()
+    bi.B, bi.n_goals, bi.qc, bi.goal_tf, bi.w_effort = B, n, qcv.ctypes.data_as(_dp), goal.ctypes.data_as(_dp), float(w_effort)
+    occ = None
+    if occupancy is not None:
+        occ = np.ascontiguousarray(occupancy, np.float32)
+        bi.occupancy = occ.ctypes.data_as(_fp)
+        bi.occ_dims[0], bi.occ_dims[1] = occ.shape
+        bi.occ_origin[0], bi.occ_origin[1] = float(occ_origin[0]), float(occ_origin[1])
+        bi.occ_resolution = float(occ_resolution)
+    res = dict(Q=np.zeros((B, n, t.ndof)), y=np.zeros((B, 3)), cost=np.zeros(B), collision=np.zeros(B), iters=np.zeros(B, np.int32),
+               status=np.zeros(B, np.int32))
+    bo = capi.BaseOut()
+    bo.Q, bo.y, bo.cost, bo.collision = (res[k].ctypes.data_as(_dp) for k in ("Q", "y", "cost", "collision"))
+    bo.iters, bo.status = res["iters"].ctypes.data_as(_ip), res["status"].ctypes.data_as(_ip)
+    opts = options if options is not None else default_options()
+    rc = lib.oracle_base_place(C.byref(d), C.byref(bi), C.byref(opts), C.byref(bo), int(nthreads))
+    if rc < 1:
+        raise RuntimeError(f"oracle_base_place failed ({rc})")
+    res["threads"] = rc
     return res

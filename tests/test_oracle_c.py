@@ -33,3 +33,23 @@ def test_c_oracle_threads_do_not_change_results():
     b = c_oracle.solve_workload(w, nthreads=4)
     np.testing.assert_array_equal(a["Q"], b["Q"])
     np.testing.assert_array_equal(a["iters"], b["iters"])
+
+
+def test_c_base_placement_matches_numpy_oracle():
+    """oracle/base_oracle.c (moment-matrix form, pthreads) against oracle/base_oracle.py (literal per-point residuals)."""
+    import base_oracle as BO
+    import c_oracle as CO
+    from helpers import base_placement_case
+
+    for name, B, n in (("panda_small", 4, 4), ("fetch_small", 3, 5), ("fetch10_c4", 2, 3)):
+        t, qc, RTs, grid, origin, res = base_placement_case(name, B=B, n=n, spread=0.5)
+        out = CO.base_place(t, qc, RTs, 0.01, grid, origin, res)
+        one = CO.base_place(t, qc, RTs, 0.01, grid, origin, res, nthreads=1)
+        assert np.array_equal(out["y"], one["y"]) and np.array_equal(out["Q"], one["Q"])  # threads do not change results
+        for b in range(B):
+            r = BO.solve_base(BO.BaseProblem(t, qc, RTs[b], 0.01, grid, origin, res))
+            assert out["status"][b] == r.status and out["iters"][b] == r.iters
+            tol = 1e-6 if r.status == 0 else 1e-4
+            assert np.abs(out["y"][b] - r.y).max() < tol and np.abs(out["Q"][b] - r.Q).max() < tol
+            assert abs(out["cost"][b] - r.cost) <= 1e-7 * max(1.0, r.cost)
+            assert abs(out["collision"][b] - r.collision) <= (0 if np.abs(out["y"][b] - r.y).max() < 1e-9 else 2)

@@ -1,5 +1,5 @@
 """SURVEY.md section 8(f) row 4, measured: gto_base_place (k_base_place) -- 4096 base-placement problems x 10 goals in one launch,
-against oracle/base_oracle.py (NumPy float64) on one host core for a bounded sample.  `python tools/bench_base.py` prints one JSON
+against oracle/base_oracle.c (the same algorithm in C, all host threads, bounded sample) and oracle/base_oracle.py (NumPy, 8 problems).  `python tools/bench_base.py` prints one JSON
 object; `--once NAME` runs a single launch (for ncu)."""
 import json, os, sys, time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,12 +28,22 @@ def run(cases=(("fetch_small", 4096, 10), ("panda_small", 4096, 10)), cpu_sample
                "converged": int((ob["status"] == 0).sum()), "at_max_iter": int((ob["status"] == 1).sum()), "iters_mean": float(ob["iters"].mean()),
                "collision_free": int((ob["collision"] == 0).sum())}
         if cpu_sample:
+            import c_oracle as CO
+            ncs = min(Bn, 1024)  # bounded sample for the C port on all host threads
+            CO.base_place(tb, qcb, RTb[:8], 0.01, grid, origin, res)
+            t0 = time.perf_counter()
+            rc = CO.base_place(tb, qcb, RTb[:ncs], 0.01, grid, origin, res)
+            dtc = time.perf_counter() - t0
             t0 = time.perf_counter()
             ro = [BO.solve_base(BO.BaseProblem(tb, qcb, RTb[i], 0.01, grid, origin, res)) for i in range(cpu_sample)]
             dto = (time.perf_counter() - t0) / cpu_sample
-            rec["cpu_port"] = {"problems_per_s": 1.0 / dto, "cores": 1, "kind": "port (oracle/base_oracle.py, NumPy float64)", "sample": cpu_sample,
-                               "max_abs_dy_vs_gpu": float(max(np.abs(ro[i].y - ob["y"][i]).max() for i in range(cpu_sample))),
-                               "iters_equal": bool(all(ro[i].iters == ob["iters"][i] for i in range(cpu_sample)))}
+            rec["cpu_baseline"] = {"value": ncs / dtc, "unit": "placements/s", "cores": int(rc["threads"]), "kind": "port",
+                                   "sample": f"{ncs} of {Bn} problems, oracle/base_oracle.c (same projected LM, float64), {int(rc['threads'])} pthreads, {dtc:.2f} s",
+                                   "max_abs_dy_vs_gpu": float(np.abs(rc["y"] - ob["y"][:ncs]).max()),
+                                   "iters_equal_frac": float((rc["iters"] == ob["iters"][:ncs]).mean())}
+            rec["numpy_oracle"] = {"problems_per_s": 1.0 / dto, "cores": 1, "sample": cpu_sample,
+                                   "max_abs_dy_vs_gpu": float(max(np.abs(ro[i].y - ob["y"][i]).max() for i in range(cpu_sample))),
+                                   "iters_equal": bool(all(ro[i].iters == ob["iters"][i] for i in range(cpu_sample)))}
         out[f"base_placement_{name}"] = rec
         ctx.close()
     return out
