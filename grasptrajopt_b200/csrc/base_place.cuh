@@ -432,7 +432,7 @@ template <int NP>
 __host__ __device__ constexpr int base_sm_doubles_per_lane() {
   constexpr int NV = NP + 3;
   constexpr int s1 = 12 * NV, s2 = NP * NP + 7 * NP;
-  return 2 * (NV * (NV + 1) / 2) + 2 * NV + (s1 > s2 ? s1 : s2);
+  return NV * (NV + 1) / 2 + NV + (s1 > s2 ? s1 : s2);
 }
 
 // packed upper triangle of a symmetric NV x NV matrix
@@ -453,8 +453,9 @@ __device__ __forceinline__ double group_max(double v, int gbase, int n) {
   return s;
 }
 
-// linearisation of one goal (see base_goal_linearize); G [NV*NV], g [NV] and the scratch area are the lane's shared-memory arrays
-template <int NP>
+// linearisation of one goal (see base_goal_linearize); G (packed), g [NV] and the scratch area are the lane's shared-memory arrays.
+// JAC = false: cost only (no shared memory is touched) -- the trial point of an iteration, which is linearised only if accepted.
+template <int NP, bool JAC>
 __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const double* __restrict__ qx, const double* __restrict__ yv,
                                                     const double* __restrict__ A, double& cost, LaneArr g, LaneArr G, LaneArr scr) {
   constexpr int NV = NP + 3;
@@ -472,7 +473,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
     const int k = R.mov_opt[j];
     const double qj = k >= 0 ? qx[k] : P.qc[R.mov_qidx[j]];
     if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
-      if (k >= 0) {
+      if (JAC && k >= 0) {
         on_chain |= 1u << k;
         E[12 * k] = zx; E[12 * k + 1] = zy; E[12 * k + 2] = zz;
         E[12 * k + 3] = U[7] * zz - U[11] * zy;  // o x z
@@ -488,7 +489,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
       M[8] = -s * ay + v * ax * az; M[9] = s * ax + v * ay * az; M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
       mul34(U, M, T);
     } else {
-      if (k >= 0) {
+      if (JAC && k >= 0) {
         on_chain |= 1u << k;
         E[12 * k] = 0.0; E[12 * k + 1] = 0.0; E[12 * k + 2] = 0.0;
         E[12 * k + 3] = zx; E[12 * k + 4] = zy; E[12 * k + 5] = zz;
@@ -515,6 +516,20 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
     RA[4 + col] = c * a0 - s * a1;
     RA[8 + col] = 0.0;
   }
+  double DM[12];
+  double cs = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+      double v = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v += D[4 * r + m] * P.mom[4 * m + col];
+      DM[4 * r + col] = v;
+      cs += v * D[4 * r + col];
+    }
+  cost = cs;
+  if constexpr (JAC) {
   for (int k = 0; k < nopt; ++k) {
     if (!((on_chain >> k) & 1u)) {
 #pragma unroll
@@ -535,19 +550,6 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
   for (int e = 0; e < 12; ++e) { E[12 * nopt + e] = 0.0; E[12 * (nopt + 1) + e] = 0.0; E[12 * (nopt + 2) + e] = -RA[e]; }
   E[12 * nopt + 3] = -1.0;
   E[12 * (nopt + 1) + 7] = -1.0;
-  double DM[12];
-  double cs = 0.0;
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int col = 0; col < 4; ++col) {
-      double v = 0.0;
-#pragma unroll
-      for (int m = 0; m < 4; ++m) v += D[4 * r + m] * P.mom[4 * m + col];
-      DM[4 * r + col] = v;
-      cs += v * D[4 * r + col];
-    }
-  cost = cs;
   for (int a = 0; a < nv; ++a) {
     double Ea[12], EM[12];
 #pragma unroll
@@ -572,6 +574,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
       G[sym_ix<NV>(a, b)] = u;
     }
   }
+  }
 }
 
 template <int NP>
@@ -587,9 +590,8 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
   const double BIG = 1e30, PI = 3.14159265358979323846;
   const double ylo[3] = {-BIG, -BIG, -PI}, yhi[3] = {BIG, BIG, PI};
   constexpr int NG = NV * (NV + 1) / 2;  // packed symmetric Gram matrix
-  LaneArr G = {base_sm + lane}, Gt = {base_sm + NG * 32 + lane};
-  LaneArr g = {base_sm + 2 * NG * 32 + lane}, gtr = {base_sm + (2 * NG + NV) * 32 + lane};
-  const LaneArr scr = {base_sm + (2 * NG + 2 * NV) * 32 + lane};
+  const LaneArr G = {base_sm + lane}, g = {base_sm + NG * 32 + lane};
+  const LaneArr scr = {base_sm + (NG + NV) * 32 + lane};
   const LaneArr Hd = scr, Z = {scr.p + NP * NP * 32}, Cm = {scr.p + (NP * NP + 4 * NP) * 32};
   double A[12];
 #pragma unroll
@@ -597,10 +599,10 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
   double qx[NP], qn[NP], dq[NP], yv[3] = {0.0, 0.0, 0.0}, yn[3];
 #pragma unroll
   for (int k = 0; k < NP; ++k) qx[k] = k < nopt ? P.qc[R.opt_qidx[k]] : 0.0;
-  for (int a = 0; a < NV; ++a) { g[a] = 0.0; gtr[a] = 0.0; }
-  for (int e = 0; e < NG; ++e) { G[e] = 0.0; Gt[e] = 0.0; }
+  for (int a = 0; a < NV; ++a) g[a] = 0.0;
+  for (int e = 0; e < NG; ++e) G[e] = 0.0;
   double ci = 0.0;
-  if (act) base_goal_linearize_sm<NP>(P, qx, yv, A, ci, g, G, scr);
+  if (act) base_goal_linearize_sm<NP, true>(P, qx, yv, A, ci, g, G, scr);
   double F = group_sum(act ? ci : 0.0, gbase, n);
   double lam = P.lambda0, nu = 2.0;
   int status = GTO_STATUS_MAX_ITER, it = 0;
@@ -753,9 +755,10 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
     }
     const double pred = -(pq + py);
     if (live) ++it;
-    // ---- trial linearisation, acceptance ----
+    // ---- cost of the trial point, acceptance; an accepted point is linearised in place ----
     double ct = 0.0;
-    if (act) base_goal_linearize_sm<NP>(P, qn, yn, A, ct, gtr, Gt, scr);
+    if (act) base_goal_linearize_sm<NP, false>(P, qn, yn, A, ct, g, G, scr);
+    bool relin = false;
     const double Ft = group_sum(act ? ct : 0.0, gbase, n) + P.w_effort * (yn[0] * yn[0] + yn[1] * yn[1] + yn[2] * yn[2]);
     if (live && (!(Ft == Ft) || fabs(Ft) > 1e300)) { status = GTO_STATUS_NAN; done = true; live = false; }
     if (live) {
@@ -767,7 +770,7 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
         for (int k = 0; k < NP; ++k) qx[k] = qn[k];
 #pragma unroll
         for (int a = 0; a < 3; ++a) yv[a] = yn[a];
-        { double* tp = G.p; G.p = Gt.p; Gt.p = tp; tp = g.p; g.p = gtr.p; gtr.p = tp; }
+        relin = true;
         F = Ft;
         lam = fmax(P.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - t * t * t));
         nu = 2.0;
@@ -781,6 +784,7 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
         }
       }
     }
+    if (relin && !done && act) base_goal_linearize_sm<NP, true>(P, qx, yv, A, ct, g, G, scr);
   }
   // ---- results ----
   if (act)
