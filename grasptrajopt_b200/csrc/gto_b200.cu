@@ -1258,6 +1258,18 @@ struct gto_ctx {
   std::vector<cudaEvent_t> ev;
 };
 
+struct EventPair {  // two timing events that are destroyed on every return path
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t create() {
+    cudaError_t e = cudaEventCreate(&a);
+    return e != cudaSuccess ? e : cudaEventCreate(&b);
+  }
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
 static int fail(gto_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
   return code;
@@ -2381,9 +2393,9 @@ extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, con
   p.mode = mode;
   p.eps = (float)epsilon; p.half_eps = (float)(epsilon / 2); p.two_eps = (float)(2 * epsilon); p.w_inside = (float)w_inside;
   p.out = ctx->cloud_out.p;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, ctx->stream));
+  EventPair ev;
+  CK(ev.create());
+  CK(cudaEventRecord(ev.a, ctx->stream));
   p.tiles = ctx->cloud_tiles.p;
   p.ntiles = (int)(((size_t)ctx->cloud_n + CLOUD_PTILE - 1) / CLOUD_PTILE);
   if (getenv("GTO_CLOUD_BRUTE")) {  // A/B reference: every query against every point
@@ -2394,13 +2406,12 @@ extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, con
     k_cloud_query_pruned<<<(unsigned)((nwarps + 3) / 4), 128, 0, ctx->stream>>>(p);
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaEventRecord(ev.b, ctx->stream));
   CK(cudaMemcpyAsync(out, ctx->cloud_out.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventElapsedTime(&ms, ev.a, ev.b);
   if (kernel_ms) *kernel_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return GTO_OK;
 }
 
@@ -2450,9 +2461,9 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
   p.wp = d + o_wp; p.npoints = P;
   p.Qx = d + o_Qx; p.y = d + o_y; p.cost = d + o_cost; p.collision = d + o_coll;
   p.iters = ctx->base_i.p; p.status = ctx->base_i.p + B;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, ctx->stream));
+  EventPair ev;
+  CK(ev.create());
+  CK(cudaEventRecord(ev.a, ctx->stream));
   if (in->occupancy) k_base_points<<<1, 256, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, p.qc, d + o_wp);
   const bool v1 = getenv("GTO_BASE_V1") != nullptr || nopt > 12;  // local-memory kernel: A/B reference, and robots with > 12 optimised joints
   if (v1) {
@@ -2472,7 +2483,7 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
     }
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaEventRecord(ev.b, ctx->stream));
   // results: optimised rows come back packed, the parameter joints are re-inflated from qc on the host (optas/solver.py:126-159)
   std::vector<double> qx((size_t)B * n * nopt);
   std::vector<int> is((size_t)2 * B);
@@ -2492,8 +2503,7 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
     if (out->status) out->status[b] = is[B + b];
   }
   float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventElapsedTime(&ms, ev.a, ev.b);
   if (kernel_ms) *kernel_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return GTO_OK;
 }

@@ -131,3 +131,24 @@ def test_base_planner_matches_oracle(robot):
     # the batched form returns the same bits for the same problem
     out = bp.plan_goalset_batch(qc, np.stack([RTs, RTs, RTs]))
     assert np.array_equal(out["y"][0], y) and np.array_equal(out["y"][2], y)
+
+
+def test_base_planner_rejection_loop(robot):
+    """The mobile example's loop (examples/pybullet_gto_planning_mobile.py:187-201) with a batch of draws per launch."""
+    import base_oracle as BO
+    from gto.base_planner import BasePlanner
+
+    rng = np.random.default_rng(9)
+    robot.setup_occupancy_grid(np.column_stack([rng.uniform(0.6, 1.2, 300), rng.uniform(-0.8, 0.8, 300), rng.uniform(0.02, 0.5, 300)]))
+    bp = BasePlanner(robot, "tool", "tool")
+    bp.setup_optimization(goal_size=2)
+    qc = np.array([0.2, -0.3, 0.01])
+    Tbi = np.linalg.inv(BO.base_tf(np.array([0.2, 0.1, 0.2])))
+    objs = [np.stack([Tbi @ robot.get_global_link_transform("tool", [a, b, 0.01]).toarray() for a in (0.3, 0.9, 1.4)]) for b in (0.4, 1.0)]
+    Q, y, err_pos, err_rot, cost, draw = bp.plan_until_collision_free(qc, objs, num=1, batch=8, rng=np.random.default_rng(0))
+    assert Q.shape == (3, 2) and y.shape == (3,) and draw.shape == (2, 4, 4) and cost >= 0
+    res = bp.last_result
+    assert res["y"].shape == (8, 3) and cost == res["collision"].min()
+    # the returned draw, solved alone through the reference signature, gives the same placement
+    Q1, y1, _, _, c1 = bp.plan_goalset(qc, draw)
+    assert np.array_equal(y1, y) and np.array_equal(Q1, Q) and c1 == cost
