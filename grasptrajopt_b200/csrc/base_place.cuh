@@ -455,12 +455,12 @@ __device__ __forceinline__ double group_max(double v, int gbase, int n) {
 
 // linearisation of one goal (see base_goal_linearize); G (packed), g [NV] and the scratch area are the lane's shared-memory arrays.
 // JAC = false: cost only (no shared memory is touched) -- the trial point of an iteration, which is linearised only if accepted.
-template <int NP, bool JAC>
+template <int NP, int NOPT, bool JAC>
 __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const double* __restrict__ qx, const double* __restrict__ yv,
                                                     const double* __restrict__ A, double& cost, LaneArr g, LaneArr G, LaneArr scr) {
   constexpr int NV = NP + 3;
   const RobotDev& R = *P.robot;
-  const int nopt = R.nopt, nv = nopt + 3;
+  const int nopt = NOPT > 0 ? NOPT : R.nopt, nv = nopt + 3;
   const LaneArr E = scr;  // [NV][12]; until the gripper frame is known, E_k[0..5] holds the joint's twist (omega, m)
   unsigned on_chain = 0u;
   double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -530,6 +530,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
     }
   cost = cs;
   if constexpr (JAC) {
+#pragma unroll
   for (int k = 0; k < nopt; ++k) {
     if (!((on_chain >> k) & 1u)) {
 #pragma unroll
@@ -550,6 +551,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
   for (int e = 0; e < 12; ++e) { E[12 * nopt + e] = 0.0; E[12 * (nopt + 1) + e] = 0.0; E[12 * (nopt + 2) + e] = -RA[e]; }
   E[12 * nopt + 3] = -1.0;
   E[12 * (nopt + 1) + 7] = -1.0;
+#pragma unroll
   for (int a = 0; a < nv; ++a) {
     double Ea[12], EM[12];
 #pragma unroll
@@ -567,6 +569,7 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
         for (int m = 0; m < 4; ++m) u += Ea[4 * r + m] * P.mom[4 * m + col];
         EM[4 * r + col] = u;
       }
+#pragma unroll
     for (int b = a; b < nv; ++b) {
       double u = 0.0;
 #pragma unroll
@@ -577,7 +580,8 @@ __device__ __noinline__ void base_goal_linearize_sm(const BaseParams& P, const d
   }
 }
 
-template <int NP>
+// NOPT > 0: the number of optimised joints is a compile-time constant (loops fully unrolled); NOPT = 0: read from the robot table
+template <int NP, int NOPT>
 __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ BaseParams P) {
   constexpr int NV = NP + 3;
   extern __shared__ double base_sm[];
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
   const int lane = threadIdx.x, n = P.n, gpw = 32 / n;
   const int grp = lane / n, gbase = grp * n, gl = lane - gbase;
   const int b = blockIdx.x * gpw + grp;
-  const int nopt = R.nopt;
+  const int nopt = NOPT > 0 ? NOPT : R.nopt;
   const bool act = grp < gpw && b < P.B;
   const double BIG = 1e30, PI = 3.14159265358979323846;
   const double ylo[3] = {-BIG, -BIG, -PI}, yhi[3] = {BIG, BIG, PI};
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
   for (int a = 0; a < NV; ++a) g[a] = 0.0;
   for (int e = 0; e < NG; ++e) G[e] = 0.0;
   double ci = 0.0;
-  if (act) base_goal_linearize_sm<NP, true>(P, qx, yv, A, ci, g, G, scr);
+  if (act) base_goal_linearize_sm<NP, NOPT, true>(P, qx, yv, A, ci, g, G, scr);
   double F = group_sum(act ? ci : 0.0, gbase, n);
   double lam = P.lambda0, nu = 2.0;
   int status = GTO_STATUS_MAX_ITER, it = 0;
@@ -642,8 +646,10 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
     pgmax = 2.0 * fmax(pgmax, group_max(pgq, gbase, n));
     if (live && pgmax <= P.tol_grad) { status = GTO_STATUS_CONVERGED; done = true; live = false; }
     // ---- per-goal solve H_i Z = [C_i | -g_i] (Cholesky in shared memory), Schur complement on the base block ----
+#pragma unroll
     for (int k = 0; k < nopt; ++k) {
       const bool fk = (fq >> k) & 1u;
+#pragma unroll
       for (int l = 0; l < nopt; ++l) Hd[k * NP + l] = (fk || ((fq >> l) & 1u)) ? 0.0 : G[sym_ix<NV>(k, l)];
       const double gkk = G[sym_ix<NV>(k, k)];
       Hd[k * NP + k] = fk ? 1.0 : gkk + lam * gkk;
@@ -655,27 +661,35 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
       }
       Z[4 * k + 3] = fk ? 0.0 : -g[k];
     }
+#pragma unroll
     for (int j = 0; j < nopt; ++j) {
       double d = Hd[j * NP + j];
+#pragma unroll
       for (int k = 0; k < j; ++k) { const double v = Hd[j * NP + k]; d -= v * v; }
       d = sqrt(d);
       Hd[j * NP + j] = d;
       const double inv = 1.0 / d;
+#pragma unroll
       for (int i = j + 1; i < nopt; ++i) {
         double v = Hd[i * NP + j];
+#pragma unroll
         for (int k = 0; k < j; ++k) v -= Hd[i * NP + k] * Hd[j * NP + k];
         Hd[i * NP + j] = v * inv;
       }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
+#pragma unroll
       for (int i = 0; i < nopt; ++i) {
         double v = Z[4 * i + r];
+#pragma unroll
         for (int k = 0; k < i; ++k) v -= Hd[i * NP + k] * Z[4 * k + r];
         Z[4 * i + r] = v / Hd[i * NP + i];
       }
+#pragma unroll
       for (int i = nopt - 1; i >= 0; --i) {
         double v = Z[4 * i + r];
+#pragma unroll
         for (int k = i + 1; k < nopt; ++k) v -= Hd[k * NP + i] * Z[4 * k + r];
         Z[4 * i + r] = v / Hd[i * NP + i];
       }
@@ -684,11 +698,13 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       double v = 0.0;
+#pragma unroll
       for (int k = 0; k < nopt; ++k) v += Cm[3 * k + a] * Z[4 * k + 3];
       M[a][3] = (fy[a] ? 0.0 : -gy[a]) - group_sum(v, gbase, n);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         double u = 0.0;
+#pragma unroll
         for (int k = 0; k < nopt; ++k) u += Cm[3 * k + a] * Z[4 * k + c];
         const double base = (fy[a] || fy[c]) ? (a == c ? 1.0 : 0.0) : S[a][c] + (a == c ? lam * S[a][a] : 0.0);
         M[a][c] = base - group_sum(u, gbase, n);
@@ -757,7 +773,7 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
     if (live) ++it;
     // ---- cost of the trial point, acceptance; an accepted point is linearised in place ----
     double ct = 0.0;
-    if (act) base_goal_linearize_sm<NP, false>(P, qn, yn, A, ct, g, G, scr);
+    if (act) base_goal_linearize_sm<NP, NOPT, false>(P, qn, yn, A, ct, g, G, scr);
     bool relin = false;
     const double Ft = group_sum(act ? ct : 0.0, gbase, n) + P.w_effort * (yn[0] * yn[0] + yn[1] * yn[1] + yn[2] * yn[2]);
     if (live && (!(Ft == Ft) || fabs(Ft) > 1e300)) { status = GTO_STATUS_NAN; done = true; live = false; }
@@ -784,10 +800,11 @@ __global__ void __launch_bounds__(32) k_base_place_sm(const __grid_constant__ Ba
         }
       }
     }
-    if (relin && !done && act) base_goal_linearize_sm<NP, true>(P, qx, yv, A, ct, g, G, scr);
+    if (relin && !done && act) base_goal_linearize_sm<NP, NOPT, true>(P, qx, yv, A, ct, g, G, scr);
   }
   // ---- results ----
   if (act)
+#pragma unroll
     for (int k = 0; k < nopt; ++k) P.Qx[((long long)b * n + gl) * nopt + k] = qx[k];
   double coll = 0.0;
   if (P.occ != nullptr && act) {

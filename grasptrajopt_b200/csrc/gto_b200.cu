@@ -2472,15 +2472,21 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
   } else {
     const int gpw = 32 / n;
     const unsigned grid = (unsigned)((B + gpw - 1) / gpw);
-    if (nopt <= 8) {
-      const size_t smem = sizeof(double) * 32 * base_sm_doubles_per_lane<8>();
-      CK(cudaFuncSetAttribute(k_base_place_sm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_base_place_sm<8><<<grid, 32, smem, ctx->stream>>>(p);
-    } else {
-      const size_t smem = sizeof(double) * 32 * base_sm_doubles_per_lane<12>();
-      CK(cudaFuncSetAttribute(k_base_place_sm<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_base_place_sm<12><<<grid, 32, smem, ctx->stream>>>(p);
+#define GTO_BASE_LAUNCH(NP_, NOPT_)                                                                              \
+  do {                                                                                                         \
+    const size_t smem = sizeof(double) * 32 * base_sm_doubles_per_lane<NP_>();                                 \
+    CK(cudaFuncSetAttribute(k_base_place_sm<NP_, NOPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_base_place_sm<NP_, NOPT_><<<grid, 32, smem, ctx->stream>>>(p);                                            \
+  } while (0)
+    switch (nopt) {  // the shipped robots get fully unrolled instances (Panda / Fetch 7, Fetch-8, Fetch-10)
+      case 7: GTO_BASE_LAUNCH(8, 7); break;
+      case 8: GTO_BASE_LAUNCH(8, 8); break;
+      case 10: GTO_BASE_LAUNCH(12, 10); break;
+      default:
+        if (nopt <= 8) GTO_BASE_LAUNCH(8, 0);
+        else GTO_BASE_LAUNCH(12, 0);
     }
+#undef GTO_BASE_LAUNCH
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev.b, ctx->stream));
