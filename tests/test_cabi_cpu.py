@@ -57,6 +57,8 @@ def test_struct_layouts_follow_header_field_order():
     assert fields("gto_batch_out") == [f[0] for f in capi.BatchOut._fields_]
     assert fields("gto_eval_out") == [f[0] for f in capi.EvalOut._fields_]
     assert fields("gto_profile") == [f[0] for f in capi.Profile._fields_]
+    assert fields("gto_base_in") == [f[0] for f in capi.BaseIn._fields_]
+    assert fields("gto_base_out") == [f[0] for f in capi.BaseOut._fields_]
 
 
 def test_status_and_flag_constants_match_header():
