@@ -43,6 +43,10 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the batch (debug only; makes the number invalid)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="problems in the cpu_baseline sample (-1: auto, 0: skip)")
     ap.add_argument("--no-jrows", action="store_true", help="secondary mode: do not materialise Jacobian rows")
+    ap.add_argument("--slow-window", type=int, default=0,
+                    help="secondary mode: stop a problem (status 'no progress', NOT counted as converged) once its cost fell by <= "
+                         "--slow-ftol * f over this many iterations (gto_options.slow_window, at most 16; 0 = off, the contract setting)")
+    ap.add_argument("--slow-ftol", type=float, default=1e-3)
     return ap.parse_args()
 
 
@@ -194,7 +198,7 @@ def run_b200(args):
     ctx.set_robot(w.table)
     for slot, cf in w.fields.items():
         ctx.set_field(slot, cf.cost, cf.origin, cf.pitch)
-    opts = capi.default_options()
+    opts = capi.default_options(slow_window=min(16, max(0, args.slow_window)), slow_ftol=args.slow_ftol) if args.slow_window > 0 else capi.default_options()
 
     # pinned host staging for the end-to-end arm
     def pin(a):
@@ -322,7 +326,8 @@ def run_b200(args):
                        "field": list(next(iter(w.fields.values())).cost.shape), "materialize_jacobian_rows": not args.no_jrows,
                        "l2": "working set per iteration (Jacobian rows, >=0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "convergence": f"|dq|inf<={opts.tol_step:g} or |proj grad|inf<={opts.tol_grad:g}, max_iter={opts.max_iter}",
-                       "converged": conv_tot, "problems": B * world, "iterations_histogram": iters_hist, "status_counts_rank0": status_counts, "wall_ms_per_step": wall_ms / args.steps,
+                       "converged": conv_tot, "problems": B * world, "iterations_histogram": iters_hist, "status_counts_rank0": status_counts,
+                       **({"secondary_mode": f"slow_window={args.slow_window}, slow_ftol={args.slow_ftol}"} if args.slow_window > 0 else {}), "wall_ms_per_step": wall_ms / args.steps,
                        "scale": args.scale},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "wall clock between device synchronisations around gto_solve_batch with pinned host buffers"},
