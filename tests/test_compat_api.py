@@ -189,3 +189,45 @@ def test_base_planner_surface(model):
     if not torch.cuda.is_available():
         with pytest.raises((capi.GtoError, capi.GtoLibraryError)):
             bp.plan_goalset(np.zeros(3), np.tile(np.eye(4), (2, 1, 1)))
+
+
+def test_base_planner_pose_errors(model):
+    """BasePlanner._errors (reference gto/base_planner.py:131-148): zero for goals that are exactly the gripper poses seen from the new
+    base, the applied offsets otherwise."""
+    from gto.base_planner import BasePlanner
+    from gto.utils import rotZ
+
+    bp = BasePlanner(model, "tool", "tool")
+    bp.setup_optimization(goal_size=2)
+    y = np.array([[0.3, -0.2, 0.4]])
+    Tb = rotZ(y[0, 2]); Tb[0, 3], Tb[1, 3] = y[0, 0], y[0, 1]
+    Q = np.array([[[0.5, 0.3, 0.01], [-0.7, 1.1, 0.01]]])
+    RTs = np.stack([np.linalg.inv(Tb) @ model.get_global_link_transform("tool", q).toarray() for q in Q[0]])[None]
+    ep, er = bp._errors(Q, y, RTs)
+    assert ep.shape == (1, 2) and np.abs(ep).max() < 1e-6 and np.abs(er).max() < 1e-2
+    RTs2 = RTs.copy()
+    RTs2[0, 0, :3, 3] += np.linalg.inv(Tb)[:3, :3] @ np.array([0.0, 0.0, 0.05])  # 5 cm along the new base's z
+    RTs2[0, 1, :3, :3] = RTs2[0, 1, :3, :3] @ rotZ(np.radians(10.0))[:3, :3]
+    ep2, er2 = bp._errors(Q, y, RTs2)
+    assert ep2[0, 0] == pytest.approx(0.05, abs=1e-6) and er2[0, 1] == pytest.approx(10.0, abs=1e-2)
+
+
+def test_plan_collision_audit_kdtree_backend(model):
+    """gto.utils.plan_collision_audit against the reference's per-knot loop (examples/pybullet_evaluate_plans.py:219-237), CPU backend."""
+    from gto.utils import plan_collision_audit
+
+    H, Wd, f = 60, 80, 70.0
+    K = np.array([[f, 0, Wd / 2], [0, f, H / 2], [0, 0, 1.0]])
+    cam = np.eye(4); cam[:3, :3] = np.array([[1.0, 0, 0], [0, -1, 0], [0, 0, -1]]); cam[:3, 3] = [0.3, 0.0, 1.0]
+    depth = np.full((H, Wd), 1.0, np.float32)
+    depth[20:40, 30:60] = 0.8  # a box on the table
+    dpc = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
+    T = 6
+    plan = np.stack([np.linspace(-1.5, 1.5, T), np.linspace(0.0, 3.0, T), np.full(T, 0.01)])
+    base = np.array([0.2, 0.0, 0.12])
+    hit, first, counts = plan_collision_audit(model, plan, dpc, base, min_points=5)
+    ref = np.array([(dpc.get_sdf(model.compute_fk_surface_points(plan[:, i])[0] + base) < 0).sum() for i in range(T)])
+    assert np.array_equal(counts, ref)
+    assert hit == bool((ref > 5).any()) and first == (int(np.flatnonzero(ref > 5)[0]) if (ref > 5).any() else -1)
+    hit0, first0, c0 = plan_collision_audit(model, plan, dpc, np.array([0.2, 0.0, 5.0]))  # far above everything
+    assert not hit0 and first0 == -1 and c0.sum() == 0
