@@ -742,6 +742,8 @@ struct StepParams {
   int max_iter;
   double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps, ftol, lambda_slow, slow_ftol;
   int slow_window;
+  int as_rounds;
+  double lambda_reject;
   double* Fhist;  // [B][16] accepted cost per iteration (ring)
   double* Qc;
   double* Qt;
@@ -1295,9 +1297,11 @@ extern "C" void gto_default_options(gto_options* o) {
   o->bound_eps = 1e-12;
   o->check_every = 4;
   o->ftol = 1e-6;
-  o->lambda_slow = 1.0;
+  o->lambda_slow = 1e30;
   o->slow_window = 0;
   o->slow_ftol = 1e-3;
+  o->as_rounds = 1;
+  o->lambda_reject = 1e-4;
 }
 
 extern "C" const char* gto_last_error(gto_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1922,6 +1926,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   st.tol_step = o.tol_step; st.tol_grad = o.tol_grad; st.lambda_min = o.lambda_min; st.lambda_max = o.lambda_max; st.eta = o.eta;
   st.noise_rel = o.noise_rel; st.bound_eps = o.bound_eps; st.ftol = o.ftol; st.lambda_slow = o.lambda_slow;
   st.slow_ftol = o.slow_ftol; st.slow_window = std::min(16, std::max(0, (int)o.slow_window));
+  st.as_rounds = std::min(4, std::max(0, (int)o.as_rounds)); st.lambda_reject = o.lambda_reject;
   CK(ctx->Fhist.ensure((size_t)B * 16));
   st.Fhist = ctx->Fhist.p;
   st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;

@@ -16,7 +16,7 @@
 
 __host__ __device__ inline size_t step_cr_smem_bytes(int T, int n) {
   const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
-  const size_t d = (size_t)2 * T * n + 4 * m * n + 3 * m * nn + 64;
+  const size_t d = (size_t)2 * T * n + 5 * m * n + 3 * m * nn + 64;
   return ((d * sizeof(double) + 2 * (m * nn + m * n) * sizeof(float) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
 }
 
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   double* Um = Lm + (size_t)m * nn;                  // [m][n*n] coupling to block i + s -> D^-1 U
   double* red = Um + (size_t)m * nn;                 // [64] reduction scratch
   double* X2 = red + 64;                             // [T][n] the other of (accepted, trial) point while the decision is open
-  float* HS = reinterpret_cast<float*>(X2 + (size_t)T * n);  // [2][m][n*n] Gauss-Newton blocks of both buffers (knots 2..T-1)
+  double* dfix = X2 + (size_t)T * n;                 // [m][n] prescribed step of the variables held at a joint limit
+  float* HS = reinterpret_cast<float*>(dfix + (size_t)m * n);  // [2][m][n*n] Gauss-Newton blocks of both buffers (knots 2..T-1)
   float* gS = HS + (size_t)2 * m * nn;                       // [2][m][n]
   unsigned* fm = reinterpret_cast<unsigned*>(gS + (size_t)2 * m * n);  // [m] bit k: variable k of knot i+2 is held at a bound
   int* sflag = reinterpret_cast<int*>(fm + m);           // [0] factorisation failed, [1] slot in the next active list
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
         if (pred <= 0.0 && step <= p.tol_step) {
           done = GTO_STATUS_CONVERGED;
         } else {
-          lam = fmin(p.lambda_max, lam * nu);
+          lam = fmin(p.lambda_max, fmax(lam * nu, p.lambda_reject));
           nu *= 2.0;
           if (lam >= p.lambda_max) done = GTO_STATUS_STALLED;
         }
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     }
   }
   for (int i = tid; i < m; i += NT) fm[i] = 0u;
+  for (int i = tid; i < m * n; i += NT) dfix[i] = 0.0;
   __syncthreads();
   STEP_MARK();  // 3: accept / reject done
 
@@ -253,7 +255,11 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   // ---------------- damped projected Gauss-Newton step: block cyclic reduction in float64 ----------------
   constexpr int OUT_A = (2 * NP * NP + NP + 31) / 32;  // results a lane holds in phase A / B before they are written back
   constexpr int OUT_B = (3 * NP * NP + NP + 31) / 32;
+  // Active-set rounds (gto_options.as_rounds, oracle lm_step): a free variable that the step pushes beyond a joint limit is
+  // moved exactly onto the limit (prescribed step dfix) and the other variables are re-solved with that step on the
+  // right-hand side.  Clipping alone distorts the coupled step (the model then often predicts an increase).
   bool ok = false;
+  int as_round = 0;
   for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
     // build the masked, damped system
     for (int idx = tid; idx < m * nn; idx += NT) {
@@ -277,7 +283,21 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     }
     for (int idx = tid; idx < m * n; idx += NT) {
       const int i = idx / n, k = idx - i * n;
-      bb[idx] = ((fm[i] >> k) & 1u) ? 0.0 : -gt[idx];
+      const unsigned mi = fm[i];
+      double v;
+      if ((mi >> k) & 1u) {
+        v = dfix[idx];
+      } else {  // free row: -g - (coupling to the prescribed steps of the held variables)
+        v = -gt[idx];
+        if (as_round > 0) {
+          const float* Hr = Hc + (size_t)i * nn + k * n;
+          for (int c = 0; c < n; ++c)
+            if (c != k && ((mi >> c) & 1u)) v -= (double)Hr[c] * dfix[i * n + c];
+          if (i > 0 && ((fm[i - 1] >> k) & 1u)) v += a2 * dfix[idx - n];
+          if (i < m - 1 && ((fm[i + 1] >> k) & 1u)) v += a2 * dfix[idx + n];
+        }
+      }
+      bb[idx] = v;
     }
     if (tid == 0) sflag[0] = 0;
     __syncthreads();
@@ -454,6 +474,22 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
         xs[i * n + r] = acc;
       }
       __syncthreads();
+    }
+    if (as_round < p.as_rounds) {  // free variables pushed beyond a limit: hold them on it and solve again
+      int viol = 0;
+      for (int idx = tid; idx < m * n; idx += NT) {
+        const int i = idx / n, r = idx - i * n;
+        if ((fm[i] >> r) & 1u) continue;
+        const double xc = X[(i + 2) * n + r], xn = xc + xs[idx];
+        if (xn < R.lo[r]) { dfix[idx] = R.lo[r] - xc; viol = 1; }
+        else if (xn > R.hi[r]) { dfix[idx] = R.hi[r] - xc; viol = 1; }
+        if (xn < R.lo[r] || xn > R.hi[r]) atomicOr(fm + i, 1u << r);
+      }
+      if (__syncthreads_or(viol)) {
+        ++as_round;
+        ok = false;
+        attempt = -1;  // the positive-definiteness retries start over for the new system
+      }
     }
   }
   if (!ok) {

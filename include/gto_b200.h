@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GTO_ABI_VERSION 3
+#define GTO_ABI_VERSION 4
 
 /* error codes */
 #define GTO_OK 0
@@ -111,10 +111,15 @@ typedef struct gto_options {
   double bound_eps;    /* 1e-12 */
   int32_t check_every; /* host polls the device convergence counter every this many iterations (4) */
   double ftol;         /* GTO_STATUS_SLOW: accepted step with cost reduction <= ftol*f ...          (1e-6) */
-  double lambda_slow;  /* ... while the damping that produced it was >= lambda_slow                  (1.0)  */
+  double lambda_slow;  /* ... while the damping that produced it was >= lambda_slow  (1e30 = the test is off: iterates resting
+                          on a kink of the trilinear field are iterated until |dq| <= tol_step like any other) */
   int32_t slow_window; /* GTO_STATUS_SLOW as well when the cost fell by <= slow_ftol*f over the last slow_window
                           iterations (default 0 = disabled: it also fires during slow but healthy linear convergence; at most 16) */
   double slow_ftol;    /* (1e-3) */
+  int32_t as_rounds;   /* active-set rounds per step (1): free variables that the step pushes beyond a joint limit are moved
+                          exactly onto it and the other variables are re-solved; 0 = plain clipping of the step */
+  double lambda_reject; /* a rejected step raises the damping to at least this value (1e-4): from lambda_min ~ 1e-9 the
+                           doubling rule alone needs ~7 rejections before the damping changes the step at all */
 } gto_options;
 
 /*

@@ -250,7 +250,7 @@ static void solve_one(job_t* J, int b) {
     prob_ctx P;
     P.R = R; P.fields = fields; P.in = in; P.b = b;
     const size_t wsz = (size_t)R->nmov * 12 + 6 * n + 2 * ((size_t)T * nd + (size_t)T * nn + (size_t)T * n + T) + 2 * (size_t)T * n +
-                       (size_t)m * nn + 4 * (size_t)m * n + 4 * n;
+                       (size_t)m * nn + 5 * (size_t)m * n + 4 * n;
     double* W = (double*)calloc(wsz, sizeof(double));
     unsigned char* fx = (unsigned char*)calloc((size_t)m * n + 1, 1);
     if (!W || !fx) {
@@ -280,6 +280,7 @@ static void solve_one(job_t* J, int b) {
     double* xs = w; w += (size_t)m * n;
     double* u = w; w += n;
     double* xnext = w; w += n;
+    double* dfix = w; w += (size_t)m * n;  /* prescribed step of the variables held at a bound */
     /* initial trajectory: seed projected on the constraints */
     memcpy(Q, in->q_seed + (size_t)b * T * nd, sizeof(double) * T * nd);
     for (int t = 0; t < T; ++t)
@@ -314,7 +315,15 @@ static void solve_one(job_t* J, int b) {
           if (!fixed && fabs(gtv) > pgmax) pgmax = fabs(gtv);
         }
       if (2.0 * pgmax <= opt->tol_grad) { status = GTO_STATUS_CONVERGED; break; }
-      int ok = 0;
+      /* Active-set rounds (gto_options.as_rounds): a free variable that the damped Gauss-Newton step pushes beyond a joint
+       * limit is moved exactly onto the limit (prescribed step dfix) and the remaining variables are re-solved with that
+       * step on the right-hand side -- one round of an active-set method for the bound-constrained quadratic model.
+       * Clipping alone (round 0) distorts the coupled step: the model then often predicts an increase and the step is
+       * rejected again and again while the damping rises. */
+      for (int i = 0; i < m * n; ++i) dfix[i] = 0.0;
+      int as_round = 0, ok;
+    resolve:
+      ok = 0;
       for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
         ok = 1;
         for (int i = 0; i < m && ok; ++i) {
@@ -335,7 +344,16 @@ static void solve_one(job_t* J, int b) {
             }
           for (int r = 0; r < n; ++r) {
             const int fr = fx[i * n + r];
-            double uu = fr ? 0.0 : -gt[i * n + r];
+            double uu;
+            if (fr) {
+              uu = dfix[i * n + r];
+            } else {  /* free row: -g - (coupling to the prescribed steps of held variables) */
+              uu = -gt[i * n + r];
+              for (int c = 0; c < n; ++c)
+                if (c != r && fx[i * n + c]) uu -= H[(size_t)t * nn + r * n + c] * dfix[i * n + c];
+              if (i > 0 && fx[(i - 1) * n + r]) uu += a2 * dfix[(i - 1) * n + r];
+              if (i < m - 1 && fx[(i + 1) * n + r]) uu += a2 * dfix[(i + 1) * n + r];
+            }
             if (i > 0) uu += ((fr || fx[(i - 1) * n + r]) ? 0.0 : a2) * vv[(i - 1) * n + r];
             u[r] = uu;
           }
@@ -372,6 +390,17 @@ static void solve_one(job_t* J, int b) {
           if (fabs(d) > stepmax) stepmax = fabs(d);
           gdot += gt[i * n + r] * d;
         }
+      }
+      if (as_round < opt->as_rounds) {
+        int nviol = 0;
+        for (int i = 0; i < m; ++i)
+          for (int r = 0; r < n; ++r) {
+            if (fx[i * n + r]) continue;
+            const double xc = X[(i + 2) * n + r], xn = xc + xs[i * n + r];
+            if (xn < R->lo[r]) { fx[i * n + r] = 1; dfix[i * n + r] = R->lo[r] - xc; ++nviol; }
+            else if (xn > R->hi[r]) { fx[i * n + r] = 1; dfix[i * n + r] = R->hi[r] - xc; ++nviol; }
+          }
+        if (nviol) { ++as_round; goto resolve; }
       }
       double quad = 0.0;
       for (int i = 0; i < m; ++i) {
@@ -413,7 +442,7 @@ static void solve_one(job_t* J, int b) {
         if (lam_used >= opt->lambda_slow && ared <= opt->ftol * F_before) { status = GTO_STATUS_SLOW; break; }
       } else {
         if (pred <= 0.0 && stepmax <= opt->tol_step) { status = GTO_STATUS_CONVERGED; break; }
-        lam = fmin(opt->lambda_max, lam * nu);
+        lam = fmin(opt->lambda_max, fmax(lam * nu, opt->lambda_reject));
         nu *= 2.0;
         if (lam >= opt->lambda_max) { status = GTO_STATUS_STALLED; break; }
       }

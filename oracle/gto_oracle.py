@@ -473,9 +473,11 @@ class SolverOptions:
     noise_rel: float = 1e-6  # reductions below noise_rel * point-cost are inside fp32 noise
     bound_eps: float = 1e-12
     ftol: float = 1e-6  # STATUS_SLOW: an accepted step reduced the cost by <= ftol*f ...
-    lambda_slow: float = 1.0  # ... while the damping that produced it was >= lambda_slow
+    lambda_slow: float = 1e30  # ... while the damping that produced it was >= lambda_slow (1e30: test off)
     slow_window: int = 0  # >0: STATUS_SLOW as well when the cost fell by <= slow_ftol*f over the last slow_window iterations (off)
     slow_ftol: float = 1e-3
+    as_rounds: int = 1  # active-set rounds per step: variables pushed beyond a limit are put on it, the rest re-solved
+    lambda_reject: float = 1e-4  # a rejected step raises the damping to at least this value
 
 
 STATUS_CONVERGED = 0
@@ -567,6 +569,34 @@ def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: So
     # variables and note that a fixed variable has d=0, so its coupling contributes nothing as long
     # as its own equation is decoupled.  We decouple by masking in the block factorisation.
     d = _solve_masked(Dd, -a2, -pg, fixed)
+    # Active-set rounds: a free variable that the step pushes beyond a joint limit is moved exactly onto the limit
+    # (prescribed step dfix) and the other variables are re-solved with that step on the right-hand side -- one round of an
+    # active-set method for the bound-constrained quadratic model.  Clipping alone distorts the coupled step: the model
+    # then often predicts an increase and the step is rejected again and again while the damping rises.
+    dfix = np.zeros_like(gt)
+    for _ in range(opts.as_rounds):
+        Xn = X + d
+        viol_lo = (~fixed) & (Xn < tb.lo)
+        viol_hi = (~fixed) & (Xn > tb.hi)
+        if not (viol_lo.any() or viol_hi.any()):
+            break
+        dfix = np.where(viol_lo, tb.lo - X, np.where(viol_hi, tb.hi - X, dfix))
+        fixed = fixed | viol_lo | viol_hi
+        rhs = np.zeros_like(gt)
+        for i in range(m):
+            fi = fixed[i]
+            Dd[i][fi, :] = 0.0
+            Dd[i][:, fi] = 0.0
+            Dd[i][fi, fi] = 1.0
+            # free rows: -g - H[free, held] dfix[held] + a2 (dfix of the same joint at the neighbouring knots)
+            Hoff = D[i] - np.diag(np.diag(D[i]))
+            r = -gt[i] - Hoff @ dfix[i]
+            if i > 0:
+                r = r + a2 * dfix[i - 1]
+            if i + 1 < m:
+                r = r + a2 * dfix[i + 1]
+            rhs[i] = np.where(fi, dfix[i], r)
+        d = _solve_masked(Dd, -a2, rhs, fixed)
     Xn = np.clip(X + d, tb.lo, tb.hi)
     d = Xn - X
     Ad = _matvec(D, -a2, d)
@@ -673,7 +703,7 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
             if pred <= 0 and step <= opts.tol_step:
                 status = STATUS_CONVERGED
                 break
-            lam = min(opts.lambda_max, lam * nu)
+            lam = min(opts.lambda_max, max(lam * nu, opts.lambda_reject))
             nu *= 2.0
             if lam >= opts.lambda_max:
                 status = STATUS_STALLED
