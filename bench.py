@@ -263,12 +263,12 @@ def run_b200(args):
     # stream.  The timed region above measures the kernels with in-kernel %globaltimer stamps instead, because an event
     # record between two launches costs ~3 us of stream serialisation (x ~300 launches per solve).
     ev = {"lin_ms": 0.0, "step_ms": 0.0, "solve_ms": 0.0}
-    os.environ["GTO_LAUNCH_EVENTS"] = "1"
+    ctx.configure(launch_events=1)
     for _ in range(args.steps):
         ctx.solve_resident(opts)
         p = ctx.profile()
         ev["lin_ms"] += p["linearize_ms"]; ev["step_ms"] += p["step_ms"]; ev["solve_ms"] += p["solve_ms"]
-    os.environ.pop("GTO_LAUNCH_EVENTS", None)
+    ctx.configure(launch_events=0)
     sync_all()
     res = ctx.download_batch()
     conv = int(np.sum(res["status"] == capi.STATUS_CONVERGED))

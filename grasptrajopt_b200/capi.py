@@ -20,12 +20,12 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgto_b200.so")
 
 GTO_OK = 0
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN, STATUS_STALLED, STATUS_SLOW = 0, 1, 2, 3, 4
-FLAG_NO_JROWS, FLAG_NO_TMA, FLAG_NO_BRICK, FLAG_V1_KERNEL, FLAG_PIPE_KERNEL, FLAG_NO_CULL = 1, 2, 4, 8, 16, 32
+FLAG_NO_JROWS, FLAG_NO_CULL = 1, 32
 
 SYMBOLS = [
     "gto_abi_version", "gto_create", "gto_destroy", "gto_last_error", "gto_default_options", "gto_set_robot",
     "gto_set_field", "gto_solve_batch", "gto_upload_batch", "gto_solve_resident", "gto_download_batch",
-    "gto_result_device_ptr", "gto_eval_batch", "gto_get_profile", "gto_plan_cost", "gto_cloud_set", "gto_cloud_query",
+    "gto_result_device_ptr", "gto_eval_batch", "gto_get_profile", "gto_configure", "gto_plan_cost", "gto_cloud_set", "gto_cloud_query",
     "gto_base_place",
 ]
 
@@ -64,7 +64,7 @@ class Options(C.Structure):
         ("max_iter", C.c_int32), ("tol_step", C.c_double), ("tol_grad", C.c_double), ("lambda0", C.c_double),
         ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("eta", C.c_double), ("noise_rel", C.c_double),
         ("bound_eps", C.c_double), ("check_every", C.c_int32), ("ftol", C.c_double), ("lambda_slow", C.c_double),
-        ("slow_window", C.c_int32), ("slow_ftol", C.c_double), ("as_rounds", C.c_int32), ("lambda_reject", C.c_double),
+        ("slow_window", C.c_int32), ("slow_ftol", C.c_double), ("as_rounds", C.c_int32), ("lambda_reject", C.c_double), ("lambda_conv", C.c_double),
     ]
 
 
@@ -82,7 +82,7 @@ class BatchOut(C.Structure):
 
 
 class EvalOut(C.Structure):
-    _fields_ = [("rows", _fp), ("H", _fp), ("g", _fp), ("cost", _fp)]
+    _fields_ = [("rows", _fp), ("H", _fp), ("g", _dp), ("cost", _dp)]
 
 
 class BaseIn(C.Structure):
@@ -141,6 +141,7 @@ def load_library(path: Optional[str] = None):
     lib.gto_result_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.gto_eval_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(EvalOut)]
     lib.gto_get_profile.argtypes = [C.c_void_p, C.POINTER(Profile)]
+    lib.gto_configure.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.gto_cloud_set.argtypes = [C.c_void_p, _dp, C.c_int64]
     lib.gto_cloud_query.argtypes = [C.c_void_p, _dp, C.c_int64, _fp, C.c_int32, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_double, _fp, _dp]
     lib.gto_plan_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp]
@@ -335,14 +336,20 @@ class GtoContext:
         s, keep = self._batch_in(b)
         B, T, n = b.B, int(b.T), t.nopt
         nrows = (T * t.npoints if b.collision_avoidance else 0) + 3 * t.grip_pt_count * (2 if b.use_standoff else 1)
-        res = dict(H=np.zeros((B, T, n, n), np.float32), g=np.zeros((B, T, n), np.float32), cost=np.zeros((B, T), np.float32))
+        res = dict(H=np.zeros((B, T, n, n), np.float32), g=np.zeros((B, T, n), np.float64), cost=np.zeros((B, T), np.float64))
         e = EvalOut()
         if want_rows:
             res["rows"] = np.zeros((B, nrows, n + 1), np.float32)
             e.rows = _ptr(res["rows"], _fp)
-        e.H, e.g, e.cost = _ptr(res["H"], _fp), _ptr(res["g"], _fp), _ptr(res["cost"], _fp)
+        e.H, e.g, e.cost = _ptr(res["H"], _fp), _ptr(res["g"], _dp), _ptr(res["cost"], _dp)
         self._check(self._lib.gto_eval_batch(self._h, C.byref(s), C.byref(e)))
         return res
+
+    def configure(self, **knobs):
+        """Run-time tuning knobs (``gto_configure``): jrows_budget_mb, pdl, launch_events, step_fk, cull_nslot, cons_warps,
+        slot_floats, step_dbg."""
+        for k, v in knobs.items():
+            self._check(self._lib.gto_configure(self._h, k.encode(), float(v)))
 
     def profile(self) -> dict:
         p = Profile()

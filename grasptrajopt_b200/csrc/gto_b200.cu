@@ -26,13 +26,10 @@
 
 #include "../../include/gto_b200.h"
 
-#define NCLASS 3
-#define BRICK_MAX 24
-// SDF brick edge per class (one TMA tensor map per field and class: the box size is baked into the descriptor)
-__host__ __device__ __forceinline__ int kBrickClassDev(int k) { return k == 0 ? 8 : (k == 1 ? 16 : 24); }
 #define MAX_FIELDS 4096
 #define MAX_CHUNKS 1024
-#define LIN_MAX_WARPS 8
+#define CULL_NAXC 7      // per-axis TMA box sizes 8,12,...,32 (one tensor map per combination and field)
+#define CULL_MAX_CONS 8  // consumer warps of k_linearize_cull
 
 // ------------------------------------------------------------------------------------------------------------------
 // device-side tables
@@ -55,7 +52,6 @@ struct RobotDev {
   float link_center[GTO_MAX_LINKS][4];  // AABB of the link's points in its visual frame
   float link_half[GTO_MAX_LINKS][4];
   int link_chunk0[GTO_MAX_LINKS + 1];   // chunk range per link
-  int part_link0[3][5];                 // link ranges when an item is split in 1 / 2 / 4 parts (tail launches)
   int grip_mov;
   float grip_tf[12];
   int grip_pt_start, grip_pt_count;
@@ -68,8 +64,7 @@ struct FieldDev {
   const float* data;  // [nx][ny][nzp]
   int nx, ny, nz, nzp;
   float ox, oy, oz, inv_pitch;
-  int has_tma;
-  const CUtensorMap* maps2;  // [7*7*7] tile maps with per-axis box sizes 8,12,...,32 (k_linearize_pipe); NULL if unavailable
+  const CUtensorMap* maps2;  // [7*7*7] TMA tile maps with per-axis box sizes 8,12,...,32; NULL if unavailable
   const unsigned* svt;       // [(nx+1)][(ny+1)][(nz+1)] summed-volume table of the non-zero nodes (culling test); NULL if unavailable
 };
 
@@ -85,24 +80,20 @@ struct LinParams {
   const float* base;       // [B][4]
   const int* field_ids;    // [B][2]
   const FieldDev* fields;
-  const CUtensorMap* tmaps;  // [MAX_FIELDS][NCLASS]
   const int* active;       // problem ids (NULL: identity)
   const int* nactive;      // device counter (NULL: use nproblems)
   int nproblems;
   int b0;                  // first problem of the chunk (rows buffer is indexed by b - b0)
   const int* bufsel;       // [B] accepted buffer per problem; output goes to the other one (NULL: buffer 0)
   float* H;                // [2][Bcap][T][nopt*nopt]
-  float* g;                // [2][Bcap][T][nopt]
-  float* costp;            // [2][Bcap][T]
+  double* g;               // [2][Bcap][T][nopt]   J^T r (float64 accumulation)
+  double* costp;           // [2][Bcap][T]         sum r^2
   long long buf_stride_H, buf_stride_g, buf_stride_c;     // accepted / trial buffer
-  long long part_stride_H, part_stride_g, part_stride_c;  // item part (an item may be split over several CTAs)
   float* rows;             // [Bchunk][nrows][RS] or NULL
   long long rows_per_problem;
   int T, t_lo, knot_standoff, use_standoff, collision;
   float sw_obs, sw_goal;
   unsigned flags;
-  int brick_max;           // largest brick edge that fits the shared memory carve-out
-  int allow_split;         // solver launches: split items over several CTAs when few are left (see split_factor)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -170,70 +161,6 @@ __device__ __forceinline__ void stamp_end(unsigned long long* ts) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-#define GTO_SPLIT_MAX 4
-// Tail launches: when few (problem, knot) items are left, each item is split over 2 or 4 CTAs (contiguous link ranges).
-// Both kernels derive the factor from the same device counter, so no host round trip is needed.
-__host__ __device__ __forceinline__ int split_factor(long long nitems, int grid) {
-  if (nitems * 4 <= grid) return 4;
-  if (nitems * 2 <= grid) return 2;
-  return 1;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// shared-memory carve-up of k_linearize
-// ------------------------------------------------------------------------------------------------------------------
-struct LinShared {
-  double Tm[GTO_MAX_MOV][12];        // movable joint frames (float64)
-  double A[GTO_MAX_MOV][12];         // origin * motion of each movable joint
-  float frames[GTO_MAX_LINKS][12];   // visual frame of each collision link (robot base frame)
-  float tw[GTO_MAX_OPT][8];          // (omega.xyz, -, m.xyz, -) per optimised joint
-  float gripf[12];
-  float goal[2][12];                 // gripper frame minus goal / stand-off frame (difference formed in float64)
-  float basep[4];
-  int brick_lo[GTO_MAX_LINKS][3];
-  int brick_cls[GTO_MAX_LINKS];      // class index, -1: no brick
-  float red[LIN_MAX_WARPS][GTO_MAX_OPT * GTO_MAX_OPT + GTO_MAX_OPT + 2];
-  unsigned long long mbar;
-};
-
-// Trilinear value + analytic gradient.  The brick is a cube of edge `bB` whose lower corner is
-// grid index (bl[0], bl[1], bl[2]); lookups whose 8 corners are not all inside it go to global memory.
-__device__ __forceinline__ void sdf_trilinear(const FieldDev& f, const float* __restrict__ brick, int bB, const int* bl, float wx,
-                                              float wy, float wz, float& val, float& gx, float& gy, float& gz) {
-  float ux = (wx - f.ox) * f.inv_pitch, uy = (wy - f.oy) * f.inv_pitch, uz = (wz - f.oz) * f.inv_pitch;
-  int ix = min(max((int)floorf(ux), 0), f.nx - 2);
-  int iy = min(max((int)floorf(uy), 0), f.ny - 2);
-  int iz = min(max((int)floorf(uz), 0), f.nz - 2);
-  float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
-  const bool inx = (fx >= 0.f) && (fx <= 1.f), iny = (fy >= 0.f) && (fy <= 1.f), inz = (fz >= 0.f) && (fz <= 1.f);
-  fx = fminf(fmaxf(fx, 0.f), 1.f);
-  fy = fminf(fmaxf(fy, 0.f), 1.f);
-  fz = fminf(fmaxf(fz, 0.f), 1.f);
-  float c000, c001, c010, c011, c100, c101, c110, c111;
-  int lx = ix - bl[0], ly = iy - bl[1], lz = iz - bl[2];
-  if (bB > 0 && lx >= 0 && ly >= 0 && lz >= 0 && lx <= bB - 2 && ly <= bB - 2 && lz <= bB - 2) {
-    const float* p = brick + (lx * bB + ly) * bB + lz;
-    const int sy = bB, sx = bB * bB;
-    c000 = p[0]; c001 = p[1]; c010 = p[sy]; c011 = p[sy + 1];
-    c100 = p[sx]; c101 = p[sx + 1]; c110 = p[sx + sy]; c111 = p[sx + sy + 1];
-  } else {
-    const float* p = f.data + ((long long)ix * f.ny + iy) * f.nzp + iz;
-    const long long sy = f.nzp, sx = (long long)f.ny * f.nzp;
-    c000 = __ldg(p); c001 = __ldg(p + 1); c010 = __ldg(p + sy); c011 = __ldg(p + sy + 1);
-    c100 = __ldg(p + sx); c101 = __ldg(p + sx + 1); c110 = __ldg(p + sx + sy); c111 = __ldg(p + sx + sy + 1);
-  }
-  // interpolate along z, then y, then x (same association order as the oracle)
-  const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
-  const float z00 = fmaf(fz, d00, c000), z01 = fmaf(fz, d01, c010), z10 = fmaf(fz, d10, c100), z11 = fmaf(fz, d11, c110);
-  const float y0 = fmaf(fy, z01 - z00, z00), y1 = fmaf(fy, z11 - z10, z10);
-  val = fmaf(fx, y1 - y0, y0);
-  const float dy0 = z01 - z00, dy1 = z11 - z10;
-  const float dz0 = fmaf(fy, d01 - d00, d00), dz1 = fmaf(fy, d11 - d10, d10);
-  gx = inx ? (y1 - y0) * f.inv_pitch : 0.f;
-  gy = iny ? fmaf(fx, dy1 - dy0, dy0) * f.inv_pitch : 0.f;
-  gz = inz ? fmaf(fx, dz1 - dz0, dz0) * f.inv_pitch : 0.f;
-}
-
 // 3x4 product C = A * B (both [R|t] row-major, implicit last row 0 0 0 1)
 // a0*b0 + a1*b1 + a2*b2 with a fixed association (explicit fused multiply-adds): every code shape that forms a frame
 // entry -- unrolled 3x4 product, one entry per lane -- gives the same bits
@@ -256,7 +183,13 @@ __device__ __forceinline__ void mul34(const TA* A, const TB* B, TC* C) {
 
 // Warp-level: add this chunk's rows (staged in shared memory as [32][RS]) into the tensor-core accumulators.
 // A[m][k] = J[point k][col m], B[k][n] = J[point k][col n]  =>  D = J^T J.  NP = 8: one 16x8 tile (rows 8..15 unused);
-// NP = 16: two n-tiles.
+// NP = 16: two n-tiles.  Error-compensated TF32 ("3xTF32"): every operand is split into hi = tf32(x) and lo = tf32(x - hi) and
+// D += hi*hi + hi*lo + lo*hi, which brings the contraction from the 10-bit TF32 mantissa (5e-4 relative per product) to
+// float32 accuracy -- the LM path (accept / reject decisions near kinks of the field) is sensitive to 1e-6 changes of J^T J.
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
 template <int NP>
 __device__ __forceinline__ void mma_rows(const float* st, int RS, int nrows32, float (&acc0)[4], float (&acc1)[4], int lane) {
   const int gq = lane >> 2, tq = lane & 3;
@@ -265,12 +198,22 @@ __device__ __forceinline__ void mma_rows(const float* st, int RS, int nrows32, f
     if (ks * 8 >= nrows32) break;
     const float* r0 = st + (ks * 8 + tq) * RS;
     const float* r1 = r0 + 4 * RS;
-    const uint32_t a0 = f2tf32(r0[gq]), a2 = f2tf32(r1[gq]);
+    uint32_t a0, a2, l0, l2;
+    tf32_split(r0[gq], a0, l0);
+    tf32_split(r1[gq], a2, l2);
     if (NP == 8) {
+      mma_tf32_16x8x8(acc0, a0, 0u, a2, 0u, l0, l2);
+      mma_tf32_16x8x8(acc0, l0, 0u, l2, 0u, a0, a2);
       mma_tf32_16x8x8(acc0, a0, 0u, a2, 0u, a0, a2);
     } else {
-      const uint32_t a1 = f2tf32(r0[gq + 8]), a3 = f2tf32(r1[gq + 8]);
+      uint32_t a1, a3, l1, l3;
+      tf32_split(r0[gq + 8], a1, l1);
+      tf32_split(r1[gq + 8], a3, l3);
+      mma_tf32_16x8x8(acc0, a0, a1, a2, a3, l0, l2);
+      mma_tf32_16x8x8(acc0, l0, l1, l2, l3, a0, a2);
       mma_tf32_16x8x8(acc0, a0, a1, a2, a3, a0, a2);
+      mma_tf32_16x8x8(acc1, a0, a1, a2, a3, l1, l3);
+      mma_tf32_16x8x8(acc1, l0, l1, l2, l3, a1, a3);
       mma_tf32_16x8x8(acc1, a0, a1, a2, a3, a1, a3);
     }
   }
@@ -287,374 +230,7 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, const float*
   }
 }
 
-template <int NP>
-__global__ void __launch_bounds__(LIN_MAX_WARPS * 32, 2) k_linearize(const __grid_constant__ LinParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  LinShared& S = *reinterpret_cast<LinShared*>(smem_raw);
-  const RobotDev& R = *p.robot;
-  const int nopt = R.nopt, RS = nopt + 1;
-  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // carve: [LinShared | brick (128B aligned) | staging per warp]
-  size_t off = (sizeof(LinShared) + 127) & ~(size_t)127;
-  float* brick = reinterpret_cast<float*>(smem_raw + off);
-  off += (size_t)p.brick_max * p.brick_max * p.brick_max * sizeof(float);
-  off = (off + 127) & ~(size_t)127;
-  const int st_floats = ((32 * RS + 16 + 31) / 32) * 32;
-  float* stage = reinterpret_cast<float*>(smem_raw + off) + warp * st_floats;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(&S.mbar);
 
-  if (threadIdx.x == 0) {
-    mbar_init(mbar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  uint32_t mbar_phase = 0;
-
-  const int nknots = p.T - p.t_lo;
-  const int nprob = p.nactive ? *p.nactive : p.nproblems;
-  const long long nitems = (long long)nprob * nknots;
-  const bool use_brick = !(p.flags & GTO_FLAG_NO_BRICK);
-  const bool use_tma = use_brick && !(p.flags & GTO_FLAG_NO_TMA);
-  const int gq = lane >> 2, tq = lane & 3;
-
-  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int a = (int)(item / nknots);
-    const int t = p.t_lo + (int)(item - (long long)a * nknots);
-    const int b = p.active ? p.active[a] : a;
-    const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
-    const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
-    const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
-    const bool is_goal = (t == p.T - 1), is_stand = (p.use_standoff && t == p.knot_standoff);
-
-    __syncthreads();  // previous item fully consumed (frames, reduction scratch)
-
-    // ---------------- forward kinematics by warp 0, in float64 ----------------
-    // The trajectory lives in float64 (k_step); doing the chain in float64 keeps the coherent frame error out of the
-    // goal residual, so the projected-gradient stopping test stays meaningful.  Frames are rounded to float32 once.
-    if (warp == 0) {
-      if (lane < R.nmov) {  // A_j = origin_j * motion_j(q_j)
-        const double qj = q[R.mov_qidx[lane]];
-        const double ax = R.mov_axis_d[lane][0], ay = R.mov_axis_d[lane][1], az = R.mov_axis_d[lane][2];
-        double M[12];
-        if (R.mov_type[lane] == GTO_JOINT_REVOLUTE) {  // Rodrigues: I + s K + (1-c) K^2
-          double s, c;
-          sincos(qj, &s, &c);
-          const double v = 1.0 - c;
-          M[0] = 1.0 - v * (ay * ay + az * az); M[1] = -s * az + v * ax * ay;      M[2] = s * ay + v * ax * az;       M[3] = 0.0;
-          M[4] = s * az + v * ax * ay;          M[5] = 1.0 - v * (ax * ax + az * az); M[6] = -s * ax + v * ay * az;   M[7] = 0.0;
-          M[8] = -s * ay + v * ax * az;         M[9] = s * ax + v * ay * az;       M[10] = 1.0 - v * (ax * ax + ay * ay); M[11] = 0.0;
-        } else {
-          M[0] = 1.0; M[1] = 0.0; M[2] = 0.0; M[3] = qj * ax;
-          M[4] = 0.0; M[5] = 1.0; M[6] = 0.0; M[7] = qj * ay;
-          M[8] = 0.0; M[9] = 0.0; M[10] = 1.0; M[11] = qj * az;
-        }
-        double C[12];
-        mul34(R.mov_origin_d[lane], M, C);
-#pragma unroll
-        for (int e = 0; e < 12; ++e) S.A[lane][e] = C[e];
-      }
-      __syncwarp();
-      for (int j = 0; j < R.nmov; ++j) {  // sequential along the tree, 12 lanes per product
-        if (lane < 12) {
-          const int r = lane >> 2, c = lane & 3;
-          const int pj = R.mov_parent[j];
-          double s;
-          if (pj < 0) {
-            s = S.A[j][lane];
-          } else {
-            const double* P = S.Tm[pj];
-            s = dot3<double>(P[r * 4 + 0], S.A[j][c], P[r * 4 + 1], S.A[j][4 + c], P[r * 4 + 2], S.A[j][8 + c]);
-            if (c == 3) s += P[r * 4 + 3];
-          }
-          S.Tm[j][lane] = s;
-        }
-        __syncwarp();
-      }
-      if (lane < R.nlinks) {  // visual frames + brick placement
-        const int mj = R.link_mov[lane];
-        double Fd[12];
-        if (mj < 0) {
-#pragma unroll
-          for (int e = 0; e < 12; ++e) Fd[e] = R.link_tf_d[lane][e];
-        } else {
-          mul34(S.Tm[mj], R.link_tf_d[lane], Fd);
-        }
-        float F[12];
-#pragma unroll
-        for (int e = 0; e < 12; ++e) {
-          F[e] = (float)Fd[e];
-          S.frames[lane][e] = F[e];
-        }
-        int cls = -1;
-        if (fid >= 0 && use_brick) {
-          const FieldDev& f = p.fields[fid];
-          const float* cc = R.link_center[lane];
-          const float* hh = R.link_half[lane];
-          const float bp[3] = {p.base[4 * b + 0], p.base[4 * b + 1], p.base[4 * b + 2]};
-          const float org[3] = {f.ox, f.oy, f.oz};
-          int need = 0, lo3[3];
-#pragma unroll
-          for (int ax3 = 0; ax3 < 3; ++ax3) {
-            const float cw = F[ax3 * 4 + 0] * cc[0] + F[ax3 * 4 + 1] * cc[1] + F[ax3 * 4 + 2] * cc[2] + F[ax3 * 4 + 3] + bp[ax3];
-            const float hw = fabsf(F[ax3 * 4 + 0]) * hh[0] + fabsf(F[ax3 * 4 + 1]) * hh[1] + fabsf(F[ax3 * 4 + 2]) * hh[2] + 1e-4f;
-            int lo = (int)floorf((cw - hw - org[ax3]) * f.inv_pitch);
-            const int hi = (int)floorf((cw + hw - org[ax3]) * f.inv_pitch);
-            if (ax3 == 2) lo &= ~3;  // TMA: the innermost start coordinate must be 16-byte aligned
-            lo3[ax3] = lo;
-            need = max(need, hi - lo + 2);
-          }
-          cls = NCLASS - 1;
-#pragma unroll
-          for (int k = NCLASS - 1; k >= 0; --k)
-            if (kBrickClassDev(k) >= need) cls = k;
-          while (cls > 0 && kBrickClassDev(cls) > p.brick_max) --cls;
-          const int Bc = kBrickClassDev(cls);
-          if (Bc > p.brick_max) cls = -1;
-          if (cls >= 0 && need > Bc) {  // partial coverage: centre the brick, the rest reads global memory
-#pragma unroll
-            for (int ax3 = 0; ax3 < 3; ++ax3) lo3[ax3] += (need - Bc) / 2;
-            lo3[2] &= ~3;
-          }
-          S.brick_lo[lane][0] = lo3[0]; S.brick_lo[lane][1] = lo3[1]; S.brick_lo[lane][2] = lo3[2];
-        }
-        S.brick_cls[lane] = cls;
-      }
-      if (lane < nopt) {  // joint twists: v(W) = omega x W + m
-        const int j = R.opt_mov[lane];
-        double om[3] = {0.0, 0.0, 0.0}, mm[3] = {0.0, 0.0, 0.0};
-        if (j >= 0) {
-          const double* Tj = S.Tm[j];
-          const double ax = R.mov_axis_d[j][0], ay = R.mov_axis_d[j][1], az = R.mov_axis_d[j][2];
-          const double zx = Tj[0] * ax + Tj[1] * ay + Tj[2] * az;
-          const double zy = Tj[4] * ax + Tj[5] * ay + Tj[6] * az;
-          const double zz = Tj[8] * ax + Tj[9] * ay + Tj[10] * az;
-          if (R.mov_type[j] == GTO_JOINT_REVOLUTE) {
-            const double ox = Tj[3], oy = Tj[7], oz = Tj[11];
-            om[0] = zx; om[1] = zy; om[2] = zz;
-            mm[0] = oy * zz - oz * zy; mm[1] = oz * zx - ox * zz; mm[2] = ox * zy - oy * zx;  // o x z
-          } else {
-            mm[0] = zx; mm[1] = zy; mm[2] = zz;
-          }
-        }
-        S.tw[lane][0] = (float)om[0]; S.tw[lane][1] = (float)om[1]; S.tw[lane][2] = (float)om[2]; S.tw[lane][3] = 0.f;
-        S.tw[lane][4] = (float)mm[0]; S.tw[lane][5] = (float)mm[1]; S.tw[lane][6] = (float)mm[2]; S.tw[lane][7] = 0.f;
-      }
-      if (lane == 31) {  // gripper link frame and its difference to the two goal frames, formed in float64
-        double F[12];
-        if (R.grip_mov < 0) {
-#pragma unroll
-          for (int e = 0; e < 12; ++e) F[e] = R.grip_tf_d[e];
-        } else {
-          mul34(S.Tm[R.grip_mov], R.grip_tf_d, F);
-        }
-#pragma unroll
-        for (int e = 0; e < 12; ++e) {
-          S.gripf[e] = (float)F[e];
-          S.goal[0][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + e]);
-          S.goal[1][e] = (float)(F[e] - p.goal_tf[(long long)b * 24 + 12 + e]);
-        }
-      }
-      if (lane >= 24 && lane < 27) S.basep[lane - 24] = p.base[4 * b + (lane - 24)];
-    }
-    __syncthreads();
-
-    // ---------------- per-thread accumulators for this (problem, knot) ----------------
-    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-    float gacc[NP];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) gacc[k] = 0.f;
-    float cacc = 0.f;
-    float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
-
-    // ---------------- obstacle rows, link by link ----------------
-    if (p.collision) {
-      const float bx = S.basep[0], by = S.basep[1], bz = S.basep[2];
-      for (int l = 0; l < R.nlinks; ++l) {
-        const int cls = (fid >= 0) ? S.brick_cls[l] : -1;
-        const int bB = (cls >= 0) ? kBrickClassDev(cls) : 0;
-        if (fid >= 0 && cls >= 0) {
-          __syncthreads();  // everyone is done with the previous brick
-          if (use_tma && p.fields[fid].has_tma) {
-            if (threadIdx.x == 0) {
-              mbar_expect_tx(mbar, (uint32_t)(bB * bB * bB * sizeof(float)));
-              tma_load_3d(brick, p.tmaps + (long long)fid * NCLASS + cls, S.brick_lo[l][2], S.brick_lo[l][1], S.brick_lo[l][0], mbar);
-            }
-            mbar_wait(mbar, mbar_phase);
-            mbar_phase ^= 1;
-          } else {
-            const FieldDev& f = p.fields[fid];
-            const int n3 = bB * bB * bB;
-            for (int i = threadIdx.x; i < n3; i += blockDim.x) {
-              const int lz = i % bB, ly = (i / bB) % bB, lx = i / (bB * bB);
-              const int gx_ = S.brick_lo[l][0] + lx, gy_ = S.brick_lo[l][1] + ly, gz_ = S.brick_lo[l][2] + lz;
-              float v = 0.f;
-              if (gx_ >= 0 && gy_ >= 0 && gz_ >= 0 && gx_ < f.nx && gy_ < f.ny && gz_ < f.nz)
-                v = __ldg(f.data + ((long long)gx_ * f.ny + gy_) * f.nzp + gz_);
-              brick[i] = v;
-            }
-            __syncthreads();
-          }
-        }
-        const unsigned mask = R.link_optmask[l];
-        const float* F = S.frames[l];
-        for (int ch = R.link_chunk0[l] + warp; ch < R.link_chunk0[l + 1]; ch += nwarps) {
-          const int p0 = p.chunk_start[ch], cnt = p.chunk_count[ch];
-          const bool act = lane < cnt;
-          float J[NP];
-#pragma unroll
-          for (int k = 0; k < NP; ++k) J[k] = 0.f;
-          float r = 0.f;
-          if (act && fid >= 0) {
-            const float x = __ldg(p.px + p0 + lane), y = __ldg(p.py + p0 + lane), z = __ldg(p.pz + p0 + lane);
-            const float wbx = F[0] * x + F[1] * y + F[2] * z + F[3];
-            const float wby = F[4] * x + F[5] * y + F[6] * z + F[7];
-            const float wbz = F[8] * x + F[9] * y + F[10] * z + F[11];
-            float val, gx, gy, gz;
-            sdf_trilinear(p.fields[fid], brick, bB, S.brick_lo[l], wbx + bx, wby + by, wbz + bz, val, gx, gy, gz);
-            r = p.sw_obs * val;
-            gx *= p.sw_obs; gy *= p.sw_obs; gz *= p.sw_obs;
-            // row_k = grad . (omega_k x W + m_k) = omega_k . (W x grad) + m_k . grad
-            const float nx = wby * gz - wbz * gy, ny = wbz * gx - wbx * gz, nz = wbx * gy - wby * gx;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              if (k < nopt && ((mask >> k) & 1u)) {
-                const float4 o4 = *reinterpret_cast<const float4*>(&S.tw[k][0]);
-                const float4 m4 = *reinterpret_cast<const float4*>(&S.tw[k][4]);
-                J[k] = o4.x * nx + o4.y * ny + o4.z * nz + m4.x * gx + m4.y * gy + m4.z * gz;
-              }
-            }
-          }
-          cacc = fmaf(r, r, cacc);
-#pragma unroll
-          for (int k = 0; k < NP; ++k) {
-            if (k < nopt) {
-              gacc[k] = fmaf(J[k], r, gacc[k]);
-              stage[lane * RS + k] = J[k];
-            }
-          }
-          stage[lane * RS + nopt] = r;
-          __syncwarp();
-          mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
-          if (rows_b) store_rows(rows_b + ((long long)t * R.npoints + p0) * RS, stage, cnt * RS, lane);
-          __syncwarp();
-        }
-      }
-    }
-
-    // ---------------- goal / stand-off rows (gripper point set, plain link frame, no base offset) ----------------
-    if (is_goal || is_stand) {
-      const int Pg = R.grip_pt_count;
-      const long long obs_rows = p.collision ? (long long)p.T * R.npoints : 0;
-      const float* Fg = S.gripf;
-      const unsigned mask = R.grip_optmask;
-      for (int which = 0; which < 2; ++which) {
-        if (which == 0 && !is_goal) continue;
-        if (which == 1 && !is_stand) continue;
-        const float* Dg = S.goal[which];
-        const long long rbase = obs_rows + (which == 1 ? 3LL * Pg : 0);
-        const int nch = (Pg + 31) / 32;
-        for (int ch = warp; ch < nch; ch += nwarps) {
-          const int k0 = ch * 32, cnt = min(32, Pg - k0);
-          const bool act = lane < cnt;
-          float w3[3] = {0.f, 0.f, 0.f}, r3[3] = {0.f, 0.f, 0.f};
-          if (act) {
-            const int pi = R.grip_pt_start + k0 + lane;
-            const float x = __ldg(p.px + pi), y = __ldg(p.py + pi), z = __ldg(p.pz + pi);
-#pragma unroll
-            for (int a3 = 0; a3 < 3; ++a3) {
-              w3[a3] = Fg[a3 * 4 + 0] * x + Fg[a3 * 4 + 1] * y + Fg[a3 * 4 + 2] * z + Fg[a3 * 4 + 3];
-              // residual = (F_gripper - F_goal) x: no cancellation between two O(1 m) positions
-              r3[a3] = p.sw_goal * (Dg[a3 * 4 + 0] * x + Dg[a3 * 4 + 1] * y + Dg[a3 * 4 + 2] * z + Dg[a3 * 4 + 3]);
-            }
-          }
-#pragma unroll
-          for (int a3 = 0; a3 < 3; ++a3) {  // rows ordered [axis][point]: each pass writes 32 contiguous rows
-            float J[NP];
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              J[k] = 0.f;
-              if (act && k < nopt && ((mask >> k) & 1u)) {
-                const float4 o4 = *reinterpret_cast<const float4*>(&S.tw[k][0]);
-                const float4 m4 = *reinterpret_cast<const float4*>(&S.tw[k][4]);
-                float v;  // (omega x W + m)[a3]
-                if (a3 == 0) v = o4.y * w3[2] - o4.z * w3[1] + m4.x;
-                else if (a3 == 1) v = o4.z * w3[0] - o4.x * w3[2] + m4.y;
-                else v = o4.x * w3[1] - o4.y * w3[0] + m4.z;
-                J[k] = p.sw_goal * v;
-              }
-            }
-            const float r = r3[a3];
-            cacc = fmaf(r, r, cacc);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              if (k < nopt) {
-                gacc[k] = fmaf(J[k], r, gacc[k]);
-                stage[lane * RS + k] = J[k];
-              }
-            }
-            stage[lane * RS + nopt] = r;
-            __syncwarp();
-            mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
-            if (rows_b) store_rows(rows_b + (rbase + (long long)a3 * Pg + k0) * RS, stage, cnt * RS, lane);
-            __syncwarp();
-          }
-        }
-      }
-    }
-
-    // ---------------- reduce over lanes / warps, write the per-knot Gauss-Newton block ----------------
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cacc += __shfl_xor_sync(0xffffffffu, cacc, o);
-    {
-      float* red = S.red[warp];
-      // accumulator fragment layout: acc[0]:(row gq, col 2tq) acc[1]:(gq, 2tq+1) acc[2]:(gq+8, 2tq) acc[3]:(gq+8, 2tq+1)
-      const int c0 = 2 * tq;
-      if (gq < nopt) {
-        if (c0 < nopt) red[gq * nopt + c0] = acc0[0];
-        if (c0 + 1 < nopt) red[gq * nopt + c0 + 1] = acc0[1];
-      }
-      if (NP == 16) {
-        if (gq + 8 < nopt) {
-          if (c0 < nopt) red[(gq + 8) * nopt + c0] = acc0[2];
-          if (c0 + 1 < nopt) red[(gq + 8) * nopt + c0 + 1] = acc0[3];
-        }
-        if (gq < nopt) {
-          if (c0 + 8 < nopt) red[gq * nopt + c0 + 8] = acc1[0];
-          if (c0 + 9 < nopt) red[gq * nopt + c0 + 9] = acc1[1];
-        }
-        if (gq + 8 < nopt) {
-          if (c0 + 8 < nopt) red[(gq + 8) * nopt + c0 + 8] = acc1[2];
-          if (c0 + 9 < nopt) red[(gq + 8) * nopt + c0 + 9] = acc1[3];
-        }
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NP; ++k)
-          if (k < nopt) red[nopt * nopt + k] = gacc[k];
-        red[nopt * nopt + nopt] = cacc;
-      }
-    }
-    __syncthreads();
-    {
-      const int nH = nopt * nopt, ntot = nH + nopt + 1;
-      for (int i = threadIdx.x; i < ntot; i += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nwarps; ++w) s += S.red[w][i];
-        const long long bt = (long long)b * p.T + t;
-        if (i < nH) p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
-        else if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
-        else p.costp[obuf * p.buf_stride_c + bt] = s;
-      }
-    }
-  }
-}
-
-#include "lin_pipe.cuh"
 #include "lin_cull.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -733,7 +309,7 @@ __global__ void k_finalize(const StateParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_step: one warp per active problem.  Mirrors oracle/gto_oracle.py solve_lm / lm_step (float64).
+// parameters of k_step_cr (step_cr.cuh); mirrors oracle/gto_oracle.py solve_lm / lm_step (float64)
 // ------------------------------------------------------------------------------------------------------------------
 struct StepParams {
   const RobotDev* robot;
@@ -743,19 +319,15 @@ struct StepParams {
   double tol_step, tol_grad, lambda_min, lambda_max, eta, noise_rel, bound_eps, ftol, lambda_slow, slow_ftol;
   int slow_window;
   int as_rounds;
-  double lambda_reject;
+  double lambda_reject, lambda_conv;
   double* Fhist;  // [B][16] accepted cost per iteration (ring)
   double* Qc;
   double* Qt;
   double* q_trial;
   const float* H;
-  const float* g;
-  float* costp;
+  const double* g;
+  double* costp;
   long long buf_stride_H, buf_stride_g, buf_stride_c;
-  long long part_stride_H, part_stride_g, part_stride_c;
-  int lin_grid;  // grid of the linearise launch (decides the item split, see split_factor)
-  int Bcap;
-  int* bufsplit;  // [2][Bcap] split factor each buffer was written with
   int* bufsel;
   double *F, *Fp, *lam, *nu, *pred, *stepn;
   int *iters, *status;
@@ -782,308 +354,7 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-// One warp (= one CTA) per active problem; the whole block-tridiagonal system of the problem lives in shared memory:
-//   X [T][n] f64 | gt [m][n] f64 | vv [m][n] f64 | dd [m][n] f64 | Sinv [m][n*n] f64 (or global) | S [2][n*n] f64 | U,V [16] f64
-//   | Hs [m][n*n] f32 | fx [m][n] u8
-__host__ __device__ inline size_t step_smem_bytes(int T, int n) {
-  const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
-  size_t d = (size_t)T * n + 3 * m * n + m * nn;
-  size_t bytes = d * sizeof(double) + (m * nn + 4) * sizeof(float) + ((m * n + 3) & ~(size_t)3) + (m + 1) * sizeof(unsigned);
-  return (bytes + 15) & ~(size_t)15;
-}
-
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// NP = padded block order (8 or 16).  Lane r < NP owns row r of the current diagonal block in registers; the
-// Gauss-Jordan inverse runs on warp shuffles (no shared-memory round trips inside the serial recurrence).
-template <int NP, bool EXACT>
-__global__ void __launch_bounds__(32) k_step(const StepParams p) {
-  extern __shared__ __align__(16) unsigned char step_smem[];
-  const RobotDev& R = *p.robot;
-  const int lane = threadIdx.x;
-  const int a_idx = blockIdx.x;
-  if (a_idx >= *p.nactive_in) return;
-  const int b = p.active_in[a_idx];
-  const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;  // EXACT: block order known at compile time
-  const double a2 = p.w_vel / (p.dt * p.dt);
-  double* X = reinterpret_cast<double*>(step_smem);
-  double* gt = X + (size_t)T * n;
-  double* vv = gt + (size_t)m * n;
-  double* dd = vv + (size_t)m * n;
-  double* Sinv = dd + (size_t)m * n;  // [m][n*n] inverse diagonal blocks of the factor (always in shared memory)
-  float* Hs = reinterpret_cast<float*>(Sinv + (size_t)m * nn);
-  unsigned char* fx = reinterpret_cast<unsigned char*>(Hs + (size_t)m * nn);
-  unsigned* fm = reinterpret_cast<unsigned*>(fx + (((size_t)m * n + 3) & ~(size_t)3));  // per-block bit-mask of fixed variables
-
-  double* Xc = p.Qc + (long long)b * T * n;
-  double* Xt = p.Qt + (long long)b * T * n;
-  int cur = p.bufsel[b];
-  const int it = p.iter;
-  double lam = p.lam[b], nu = p.nu[b];
-  // the linearise launch that produced the trial buffers split every item in `nsplit` parts
-  const int nsplit = split_factor((long long)(*p.nactive_in) * (it == 0 ? T : T - 2), p.lin_grid);
-  const int tri_buf = 1 - cur;
-  if (lane == 0) p.bufsplit[tri_buf * p.Bcap + b] = nsplit;
-
-  // ---------------- evaluate the trial point produced by the previous call ----------------
-  {
-    const int tri = 1 - cur;
-    float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
-    double s = 0.0;
-    for (int t = lane; t < T; t += 32) {
-      double c = (double)ct[t];
-      if (t >= 2 || it == 0)  // knots 0,1 live in part 0 only (see below)
-        for (int part = 1; part < nsplit; ++part) c += (double)ct[part * p.part_stride_c + t];
-      s += c;
-    }
-    const double Fp_t = warp_sum(s);
-    s = 0.0;
-    for (int i = lane; i < (T - 1) * n; i += 32) {
-      const double d = Xt[i + n] - Xt[i];
-      s += d * d;
-    }
-    const double Ft = Fp_t + a2 * warp_sum(s);
-    int done = -1;  // -1: keep running, otherwise final status
-    if (!isfinite(Ft)) {
-      done = GTO_STATUS_NAN;
-    } else if (it == 0) {  // initial point: accept unconditionally
-      // knots 0 and 1 never move and are linearised only once: keep their summed cost in part 0 of both buffers
-      if (lane < 2) {
-        float c01 = ct[lane];
-        for (int part = 1; part < nsplit; ++part) c01 += ct[part * p.part_stride_c + lane];
-        for (int buf = 0; buf < 2; ++buf) p.costp[buf * p.buf_stride_c + (long long)b * T + lane] = c01;
-      }
-      cur = tri;
-      if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
-    } else {
-      const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
-      const double ared = 0.5 * (Fcur - Ft);
-      const double noise = p.noise_rel * fmax(Fpcur, Fp_t);
-      if (pred > 0.0 && ared + noise >= p.eta * pred) {
-        const double rho = ared / pred;
-        for (int i = lane; i < T * n; i += 32) Xc[i] = Xt[i];
-        cur = tri;
-        if (lane == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
-        const double lam_used = lam;
-        const double w = 2.0 * fmin(rho, 1.0) - 1.0;
-        lam = fmax(p.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - w * w * w));
-        nu = 2.0;
-        if (step <= p.tol_step) done = GTO_STATUS_CONVERGED;
-        else if (lam_used >= p.lambda_slow && ared <= p.ftol * Fcur) done = GTO_STATUS_SLOW;
-      } else {
-        if (pred <= 0.0 && step <= p.tol_step) {
-          done = GTO_STATUS_CONVERGED;
-        } else {
-          lam = fmin(p.lambda_max, lam * nu);
-          nu *= 2.0;
-          if (lam >= p.lambda_max) done = GTO_STATUS_STALLED;
-        }
-      }
-    }
-    if (done < 0 && isfinite(Ft) && p.slow_window > 0) {  // windowed progress test on the accepted cost
-      const double Fnow = (cur == tri) ? Ft : p.F[b];
-      double* hist = p.Fhist + (long long)b * 16;
-      if (it >= p.slow_window) {
-        const double Fold = hist[(it - p.slow_window) & 15];
-        if (Fold - Fnow <= p.slow_ftol * Fnow) done = GTO_STATUS_SLOW;
-      }
-      __syncwarp();
-      if (lane == 0) hist[it & 15] = Fnow;
-    }
-    if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
-    if (done >= 0) {
-      if (lane == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
-      return;
-    }
-  }
-  __syncwarp();
-
-  // ---------------- stage the accepted point and its Gauss-Newton blocks in shared memory ----------------
-  const float* Hc = p.H + cur * p.buf_stride_H + (long long)b * T * nn;
-  const float* gc = p.g + cur * p.buf_stride_g + (long long)b * T * n;
-  // Gauss-Newton blocks: asynchronous 4-byte copies (cp.async), all in flight at once, no register staging
-  // split factor the accepted buffer was written with (it may stem from an earlier launch if trials were rejected since)
-  const int hsplit = (cur == tri_buf) ? nsplit : p.bufsplit[cur * p.Bcap + b];
-  if (hsplit == 1) {
-    for (int i = lane; i < m * nn; i += 32)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(Hs + i)), "l"(Hc + 2 * nn + i) : "memory");
-  } else {
-    for (int i = lane; i < m * nn; i += 32) {
-      float h = Hc[2 * nn + i];
-      for (int part = 1; part < hsplit; ++part) h += Hc[part * p.part_stride_H + 2 * nn + i];
-      Hs[i] = h;
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = lane; i < T * n; i += 32) X[i] = Xc[i];
-  __syncwarp();
-
-  double pgmax = 0.0;
-  {
-    const int krow = lane % n, irow0 = lane / n, istride = 32 / n;  // lanes >= istride*n idle in this loop
-    for (int i = irow0; i < m && lane < istride * n; i += istride) {
-      const int k = krow, t = i + 2, idx = i * n + k;
-      double gv = X[t * n + k] - X[(t - 1) * n + k];
-      if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
-      double gsum = (double)gc[t * n + k];
-      for (int part = 1; part < hsplit; ++part) gsum += (double)gc[part * p.part_stride_g + t * n + k];
-      const double gtv = gsum + a2 * gv;
-      const double x = X[t * n + k];
-      const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
-      gt[idx] = gtv;
-      fx[idx] = fixed ? 1 : 0;
-      if (!fixed) pgmax = fmax(pgmax, fabs(gtv));
-    }
-  }
-  pgmax = warp_max(pgmax);
-  if (2.0 * pgmax <= p.tol_grad) {
-    if (lane == 0) { p.status[b] = GTO_STATUS_CONVERGED; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
-    return;
-  }
-  __syncwarp();
-
-  for (int i = lane; i < m; i += 32) {
-    unsigned mk = 0;
-    for (int k = 0; k < n; ++k) mk |= (unsigned)fx[i * n + k] << k;
-    fm[i] = mk;
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-  // ---------------- damped projected Gauss-Newton step: block Thomas algorithm in float64 ----------------
-  const int r = lane;            // row owned by this lane (rows >= n are identity padding)
-  const bool rin = r < n;
-  bool ok = false;
-  for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
-    ok = true;
-    double prev[NP];  // row r of Sinv_{i-1}
-#pragma unroll
-    for (int c = 0; c < NP; ++c) prev[c] = 0.0;
-    double vprev = 0.0;  // v_{i-1}[r]
-    // forward sweep: S_i = D_i - C_i Sinv_{i-1} C_i ; u_i = b_i - C_i v_{i-1} ; v_i = Sinv_i u_i
-    for (int i = 0; i < m; ++i) {
-      const int t = i + 2;
-      const double cnt = (t < T - 1) ? 2.0 : 1.0;
-      const unsigned mi = fm[i], mp = (i > 0) ? fm[i - 1] : 0u;  // fixed-variable masks of this and the previous knot
-      const bool fr = rin ? ((mi >> r) & 1u) != 0 : true;
-      const bool frp = rin ? ((mp >> r) & 1u) != 0 : true;
-      const double cr = (i == 0 || fr || frp) ? 0.0 : a2;
-      const unsigned coupled = ~(mi | mp);  // bit c set: variable c is free at both knots
-      double row[NP];
-#pragma unroll
-      for (int c = 0; c < NP; ++c) {
-        double v = 0.0;
-        if (c < n) {
-          const bool fc = ((mi >> c) & 1u) != 0;
-          if (rin) {
-            v = (double)Hs[i * nn + r * n + c];
-            if (r == c) {
-              v += a2 * cnt;
-              v += lam * v;
-            }
-          }
-          if (fr || fc) v = (r == c) ? 1.0 : 0.0;
-          if (i > 0 && ((coupled >> c) & 1u)) v -= cr * a2 * prev[c];
-        } else {
-          v = (r == c) ? 1.0 : 0.0;
-        }
-        row[c] = v;
-      }
-      double u = (rin && !fr) ? -gt[i * n + r] : 0.0;
-      if (i > 0) u += cr * vprev;
-      // Gauss-Jordan inverse in registers; the pivot row travels by warp shuffle
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        const double piv = shfl_d(row[k], k);
-        if (!(piv > 0.0)) ok = false;  // uniform: every lane sees the same pivot
-        double ip = (double)__frcp_rn((float)piv);
-        ip = ip * (2.0 - piv * ip);
-        ip = ip * (2.0 - piv * ip);
-        // one fused form for every lane: row[c] += coef * pivot_row[c] with coef = ip - 1 on the pivot lane (-> row*ip) and
-        // -f*ip elsewhere; column k becomes the multiplier itself (ip on the pivot lane)
-        const bool isk = (r == k);
-        const double mult = -row[k] * ip;
-        const double coef = isk ? ip - 1.0 : mult;
-#pragma unroll
-        for (int c = 0; c < NP; ++c) {
-          if (c == k) continue;
-          row[c] = fma(coef, shfl_d(row[c], k), row[c]);
-        }
-        row[k] = isk ? ip : mult;
-      }
-      if (!ok) break;
-      // v_i = Sinv_i u_i
-      double v = 0.0;
-#pragma unroll
-      for (int c = 0; c < NP; ++c) v += row[c] * shfl_d(u, c);
-      if (rin) {
-        vv[i * n + r] = v;
-#pragma unroll
-        for (int c = 0; c < NP; ++c)
-          if (c < n) Sinv[(size_t)i * nn + r * n + c] = row[c];
-      }
-#pragma unroll
-      for (int c = 0; c < NP; ++c) prev[c] = row[c];
-      vprev = v;
-    }
-    if (!ok) lam = fmin(p.lambda_max, lam * 10.0);  // not positive definite: add damping and refactor
-    __syncwarp();
-  }
-  if (!ok) {
-    if (lane == 0) { p.status[b] = GTO_STATUS_NAN; p.iters[b] = it; }
-    return;
-  }
-  // backward sweep: x_i = v_i + Sinv_i (c_{i+1} o x_{i+1}); trial point = clip(X + x)
-  double stepmax = 0.0, gdot = 0.0, xnext = 0.0;
-  for (int i = m - 1; i >= 0; --i) {
-    const int t = i + 2;
-    double x = rin ? vv[i * n + r] : 0.0;
-    if (i < m - 1) {
-      const unsigned coupled = ~(fm[i] | fm[i + 1]);
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < NP; ++c) {
-        const double xc_ = shfl_d(xnext, c);
-        if (c < n && rin && ((coupled >> c) & 1u)) s += Sinv[(size_t)i * nn + r * n + c] * xc_;
-      }
-      x += a2 * s;
-    }
-    xnext = x;  // the unclipped solution feeds the recursion
-    if (rin) {
-      const double xc = X[t * n + r];
-      const double xn = fmin(fmax(xc + x, R.lo[r]), R.hi[r]);
-      const double d = xn - xc;
-      Xt[t * n + r] = xn;
-      p.q_trial[((long long)b * T + t) * R.ndof + R.opt_qidx[r]] = xn;
-      dd[i * n + r] = d;
-      stepmax = fmax(stepmax, fabs(d));
-      gdot += gt[i * n + r] * d;
-    }
-  }
-  __syncwarp();
-  stepmax = warp_max(stepmax);
-  gdot = warp_sum(gdot);
-  // predicted reduction with the undamped, unmasked model: -(g.d + 0.5 d^T A d); lane r sums its rows
-  double quad = 0.0;
-  if (rin) {
-    for (int i = 0; i < m; ++i) {
-      const double dg = a2 * ((i + 2 < T - 1) ? 2.0 : 1.0);
-      double hd = dg * dd[i * n + r];
-      for (int c = 0; c < n; ++c) hd += (double)Hs[i * nn + r * n + c] * dd[i * n + c];
-      quad += dd[i * n + r] * hd;
-      if (i < m - 1) quad -= 2.0 * a2 * dd[i * n + r] * dd[(i + 1) * n + r];
-    }
-  }
-  quad = warp_sum(quad);
-  if (lane == 0) {
-    p.pred[b] = -(gdot + 0.5 * quad);
-    p.stepn[b] = stepmax;
-    p.lam[b] = lam;
-    p.nu[b] = nu;
-    p.iters[b] = it + 1;
-    const int slot = atomicAdd(p.nactive_out, 1);
-    p.active_out[slot] = b;
-  }
-}
 
 #include "step_cr.cuh"
 #include "cloud_sdf.cuh"
@@ -1215,14 +486,11 @@ struct gto_ctx {
   RobotDev* robot_d = nullptr;
   DevBuf<float> px, py, pz;
   DevBuf<int> chunk_start, chunk_count;
-  int lin_warps = 8;
-  int last_lin_grid = 0;
   int pipe_cons = 8;
   double max_link_diag = 0.0;  // largest |half extent|_2 over links
   // fields
   std::vector<FieldHost> fields;
   FieldDev* fields_d = nullptr;
-  CUtensorMap* tmaps_d = nullptr;
   double min_pitch = 0.0;
   // batch (resident)
   bool has_batch = false;
@@ -1231,10 +499,11 @@ struct gto_ctx {
   double dt = 0, w_goal = 1, w_obs = 10, w_vel = 0.01;
   int standoff_offset = -10, use_standoff = 1, collision = 1;
   unsigned flags = 0;
-  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Sinv, Fhist, outQ, outdQ, outcost;
+  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Fhist, outQ, outdQ, outcost;
   DevBuf<double> q_trial, goal_tf;
-  DevBuf<float> base, H, g, costp, rows, result;
-  DevBuf<int> field_ids, bufsel, bufsplit, iters, status, active, nactive, work_ctr;
+  DevBuf<float> base, H, rows, result;
+  DevBuf<double> g, costp;
+  DevBuf<int> field_ids, bufsel, iters, status, active, nactive, work_ctr;
   DevBuf<unsigned long long> stats;
   DevBuf<long long> dbg;
   DevBuf<float4> cloud;      // depth point cloud (gto_cloud_set), padded to a multiple of CLOUD_TILE
@@ -1247,12 +516,14 @@ struct gto_ctx {
   DevBuf<float> base_occ;
   DevBuf<int> base_i;
   DevBuf<CullCtx> recs, rec_dummy;
-  bool use_pdl = true;       // programmatic dependent launch of the solver kernels (GTO_NO_PDL=1 turns it off)
+  bool use_pdl = true;       // programmatic dependent launch of the solver kernels (gto_configure "pdl")
+  // run-time tuning (gto_configure; defaults from the environment, read once in gto_create)
+  double tune_jrows_budget_mb = 24576.0;
+  int tune_step_fk = 0, tune_launch_events = 0, tune_step_dbg = 0, tune_cons = 0, tune_nslot = 4, tune_slot_floats = 0;
+  long long cull_smem_set = -1, step_smem_set = -1;  // dynamic shared memory the kernels were last configured for
+  int cull_occ = 0;
   int* h_counter = nullptr;  // pinned, 16 ints
-  std::vector<cudaStream_t> gstreams;  // one stream per problem group (see gto_solve_resident)
-  cudaEvent_t ev_fork = nullptr;
-  std::vector<cudaEvent_t> ev_join;
-  cudaEvent_t ev_poll[16] = {nullptr};  // convergence polls in flight: [group][parity]
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};  // convergence polls in flight (two parities)
   long long rows_per_problem = 0;
   int Bchunk = 0;
   // profiling
@@ -1302,6 +573,22 @@ extern "C" void gto_default_options(gto_options* o) {
   o->slow_ftol = 1e-3;
   o->as_rounds = 1;
   o->lambda_reject = 1e-4;
+  o->lambda_conv = 1e-2;
+}
+
+extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
+  if (!ctx || !key) return GTO_ERR_INVALID;
+  const std::string k(key);
+  if (k == "jrows_budget_mb") ctx->tune_jrows_budget_mb = value > 0 ? value : 24576.0;
+  else if (k == "pdl") ctx->use_pdl = value != 0;
+  else if (k == "launch_events") ctx->tune_launch_events = value != 0;
+  else if (k == "step_fk") ctx->tune_step_fk = (int)value;
+  else if (k == "cull_nslot") { ctx->tune_nslot = (int)value; ctx->cull_smem_set = -1; }
+  else if (k == "cons_warps") { ctx->tune_cons = (int)value; ctx->cull_smem_set = -1; }
+  else if (k == "slot_floats") { ctx->tune_slot_floats = (int)value; ctx->cull_smem_set = -1; }
+  else if (k == "step_dbg") ctx->tune_step_dbg = value != 0;
+  else return fail(ctx, GTO_ERR_INVALID, "gto_configure: unknown key '" + k + "'");
+  return GTO_OK;
 }
 
 extern "C" const char* gto_last_error(gto_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1329,11 +616,17 @@ extern "C" int gto_create(gto_ctx** out, int device) {
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     ctx->encode = (PFN_encodeTiled)fn;
-  ctx->use_pdl = getenv("GTO_NO_PDL") == nullptr;
+  {  // tuning defaults from the environment (read once; gto_configure changes them afterwards)
+    static const char* keys[] = {"jrows_budget_mb", "pdl", "launch_events", "step_fk", "cull_nslot", "cons_warps", "slot_floats", "step_dbg"};
+    for (const char* k : keys) {
+      std::string e = std::string("GTO_") + k;
+      for (auto& ch : e) ch = (char)toupper((unsigned char)ch);
+      if (const char* v = getenv(e.c_str())) gto_configure(ctx, k, atof(v));
+    }
+  }
   ctx->fields.resize(MAX_FIELDS);
   if (cudaMalloc((void**)&ctx->robot_d, sizeof(RobotDev)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->fields_d, sizeof(FieldDev) * MAX_FIELDS) != cudaSuccess ||
-      cudaMalloc((void**)&ctx->tmaps_d, sizeof(CUtensorMap) * MAX_FIELDS * NCLASS) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_counter, sizeof(int) * 16) != cudaSuccess) {
     gto_destroy(ctx);
     return GTO_ERR_NOMEM;
@@ -1353,21 +646,17 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
     if (f.svt) cudaFree(f.svt);
   }
   for (auto e : ctx->ev) cudaEventDestroy(e);
-  for (auto e : ctx->ev_join) cudaEventDestroy(e);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < 2; ++i)
     if (ctx->ev_poll[i]) cudaEventDestroy(ctx->ev_poll[i]);
-  for (auto st_ : ctx->gstreams) cudaStreamDestroy(st_);
   if (ctx->robot_d) cudaFree(ctx->robot_d);
   if (ctx->fields_d) cudaFree(ctx->fields_d);
-  if (ctx->tmaps_d) cudaFree(ctx->tmaps_d);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   ctx->px.release(); ctx->py.release(); ctx->pz.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
   ctx->qc.release(); ctx->q_seed.release(); ctx->Qc.release(); ctx->Qt.release(); ctx->F.release(); ctx->Fp.release();
-  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Sinv.release(); ctx->Fhist.release();
+  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Fhist.release();
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
-  ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->bufsplit.release(); ctx->iters.release();
+  ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
   ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release();
   ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->cloud_tiles.release(); ctx->recs.release(); ctx->rec_dummy.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1407,7 +696,6 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
   for (int i = 0; i < r->npoints; ++i) { hx[i] = r->points[3 * i]; hy[i] = r->points[3 * i + 1]; hz[i] = r->points[3 * i + 2]; }
   std::vector<int> cs, cc;
   ctx->max_link_diag = 0.0;
-  int max_chunks_per_link = 1;
   for (int l = 0; l < r->nlinks; ++l) {
     const int s = r->link_pt_start[l], n = r->link_pt_count[l];
     if (s < 0 || n < 0 || s + n > r->npoints || r->link_mov[l] >= r->nmov) return fail(ctx, GTO_ERR_INVALID, "link table out of range");
@@ -1427,22 +715,9 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
     ctx->max_link_diag = std::max(ctx->max_link_diag, sqrt(diag));
     h.link_chunk0[l] = (int)cs.size();
     for (int o = 0; o < n; o += 32) { cs.push_back(s + o); cc.push_back(std::min(32, n - o)); }
-    max_chunks_per_link = std::max(max_chunks_per_link, (n + 31) / 32);
   }
   h.link_chunk0[r->nlinks] = (int)cs.size();
   h.nchunks = (int)cs.size();
-  for (int si = 0; si < 3; ++si) {  // contiguous link ranges with balanced chunk counts for 1 / 2 / 4 parts
-    const int S = 1 << si;
-    h.part_link0[si][0] = 0;
-    int l = 0;
-    for (int part = 1; part <= S; ++part) {
-      const int target = (int)((long long)h.nchunks * part / S);
-      while (l < r->nlinks && h.link_chunk0[l + 1] <= target) ++l;
-      if (part == S) l = r->nlinks;
-      h.part_link0[si][part] = std::max(l, h.part_link0[si][part - 1]);
-    }
-    for (int part = S + 1; part < 5; ++part) h.part_link0[si][part] = r->nlinks;
-  }
   if (h.nchunks > MAX_CHUNKS * 64) return fail(ctx, GTO_ERR_INVALID, "too many surface points");
   h.grip_mov = r->grip_mov; h.grip_pt_start = r->grip_pt_start; h.grip_pt_count = r->grip_pt_count; h.grip_optmask = r->grip_optmask;
   if (r->grip_pt_start < 0 || r->grip_pt_count < 1 || r->grip_pt_start + r->grip_pt_count > r->npoints || r->grip_mov >= r->nmov)
@@ -1454,24 +729,10 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
     for (int a = 0; a < 4; ++a)
       for (int c = 0; c < 4; ++c) ctx->grip_mom[4 * a + c] += v[a] * v[c];
   }
-  // warps per CTA: least idle lanes when a link's chunks are dealt round-robin to the warps
-  int best = 8;
-  double best_eff = 0;
-  for (int w = 4; w <= LIN_MAX_WARPS; ++w) {
-    double used = 0, slots = 0;
-    for (int l = 0; l < r->nlinks; ++l) {
-      const int c = (r->link_pt_count[l] + 31) / 32;
-      used += c;
-      slots += (double)((c + w - 1) / w) * w;
-    }
-    const double eff = slots > 0 ? used / slots : 1;
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
-  }
-  ctx->lin_warps = best;
-  {  // consumer warps of the pipelined kernel: chunks are dealt round-robin over the whole item
+  {  // consumer warps of k_linearize_cull: chunks are dealt round-robin over the whole item
     int bestc = 8;
     double beff = 0;
-    for (int w = PIPE_MAX_CONS; w >= 5; --w) {  // prefer more warps on ties (latency hiding)
+    for (int w = CULL_MAX_CONS; w >= 5; --w) {  // prefer more warps on ties (latency hiding)
       const double eff = (double)h.nchunks / ((double)((h.nchunks + w - 1) / w) * w);
       if (eff > beff + 1e-9) { beff = eff; bestc = w; }
     }
@@ -1496,6 +757,7 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
   if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2 || !(pitch > 0)) return fail(ctx, GTO_ERR_INVALID, "field needs >= 2 nodes per axis and pitch > 0");
   CK(cudaSetDevice(ctx->device));
   FieldHost& f = ctx->fields[slot];
+  f.set = false;  // until every upload below has succeeded, the slot counts as unset (a failed re-upload must not leave stale maps in use)
   const int nzp = (dims[2] + 3) & ~3;  // TMA: global strides must be multiples of 16 bytes
   const size_t n = (size_t)dims[0] * dims[1] * nzp;
   if (f.data && (size_t)f.nx * f.ny * f.nzp != n) { cudaFree(f.data); f.data = nullptr; }
@@ -1503,43 +765,23 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
   CK(cudaMemset(f.data, 0, n * sizeof(float)));
   CK(cudaMemcpy2D(f.data, (size_t)nzp * sizeof(float), cost, (size_t)dims[2] * sizeof(float), (size_t)dims[2] * sizeof(float),
                   (size_t)dims[0] * dims[1], cudaMemcpyHostToDevice));
-  f.nx = dims[0]; f.ny = dims[1]; f.nz = dims[2]; f.nzp = nzp; f.pitch = pitch; f.set = true;
+  f.nx = dims[0]; f.ny = dims[1]; f.nz = dims[2]; f.nzp = nzp; f.pitch = pitch;
   for (int a = 0; a < 3; ++a) f.origin[a] = origin[a];
   FieldDev d;
   d.data = f.data; d.nx = f.nx; d.ny = f.ny; d.nz = f.nz; d.nzp = nzp;
   d.ox = (float)origin[0]; d.oy = (float)origin[1]; d.oz = (float)origin[2]; d.inv_pitch = (float)(1.0 / pitch);
-  d.has_tma = 0;
-  if (ctx->encode && !getenv("GTO_DISABLE_TMA")) {
-    CUtensorMap maps[NCLASS];
-    bool ok = true;
-    for (int c = 0; c < NCLASS && ok; ++c) {
-      const cuuint64_t gdim[3] = {(cuuint64_t)f.nz, (cuuint64_t)f.ny, (cuuint64_t)f.nx};
-      const cuuint64_t gstr[2] = {(cuuint64_t)nzp * sizeof(float), (cuuint64_t)f.ny * nzp * sizeof(float)};
-      const cuuint32_t Bc = (cuuint32_t)kBrickClassDev(c);
-      const cuuint32_t box[3] = {Bc, Bc, Bc};
-      const cuuint32_t estr[3] = {1, 1, 1};
-      CUresult rc = ctx->encode(&maps[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)f.data, gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      ok = (rc == CUDA_SUCCESS);
-    }
-    if (ok) {
-      CK(cudaMemcpy(ctx->tmaps_d + (size_t)slot * NCLASS, maps, sizeof(maps), cudaMemcpyHostToDevice));
-      d.has_tma = 1;
-    }
-  }
   d.maps2 = nullptr;
-  if (d.has_tma) {  // per-axis box sizes for the pipelined kernel
-    std::vector<CUtensorMap> m2((size_t)PIPE_NAXC * PIPE_NAXC * PIPE_NAXC);
+  if (ctx->encode) {  // one tile map per combination of per-axis box sizes
+    std::vector<CUtensorMap> m2((size_t)CULL_NAXC * CULL_NAXC * CULL_NAXC);
     bool ok = true;
-    for (int cx = 0; cx < PIPE_NAXC && ok; ++cx)
-      for (int cy = 0; cy < PIPE_NAXC && ok; ++cy)
-        for (int cz = 0; cz < PIPE_NAXC && ok; ++cz) {
+    for (int cx = 0; cx < CULL_NAXC && ok; ++cx)
+      for (int cy = 0; cy < CULL_NAXC && ok; ++cy)
+        for (int cz = 0; cz < CULL_NAXC && ok; ++cz) {
           const cuuint64_t gdim[3] = {(cuuint64_t)f.nz, (cuuint64_t)f.ny, (cuuint64_t)f.nx};
           const cuuint64_t gstr[2] = {(cuuint64_t)nzp * sizeof(float), (cuuint64_t)f.ny * nzp * sizeof(float)};
           const cuuint32_t box[3] = {(cuuint32_t)(8 + 4 * cz), (cuuint32_t)(8 + 4 * cy), (cuuint32_t)(8 + 4 * cx)};
           const cuuint32_t estr[3] = {1, 1, 1};
-          CUresult rc = ctx->encode(&m2[((size_t)cx * PIPE_NAXC + cy) * PIPE_NAXC + cz], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)f.data, gdim,
+          CUresult rc = ctx->encode(&m2[((size_t)cx * CULL_NAXC + cy) * CULL_NAXC + cz], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)f.data, gdim,
                                     gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           ok = (rc == CUDA_SUCCESS);
@@ -1574,6 +816,7 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
     f.nonzero = S[ns - 1];
   }
   CK(cudaMemcpy(ctx->fields_d + slot, &d, sizeof(d), cudaMemcpyHostToDevice));
+  f.set = true;
   ctx->min_pitch = 0.0;
   for (auto& ff : ctx->fields)
     if (ff.set) ctx->min_pitch = (ctx->min_pitch == 0.0) ? ff.pitch : std::min(ctx->min_pitch, ff.pitch);
@@ -1615,15 +858,16 @@ extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
   ctx->flags = in->flags;
   ctx->has_batch = false;
   ctx->solved = false;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  EventPair evp;
+  CK(evp.create());
+  cudaEvent_t e0 = evp.a, e1 = evp.b;
   CK(ctx->qc.ensure((size_t)B * nd)); CK(ctx->q_seed.ensure((size_t)B * T * nd));
   CK(ctx->goal_tf.ensure((size_t)B * 24)); CK(ctx->base.ensure((size_t)B * 4)); CK(ctx->field_ids.ensure((size_t)B * 2));
   CK(ctx->Qc.ensure((size_t)B * T * n)); CK(ctx->Qt.ensure((size_t)B * T * n)); CK(ctx->q_trial.ensure((size_t)B * T * nd));
   CK(ctx->F.ensure(B)); CK(ctx->Fp.ensure(B)); CK(ctx->lam.ensure(B)); CK(ctx->nu.ensure(B)); CK(ctx->pred.ensure(B)); CK(ctx->stepn.ensure(B));
   CK(ctx->bufsel.ensure(B)); CK(ctx->iters.ensure(B)); CK(ctx->status.ensure(B)); CK(ctx->active.ensure((size_t)2 * B));
-  CK(ctx->H.ensure((size_t)2 * GTO_SPLIT_MAX * B * T * n * n)); CK(ctx->g.ensure((size_t)2 * GTO_SPLIT_MAX * B * T * n));
-  CK(ctx->costp.ensure((size_t)2 * GTO_SPLIT_MAX * B * T));
+  CK(ctx->H.ensure((size_t)2 * B * T * n * n)); CK(ctx->g.ensure((size_t)2 * B * T * n));
+  CK(ctx->costp.ensure((size_t)2 * B * T));
   (void)m;
   CK(ctx->outQ.ensure((size_t)B * T * nd)); CK(ctx->outdQ.ensure((size_t)B * (T - 1) * nd)); CK(ctx->outcost.ensure(B));
   CK(ctx->result.ensure((size_t)B * (n * T + 2)));
@@ -1647,29 +891,9 @@ extern "C" int gto_upload_batch(gto_ctx* ctx, const gto_batch_in* in) {
   cudaEventElapsedTime(&ms, e0, e1);
   ctx->prof.h2d_ms = ms;
   ctx->prof.h2d_bytes = (long long)sizeof(double) * B * (nd * (1 + T) + 24) + sizeof(float) * bs.size() + sizeof(int) * fid.size();
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ctx->rows_per_problem = rows_per_problem(ctx);
   ctx->has_batch = true;
   return GTO_OK;
-}
-
-static int pick_brick_max(const gto_ctx* ctx) {
-  if (ctx->min_pitch <= 0) return kBrickClassDev(0);
-  const int need = (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 3;
-  int cls = NCLASS - 1;
-  for (int k = NCLASS - 1; k >= 0; --k)
-    if (kBrickClassDev(k) >= need) cls = k;
-  return kBrickClassDev(cls);
-}
-
-static size_t lin_smem_bytes(const gto_ctx* ctx, int brick_max, int warps) {
-  const int RS = ctx->robot_h.nopt + 1;
-  size_t off = (sizeof(LinShared) + 127) & ~(size_t)127;
-  off += (size_t)brick_max * brick_max * brick_max * sizeof(float);
-  off = (off + 127) & ~(size_t)127;
-  const int st_floats = ((32 * RS + 16 + 31) / 32) * 32;
-  off += (size_t)warps * st_floats * sizeof(float);
-  return off;
 }
 
 // launches one linearisation on ctx->stream
@@ -1696,16 +920,12 @@ static void fill_lin_params(gto_ctx* ctx, LinParams& p, const double* q, const i
   p.robot = ctx->robot_d; p.chunk_start = ctx->chunk_start.p; p.chunk_count = ctx->chunk_count.p;
   p.px = ctx->px.p; p.py = ctx->py.p; p.pz = ctx->pz.p;
   p.q = q; p.goal_tf = ctx->goal_tf.p; p.base = ctx->base.p; p.field_ids = ctx->field_ids.p;
-  p.fields = ctx->fields_d; p.tmaps = ctx->tmaps_d;
+  p.fields = ctx->fields_d;
   p.active = active; p.nactive = nactive; p.nproblems = nproblems; p.b0 = b0; p.bufsel = bufsel;
   p.H = ctx->H.p; p.g = ctx->g.p; p.costp = ctx->costp.p;
-  p.part_stride_H = (long long)ctx->B * ctx->T * R.nopt * R.nopt;
-  p.part_stride_g = (long long)ctx->B * ctx->T * R.nopt;
-  p.part_stride_c = (long long)ctx->B * ctx->T;
-  p.buf_stride_H = GTO_SPLIT_MAX * p.part_stride_H;
-  p.buf_stride_g = GTO_SPLIT_MAX * p.part_stride_g;
-  p.buf_stride_c = GTO_SPLIT_MAX * p.part_stride_c;
-  p.allow_split = (nactive != nullptr) && getenv("GTO_SPLIT_TAIL") != nullptr;  // measured on C2: no gain (tail launches are fixed-latency bound), off by default
+  p.buf_stride_H = (long long)ctx->B * ctx->T * R.nopt * R.nopt;
+  p.buf_stride_g = (long long)ctx->B * ctx->T * R.nopt;
+  p.buf_stride_c = (long long)ctx->B * ctx->T;
   p.rows = rows; p.rows_per_problem = ctx->rows_per_problem;
   p.T = ctx->T; p.t_lo = t_lo; p.knot_standoff = ctx->T + ctx->standoff_offset; p.use_standoff = ctx->use_standoff;
   p.collision = ctx->collision;
@@ -1713,169 +933,78 @@ static void fill_lin_params(gto_ctx* ctx, LinParams& p, const double* q, const i
   p.flags = flags;
 }
 
-// the kernels with TMA-staged bricks need a tile map for every field
-static bool pipe_path_ok(const gto_ctx* ctx, unsigned flags) {
-  bool ok = !(flags & (GTO_FLAG_V1_KERNEL | GTO_FLAG_NO_TMA | GTO_FLAG_NO_BRICK)) && !getenv("GTO_V1_KERNEL");
+// the linearise kernel stages SDF bricks by TMA: every field needs its tile maps (encoded at gto_set_field)
+static bool fields_have_tile_maps(const gto_ctx* ctx) {
   for (auto& ff : ctx->fields)
-    if (ff.set && !ff.maps2) ok = false;
-  return ok;
-}
-static bool cull_path_ok(const gto_ctx* ctx, unsigned flags) {
-  return pipe_path_ok(ctx, flags) && !(flags & GTO_FLAG_PIPE_KERNEL) && !getenv("GTO_PIPE_KERNEL");
+    if (ff.set && !ff.maps2) return false;
+  return true;
 }
 static int brick_slot_floats(const gto_ctx* ctx) {
+  if (ctx->tune_slot_floats > 0) return std::max(512, ctx->tune_slot_floats & ~127);
   const int n3 = ctx->min_pitch > 0 ? (int)ceil(2.0 * ctx->max_link_diag / ctx->min_pitch) + 5 : 8;
-  int slot_floats = n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
-  if (const char* e = getenv("GTO_SLOT_FLOATS")) slot_floats = std::max(512, atoi(e) & ~127);
-  return slot_floats;
+  return n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
 }
 
-// launches one linearisation on ctx->stream; `have_recs`: the item records of this launch were already written (by the
-// step kernel that produced the trial point), so k_item_fk is skipped
+typedef void (*cull_kernel_t)(const CullParams);
+static cull_kernel_t pick_cull_kernel(int nopt) {
+  if (nopt == 7) return k_linearize_cull<8, 7>;
+  if (nopt == 8) return k_linearize_cull<8, 8>;
+  if (nopt == 10) return k_linearize_cull<16, 10>;
+  return nopt < 8 ? k_linearize_cull<8, 0> : k_linearize_cull<16, 0>;
+}
+
+// One linearisation on ctx->stream = k_item_fk (per-item records) + k_linearize_cull (points, rows, Gauss-Newton blocks).
+// `have_recs`: the records of this launch were already written by the step kernel that produced the trial point.
 static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, const int* nactive, int nproblems, int b0, const int* bufsel,
-                            float* rows, int t_lo, unsigned flags, int* work_counter, bool have_recs = false, cudaStream_t stream = nullptr,
-                            CullCtx* recs = nullptr, unsigned long long* ts = nullptr) {
-  if (!stream) stream = ctx->stream;
+                            float* rows, int t_lo, unsigned flags, int* work_counter, bool have_recs = false, unsigned long long* ts = nullptr) {
+  cudaStream_t stream = ctx->stream;
   const RobotDev& R = ctx->robot_h;
-  LinParams p;
-  fill_lin_params(ctx, p, q, active, nactive, nproblems, b0, bufsel, rows, t_lo, flags);
-  const bool pipe_ok = pipe_path_ok(ctx, flags);
-  // ---- default: culling + TMA-pipelined kernel with dynamic item scheduling ----
-  if (work_counter && cull_path_ok(ctx, flags)) {
-    CullParams cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.lin = p;
-    cp.lin.allow_split = 0;
-    const int slot_floats = brick_slot_floats(ctx);
-    cp.slot_floats = slot_floats;
-    int nc = ctx->pipe_cons;
-    if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
-    cp.ncons = nc;
-    int nslot = 4;
-    if (const char* e = getenv("GTO_CULL_NSLOT")) nslot = std::min(CULL_NSLOT_MAX, std::max(2, atoi(e)));
-    cp.nslot = nslot;
-    cp.count_early = have_recs ? 0 : 1;
-    cp.work_counter = work_counter;
-    cp.stats = ctx->stats.p;
-    const int RS = R.nopt + 1;
-    size_t sm = (sizeof(CullShared) + 127) & ~(size_t)127;
-    sm += CULL_ZERO_BYTES;
-    sm += (size_t)nslot * slot_floats * sizeof(float);
-    sm += (size_t)nc * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
-    sm += (size_t)2 * nc * (R.nopt * R.nopt + R.nopt + 2) * sizeof(float);
-    sm = (sm + 127) & ~(size_t)127;
-    const int threads = (nc + 2) * 32;  // consumers + producer + zero-row warp
+  if (!fields_have_tile_maps(ctx)) return fail(ctx, GTO_ERR_STATE, "a cost field has no TMA tile maps (cuTensorMapEncodeTiled unavailable)");
+  CullParams cp;
+  memset(&cp, 0, sizeof(cp));
+  fill_lin_params(ctx, cp.lin, q, active, nactive, nproblems, b0, bufsel, rows, t_lo, flags);
+  const int slot_floats = brick_slot_floats(ctx);
+  cp.slot_floats = slot_floats;
+  const int nc = ctx->tune_cons > 0 ? std::min(CULL_MAX_CONS, ctx->tune_cons) : ctx->pipe_cons;
+  cp.ncons = nc;
+  const int nslot = std::min(CULL_NSLOT_MAX, std::max(2, ctx->tune_nslot));
+  cp.nslot = nslot;
+  cp.count_early = have_recs ? 0 : 1;
+  cp.work_counter = work_counter;
+  cp.stats = ctx->stats.p;
+  const size_t sm = cull_smem_bytes(R.nopt, nc, nslot, slot_floats);
+  const int threads = (nc + 2) * 32;  // consumers + producer + zero-row warp
+  cull_kernel_t kern = pick_cull_kernel(R.nopt);
+  if (ctx->cull_smem_set != (long long)sm) {
     int occ = 0;
-    void (*kern)(const CullParams) = nullptr;
-    if (R.nopt == 7) kern = k_linearize_cull<8, 7>;
-    else if (R.nopt == 8) kern = k_linearize_cull<8, 8>;
-    else if (R.nopt == 10) kern = k_linearize_cull<16, 10>;
-    else if (R.nopt < 8) kern = k_linearize_cull<8, 0>;
-    else kern = k_linearize_cull<16, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, sm);
-    if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("culling linearize launch setup: ") + cudaGetErrorString(e));
-    if (occ >= 1) {
-      const long long max_items = (long long)nproblems * (ctx->T - t_lo);
-      const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
-      ctx->last_lin_grid = 0;
-      if (!recs) {
-        e = ctx->recs.ensure((size_t)max_items);
-        if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
-        recs = ctx->recs.p;
-      }
-      cp.recs = recs;
-      e = ctx->rec_dummy.ensure(1);
-      if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
-      cp.rec_dummy = ctx->rec_dummy.p;
-      cp.dbg = getenv("GTO_STEP_DBG") ? ctx->dbg.p : nullptr;
-      cp.ts_fk = ts;
-      cp.ts_lin = ts ? ts + 2 : nullptr;
-      ctx->prof.kernel_launches += 1;
-      if (!have_recs) {
-        const size_t fk_smem = ((sizeof(RobotDev) + 15) & ~(size_t)15) + (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
-        e = launch_pdl<CullParams>(k_item_fk, (unsigned)((max_items + 7) / 8), 128, fk_smem, stream, ctx->use_pdl, cp);
-        if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
-        ctx->prof.kernel_launches += 1;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
-      }
-      e = launch_pdl<CullParams>(kern, (unsigned)grid, (unsigned)threads, sm, stream, ctx->use_pdl, cp);
-      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
-      return GTO_OK;
-    }
+    if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("linearise launch setup: ") + cudaGetErrorString(e));
+    if (occ < 1) return fail(ctx, GTO_ERR_INVALID, "linearise kernel does not fit on an SM (brick slots too large)");
+    ctx->cull_smem_set = (long long)sm;
+    ctx->cull_occ = occ;
   }
-  // ---- warp-specialised TMA-pipelined kernel without culling (A/B reference) ----
-  if (pipe_ok) {
-    PipeParams pp;
-    memset(&pp, 0, sizeof(pp));
-    pp.lin = p;
-    pp.chunk_link = nullptr;
-    const int slot_floats = brick_slot_floats(ctx);
-    pp.slot_floats = slot_floats;
-    int nc = ctx->pipe_cons;
-    if (const char* e = getenv("GTO_PIPE_CONS")) nc = std::min(PIPE_MAX_CONS, std::max(1, atoi(e)));
-    pp.ncons = nc;
-    const int RS = R.nopt + 1;
-    size_t sm = (sizeof(PipeShared) + 127) & ~(size_t)127;
-    sm += (size_t)PIPE_NSLOT * slot_floats * sizeof(float);
-    sm += (size_t)nc * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
-    sm += (size_t)2 * nc * (R.nopt * R.nopt + R.nopt + 2) * sizeof(float);
-    sm = (sm + 127) & ~(size_t)127;
-    const int threads = (nc + 1) * 32;
-    int occ = 0;
-    cudaError_t e;
-    void (*kern)(const PipeParams) = nullptr;
-    if (R.nopt == 7) kern = k_linearize_pipe<8, 7>;
-    else if (R.nopt == 8) kern = k_linearize_pipe<8, 8>;
-    else if (R.nopt == 10) kern = k_linearize_pipe<16, 10>;
-    else if (R.nopt < 8) kern = k_linearize_pipe<8, 0>;
-    else kern = k_linearize_pipe<16, 0>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, sm);
-    if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("pipelined linearize launch setup: ") + cudaGetErrorString(e));
-    if (occ >= 1) {
-      const long long max_items = (long long)nproblems * (ctx->T - t_lo);
-      // solver launches use the full persistent grid: the device decides how many parts an item is split into
-      const int grid = p.allow_split ? ctx->sm_count * occ : (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
-      ctx->last_lin_grid = p.allow_split ? grid : 0;
-      kern<<<grid, threads, sm, stream>>>(pp);
-      ctx->prof.kernel_launches += 1;
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_pipe launch: ") + cudaGetErrorString(e));
-      return GTO_OK;
-    }
-  }
-  ctx->last_lin_grid = 0;  // the v1 kernel never splits items
-  p.allow_split = 0;
-  int bm = pick_brick_max(ctx);
-  size_t smem = lin_smem_bytes(ctx, bm, ctx->lin_warps);
-  while (smem > (size_t)ctx->max_smem_optin / 2 && bm > kBrickClassDev(0)) {  // keep two CTAs per SM
-    bm = (bm == 24) ? 16 : 8;
-    smem = lin_smem_bytes(ctx, bm, ctx->lin_warps);
-  }
-  p.brick_max = bm;
-  const int threads = ctx->lin_warps * 32;
-  int occ = 1;
-  cudaError_t e;
-  if (R.nopt <= 8) {
-    e = cudaFuncSetAttribute(k_linearize<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize<8>, threads, smem);
-  } else {
-    e = cudaFuncSetAttribute(k_linearize<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_linearize<16>, threads, smem);
-  }
-  if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("linearize launch setup: ") + cudaGetErrorString(e));
-  if (occ < 1) return fail(ctx, GTO_ERR_CUDA, "linearize kernel does not fit on an SM");
   const long long max_items = (long long)nproblems * (ctx->T - t_lo);
-  const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * occ, max_items));
-  if (R.nopt <= 8) k_linearize<8><<<grid, threads, smem, stream>>>(p);
-  else k_linearize<16><<<grid, threads, smem, stream>>>(p);
+  const int grid = (int)std::max(1LL, std::min<long long>((long long)ctx->sm_count * ctx->cull_occ, max_items));
+  cudaError_t e = ctx->recs.ensure((size_t)std::max<long long>(max_items, (long long)ctx->Bchunk * ctx->T));
+  if (e == cudaSuccess) e = ctx->rec_dummy.ensure(1);
+  if (e != cudaSuccess) return fail(ctx, GTO_ERR_NOMEM, "item records");
+  cp.recs = ctx->recs.p;
+  cp.rec_dummy = ctx->rec_dummy.p;
+  cp.dbg = ctx->tune_step_dbg ? ctx->dbg.p : nullptr;
+  cp.ts_fk = ts;
+  cp.ts_lin = ts ? ts + 2 : nullptr;
+  if (!have_recs) {
+    const size_t fk_smem = ((sizeof(RobotDev) + 15) & ~(size_t)15) + (size_t)8 * 2 * R.nmov * 12 * sizeof(double);
+    e = launch_pdl<CullParams>(k_item_fk, (unsigned)((max_items + 7) / 8), 128, fk_smem, stream, ctx->use_pdl, cp);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_item_fk launch: ") + cudaGetErrorString(e));
+    ctx->prof.kernel_launches += 1;
+  }
+  e = launch_pdl<CullParams>(kern, (unsigned)grid, (unsigned)threads, sm, stream, ctx->use_pdl, cp);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize_cull launch: ") + cudaGetErrorString(e));
   ctx->prof.kernel_launches += 1;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(ctx, GTO_ERR_CUDA, std::string("k_linearize launch: ") + cudaGetErrorString(e));
   return GTO_OK;
 }
 
@@ -1886,6 +1015,14 @@ static cudaEvent_t get_event(gto_ctx* ctx, size_t i) {
     ctx->ev.push_back(e);
   }
   return ctx->ev[i];
+}
+
+typedef void (*step_kernel_t)(const StepParams);
+static step_kernel_t pick_step_kernel(int n) {
+  if (n == 7) return k_step_cr<7, true>;
+  if (n == 8) return k_step_cr<8, true>;
+  if (n == 10) return k_step_cr<10, true>;
+  return n < 8 ? k_step_cr<8, false> : k_step_cr<16, false>;
 }
 
 extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
@@ -1900,8 +1037,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   const int B = ctx->B, T = ctx->T, n = R.nopt;
   const bool want_rows = !(ctx->flags & GTO_FLAG_NO_JROWS);
   // Jacobian-row buffer: problems are processed in chunks that fit the budget
-  const char* env = getenv("GTO_JROWS_BUDGET_MB");
-  const double budget = (env ? atof(env) : 24576.0) * 1048576.0;
+  const double budget = ctx->tune_jrows_budget_mb * 1048576.0;
   const double per_problem = (double)ctx->rows_per_problem * (n + 1) * sizeof(float);
   int Bchunk = B;
   if (want_rows) {
@@ -1926,51 +1062,27 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   st.tol_step = o.tol_step; st.tol_grad = o.tol_grad; st.lambda_min = o.lambda_min; st.lambda_max = o.lambda_max; st.eta = o.eta;
   st.noise_rel = o.noise_rel; st.bound_eps = o.bound_eps; st.ftol = o.ftol; st.lambda_slow = o.lambda_slow;
   st.slow_ftol = o.slow_ftol; st.slow_window = std::min(16, std::max(0, (int)o.slow_window));
-  st.as_rounds = std::min(4, std::max(0, (int)o.as_rounds)); st.lambda_reject = o.lambda_reject;
+  st.as_rounds = std::min(4, std::max(0, (int)o.as_rounds)); st.lambda_reject = o.lambda_reject; st.lambda_conv = o.lambda_conv;
   CK(ctx->Fhist.ensure((size_t)B * 16));
   st.Fhist = ctx->Fhist.p;
   st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;
-  st.part_stride_H = (long long)B * T * n * n; st.part_stride_g = (long long)B * T * n; st.part_stride_c = (long long)B * T;
-  st.buf_stride_H = GTO_SPLIT_MAX * st.part_stride_H; st.buf_stride_g = GTO_SPLIT_MAX * st.part_stride_g;
-  st.buf_stride_c = GTO_SPLIT_MAX * st.part_stride_c;
-  st.Bcap = B;
-  CK(ctx->bufsplit.ensure((size_t)2 * B));
-  st.bufsplit = ctx->bufsplit.p;
+  st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
   st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;
   st.stepn = ctx->stepn.p; st.iters = ctx->iters.p; st.status = ctx->status.p;
-  const size_t step_smem = step_smem_bytes(T, n);
-  if (step_smem > (size_t)ctx->max_smem_optin)
-    return fail(ctx, GTO_ERR_INVALID, "(T-2) * nopt^2 too large: the block-tridiagonal factor must fit in shared memory");
-  void (*step_kern)(const StepParams) = nullptr;
-  if (n == 7) step_kern = k_step<7, true>;
-  else if (n == 8) step_kern = k_step<8, true>;
-  else if (n == 10) step_kern = k_step<10, true>;
-  else if (n < 8) step_kern = k_step<8, false>;
-  else step_kern = k_step<16, false>;
-  CK(cudaFuncSetAttribute(step_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
-  // default: block cyclic reduction, one CTA per problem (k_step_cr); the sequential block Thomas kernel is the A/B reference
-  void (*step_cr_kern)(const StepParams) = nullptr;
-  if (n == 7) step_cr_kern = k_step_cr<7, true>;
-  else if (n == 8) step_cr_kern = k_step_cr<8, true>;
-  else if (n == 10) step_cr_kern = k_step_cr<10, true>;
-  else if (n < 8) step_cr_kern = k_step_cr<8, false>;
-  else step_cr_kern = k_step_cr<16, false>;
+  // LM step: block cyclic reduction, one CTA per problem (k_step_cr)
+  step_kernel_t step_kern = pick_step_kernel(n);
   const size_t cr_smem = step_cr_smem_bytes(T, n);
-  bool use_cr = !getenv("GTO_STEP_V1") && !getenv("GTO_SPLIT_TAIL") && cr_smem <= (size_t)ctx->max_smem_optin;
-  if (use_cr) CK(cudaFuncSetAttribute(step_cr_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_smem));
-  // the step kernel also writes the item records of its new trial point when the culling kernel will consume them and
-  // its FK scratch fits into the (by then free) factorisation storage
-  // GTO_STEP_FK = "all": every step launch; "tail" (or a number): only once at most that many problems (default 16) are left,
-  // where a launch of k_item_fk costs more than two extra FK rounds at the end of the step kernel; unset: never
-  int step_fk_limit = 0;
-  if (const char* e = getenv("GTO_STEP_FK")) {
-    if (!strcmp(e, "all") || !strcmp(e, "1")) step_fk_limit = 1 << 30;
-    else if (!strcmp(e, "tail")) step_fk_limit = 16;
-    else step_fk_limit = atoi(e);
+  if (cr_smem > (size_t)ctx->max_smem_optin)
+    return fail(ctx, GTO_ERR_INVALID, "(T-2) * nopt^2 too large: the block-tridiagonal factor must fit in shared memory");
+  if (ctx->step_smem_set != (long long)cr_smem) {
+    CK(cudaFuncSetAttribute(step_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cr_smem));
+    ctx->step_smem_set = (long long)cr_smem;
   }
-  const bool step_fk_ok = use_cr && cull_path_ok(ctx, ctx->flags) && step_fk_limit > 0 &&
-                          (size_t)(STEP_CR_THREADS / 16) * 2 * R.nmov * 12 <= (size_t)3 * (T - 2) * n * n;
-  if (step_fk_ok) CK(ctx->recs.ensure((size_t)Bchunk * T));
+  // optionally the step kernel also writes the item records of its new trial point (tune "step_fk" = problem count below
+  // which it does; measured slower than a k_item_fk launch on C2, off by default)
+  const int step_fk_limit = ctx->tune_step_fk;
+  const bool step_fk_ok = step_fk_limit > 0 && (size_t)(STEP_CR_THREADS / 16) * 2 * R.nmov * 12 <= (size_t)3 * (T - 2) * n * n;
+  CK(ctx->recs.ensure((size_t)Bchunk * T));
 
   gto_profile& pf = ctx->prof;
   pf.solve_ms = pf.linearize_ms = pf.step_ms = 0;
@@ -1979,7 +1091,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   pf.links_tested = pf.links_active = 0;
   pf.kernel_launches = 2;  // k_init + k_finalize; the linearise / step launches are added where they happen
   size_t nev = 0;
-  std::vector<int> ev_kind;  // per recorded interval: 0 linearize, 1 step
+  std::vector<int> ev_kind;
   cudaEvent_t ev_begin = get_event(ctx, nev++);
   CK(cudaEventRecord(ev_begin, ctx->stream));
   {
@@ -1989,50 +1101,22 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   }
   std::vector<int> ident(B);
   for (int b = 0; b < B; ++b) ident[b] = b;
-
-  // Problem groups: the problems of a chunk are split into G contiguous groups, each iterating on a stream of its own.
-  // Once most problems have converged the launches are latency bound (a handful of CTAs); the groups' dependency chains
-  // (linearise -> step -> linearise ...) then overlap on the otherwise idle SMs.  Results do not depend on the grouping.
-  int G = 1;  // measured on C2: no gain from G > 1 (the chain of the slowest problem sets the time), kept as an option
-  if (const char* e = getenv("GTO_GROUPS")) G = atoi(e);
-  if (getenv("GTO_SPLIT_TAIL")) G = 1;
-  G = std::max(1, std::min(G, 8));
-  while ((int)ctx->gstreams.size() < G) {
-    cudaStream_t s_;
-    CK(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
-    ctx->gstreams.push_back(s_);
-    cudaEvent_t ej;
-    CK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
-    ctx->ev_join.push_back(ej);
-  }
-  if (!ctx->ev_fork) CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < 2; ++i)
     if (!ctx->ev_poll[i]) CK(cudaEventCreateWithFlags(&ctx->ev_poll[i], cudaEventDisableTiming));
-  const size_t cstride = (size_t)o.max_iter + 3;  // per-group counter arrays
-  CK(ctx->nactive.ensure(cstride * G));
-  CK(ctx->work_ctr.ensure(cstride * G));
-  const bool cull_ok = cull_path_ok(ctx, ctx->flags);
-  if (getenv("GTO_STEP_DBG")) {
+  const size_t cstride = (size_t)o.max_iter + 3;  // one counter per iteration
+  CK(ctx->nactive.ensure(cstride));
+  CK(ctx->work_ctr.ensure(cstride));
+  if (ctx->tune_step_dbg) {
     CK(ctx->dbg.ensure(64));
     CK(cudaMemsetAsync(ctx->dbg.p, 0, 64 * sizeof(long long), ctx->stream));
     st.dbg = ctx->dbg.p;
   }
-  if (cull_ok) CK(ctx->recs.ensure((size_t)Bchunk * T));
-  struct Grp {
-    int b0, nb;
-    cudaStream_t s;
-    int *act0, *act1, *nact, *wctr;
-    CullCtx* recs;
-    bool done;
-    bool recs_ready;  // the last step launch of this group wrote the item records of its trial point
-    int known;  // upper bound of the problems still active (last polled count; the count only decreases): sizes the grids
-  };
-  std::vector<int> h_nact(cstride * G);
+  std::vector<int> h_nact(cstride);
   // per-launch durations for the profile (linearize_ms / step_ms): in-kernel %globaltimer stamps by default; CUDA events
-  // between the launches on request or when a kernel without stamps is selected (they cost ~3 us of serialisation each)
-  const bool launch_events = getenv("GTO_LAUNCH_EVENTS") != nullptr || !cull_ok || !use_cr;
+  // between the launches on request (they cost ~3 us of stream serialisation each)
+  const bool launch_events = ctx->tune_launch_events != 0;
   const bool launch_stamps = !launch_events;
-  const size_t ts_n = cstride * G * 6;
+  const size_t ts_n = cstride * 6;
   if (launch_stamps) {
     CK(ctx->tstamps.ensure(ts_n));
     CK(cudaMemsetAsync(ctx->tstamps.p, 0, ts_n * sizeof(unsigned long long), ctx->stream));
@@ -2040,107 +1124,69 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
 
   for (int b0 = 0; b0 < B; b0 += Bchunk) {
     const int nb = std::min(Bchunk, B - b0);
-    const int ng = std::min(G, nb);
-    std::vector<Grp> grp(ng);
-    CK(cudaMemsetAsync(ctx->nactive.p, 0, sizeof(int) * cstride * G, ctx->stream));
-    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, sizeof(int) * cstride * G, ctx->stream));
+    CK(cudaMemsetAsync(ctx->nactive.p, 0, sizeof(int) * cstride, ctx->stream));
+    CK(cudaMemsetAsync(ctx->work_ctr.p, 0, sizeof(int) * cstride, ctx->stream));
     CK(cudaMemcpyAsync(ctx->active.p + b0, ident.data() + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
-    for (int g = 0; g < ng; ++g) {
-      Grp& r = grp[g];
-      r.b0 = b0 + (int)((long long)nb * g / ng);
-      r.nb = b0 + (int)((long long)nb * (g + 1) / ng) - r.b0;
-      r.s = (ng == 1) ? ctx->stream : ctx->gstreams[g];
-      r.act0 = ctx->active.p + r.b0;
-      r.act1 = ctx->active.p + B + r.b0;
-      r.nact = ctx->nactive.p + cstride * g;
-      r.wctr = ctx->work_ctr.p + cstride * g;
-      r.recs = cull_ok ? ctx->recs.p + (size_t)(r.b0 - b0) * T : nullptr;
-      r.done = false;
-      r.recs_ready = false;
-      r.known = r.nb;
-      CK(cudaMemcpyAsync(r.nact, &r.nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (ng > 1) {
-      CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-      for (int g = 0; g < ng; ++g) CK(cudaStreamWaitEvent(grp[g].s, ctx->ev_fork, 0));
-    }
+    CK(cudaMemcpyAsync(ctx->nactive.p, &nb, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    int* act0 = ctx->active.p + b0;
+    int* act1 = ctx->active.p + B + b0;
+    int known = nb;  // upper bound of the problems still active (last polled count; it only decreases): sizes the grids
+    bool recs_ready = false, done = false;
     size_t nblk = 0;
-    for (int it = 0; it <= o.max_iter; ++it) {
-      bool any = false;
-      for (int g = 0; g < ng; ++g) {
-        Grp& r = grp[g];
-        if (r.done) continue;
-        any = true;
-        int* ain = (it & 1) ? r.act1 : r.act0;
-        int* aout = (it & 1) ? r.act0 : r.act1;
-        cudaEvent_t a = nullptr, bE = nullptr, c = nullptr;
-        if (launch_events) {
-          a = get_event(ctx, nev++); bE = get_event(ctx, nev++); c = get_event(ctx, nev++);
-          CK(cudaEventRecord(a, r.s));
-        }
-        int rc = launch_linearize(ctx, ctx->q_trial.p, ain, r.nact + it, r.known, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
-                                  it == 0 ? 0 : 2, ctx->flags, r.wctr + it, r.recs_ready && it > 0, r.s, r.recs,
-                                  launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 : nullptr);
-        if (rc) return rc;
-        if (launch_events) CK(cudaEventRecord(bE, r.s));
-        st.active_in = ain; st.nactive_in = r.nact + it; st.active_out = aout; st.nactive_out = r.nact + it + 1;
-        st.iter = it;
-        st.ts = launch_stamps ? ctx->tstamps.p + (cstride * g + it) * 6 + 4 : nullptr;
-        st.lin_grid = ctx->last_lin_grid;
-        const bool step_fk = step_fk_ok && r.known <= step_fk_limit;
-        st.do_fk = step_fk ? 1 : 0;
-        st.fk_robot_smem = sizeof(RobotDev) <= (size_t)T * n * 8 + (size_t)2 * ((T - 2) * n * n + (T - 2) * n) * 4 ? 1 : 0;
-        r.recs_ready = step_fk;
-        if (step_fk) {
-          memset(&st.fk, 0, sizeof(st.fk));
-          fill_lin_params(ctx, st.fk.lin, ctx->q_trial.p, nullptr, nullptr, r.nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr, 2, ctx->flags);
-          st.fk.lin.allow_split = 0;
-          st.fk.slot_floats = brick_slot_floats(ctx);
-          st.fk.recs = r.recs;
-          CK(ctx->rec_dummy.ensure(1));
-          st.fk.rec_dummy = ctx->rec_dummy.p;
-          st.fk.stats = ctx->stats.p;
-        }
-        if (use_cr) CK(launch_pdl<StepParams>(step_cr_kern, (unsigned)r.known, STEP_CR_THREADS, cr_smem, r.s, ctx->use_pdl, st));
-        else step_kern<<<r.known, 32, step_smem, r.s>>>(st);
-        pf.kernel_launches += 1;
-        CK(cudaGetLastError());
-        if (launch_events) {
-          CK(cudaEventRecord(c, r.s));
-          ev_kind.push_back(0);
-        }
-        pf.linearize_launches++;
-        pf.step_launches++;
-        pf.iterations = std::max(pf.iterations, it);
+    for (int it = 0; it <= o.max_iter && !done; ++it) {
+      int* ain = (it & 1) ? act1 : act0;
+      int* aout = (it & 1) ? act0 : act1;
+      cudaEvent_t a = nullptr, bE = nullptr, c = nullptr;
+      if (launch_events) {
+        a = get_event(ctx, nev++); bE = get_event(ctx, nev++); c = get_event(ctx, nev++);
+        CK(cudaEventRecord(a, ctx->stream));
       }
-      if (!any) break;
+      int rc = launch_linearize(ctx, ctx->q_trial.p, ain, ctx->nactive.p + it, known, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr,
+                                it == 0 ? 0 : 2, ctx->flags, ctx->work_ctr.p + it, recs_ready && it > 0,
+                                launch_stamps ? ctx->tstamps.p + (size_t)it * 6 : nullptr);
+      if (rc) return rc;
+      if (launch_events) CK(cudaEventRecord(bE, ctx->stream));
+      st.active_in = ain; st.nactive_in = ctx->nactive.p + it; st.active_out = aout; st.nactive_out = ctx->nactive.p + it + 1;
+      st.iter = it;
+      st.ts = launch_stamps ? ctx->tstamps.p + (size_t)it * 6 + 4 : nullptr;
+      const bool step_fk = step_fk_ok && known <= step_fk_limit;
+      st.do_fk = step_fk ? 1 : 0;
+      st.fk_robot_smem = sizeof(RobotDev) <= (size_t)T * n * 8 + (size_t)(T - 2) * n * 8 + (size_t)2 * (T - 2) * n * n * 4 ? 1 : 0;
+      recs_ready = step_fk;
+      if (step_fk) {
+        memset(&st.fk, 0, sizeof(st.fk));
+        fill_lin_params(ctx, st.fk.lin, ctx->q_trial.p, nullptr, nullptr, nb, b0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr, 2, ctx->flags);
+        st.fk.slot_floats = brick_slot_floats(ctx);
+        st.fk.recs = ctx->recs.p;
+        CK(ctx->rec_dummy.ensure(1));
+        st.fk.rec_dummy = ctx->rec_dummy.p;
+        st.fk.stats = ctx->stats.p;
+      }
+      CK(launch_pdl<StepParams>(step_kern, (unsigned)known, STEP_CR_THREADS, cr_smem, ctx->stream, ctx->use_pdl, st));
+      pf.kernel_launches += 1;
+      CK(cudaGetLastError());
+      if (launch_events) {
+        CK(cudaEventRecord(c, ctx->stream));
+        ev_kind.push_back(0);
+      }
+      pf.linearize_launches++;
+      pf.step_launches++;
+      pf.iterations = std::max(pf.iterations, it);
       if (((it + 1) % o.check_every) == 0 || it == o.max_iter) {
         // convergence poll, one block behind: the counter of this block is requested now and looked at after the NEXT block
         // has been enqueued, so the GPU never waits for the host (cost: up to check_every empty iterations at the end)
         const int par = (int)(nblk & 1);
-        for (int g = 0; g < ng; ++g) {
-          if (grp[g].done) continue;
-          CK(cudaMemcpyAsync(ctx->h_counter + 2 * g + par, grp[g].nact + it + 1, sizeof(int), cudaMemcpyDeviceToHost, grp[g].s));
-          CK(cudaEventRecord(ctx->ev_poll[2 * g + par], grp[g].s));
-        }
-        for (int g = 0; g < ng; ++g) {
-          if (grp[g].done) continue;
-          if (it == o.max_iter) {
-            CK(cudaStreamSynchronize(grp[g].s));
-            grp[g].done = true;
-          } else if (nblk > 0) {
-            CK(cudaEventSynchronize(ctx->ev_poll[2 * g + (par ^ 1)]));
-            if (ctx->h_counter[2 * g + (par ^ 1)] == 0) grp[g].done = true;
-            else grp[g].known = std::min(grp[g].known, ctx->h_counter[2 * g + (par ^ 1)]);
-          }
+        CK(cudaMemcpyAsync(ctx->h_counter + par, ctx->nactive.p + it + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_poll[par], ctx->stream));
+        if (it == o.max_iter) {
+          CK(cudaStreamSynchronize(ctx->stream));
+          done = true;
+        } else if (nblk > 0) {
+          CK(cudaEventSynchronize(ctx->ev_poll[par ^ 1]));
+          if (ctx->h_counter[par ^ 1] == 0) done = true;
+          else known = std::min(known, ctx->h_counter[par ^ 1]);
         }
         ++nblk;
-      }
-    }
-    if (ng > 1) {  // join: the chunk's groups are finished before the next chunk reuses the row buffer / k_finalize runs
-      for (int g = 0; g < ng; ++g) {
-        CK(cudaEventRecord(ctx->ev_join[g], grp[g].s));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
       }
     }
     if (launch_stamps) {  // per-launch durations of this chunk; the stamp array is reused by the next chunk
@@ -2158,18 +1204,17 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
       }
     }
     // exact work accounting for the roofline: problems active in every linearise launch of this chunk
-    CK(cudaMemcpyAsync(h_nact.data(), ctx->nactive.p, sizeof(int) * cstride * G, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_nact.data(), ctx->nactive.p, sizeof(int) * cstride, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int g = 0; g < ng; ++g)
-      for (int it = 0; it <= o.max_iter; ++it) {
-        const long long na = h_nact[cstride * g + it];
-        if (na <= 0) break;
-        pf.problem_iterations += na;
-        pf.linearize_launches_with_work++;
-        pf.knot_items += na * (it == 0 ? T : T - 2);
-        if (want_rows)
-          pf.jrow_bytes += na * (it == 0 ? ctx->rows_per_problem : ctx->rows_per_problem - 2LL * (ctx->collision ? R.npoints : 0)) * (n + 1) * 4;
-      }
+    for (int it = 0; it <= o.max_iter; ++it) {
+      const long long na = h_nact[it];
+      if (na <= 0) break;
+      pf.problem_iterations += na;
+      pf.linearize_launches_with_work++;
+      pf.knot_items += na * (it == 0 ? T : T - 2);
+      if (want_rows)
+        pf.jrow_bytes += na * (it == 0 ? ctx->rows_per_problem : ctx->rows_per_problem - 2LL * (ctx->collision ? R.npoints : 0)) * (n + 1) * 4;
+    }
   }
   {
     const long long tot = (long long)B * T;
@@ -2213,8 +1258,9 @@ extern "C" int gto_download_batch(gto_ctx* ctx, gto_batch_out* out) {
   if (!ctx->solved) return fail(ctx, GTO_ERR_STATE, "no solved batch to download");
   CK(cudaSetDevice(ctx->device));
   const int B = ctx->B, T = ctx->T, nd = ctx->robot_h.ndof;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  EventPair evp;
+  CK(evp.create());
+  cudaEvent_t e0 = evp.a, e1 = evp.b;
   CK(cudaEventRecord(e0, ctx->stream));
   long long bytes = 0;
   if (out->Q) { CK(cudaMemcpyAsync(out->Q, ctx->outQ.p, sizeof(double) * B * T * nd, cudaMemcpyDeviceToHost, ctx->stream)); bytes += sizeof(double) * B * T * nd; }
@@ -2228,7 +1274,6 @@ extern "C" int gto_download_batch(gto_ctx* ctx, gto_batch_out* out) {
   cudaEventElapsedTime(&ms, e0, e1);
   ctx->prof.d2h_ms = ms;
   ctx->prof.d2h_bytes = bytes;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return GTO_OK;
 }
 
@@ -2256,6 +1301,7 @@ extern "C" int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out
   const int B = ctx->B, T = ctx->T, n = R.nopt;
   const size_t nrows = (size_t)B * ctx->rows_per_problem * (n + 1);
   if (out->rows) CK(ctx->rows.ensure(nrows));
+  ctx->Bchunk = B;
   StateParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.robot = ctx->robot_d; sp.B = B; sp.T = T; sp.q_seed = ctx->q_seed.p; sp.q_trial = ctx->q_trial.p; sp.project = 0;
@@ -2271,8 +1317,8 @@ extern "C" int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out
   CK(cudaStreamSynchronize(ctx->stream));
   if (out->rows) CK(cudaMemcpy(out->rows, ctx->rows.p, nrows * sizeof(float), cudaMemcpyDeviceToHost));
   if (out->H) CK(cudaMemcpy(out->H, ctx->H.p, sizeof(float) * B * T * n * n, cudaMemcpyDeviceToHost));
-  if (out->g) CK(cudaMemcpy(out->g, ctx->g.p, sizeof(float) * B * T * n, cudaMemcpyDeviceToHost));
-  if (out->cost) CK(cudaMemcpy(out->cost, ctx->costp.p, sizeof(float) * B * T, cudaMemcpyDeviceToHost));
+  if (out->g) CK(cudaMemcpy(out->g, ctx->g.p, sizeof(double) * B * T * n, cudaMemcpyDeviceToHost));
+  if (out->cost) CK(cudaMemcpy(out->cost, ctx->costp.p, sizeof(double) * B * T, cudaMemcpyDeviceToHost));
   return GTO_OK;
 }
 

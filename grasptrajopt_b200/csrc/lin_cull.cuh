@@ -1,8 +1,10 @@
-// lin_cull.cuh -- k_linearize_cull: the default fused linearisation kernel.
-// Included by gto_b200.cu after lin_pipe.cuh (shares its PTX helpers, LinkMeta and the generic trilinear lookup).
+// lin_cull.cuh -- k_item_fk + k_linearize_cull: the fused linearisation of one Gauss-Newton iteration.
+// Included by gto_b200.cu (uses its device tables and PTX helpers).
 //
-// Same warp-specialised structure as k_linearize_pipe (1 producer warp + NC consumer warps per persistent CTA, SDF bricks
-// staged by TMA into a shared-memory ring), plus three things:
+// Warp-specialised persistent CTAs (1 producer warp + NC consumer warps + 1 zero-row warp), SDF bricks staged by TMA into a
+// shared-memory ring (box sizes per axis from {8,12,...,32}, one tensor map per combination and field; the start coordinate
+// of the innermost (z) axis is kept a multiple of 4 elements: TMA faults on a tile whose innermost start is not 16-byte
+// aligned), plus three things:
 //   * exact culling   the cost field is identically zero away from obstacles (DepthPointCloud.get_sdf_cost is 0 for
 //                     d >= epsilon, mesh_to_sdf/depth_point_cloud.py:65-91).  The producer tests, per link, whether the
 //                     box of grid nodes its points can touch holds any non-zero node -- 8 reads of a summed-volume table
@@ -17,6 +19,69 @@
 
 #define CULL_NSLOT_MAX 8  // brick ring slots: run-time (CullParams.nslot), default 4
 #define CULL_ZERO_BYTES 8192
+
+struct LinkMeta {
+  int c0, c1, pt_start, pt_end;
+  unsigned mask;
+};
+
+// try_wait with a suspend-time hint: the hardware parks the thread instead of burning issue slots on polling
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int tries = 0; tries < (1 << 20); ++tries) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();  // a lost transaction must abort the launch, never hang the device
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// generic (slow-path) trilinear lookup for points whose cell may need index clamping or lies outside
+// the staged brick; same arithmetic and association order as the fast path below and as the oracle
+__device__ __forceinline__ void sdf_trilinear_box(const FieldDev& f, const float* __restrict__ brick, const int* bdim, const int* bl,
+                                                  float wx, float wy, float wz, float& val, float& gx, float& gy, float& gz) {
+  float ux = (wx - f.ox) * f.inv_pitch, uy = (wy - f.oy) * f.inv_pitch, uz = (wz - f.oz) * f.inv_pitch;
+  int ix = min(max((int)floorf(ux), 0), f.nx - 2);
+  int iy = min(max((int)floorf(uy), 0), f.ny - 2);
+  int iz = min(max((int)floorf(uz), 0), f.nz - 2);
+  float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
+  const bool inx = (fx >= 0.f) && (fx <= 1.f), iny = (fy >= 0.f) && (fy <= 1.f), inz = (fz >= 0.f) && (fz <= 1.f);
+  fx = fminf(fmaxf(fx, 0.f), 1.f);
+  fy = fminf(fmaxf(fy, 0.f), 1.f);
+  fz = fminf(fmaxf(fz, 0.f), 1.f);
+  float c000, c001, c010, c011, c100, c101, c110, c111;
+  const int lx = ix - bl[0], ly = iy - bl[1], lz = iz - bl[2];
+  if (lx >= 0 && ly >= 0 && lz >= 0 && lx <= bdim[0] - 2 && ly <= bdim[1] - 2 && lz <= bdim[2] - 2) {
+    const int sy = bdim[2], sx = bdim[1] * bdim[2];
+    const float* p = brick + lx * sx + ly * sy + lz;
+    c000 = p[0]; c001 = p[1]; c010 = p[sy]; c011 = p[sy + 1];
+    c100 = p[sx]; c101 = p[sx + 1]; c110 = p[sx + sy]; c111 = p[sx + sy + 1];
+  } else {
+    const float* p = f.data + ((long long)ix * f.ny + iy) * f.nzp + iz;
+    const long long sy = f.nzp, sx = (long long)f.ny * f.nzp;
+    c000 = __ldg(p); c001 = __ldg(p + 1); c010 = __ldg(p + sy); c011 = __ldg(p + sy + 1);
+    c100 = __ldg(p + sx); c101 = __ldg(p + sx + 1); c110 = __ldg(p + sx + sy); c111 = __ldg(p + sx + sy + 1);
+  }
+  const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+  const float z00 = fmaf(fz, d00, c000), z01 = fmaf(fz, d01, c010), z10 = fmaf(fz, d10, c100), z11 = fmaf(fz, d11, c110);
+  const float y0 = fmaf(fy, z01 - z00, z00), y1 = fmaf(fy, z11 - z10, z10);
+  val = fmaf(fx, y1 - y0, y0);
+  const float dy0 = z01 - z00, dy1 = z11 - z10;
+  const float dz0 = fmaf(fy, d01 - d00, d00), dz1 = fmaf(fy, d11 - d10, d10);
+  gx = inx ? (y1 - y0) * f.inv_pitch : 0.f;
+  gy = iny ? fmaf(fx, dy1 - dy0, dy0) * f.inv_pitch : 0.f;
+  gz = inz ? fmaf(fx, dz1 - dz0, dz0) * f.inv_pitch : 0.f;
+}
 
 struct __align__(16) CullCtx {
   float frames[GTO_MAX_LINKS][12];  // visual frame of each collision link (robot base frame)
@@ -94,7 +159,7 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
   CullCtx& C = valid ? pp.recs[item] : *pp.rec_dummy;
   // issued before the FK chain, consumed after it: field geometry, base offset
   FieldDev fld;
-  fld.data = nullptr; fld.nx = fld.ny = fld.nz = fld.nzp = 2; fld.ox = fld.oy = fld.oz = 0.f; fld.inv_pitch = 1.f; fld.has_tma = 0;
+  fld.data = nullptr; fld.nx = fld.ny = fld.nz = fld.nzp = 2; fld.ox = fld.oy = fld.oz = 0.f; fld.inv_pitch = 1.f;
   fld.maps2 = nullptr; fld.svt = nullptr;
   if (fid >= 0) fld = p.fields[fid];
   const float bpx = p.base[4 * b + 0], bpy = p.base[4 * b + 1], bpz = p.base[4 * b + 2];
@@ -253,8 +318,8 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
     const int nH = nopt * nopt;
     const long long bt = (long long)b * p.T + t;
     for (int i = hl; i < nH; i += 16) p.H[obuf * p.buf_stride_H + bt * nH + i] = 0.f;
-    if (hl < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + hl] = 0.f;
-    if (hl == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.f;
+    if (hl < nopt) p.g[obuf * p.buf_stride_g + bt * nopt + hl] = 0.0;
+    if (hl == 0) p.costp[obuf * p.buf_stride_c + bt] = 0.0;
   }
   FK_MARK(6);
   if (pp.stats && valid && hl == 0) {
@@ -306,9 +371,21 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
                : "memory");
 }
 
+// per-warp reduction record: [nopt*nopt] float (J^T J), then [nopt + 1] double (J^T r, sum r^2), 8-byte aligned
+__host__ __device__ inline int cull_red_floats(int nopt) { return ((nopt * nopt + 1) & ~1) + 2 * (nopt + 1); }
+__host__ __device__ inline size_t cull_smem_bytes(int nopt, int ncons, int nslot, int slot_floats) {
+  const int RS = nopt + 1;
+  size_t sm = (sizeof(CullShared) + 127) & ~(size_t)127;
+  sm += CULL_ZERO_BYTES;
+  sm += (size_t)nslot * slot_floats * sizeof(float);
+  sm += (size_t)ncons * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
+  sm += (size_t)2 * ncons * cull_red_floats(nopt) * sizeof(float);
+  return (sm + 127) & ~(size_t)127;
+}
+
 // NP: padded tensor-core tile width (8 or 16); NOPT_CT: number of optimised joints when known at compile time (0: runtime)
 template <int NP, int NOPT_CT>
-__global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
+__global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LinParams& p = pp.lin;
   CullShared& S = *reinterpret_cast<CullShared*>(smem_raw);
@@ -324,7 +401,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
   const int st_floats = ((32 * RS + 16 + 31) / 32) * 32;
   float* stage_base = reinterpret_cast<float*>(smem_raw + off);
   off += (size_t)NC * st_floats * sizeof(float);
-  const int red_floats = nopt * nopt + nopt + 2;
+  const int red_floats = cull_red_floats(nopt), red_g0 = (nopt * nopt + 1) & ~1;  // doubles start at an even float index
   float* red_base = reinterpret_cast<float*>(smem_raw + off);  // [2][NC][red_floats]
   uint64_t* slot_full = reinterpret_cast<uint64_t*>(S.slot_full);
   uint64_t* slot_empty = reinterpret_cast<uint64_t*>(S.slot_empty);
@@ -425,7 +502,7 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
           if (lane == 0) {
             const unsigned s = idx % CULL_NSLOT;
             if (idx >= CULL_NSLOT) mbar_wait_sleep(slot_empty + s, ((idx / CULL_NSLOT) - 1) & 1);
-            const int mi = ((sx / 4 - 2) * PIPE_NAXC + (sy / 4 - 2)) * PIPE_NAXC + (sz / 4 - 2);
+            const int mi = ((sx / 4 - 2) * CULL_NAXC + (sy / 4 - 2)) * CULL_NAXC + (sz / 4 - 2);
             mbar_expect_tx(slot_full + s, (uint32_t)(sx * sy * sz * sizeof(float)));
             tma_load_3d(ring + (size_t)s * pp.slot_floats, maps + mi, lz, ly, lx, slot_full + s);
           }
@@ -522,10 +599,13 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
     const int t = C.t, fid = C.fid, nact = C.nact;
     const bool is_goal = (C.kind & 1) != 0, is_stand = (C.kind & 2) != 0;
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-    float gacc[NP];
+    // J^T r and sum r^2 are accumulated in float64: at the optimum J^T r is the small difference of large sums (goal pull against
+    // obstacle push), and the float32 rounding of a running sum of magnitude ~10 (6e-7 per add) would move the fixed point
+    // by more than the 1e-4 rad parity bar along the weakly determined directions of the redundant arm
+    double gacc[NP];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) gacc[k] = 0.f;
-    float cacc = 0.f;
+    for (int k = 0; k < NP; ++k) gacc[k] = 0.0;
+    double cacc = 0.0;
     float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
 
     int next = warp, cb = 0;  // chunks of the surviving links are dealt round-robin: warp, warp+NC, ... of the concatenation
@@ -592,10 +672,13 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
               }
             }
           }
-          cacc = fmaf(r, r, cacc);
+          if (act) {  // (inactive lanes hold zeros)
+            const double rd = (double)r;
+            cacc = fma(rd, rd, cacc);
 #pragma unroll
-          for (int k = 0; k < NP; ++k)
-            if (k < nopt) gacc[k] = fmaf(J[k], r, gacc[k]);
+            for (int k = 0; k < NP; ++k)
+              if (k < nopt) gacc[k] = fma((double)J[k], rd, gacc[k]);
+          }
           if (NOPT_CT == 7) {  // row = [J0..J6 | r] = 32 bytes: two 128-bit shared stores
             float4* s4 = reinterpret_cast<float4*>(stage + lane * 8);
             s4[0] = make_float4(J[0], J[1], J[2], J[3]);
@@ -671,11 +754,11 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
               }
             }
             const float r = r3[a3];
-            cacc = fmaf(r, r, cacc);
+            cacc = fma((double)r, (double)r, cacc);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
               if (k < nopt) {
-                gacc[k] = fmaf(J[k], r, gacc[k]);
+                gacc[k] = fma((double)J[k], (double)r, gacc[k]);
                 stage[lane * RS + k] = J[k];
               }
             }
@@ -719,23 +802,29 @@ __global__ void __launch_bounds__((PIPE_MAX_CONS + 2) * 32, 2) k_linearize_cull(
         }
       }
       if (lane == 0) {
+        double* redd = reinterpret_cast<double*>(red + red_g0);
 #pragma unroll
         for (int k = 0; k < NP; ++k)
-          if (k < nopt) red[nopt * nopt + k] = gacc[k];
-        red[nopt * nopt + nopt] = cacc;
+          if (k < nopt) redd[k] = gacc[k];
+        redd[nopt] = cacc;
       }
     }
     const int obuf = C.obuf;
     asm volatile("bar.sync 1, %0;" ::"r"(NC * 32) : "memory");  // consumers only; the producer keeps running ahead
     {
       const int ntot = nH + nopt + 1;
+      const long long bt = (long long)b * p.T + t;
       for (int i = threadIdx.x; i < ntot; i += NC * 32) {
-        float s = 0.f;
-        for (int w = 0; w < NC; ++w) s += red_base[((size_t)ci * NC + w) * red_floats + i];
-        const long long bt = (long long)b * p.T + t;
-        if (i < nH) p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
-        else if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
-        else p.costp[obuf * p.buf_stride_c + bt] = s;
+        if (i < nH) {
+          float s = 0.f;
+          for (int w = 0; w < NC; ++w) s += red_base[((size_t)ci * NC + w) * red_floats + i];
+          p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
+        } else {
+          double s = 0.0;
+          for (int w = 0; w < NC; ++w) s += reinterpret_cast<const double*>(red_base + ((size_t)ci * NC + w) * red_floats + red_g0)[i - nH];
+          if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
+          else p.costp[obuf * p.buf_stride_c + bt] = s;
+        }
       }
     }
     __syncwarp();

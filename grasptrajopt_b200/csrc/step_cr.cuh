@@ -16,8 +16,8 @@
 
 __host__ __device__ inline size_t step_cr_smem_bytes(int T, int n) {
   const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
-  const size_t d = (size_t)2 * T * n + 5 * m * n + 3 * m * nn + 64;
-  return ((d * sizeof(double) + 2 * (m * nn + m * n) * sizeof(float) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
+  const size_t d = (size_t)2 * T * n + 7 * m * n + 3 * m * nn + 64;
+  return ((d * sizeof(double) + 2 * (m * nn) * sizeof(float) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
 }
 
 // deterministic block reductions (fixed tree): every thread of the CTA must call them
@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   double* red = Um + (size_t)m * nn;                 // [64] reduction scratch
   double* X2 = red + 64;                             // [T][n] the other of (accepted, trial) point while the decision is open
   double* dfix = X2 + (size_t)T * n;                 // [m][n] prescribed step of the variables held at a joint limit
-  float* HS = reinterpret_cast<float*>(dfix + (size_t)m * n);  // [2][m][n*n] Gauss-Newton blocks of both buffers (knots 2..T-1)
-  float* gS = HS + (size_t)2 * m * nn;                       // [2][m][n]
-  unsigned* fm = reinterpret_cast<unsigned*>(gS + (size_t)2 * m * n);  // [m] bit k: variable k of knot i+2 is held at a bound
+  double* gS = dfix + (size_t)m * n;                 // [2][m][n] J^T r of both buffers (knots 2..T-1)
+  float* HS = reinterpret_cast<float*>(gS + (size_t)2 * m * n);  // [2][m][n*n] Gauss-Newton blocks of both buffers
+  unsigned* fm = reinterpret_cast<unsigned*>(HS + (size_t)2 * m * nn);  // [m] bit k: variable k of knot i+2 is held at a bound
   int* sflag = reinterpret_cast<int*>(fm + m);           // [0] factorisation failed, [1] slot in the next active list
 
   double* Xc = p.Qc + (long long)b * T * n;
@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   double lam = p.lam[b], nu = p.nu[b];
   const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
   const int tri = 1 - cur;
-  if (tid == 0) p.bufsplit[tri * p.Bcap + b] = 1;
   bool accepted = false;
   double s0 = 0.0, s1 = 0.0, sv = 0.0;
   for (int i = tid; i < T * n; i += NT) {
@@ -136,24 +135,24 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   stamp_begin(p.ts);
   for (int buf = 0; buf < 2; ++buf) {  // Gauss-Newton blocks of both buffers (which one is "accepted" is decided below)
     const float* Hg = p.H + buf * p.buf_stride_H + (long long)b * T * nn + 2 * nn;
-    const float* gg = p.g + buf * p.buf_stride_g + (long long)b * T * n + 2 * n;
+    const double* gg = p.g + buf * p.buf_stride_g + (long long)b * T * n + 2 * n;
     for (int i = tid; i < m * nn; i += NT)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(HS + (size_t)buf * m * nn + i)), "l"(Hg + i) : "memory");
     for (int i = tid; i < m * n; i += NT)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(gS + (size_t)buf * m * n + i)), "l"(gg + i) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(gS + (size_t)buf * m * n + i)), "l"(gg + i) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   // ---------------- evaluate the trial point produced by the previous call ----------------
   {
     for (int t = tid; t < T; t += NT) {
-      s0 += (double)p.costp[(long long)b * T + t];
-      s1 += (double)p.costp[p.buf_stride_c + (long long)b * T + t];
+      s0 += p.costp[(long long)b * T + t];
+      s1 += p.costp[p.buf_stride_c + (long long)b * T + t];
     }
     STEP_MARK();  // 1: loads issued
     cta_sum3(s0, s1, sv, red);
     STEP_MARK();  // 2: trial cost known
-    float* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
+    double* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
     const double Fp_t = tri ? s1 : s0;
     const double Ft = Fp_t + a2 * sv;
     int done = -1;  // -1: keep running, otherwise final status
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     } else if (it == 0) {  // initial point: accept unconditionally
       // knots 0 and 1 never move and are linearised only once: keep their cost in both buffers
       if (tid < 2) {
-        const float c01 = ct[tid];
+        const double c01 = ct[tid];
         for (int buf = 0; buf < 2; ++buf) p.costp[buf * p.buf_stride_c + (long long)b * T + tid] = c01;
       }
       cur = tri;
@@ -180,11 +179,13 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
         const double w = 2.0 * fmin(rho, 1.0) - 1.0;
         lam = fmax(p.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - w * w * w));
         nu = 2.0;
-        if (step <= p.tol_step) done = GTO_STATUS_CONVERGED;
+        // a small step only certifies a stationary point when it was (nearly) the undamped Gauss-Newton step; under heavy
+        // damping it means the iterate rests on a gradient jump of the trilinear field (GTO_STATUS_SLOW, not converged)
+        if (step <= p.tol_step) done = (lam_used <= p.lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW;
         else if (lam_used >= p.lambda_slow && ared <= p.ftol * Fcur) done = GTO_STATUS_SLOW;
       } else {
         if (pred <= 0.0 && step <= p.tol_step) {
-          done = GTO_STATUS_CONVERGED;
+          done = (lam <= p.lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW;
         } else {
           lam = fmin(p.lambda_max, fmax(lam * nu, p.lambda_reject));
           nu *= 2.0;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const float* Hc = HS + (size_t)cur * m * nn;  // knots 2..T-1 of the accepted buffer
-  const float* gc = gS + (size_t)cur * m * n;
+  const double* gc = gS + (size_t)cur * m * n;
   {
     double pgmax = 0.0;
     for (int idx = tid; idx < m * n; idx += NT) {
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       const double x = X[t * n + k];
       double gv = x - X[(t - 1) * n + k];
       if (t < T - 1) gv -= X[(t + 1) * n + k] - x;
-      const double gtv = (double)gc[idx] + a2 * gv;
+      const double gtv = gc[idx] + a2 * gv;
       const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
       gt[idx] = gtv;
       if (fixed) atomicOr(fm + i, 1u << k);

@@ -40,8 +40,9 @@ extern "C" {
 #define GTO_STATUS_MAX_ITER 1
 #define GTO_STATUS_NAN 2
 #define GTO_STATUS_STALLED 3  /* damping hit lambda_max without an acceptable step */
-#define GTO_STATUS_SLOW 4     /* heavily damped accepted steps no longer reduce the cost (iterate sits at a kink of the
-                                 piecewise-trilinear field); the trajectory is returned but not counted as converged */
+#define GTO_STATUS_SLOW 4     /* |dq| fell below tol_step only under heavy damping (> lambda_conv): the iterate rests on a
+                                 gradient jump (cell face) of the piecewise-trilinear field, where no descent step longer than
+                                 tol_step is accepted; the trajectory is returned but not counted as converged */
 
 /* joint types in the robot table */
 #define GTO_JOINT_REVOLUTE 1
@@ -53,11 +54,7 @@ extern "C" {
 
 /* flags for gto_batch_in.flags */
 #define GTO_FLAG_NO_JROWS 1u      /* do not materialise the Jacobian rows in HBM (assembly still fused) */
-#define GTO_FLAG_NO_TMA 2u        /* stage SDF bricks with plain loads instead of TMA (debug / A-B check) */
-#define GTO_FLAG_NO_BRICK 4u      /* read the SDF straight from global memory (debug / A-B check) */
-#define GTO_FLAG_V1_KERNEL 8u     /* use the non-pipelined linearise kernel (A-B check) */
-#define GTO_FLAG_PIPE_KERNEL 16u  /* use the pipelined kernel without culling / dynamic scheduling (A-B check) */
-#define GTO_FLAG_NO_CULL 32u      /* default kernel, but every link is treated as touching a non-zero node (A-B check) */
+#define GTO_FLAG_NO_CULL 32u      /* every link is treated as touching a non-zero node of the field (A-B check of the culling) */
 
 typedef struct gto_ctx gto_ctx;
 
@@ -120,6 +117,8 @@ typedef struct gto_options {
                           exactly onto it and the other variables are re-solved; 0 = plain clipping of the step */
   double lambda_reject; /* a rejected step raises the damping to at least this value (1e-4): from lambda_min ~ 1e-9 the
                            doubling rule alone needs ~7 rejections before the damping changes the step at all */
+  double lambda_conv;   /* |dq| <= tol_step counts as GTO_STATUS_CONVERGED only when the damping that produced the step was
+                           <= lambda_conv (1e-2), i.e. the step was the Gauss-Newton step to within 1 %; otherwise GTO_STATUS_SLOW */
 } gto_options;
 
 /*
@@ -162,9 +161,9 @@ typedef struct gto_batch_out {
  * then goal [axis][k] (3*Pg), then stand-off [axis][k] (3*Pg, if use_standoff).  Any pointer may be NULL. */
 typedef struct gto_eval_out {
   float* rows;   /* [B][nrows][nopt+1] */
-  float* H;      /* [B][T][nopt][nopt]  sum_rows j j^T per knot (TF32 tensor-core contraction) */
-  float* g;      /* [B][T][nopt]        sum_rows j r   per knot (fp32) */
-  float* cost;   /* [B][T]              sum_rows r^2   per knot (fp32) */
+  float* H;      /* [B][T][nopt][nopt]  sum_rows j j^T per knot (error-compensated TF32 tensor-core contraction) */
+  double* g;     /* [B][T][nopt]        sum_rows j r   per knot (float32 products, float64 accumulation) */
+  double* cost;  /* [B][T]              sum_rows r^2   per knot (float64 accumulation) */
 } gto_eval_out;
 
 /* Timings measured with CUDA events on the library's stream. */
@@ -216,6 +215,17 @@ int gto_result_device_ptr(gto_ctx* ctx, void** ptr, int64_t* nfloats_per_problem
 int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out* out);
 
 int gto_get_profile(gto_ctx* ctx, gto_profile* prof);
+
+/* Run-time tuning knobs of a context (defaults in parentheses; the environment variable of the same upper-case name with the
+ * prefix GTO_ is read once in gto_create):
+ *   "jrows_budget_mb" (24576)  size of the Jacobian-row buffer; larger batches are solved in chunks that fit
+ *   "pdl" (1)                  programmatic dependent launch of the solver kernels
+ *   "launch_events" (0)        CUDA events between the launches instead of in-kernel time stamps (profile cross-check)
+ *   "step_fk" (0)              the step kernel also writes the item records once at most this many problems are active
+ *   "cull_nslot" (4), "cons_warps" (0 = automatic), "slot_floats" (0 = automatic)   shared-memory ring of k_linearize_cull
+ *   "step_dbg" (0)             print clock64() phase times of CTA 0 of the step / FK kernels to stderr
+ * Unknown keys return GTO_ERR_INVALID. */
+int gto_configure(gto_ctx* ctx, const char* key, double value);
 
 /* Value-only pass: sum over knots and points of the nearest-node cost along given plans -- the reference's seed
  * ranking GTORobotModel.compute_plan_cost (gto/gto_models.py:204-215).  plans [n][T][ndof]; cost[n], dist[n]. */

@@ -438,10 +438,12 @@ static void solve_one(job_t* J, int b) {
         const double ww = 2.0 * fmin(rho, 1.0) - 1.0;
         lam = fmax(opt->lambda_min, lam * fmax(1.0 / 3.0, 1.0 - ww * ww * ww));
         nu = 2.0;
-        if (stepmax <= opt->tol_step) { status = GTO_STATUS_CONVERGED; break; }
+        /* a small step certifies a stationary point only when it was (nearly) the undamped Gauss-Newton step; under heavy
+         * damping the iterate rests on a gradient jump of the trilinear field (GTO_STATUS_SLOW, not converged) */
+        if (stepmax <= opt->tol_step) { status = (lam_used <= opt->lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW; break; }
         if (lam_used >= opt->lambda_slow && ared <= opt->ftol * F_before) { status = GTO_STATUS_SLOW; break; }
       } else {
-        if (pred <= 0.0 && stepmax <= opt->tol_step) { status = GTO_STATUS_CONVERGED; break; }
+        if (pred <= 0.0 && stepmax <= opt->tol_step) { status = (lam <= opt->lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW; break; }
         lam = fmin(opt->lambda_max, fmax(lam * nu, opt->lambda_reject));
         nu *= 2.0;
         if (lam >= opt->lambda_max) { status = GTO_STATUS_STALLED; break; }

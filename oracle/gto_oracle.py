@@ -478,6 +478,7 @@ class SolverOptions:
     slow_ftol: float = 1e-3
     as_rounds: int = 1  # active-set rounds per step: variables pushed beyond a limit are put on it, the rest re-solved
     lambda_reject: float = 1e-4  # a rejected step raises the damping to at least this value
+    lambda_conv: float = 1e-2  # |dq| <= tol_step counts as converged only if the damping that produced the step was <= this
 
 
 STATUS_CONVERGED = 0
@@ -694,14 +695,16 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
             nu = 2.0
             hist.append(F)
             if step <= opts.tol_step:
-                status = STATUS_CONVERGED
+                # a small step certifies a stationary point only when it was (nearly) the undamped Gauss-Newton step;
+                # under heavy damping the iterate rests on a gradient jump of the trilinear field (not converged)
+                status = STATUS_CONVERGED if lam_used <= opts.lambda_conv else STATUS_SLOW
                 break
             if lam_used >= opts.lambda_slow and ared <= opts.ftol * F_before:
                 status = STATUS_SLOW  # heavily damped and no longer reducing the cost: a kink of the trilinear field
                 break
         else:
             if pred <= 0 and step <= opts.tol_step:
-                status = STATUS_CONVERGED
+                status = STATUS_CONVERGED if lam <= opts.lambda_conv else STATUS_SLOW
                 break
             lam = min(opts.lambda_max, max(lam * nu, opts.lambda_reject))
             nu *= 2.0

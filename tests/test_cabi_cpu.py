@@ -66,7 +66,7 @@ def test_status_and_flag_constants_match_header():
     for name, val in (("GTO_STATUS_CONVERGED", capi.STATUS_CONVERGED), ("GTO_STATUS_MAX_ITER", capi.STATUS_MAX_ITER),
                       ("GTO_STATUS_NAN", capi.STATUS_NAN), ("GTO_STATUS_STALLED", capi.STATUS_STALLED), ("GTO_STATUS_SLOW", capi.STATUS_SLOW)):
         assert int(re.search(r"#define %s (\d+)" % name, hdr).group(1)) == val
-    for name, val in (("GTO_FLAG_NO_JROWS", capi.FLAG_NO_JROWS), ("GTO_FLAG_NO_TMA", capi.FLAG_NO_TMA), ("GTO_FLAG_NO_BRICK", capi.FLAG_NO_BRICK)):
+    for name, val in (("GTO_FLAG_NO_JROWS", capi.FLAG_NO_JROWS), ("GTO_FLAG_NO_CULL", capi.FLAG_NO_CULL)):
         assert int(re.search(r"#define %s (\d+)u" % name, hdr).group(1)) == val
 
 

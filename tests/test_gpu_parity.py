@@ -42,17 +42,17 @@ def _check_eval(ctx, w, frac_bad_rows=2e-4):
     bad = err > 1e-4 * scale
     assert bad.mean() <= frac_bad_rows, f"{bad.sum()} of {bad.size} Jacobian rows differ"
     if not bad.any():
-        # tensor-core J^T J (TF32 inputs, fp32 accumulate), fp32 J^T r and cost
+        # tensor-core J^T J (error-compensated TF32, fp32 accumulate); J^T r and cost: float32 products, float64 sums
         Hs = np.abs(H).max(axis=(-1, -2), keepdims=True) + 1e-6
-        assert np.max(np.abs(out["H"] - H) / Hs) < 4e-3
+        assert np.max(np.abs(out["H"] - H) / Hs) < 2e-5
         gs = np.abs(g).max(axis=-1, keepdims=True) + 1e-4
-        assert np.max(np.abs(out["g"] - g) / gs) < 2e-4
-        np.testing.assert_allclose(out["cost"], cost, rtol=2e-5, atol=1e-7)
+        assert np.max(np.abs(out["g"] - g) / gs) < 2e-5
+        np.testing.assert_allclose(out["cost"], cost, rtol=5e-6, atol=1e-8)
     assert np.abs(rows[..., :n]).max() > 0.1 and cost.max() > 0
     return out
 
 
-KERNELS = [pytest.param(0, id="cull"), pytest.param(capi.FLAG_PIPE_KERNEL, id="pipelined"), pytest.param(capi.FLAG_V1_KERNEL, id="v1")]
+KERNELS = [pytest.param(0, id="cull"), pytest.param(capi.FLAG_NO_CULL, id="nocull")]
 
 
 @pytest.mark.parametrize("kflag", KERNELS)
@@ -95,32 +95,16 @@ def test_eval_parity_points_outside_the_field(ctx):
     _check_eval(ctx, w, frac_bad_rows=1e-3)
 
 
-def test_brick_paths_bit_identical(ctx):
-    """TMA-staged brick, cooperatively loaded brick and direct global reads must give identical bits."""
-    w = small_workload("C2", "panda_small", B=3, n_field=64)
-    ctx.set_robot(w.table)
-    upload_fields(ctx, w)
-    outs = []
-    for flags in (capi.FLAG_V1_KERNEL, capi.FLAG_NO_TMA, capi.FLAG_NO_BRICK):
-        w.batch.flags = flags
-        outs.append(ctx.eval_batch(w.batch))
-    w.batch.flags = 0
-    for o in outs[1:]:
-        np.testing.assert_array_equal(o["rows"], outs[0]["rows"])
-        np.testing.assert_array_equal(o["g"], outs[0]["g"])
-        np.testing.assert_array_equal(o["cost"], outs[0]["cost"])
-
-
 def test_culling_is_exact(ctx):
     """Links whose node box holds only zero cost nodes are culled (zero rows written by bulk copies): the result must be
-    identical to the same kernel with the test disabled (rows bit for bit, the per-knot sums up to summation order), and to the kernel without culling, and links must actually
-    be culled in this scene."""
+    identical to the same kernel with the test disabled (rows bit for bit, the per-knot sums up to summation order), and
+    links must actually be culled in this scene."""
     for cfg, tab, nf in (("C2", "panda_small", 64), ("C3", None, 96), ("C4", None, 64)):
         w = small_workload(cfg, tab, B=3, n_field=nf)
         ctx.set_robot(w.table)
         upload_fields(ctx, w)
         outs = []
-        for flags in (0, capi.FLAG_NO_CULL, capi.FLAG_PIPE_KERNEL):
+        for flags in (0, capi.FLAG_NO_CULL):
             w.batch.flags = flags
             outs.append(ctx.eval_batch(w.batch))
         w.batch.flags = 0
@@ -197,8 +181,8 @@ def test_solve_properties_full_c2(ctx):
     Q = res["Q"]
     oi = t.opt_qidx
     st = res["status"]
-    assert np.mean(st == capi.STATUS_CONVERGED) > 0.9  # step / gradient criterion
-    assert np.mean((st == capi.STATUS_CONVERGED) | (st == capi.STATUS_SLOW)) > 0.98  # + stopped at a kink of the field
+    assert np.mean(st == capi.STATUS_CONVERGED) > 0.85  # step (under light damping) / gradient criterion
+    assert np.mean((st == capi.STATUS_CONVERGED) | (st == capi.STATUS_SLOW)) > 0.95  # + resting on a kink of the field
     np.testing.assert_array_equal(Q[:, 0, oi], b.qc[:, oi])  # initial configuration
     np.testing.assert_array_equal(Q[:, 1, oi], b.qc[:, oi])  # zero initial velocity
     assert np.all(Q[:, :, oi] >= t.lo - 1e-12) and np.all(Q[:, :, oi] <= t.hi + 1e-12)
@@ -224,27 +208,38 @@ def test_chunked_solve_is_identical(ctx, monkeypatch):
     upload_fields(ctx, w)
     ref = ctx.solve_batch(w.batch)
     per_problem_mb = (w.batch.T * w.table.npoints + 6 * w.table.grip_pt_count) * (w.table.nopt + 1) * 4 / 2**20
-    monkeypatch.setenv("GTO_JROWS_BUDGET_MB", str(3.5 * per_problem_mb))  # 3 problems per chunk -> chunks of 3, 3, 2
-    res = ctx.solve_batch(w.batch)
-    pf = ctx.profile()
+    ctx.configure(jrows_budget_mb=3.5 * per_problem_mb)  # 3 problems per chunk -> chunks of 3, 3, 2
+    try:
+        res = ctx.solve_batch(w.batch)
+        pf = ctx.profile()
+    finally:
+        ctx.configure(jrows_budget_mb=24576)
     for k in ("Q", "dQ", "cost", "iters", "status"):
         np.testing.assert_array_equal(res[k], ref[k], err_msg=k)
     assert 0 < pf["linearize_ms"] + pf["step_ms"] <= pf["solve_ms"] * 1.05
 
 
-@pytest.mark.parametrize("env", [{"GTO_STEP_FK": "all"}, {"GTO_STEP_FK": "4"}, {"GTO_NO_PDL": "1"}, {"GTO_LAUNCH_EVENTS": "1"}, {"GTO_GROUPS": "2"}])
-def test_launch_options_do_not_change_the_result(ctx, monkeypatch, env):
+@pytest.mark.parametrize("knobs", [{"step_fk": 1 << 30}, {"step_fk": 4}, {"pdl": 0}, {"launch_events": 1}, {"cull_nslot": 2}, {"cons_warps": 5}])
+def test_launch_options_do_not_change_the_result(ctx, knobs):
     """Optional launch structures (FK records written by the step kernel, plain stream-ordered launches, CUDA events between the
-    launches, two problem groups on separate streams) must reproduce the default path bit for bit."""
+    launches, a shorter brick ring) must reproduce the default path bit for bit; a different number of consumer warps changes
+    the summation order of the per-knot blocks only."""
     w = small_workload("C2", "panda_small", B=12, n_field=64)
     ctx.set_robot(w.table)
     upload_fields(ctx, w)
     ref = ctx.solve_batch(w.batch)
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    res = ctx.solve_batch(w.batch)
-    for k in ("Q", "dQ", "cost", "iters", "status"):
-        np.testing.assert_array_equal(res[k], ref[k], err_msg=f"{env} {k}")
+    default = dict(step_fk=0, pdl=1, launch_events=0, cull_nslot=4, cons_warps=0)
+    ctx.configure(**knobs)
+    try:
+        res = ctx.solve_batch(w.batch)
+    finally:
+        ctx.configure(**default)
+    if "cons_warps" in knobs:
+        ok = (ref["status"] == 0) & (res["status"] == 0)
+        assert ok.sum() >= 8 and np.abs(res["Q"][ok] - ref["Q"][ok]).max() < 1e-4
+    else:
+        for k in ("Q", "dQ", "cost", "iters", "status"):
+            np.testing.assert_array_equal(res[k], ref[k], err_msg=f"{knobs} {k}")
 
 
 def _sub_batch(b, idx):
