@@ -64,6 +64,7 @@ struct FieldDev {
   const float* data;  // [nx][ny][nzp]
   int nx, ny, nz, nzp;
   float ox, oy, oz, inv_pitch;
+  double org_d[3], inv_pitch_d;  // float64 copies for the voxel coordinate of a point (k_item_fk)
   const CUtensorMap* maps2;  // [7*7*7] TMA tile maps with per-axis box sizes 8,12,...,32; NULL if unavailable
   const unsigned* svt;       // [(nx+1)][(ny+1)][(nz+1)] summed-volume table of the non-zero nodes (culling test); NULL if unavailable
 };
@@ -770,6 +771,7 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
   FieldDev d;
   d.data = f.data; d.nx = f.nx; d.ny = f.ny; d.nz = f.nz; d.nzp = nzp;
   d.ox = (float)origin[0]; d.oy = (float)origin[1]; d.oz = (float)origin[2]; d.inv_pitch = (float)(1.0 / pitch);
+  d.org_d[0] = origin[0]; d.org_d[1] = origin[1]; d.org_d[2] = origin[2]; d.inv_pitch_d = 1.0 / pitch;
   d.maps2 = nullptr;
   if (ctx->encode) {  // one tile map per combination of per-axis box sizes
     std::vector<CUtensorMap> m2((size_t)CULL_NAXC * CULL_NAXC * CULL_NAXC);

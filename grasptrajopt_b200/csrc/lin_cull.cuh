@@ -48,13 +48,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // generic (slow-path) trilinear lookup for points whose cell may need index clamping or lies outside
 // the staged brick; same arithmetic and association order as the fast path below and as the oracle
+// (ulx, uly, ulz): float64 voxel coordinate relative to the brick's lower corner bl
 __device__ __forceinline__ void sdf_trilinear_box(const FieldDev& f, const float* __restrict__ brick, const int* bdim, const int* bl,
-                                                  float wx, float wy, float wz, float& val, float& gx, float& gy, float& gz) {
-  float ux = (wx - f.ox) * f.inv_pitch, uy = (wy - f.oy) * f.inv_pitch, uz = (wz - f.oz) * f.inv_pitch;
-  int ix = min(max((int)floorf(ux), 0), f.nx - 2);
-  int iy = min(max((int)floorf(uy), 0), f.ny - 2);
-  int iz = min(max((int)floorf(uz), 0), f.nz - 2);
-  float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
+                                                  double ulx, double uly, double ulz, float& val, float& gx, float& gy, float& gz) {
+  const double ux = ulx + (double)bl[0], uy = uly + (double)bl[1], uz = ulz + (double)bl[2];  // grid voxel coordinate
+  int ix = min(max((int)floor(ux), 0), f.nx - 2);
+  int iy = min(max((int)floor(uy), 0), f.ny - 2);
+  int iz = min(max((int)floor(uz), 0), f.nz - 2);
+  float fx = (float)(ux - (double)ix), fy = (float)(uy - (double)iy), fz = (float)(uz - (double)iz);
   const bool inx = (fx >= 0.f) && (fx <= 1.f), iny = (fy >= 0.f) && (fy <= 1.f), inz = (fz >= 0.f) && (fz <= 1.f);
   fx = fminf(fmaxf(fx, 0.f), 1.f);
   fy = fminf(fmaxf(fy, 0.f), 1.f);
@@ -88,7 +89,7 @@ struct __align__(16) CullCtx {
   float tw[GTO_MAX_OPT][8];         // (omega.xyz, -, m.xyz, -) per optimised joint
   float gripf[12];
   float goal[2][12];                // gripper frame minus goal / stand-off frame
-  float cl[GTO_MAX_LINKS][4];       // brick-local voxel coordinate = Wb * inv_pitch + cl
+  double vf[GTO_MAX_LINKS][12];     // float64 3x4 map: point in the link's visual frame -> brick-local voxel coordinate
   int blo[GTO_MAX_LINKS][4];        // brick lower corner (grid index) per link
   int bdim[GTO_MAX_LINKS][4];       // brick dims (x, y, z) and fast flag
   float basep[4];
@@ -159,7 +160,7 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
   CullCtx& C = valid ? pp.recs[item] : *pp.rec_dummy;
   // issued before the FK chain, consumed after it: field geometry, base offset
   FieldDev fld;
-  fld.data = nullptr; fld.nx = fld.ny = fld.nz = fld.nzp = 2; fld.ox = fld.oy = fld.oz = 0.f; fld.inv_pitch = 1.f;
+  fld.data = nullptr; fld.nx = fld.ny = fld.nz = fld.nzp = 2; fld.ox = fld.oy = fld.oz = 0.f; fld.inv_pitch = 1.f; fld.inv_pitch_d = 1.0; fld.org_d[0] = fld.org_d[1] = fld.org_d[2] = 0.0;
   fld.maps2 = nullptr; fld.svt = nullptr;
   if (fid >= 0) fld = p.fields[fid];
   const float bpx = p.base[4 * b + 0], bpy = p.base[4 * b + 1], bpz = p.base[4 * b + 2];
@@ -259,8 +260,18 @@ __device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDe
         }
         *reinterpret_cast<int4*>(C.blo[l]) = make_int4(lo3[0], lo3[1], lo3[2], 0);
         *reinterpret_cast<int4*>(C.bdim[l]) = make_int4(sz3[0], sz3[1], sz3[2], fast ? 1 : 0);
-        *reinterpret_cast<float4*>(C.cl[l]) = make_float4((bp[0] - org[0]) * f.inv_pitch - (float)lo3[0], (bp[1] - org[1]) * f.inv_pitch - (float)lo3[1],
-                                                          (bp[2] - org[2]) * f.inv_pitch - (float)lo3[2], f.inv_pitch);
+        // voxel coordinate of a point x of this link, relative to the brick's lower corner, formed in float64:
+        // u = (Fd x + base - origin) / pitch - lo.  The float32 position (frames rounded to float32, |W| ~ 1 m) is only good to
+        // 6e-8 m, which puts 1e-6 of pseudo-random noise on the cost of a trajectory -- more than the cost reductions that
+        // decide the last accept / reject steps of the solver.
+#pragma unroll
+        for (int a3 = 0; a3 < 3; ++a3) {
+          const double ip = f.inv_pitch_d;
+          C.vf[l][a3 * 4 + 0] = Fd[a3 * 4 + 0] * ip;
+          C.vf[l][a3 * 4 + 1] = Fd[a3 * 4 + 1] * ip;
+          C.vf[l][a3 * 4 + 2] = Fd[a3 * 4 + 2] * ip;
+          C.vf[l][a3 * 4 + 3] = (Fd[a3 * 4 + 3] + ((double)bp[a3] - f.org_d[a3])) * ip - (double)lo3[a3];
+        }
         survives = (R.link_pt_count[l] > 0) &&
                    (!cull || f.svt == nullptr || svt_count(f, c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]) != 0u);
       }
@@ -616,7 +627,8 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
       const unsigned idx = bc + ai;
       mbar_wait_sleep(slot_full + (idx % CULL_NSLOT), (idx / CULL_NSLOT) & 1);
       const float* brick = ring + (size_t)(idx % CULL_NSLOT) * pp.slot_floats;
-      const float clx = C.cl[l][0], cly = C.cl[l][1], clz = C.cl[l][2], ipitch = C.cl[l][3];
+      const double* vf = C.vf[l];
+      const float ipitch = p.fields[fid].inv_pitch;
       const int dy = C.bdim[l][1], dz = C.bdim[l][2], fast = C.bdim[l][3];
       const int dxm2 = C.bdim[l][0] - 2, dym2 = dy - 2, dzm2 = dz - 2;
       const LinkMeta lm = S.links[l];
@@ -639,11 +651,15 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
             const float wby = F[4] * x + F[5] * y + F[6] * z + F[7];
             const float wbz = F[8] * x + F[9] * y + F[10] * z + F[11];
             float val, gx, gy, gz;
+            // brick-local voxel coordinate in float64 (see k_item_fk), cell index, float32 fraction inside the cell
+            const double xd = (double)x, yd = (double)y, zd = (double)z;
+            const double ux = fma(vf[0], xd, fma(vf[1], yd, fma(vf[2], zd, vf[3])));
+            const double uy = fma(vf[4], xd, fma(vf[5], yd, fma(vf[6], zd, vf[7])));
+            const double uz = fma(vf[8], xd, fma(vf[9], yd, fma(vf[10], zd, vf[11])));
             if (fast) {
               // the brick encloses every point of this link and lies inside the grid: no grid clamping can occur
-              const float ux = fmaf(wbx, ipitch, clx), uy = fmaf(wby, ipitch, cly), uz = fmaf(wbz, ipitch, clz);
-              const int ix = min(max((int)floorf(ux), 0), dxm2), iy = min(max((int)floorf(uy), 0), dym2), iz = min(max((int)floorf(uz), 0), dzm2);
-              const float fx = ux - (float)ix, fy = uy - (float)iy, fz = uz - (float)iz;
+              const int ix = min(max((int)floor(ux), 0), dxm2), iy = min(max((int)floor(uy), 0), dym2), iz = min(max((int)floor(uz), 0), dzm2);
+              const float fx = (float)(ux - (double)ix), fy = (float)(uy - (double)iy), fz = (float)(uz - (double)iz);
               const float* q8 = brick + (ix * dy + iy) * dz + iz;
               const int sx = dy * dz;
               const float c000 = q8[0], c001 = q8[1], c010 = q8[dz], c011 = q8[dz + 1];
@@ -658,7 +674,7 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
               gy = fmaf(fx, dy1 - dy0, dy0) * ipitch;
               gz = fmaf(fx, dz1 - dz0, dz0) * ipitch;
             } else {
-              sdf_trilinear_box(p.fields[fid], brick, C.bdim[l], C.blo[l], wbx + C.basep[0], wby + C.basep[1], wbz + C.basep[2], val, gx, gy, gz);
+              sdf_trilinear_box(p.fields[fid], brick, C.bdim[l], C.blo[l], ux, uy, uz, val, gx, gy, gz);
             }
             r = p.sw_obs * val;
             gx *= p.sw_obs; gy *= p.sw_obs; gz *= p.sw_obs;

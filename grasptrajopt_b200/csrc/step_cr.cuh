@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
         accepted = true;
         if (tid == 0) { p.bufsel[b] = cur; p.F[b] = Ft; p.Fp[b] = Fp_t; }
         const double lam_used = lam;
-        const double w = 2.0 * fmin(rho, 1.0) - 1.0;
+        // gain ratio clamped to [0, 1]: a step accepted only thanks to the noise allowance can have rho << 0, and Nielsen's
+        // cubic would then multiply the damping by hundreds in one step (float32 cost noise near convergence)
+        const double w = 2.0 * fmin(fmax(rho, 0.0), 1.0) - 1.0;
         lam = fmax(p.lambda_min, lam * fmax(1.0 / 3.0, 1.0 - w * w * w));
         nu = 2.0;
         // a small step only certifies a stationary point when it was (nearly) the undamped Gauss-Newton step; under heavy

@@ -435,7 +435,9 @@ static void solve_one(job_t* J, int b) {
         tmp = g; g = gtr; gtr = tmp;
         tmp = cp; cp = cpt; cpt = tmp;
         F = Ft; Fp = Fp_t;
-        const double ww = 2.0 * fmin(rho, 1.0) - 1.0;
+        /* gain ratio clamped to [0, 1]: a step accepted only thanks to the noise allowance can have rho << 0, and Nielsen's
+         * cubic would then multiply the damping by hundreds in one step */
+        const double ww = 2.0 * fmin(fmax(rho, 0.0), 1.0) - 1.0;
         lam = fmax(opt->lambda_min, lam * fmax(1.0 / 3.0, 1.0 - ww * ww * ww));
         nu = 2.0;
         /* a small step certifies a stationary point only when it was (nearly) the undamped Gauss-Newton step; under heavy

@@ -691,7 +691,9 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
             rho = ared / pred if pred > 0 else 1.0
             F_before, lam_used = F, lam
             Q, lin, F = Qt, lin_t, Ft
-            lam = max(opts.lambda_min, lam * max(1.0 / 3.0, 1.0 - (2.0 * min(rho, 1.0) - 1.0) ** 3))
+            # gain ratio clamped to [0, 1]: a step accepted only thanks to the noise allowance can have rho << 0, and
+            # Nielsen's cubic would then multiply the damping by hundreds in one step
+            lam = max(opts.lambda_min, lam * max(1.0 / 3.0, 1.0 - (2.0 * min(max(rho, 0.0), 1.0) - 1.0) ** 3))
             nu = 2.0
             hist.append(F)
             if step <= opts.tol_step:

@@ -53,3 +53,24 @@ def test_c_base_placement_matches_numpy_oracle():
             assert np.abs(out["y"][b] - r.y).max() < tol and np.abs(out["Q"][b] - r.Q).max() < tol
             assert abs(out["cost"][b] - r.cost) <= 1e-7 * max(1.0, r.cost)
             assert abs(out["collision"][b] - r.collision) <= (0 if np.abs(out["y"][b] - r.y).max() < 1e-9 else 2)
+
+
+def test_active_set_round_and_status_semantics_match_between_c_and_numpy():
+    """Fetch-8 shelf problems push joints against their limits: the active-set round (held variables get the step to the
+    limit, the rest is re-solved) must engage, give the same iterates in both oracles, and beat plain clipping."""
+    w = small_workload("C3", None, B=3, n_field=48)
+    with_as = c_oracle.solve_workload(w, nthreads=2)
+    clip = c_oracle.solve_workload(w, nthreads=2, options=c_oracle.default_options(as_rounds=0))
+    assert np.any(with_as["iters"] != clip["iters"]) or np.abs(with_as["Q"] - clip["Q"]).max() > 1e-9  # the round changes the path
+    assert with_as["cost"].sum() <= clip["cost"].sum() * (1 + 1e-6)
+    for i, p in enumerate(problems_from_workload(w)):
+        r = O.solve_lm(p)
+        assert with_as["status"][i] == r.status and with_as["iters"][i] == r.iters
+        np.testing.assert_allclose(with_as["Q"][i], r.Q, atol=1e-8)
+        r0 = O.solve_lm(p, O.SolverOptions(as_rounds=0))
+        assert clip["iters"][i] == r0.iters
+        np.testing.assert_allclose(clip["Q"][i], r0.Q, atol=1e-8)
+    # |dq| <= tol_step under heavy damping is "rests on a kink" (STATUS_SLOW), not converged
+    loose = c_oracle.solve_workload(w, nthreads=2, options=c_oracle.default_options(lambda_conv=1e30))
+    assert np.all((loose["status"] == 0) | (loose["status"] == with_as["status"]))
+    assert np.all(with_as["status"][loose["status"] == 4] == 4)
