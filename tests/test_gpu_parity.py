@@ -182,7 +182,7 @@ def test_solve_properties_full_c2(ctx):
     oi = t.opt_qidx
     st = res["status"]
     assert np.mean(st == capi.STATUS_CONVERGED) > 0.85  # step (under light damping) / gradient criterion
-    assert np.mean((st == capi.STATUS_CONVERGED) | (st == capi.STATUS_SLOW)) > 0.95  # + resting on a kink of the field
+    assert not np.any((st == capi.STATUS_NAN) | (st == capi.STATUS_STALLED))
     np.testing.assert_array_equal(Q[:, 0, oi], b.qc[:, oi])  # initial configuration
     np.testing.assert_array_equal(Q[:, 1, oi], b.qc[:, oi])  # zero initial velocity
     assert np.all(Q[:, :, oi] >= t.lo - 1e-12) and np.all(Q[:, :, oi] <= t.hi + 1e-12)
