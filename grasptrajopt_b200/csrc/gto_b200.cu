@@ -358,6 +358,7 @@ __device__ __forceinline__ double warp_max(double v) {
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 #include "step_cr.cuh"
+#include "solve_fused.cuh"
 #include "cloud_sdf.cuh"
 #include "base_place.cuh"
 
@@ -521,7 +522,12 @@ struct gto_ctx {
   // run-time tuning (gto_configure; defaults from the environment, read once in gto_create)
   double tune_jrows_budget_mb = 24576.0;
   int tune_step_fk = 0, tune_launch_events = 0, tune_step_dbg = 0, tune_cons = 0, tune_nslot = 4, tune_slot_floats = 0;
-  long long cull_smem_set = -1, step_smem_set = -1;  // dynamic shared memory the kernels were last configured for
+  int tune_fused = 0;  // 1: one persistent CTA per problem runs the whole solver loop (k_solve_fused, no launches, no chunking); default 0:
+                       // one launch per phase and iteration -- measured faster on C2, where a problem's 28 knots spread over 28 CTAs
+  long long cull_smem_set = -1, step_smem_set = -1, fused_smem_set = -1;
+  int fused_occ = 0;
+  DevBuf<int> queue;
+  DevBuf<unsigned long long> phase_ns;  // dynamic shared memory the kernels were last configured for
   int cull_occ = 0;
   int* h_counter = nullptr;  // pinned, 16 ints
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};  // convergence polls in flight (two parities)
@@ -584,10 +590,11 @@ extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
   else if (k == "pdl") ctx->use_pdl = value != 0;
   else if (k == "launch_events") ctx->tune_launch_events = value != 0;
   else if (k == "step_fk") ctx->tune_step_fk = (int)value;
-  else if (k == "cull_nslot") { ctx->tune_nslot = (int)value; ctx->cull_smem_set = -1; }
-  else if (k == "cons_warps") { ctx->tune_cons = (int)value; ctx->cull_smem_set = -1; }
-  else if (k == "slot_floats") { ctx->tune_slot_floats = (int)value; ctx->cull_smem_set = -1; }
+  else if (k == "cull_nslot") { ctx->tune_nslot = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
+  else if (k == "cons_warps") { ctx->tune_cons = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
+  else if (k == "slot_floats") { ctx->tune_slot_floats = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
   else if (k == "step_dbg") ctx->tune_step_dbg = value != 0;
+  else if (k == "fused") ctx->tune_fused = value != 0;
   else return fail(ctx, GTO_ERR_INVALID, "gto_configure: unknown key '" + k + "'");
   return GTO_OK;
 }
@@ -618,7 +625,7 @@ extern "C" int gto_create(gto_ctx** out, int device) {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     ctx->encode = (PFN_encodeTiled)fn;
   {  // tuning defaults from the environment (read once; gto_configure changes them afterwards)
-    static const char* keys[] = {"jrows_budget_mb", "pdl", "launch_events", "step_fk", "cull_nslot", "cons_warps", "slot_floats", "step_dbg"};
+    static const char* keys[] = {"jrows_budget_mb", "pdl", "launch_events", "step_fk", "cull_nslot", "cons_warps", "slot_floats", "step_dbg", "fused"};
     for (const char* k : keys) {
       std::string e = std::string("GTO_") + k;
       for (auto& ch : e) ch = (char)toupper((unsigned char)ch);
@@ -659,7 +666,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
   ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release();
-  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->cloud_tiles.release(); ctx->recs.release(); ctx->rec_dummy.release();
+  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->cloud_tiles.release(); ctx->recs.release(); ctx->rec_dummy.release(); ctx->queue.release(); ctx->phase_ns.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1100,6 +1107,87 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     const long long tot = (long long)B * T;
     k_init<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(sp);
     CK(cudaGetLastError());
+  }
+  if (ctx->tune_fused) {
+    // ---- default: one persistent CTA per problem runs the whole solver loop (solve_fused.cuh) ----
+    if (!fields_have_tile_maps(ctx)) return fail(ctx, GTO_ERR_STATE, "a cost field has no TMA tile maps (cuTensorMapEncodeTiled unavailable)");
+    FusedParams fp;
+    memset(&fp, 0, sizeof(fp));
+    const int slot_floats = brick_slot_floats(ctx);
+    const int nc = ctx->tune_cons > 0 ? std::min(CULL_MAX_CONS, ctx->tune_cons) : ctx->pipe_cons;
+    const int nslot = std::min(CULL_NSLOT_MAX, std::max(2, ctx->tune_nslot));
+    const int threads = (nc + 2) * 32;
+    const size_t phase_smem = std::max(std::max(cull_smem_bytes(n, nc, nslot, slot_floats), (cr_smem + 127) & ~(size_t)127),
+                                       (fused_fk_smem_bytes(R.nmov, threads) + 127) & ~(size_t)127);
+    const size_t smem = fused_robot_bytes() + phase_smem;
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, GTO_ERR_INVALID, "fused solver kernel does not fit in shared memory");
+    void (*kern)(const FusedParams) = nullptr;
+    if (n == 7) kern = k_solve_fused<8, 7, 7, true>;
+    else if (n == 8) kern = k_solve_fused<8, 8, 8, true>;
+    else if (n == 10) kern = k_solve_fused<16, 10, 10, true>;
+    else if (n < 8) kern = k_solve_fused<8, 0, 8, false>;
+    else kern = k_solve_fused<16, 0, 16, false>;
+    if (ctx->fused_smem_set != (long long)smem) {
+      int occ = 0;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+      if (occ < 1) return fail(ctx, GTO_ERR_INVALID, "fused solver kernel does not fit on an SM");
+      ctx->fused_smem_set = (long long)smem;
+      ctx->fused_occ = occ;
+    }
+    const int grid = std::max(1, std::min(B, ctx->sm_count * ctx->fused_occ));
+    // the row buffer and the item records are per CTA slot, not per problem: no chunking, whatever the batch size
+    if (want_rows) CK(ctx->rows.ensure((size_t)grid * ctx->rows_per_problem * (n + 1)));
+    CK(ctx->recs.ensure((size_t)grid * T));
+    CK(ctx->rec_dummy.ensure(1));
+    CK(ctx->queue.ensure(1));
+    CK(ctx->phase_ns.ensure(4));
+    CK(cudaMemsetAsync(ctx->queue.p, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->phase_ns.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    fill_lin_params(ctx, fp.cull.lin, ctx->q_trial.p, nullptr, nullptr, B, 0, ctx->bufsel.p, want_rows ? ctx->rows.p : nullptr, 2, ctx->flags);
+    fp.cull.slot_floats = slot_floats; fp.cull.ncons = nc; fp.cull.nslot = nslot; fp.cull.count_early = 0;
+    fp.cull.stats = ctx->stats.p; fp.cull.recs = ctx->recs.p; fp.cull.rec_dummy = ctx->rec_dummy.p;
+    fp.step = st;
+    fp.B = B; fp.queue = ctx->queue.p; fp.phase_ns = ctx->phase_ns.p;
+    ctx->Bchunk = grid;
+    kern<<<grid, threads, smem, ctx->stream>>>(fp);
+    CK(cudaGetLastError());
+    pf.kernel_launches += 1;
+    {
+      const long long tot = (long long)B * T;
+      k_finalize<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(sp);
+      CK(cudaGetLastError());
+    }
+    cudaEvent_t ev_end = get_event(ctx, nev++);
+    CK(cudaEventRecord(ev_end, ctx->stream));
+    std::vector<int> h_it(B);
+    unsigned long long hs[4] = {0, 0, 0, 0}, hp[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_it.data(), ctx->iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs, ctx->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hp, ctx->phase_ns.p, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    pf.solve_ms = ms;
+    // exact work accounting: a problem that stopped after `it` steps was linearised it + 1 times (all T knots the first
+    // time, T - 2 afterwards; a problem that ran into max_iter is linearised once more to judge its last trial point)
+    const long long rows_it = ctx->rows_per_problem - 2LL * (ctx->collision ? R.npoints : 0);
+    for (int b = 0; b < B; ++b) {
+      const long long nl = (long long)std::min(h_it[b], o.max_iter) + 1;
+      pf.problem_iterations += nl;
+      pf.knot_items += T + (nl - 1) * (T - 2);
+      if (want_rows) pf.jrow_bytes += (ctx->rows_per_problem + (nl - 1) * rows_it) * (n + 1) * 4;
+      pf.iterations = std::max(pf.iterations, h_it[b]);
+    }
+    pf.linearize_launches = pf.step_launches = 0;
+    pf.linearize_launches_with_work = 0;
+    pf.links_tested = (long long)hs[1];
+    pf.links_active = (long long)hs[2];
+    // phase times: ns summed over the CTAs / number of CTAs = average time a CTA spent in each phase
+    pf.linearize_ms = (double)(hp[0] + hp[1]) * 1e-6 / grid;
+    pf.step_ms = (double)hp[2] * 1e-6 / grid;
+    ctx->solved = true;
+    return GTO_OK;
   }
   std::vector<int> ident(B);
   for (int b = 0; b < B; ++b) ident[b] = b;

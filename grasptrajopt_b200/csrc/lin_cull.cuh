@@ -151,13 +151,13 @@ __device__ __forceinline__ unsigned svt_count(const FieldDev& f, int x0, int x1,
 // halves of a warp run in lock step (full-warp barriers, one instruction stream for two items): a half without an item
 // of its own (`valid` false) recomputes a neighbour's item into the dummy record.
 #define FK_MARK(k) do { if (pp.dbg && blockIdx.x == 0 && threadIdx.x == 0) pp.dbg[32 + (k)] = clock64(); } while (0)
-__device__ __forceinline__ void item_fk_body(const CullParams& pp, const RobotDev& R, int item, bool valid, int b, int t, int obuf, const double* q,
-                                             double* A, double* Tm, int hl, int hshift) {
+__device__ __forceinline__ void item_fk_body(const CullParams& pp, CullCtx* recs, const RobotDev& R, int item, bool valid, int b, int t, int obuf,
+                                             const double* q, double* A, double* Tm, int hl, int hshift) {
   const LinParams& p = pp.lin;
   const int nopt = R.nopt, nmov = R.nmov, nlinks = R.nlinks;
   const int fid = p.collision ? p.field_ids[2 * b + (t < p.knot_standoff ? 0 : 1)] : -1;
   const bool cull = !(p.flags & GTO_FLAG_NO_CULL);
-  CullCtx& C = valid ? pp.recs[item] : *pp.rec_dummy;
+  CullCtx& C = valid ? recs[item] : *pp.rec_dummy;
   // issued before the FK chain, consumed after it: field geometry, base offset
   FieldDev fld;
   fld.data = nullptr; fld.nx = fld.ny = fld.nz = fld.nzp = 2; fld.ox = fld.oy = fld.oz = 0.f; fld.inv_pitch = 1.f; fld.inv_pitch_d = 1.0; fld.org_d[0] = fld.org_d[1] = fld.org_d[2] = 0.0;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(128) k_item_fk(const __grid_constant__ CullPar
   const int b = p.active ? p.active[a] : a;
   const double* q = p.q + ((long long)b * p.T + t) * R.ndof;
   const int obuf = p.bufsel ? (1 - p.bufsel[b]) : 0;
-  item_fk_body(pp, R, item, valid, b, t, obuf, q, A, Tm, hl, hshift);
+  item_fk_body(pp, pp.recs, R, item, valid, b, t, obuf, q, A, Tm, hl, hshift);
   FK_MARK(7);
   stamp_end(pp.ts_fk);
 }
@@ -395,12 +395,17 @@ __host__ __device__ inline size_t cull_smem_bytes(int nopt, int ncons, int nslot
 }
 
 // NP: padded tensor-core tile width (8 or 16); NOPT_CT: number of optimised joints when known at compile time (0: runtime)
-template <int NP, int NOPT_CT>
-__global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// cull_body: the linearisation of a list of (problem, knot) items whose records are recs[0 .. nitems).  Two callers:
+//   k_linearize_cull  one launch per iteration for the whole batch: items are handed out through the global counter
+//                     pp.work_counter (FUSED = false; nitems is read from the device-side active count)
+//   k_solve_fused     (solve_fused.cuh) one CTA per problem runs the whole solver loop: the CTA's own items, counted locally
+//                     (FUSED = true; rows_slot = the CTA's slot in the row buffer)
+// smem_raw: cull_smem_bytes() bytes, 128-byte aligned; every warp of the CTA must call it ((NC + 2) warps).
+template <int NP, int NOPT_CT, bool FUSED>
+__device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* smem_raw, const RobotDev& R, const CullCtx* recs, int nitems_fused,
+                                          int rows_slot) {
   const LinParams& p = pp.lin;
   CullShared& S = *reinterpret_cast<CullShared*>(smem_raw);
-  const RobotDev& R = *p.robot;
   const int nopt = NOPT_CT ? NOPT_CT : R.nopt, RS = nopt + 1, NC = pp.ncons;
   const unsigned CULL_NSLOT = (unsigned)pp.nslot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -446,15 +451,16 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
   __syncthreads();
   // the active count is written by the step kernel: two launches back (long complete, read it ahead of the wait) when a
   // k_item_fk launch sits in between, directly before us when the step kernel wrote the item records itself
-  int nprob = p.nproblems;
-  if (p.nactive && pp.count_early) nprob = *p.nactive;
-  pdl_wait();  // the item records and everything before them
-  pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
-  if (p.nactive && !pp.count_early) nprob = *p.nactive;
-  stamp_begin(pp.ts_lin);
-
-  const int nknots = p.T - p.t_lo;
-  const int nitems = nprob * nknots;
+  int nitems = nitems_fused;
+  if (!FUSED) {
+    int nprob = p.nproblems;
+    if (p.nactive && pp.count_early) nprob = *p.nactive;
+    pdl_wait();  // the item records and everything before them
+    pdl_trigger();  // the successor may be scheduled from here on (it blocks in its own pdl_wait until we are done)
+    if (p.nactive && !pp.count_early) nprob = *p.nactive;
+    stamp_begin(pp.ts_lin);
+    nitems = nprob * (p.T - p.t_lo);
+  }
   const int nH = nopt * nopt;
 
   if (warp == NC) {
@@ -464,21 +470,22 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
     // into the ring (one TMA tile each).  The next item index is fetched one item ahead.
     unsigned pub = 0, bc = 0;
     int next_item = 0;
-    if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
+    if (!FUSED && lane == 0) next_item = atomicAdd(pp.work_counter, 1);
     for (;;) {
-      const int item = __shfl_sync(0xffffffffu, next_item, 0);
+      const int item = FUSED ? next_item : __shfl_sync(0xffffffffu, next_item, 0);
       if (item >= nitems) break;
-      if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
-      const CullCtx* G = pp.recs + item;
-      const int4 h0 = __ldg(reinterpret_cast<const int4*>(&G->b));     // b, t, fid, obuf
-      const int4 h1 = __ldg(reinterpret_cast<const int4*>(&G->nact));  // nact, kind, amask, -
+      if (FUSED) ++next_item;
+      else if (lane == 0) next_item = atomicAdd(pp.work_counter, 1);
+      const CullCtx* G = recs + item;  // (records are rewritten every iteration: __ldcg, never the non-coherent read-only path)
+      const int4 h0 = __ldcg(reinterpret_cast<const int4*>(&G->b));     // b, t, fid, obuf
+      const int4 h1 = __ldcg(reinterpret_cast<const int4*>(&G->nact));  // nact, kind, amask, -
       int4 mydim = make_int4(0, 0, 0, 0), mylo = make_int4(0, 0, 0, 0);
       const int b = h0.x, t = h0.y, fid = h0.z;
       const unsigned amask = (unsigned)h1.z;
       const bool survives = (amask >> lane) & 1u;
       if (survives) {
-        mydim = __ldg(reinterpret_cast<const int4*>(G->bdim[lane]));
-        mylo = __ldg(reinterpret_cast<const int4*>(G->blo[lane]));
+        mydim = __ldcg(reinterpret_cast<const int4*>(G->bdim[lane]));
+        mylo = __ldcg(reinterpret_cast<const int4*>(G->blo[lane]));
       }
       // ---- the zero rows of the culled links are handed to the zero-row warp (nobody waits for them) ----
       if (p.collision && p.rows) {
@@ -542,7 +549,7 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
       __threadfence_block();
       S.zq_tail = tail + 1;
     }
-    stamp_end(pp.ts_lin);
+    if (!FUSED) stamp_end(pp.ts_lin);
     return;
   }
   if (warp == NC + 1) {
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
       const unsigned amask = (unsigned)e.z;
       const bool survives = (amask >> lane) & 1u;
       {
-        float* rows_b = p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS;
+        float* rows_b = p.rows + (long long)(FUSED ? rows_slot : b - p.b0) * p.rows_per_problem * RS;
         bool slow_zero = false;
         if (lane < nlinks && !survives) {
           char* dst = reinterpret_cast<char*>(rows_b + ((long long)t * R.npoints + my_start) * RS);
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    stamp_end(pp.ts_lin);
+    if (!FUSED) stamp_end(pp.ts_lin);
     return;
   }
 
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
 #pragma unroll
     for (int k = 0; k < NP; ++k) gacc[k] = 0.0;
     double cacc = 0.0;
-    float* rows_b = p.rows ? p.rows + (long long)(b - p.b0) * p.rows_per_problem * RS : nullptr;
+    float* rows_b = p.rows ? p.rows + (long long)(FUSED ? rows_slot : b - p.b0) * p.rows_per_problem * RS : nullptr;
 
     int next = warp, cb = 0;  // chunks of the surviving links are dealt round-robin: warp, warp+NC, ... of the concatenation
     for (int ai = 0; ai < nact; ++ai) {
@@ -846,5 +853,11 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(
     __syncwarp();
     if (lane == 0) mbar_arrive(ctx_empty + ci);  // this warp no longer reads ctx[ci] / red[ci]
   }
-  stamp_end(pp.ts_lin);
+  if (!FUSED) stamp_end(pp.ts_lin);
+}
+
+template <int NP, int NOPT_CT>
+__global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_linearize_cull(const __grid_constant__ CullParams pp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cull_body<NP, NOPT_CT, false>(pp, smem_raw, *pp.lin.robot, pp.recs, 0, 0);
 }

@@ -78,20 +78,20 @@ __device__ __forceinline__ bool gj_inverse(double (&row)[NP], int r) {
   return ok;
 }
 
-template <int NP, bool EXACT>
-__global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p) {
-  extern __shared__ __align__(16) unsigned char step_smem[];
-  const RobotDev& R = *p.robot;
+// step_body: one LM step of problem b (iteration counter `it`): judge the trial point of the previous call, update the
+// damping, test convergence, solve for the next trial point.  Returns true (uniformly over the CTA) when the problem stays
+// active.  Two callers: k_step_cr (one launch per iteration, a CTA per active problem; FUSED = false) and k_solve_fused
+// (solve_fused.cuh: the CTA that owns the problem loops over the iterations; FUSED = true).
+// step_smem: step_cr_smem_bytes(T, n) bytes, 16-byte aligned; every thread of the CTA must call it.
+template <int NP, bool EXACT, bool FUSED>
+__device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* step_smem, const RobotDev& R, const int b, const int it) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
-  const int a_idx = blockIdx.x;
   int dbg_i = 0;
 #define STEP_MARK() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
   // Programmatic dependent launch: the per-problem solver state read below (active list, damping, accepted / trial point) was
   // written by the PREVIOUS step kernel, which completed before the linearise kernel ahead of us even started -- only the
   // Gauss-Newton blocks and costs need pdl_wait(), so the dependent round trips for the state overlap the linearise kernel.
   STEP_MARK();
-  if (a_idx >= *p.nactive_in) return;
-  const int b = p.active_in[a_idx];
   const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;
   const double a2 = p.w_vel / (p.dt * p.dt);
   double* X = reinterpret_cast<double*>(step_smem);  // [T][n] accepted point
@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
 
   double* Xc = p.Qc + (long long)b * T * n;
   double* Xt = p.Qt + (long long)b * T * n;
-  const int it = p.iter;
   // ---- everything that only depends on b is requested in one batch: the launch is latency bound, and every dependent
   //      round trip to L2 / HBM costs the better part of a microsecond ----
   int cur = p.bufsel[b];
@@ -130,9 +129,11 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       sv += d * d;
     }
   }
-  pdl_wait();     // from here on: results of the linearise kernel before us
-  pdl_trigger();  // the successor may be scheduled (it blocks in its own pdl_wait until we are done)
-  stamp_begin(p.ts);
+  if (!FUSED) {
+    pdl_wait();     // from here on: results of the linearise kernel before us
+    pdl_trigger();  // the successor may be scheduled (it blocks in its own pdl_wait until we are done)
+    stamp_begin(p.ts);
+  }
   for (int buf = 0; buf < 2; ++buf) {  // Gauss-Newton blocks of both buffers (which one is "accepted" is decided below)
     const float* Hg = p.H + buf * p.buf_stride_H + (long long)b * T * nn + 2 * nn;
     const double* gg = p.g + buf * p.buf_stride_g + (long long)b * T * n + 2 * n;
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     if (done >= 0) {
       if (tid == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      stamp_end(p.ts);
-      return;
+      if (!FUSED) stamp_end(p.ts);
+      return false;
     }
   }
   for (int i = tid; i < m; i += NT) fm[i] = 0u;
@@ -248,8 +249,8 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     pgmax = cta_max(pgmax, red);
     if (2.0 * pgmax <= p.tol_grad) {
       if (tid == 0) { p.status[b] = GTO_STATUS_CONVERGED; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
-      stamp_end(p.ts);
-      return;
+      if (!FUSED) stamp_end(p.ts);
+      return false;
     }
   }
   __syncthreads();
@@ -497,8 +498,8 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
   }
   if (!ok) {
     if (tid == 0) { p.status[b] = GTO_STATUS_NAN; p.iters[b] = it; }
-    stamp_end(p.ts);
-    return;
+    if (!FUSED) stamp_end(p.ts);
+    return false;
   }
 
   STEP_MARK();  // back substitution done
@@ -536,11 +537,14 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
     p.lam[b] = lam;
     p.nu[b] = nu;
     p.iters[b] = it + 1;
-    const int slot = atomicAdd(p.nactive_out, 1);
-    p.active_out[slot] = b;
-    sflag[1] = slot;
+    if (!FUSED) {
+      const int slot = atomicAdd(p.nactive_out, 1);
+      p.active_out[slot] = b;
+      sflag[1] = slot;
+    }
   }
-  if (!p.do_fk) { stamp_end(p.ts); return; }
+  if (FUSED) return true;
+  if (!p.do_fk) { stamp_end(p.ts); return true; }
   // ---------------- item records of the trial point (what k_item_fk would compute in a launch of its own) ----------------
   __syncthreads();  // q_trial of this problem and the slot are visible to the whole CTA
   {
@@ -562,9 +566,18 @@ __global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p)
       const bool valid = (i0 + grp) < m;
       const int i = valid ? i0 + grp : m - 1;
       const int t = i + 2;
-      item_fk_body(p.fk, *Rf, slot * m + i, valid, b, t, 1 - cur, p.q_trial + ((long long)b * T + t) * R.ndof, A, Tm, hl, hshift);
+      item_fk_body(p.fk, p.fk.recs, *Rf, slot * m + i, valid, b, t, 1 - cur, p.q_trial + ((long long)b * T + t) * R.ndof, A, Tm, hl, hshift);
       __syncwarp();
     }
   }
   stamp_end(p.ts);
+  return true;
 }
+
+template <int NP, bool EXACT>
+__global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char step_smem[];
+  if ((int)blockIdx.x >= *p.nactive_in) return;  // written by the step kernel two launches back: may be read ahead of pdl_wait
+  step_body<NP, EXACT, false>(p, step_smem, *p.robot, p.active_in[blockIdx.x], p.iter);
+}
+

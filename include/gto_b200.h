@@ -224,6 +224,7 @@ int gto_get_profile(gto_ctx* ctx, gto_profile* prof);
  *   "step_fk" (0)              the step kernel also writes the item records once at most this many problems are active
  *   "cull_nslot" (4), "cons_warps" (0 = automatic), "slot_floats" (0 = automatic)   shared-memory ring of k_linearize_cull
  *   "step_dbg" (0)             print clock64() phase times of CTA 0 of the step / FK kernels to stderr
+ *   "fused" (0)                1: k_solve_fused, one persistent CTA per problem runs the whole solver loop (identical results)
  * Unknown keys return GTO_ERR_INVALID. */
 int gto_configure(gto_ctx* ctx, const char* key, double value);
 

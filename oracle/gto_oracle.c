@@ -299,6 +299,9 @@ static void solve_one(job_t* J, int b) {
     double F = Fp + velocity_cost(in, X, n);
     double lam = opt->lambda0, nu = 2.0;
     int status = GTO_STATUS_MAX_ITER, it = 0;
+    double fhist[16];
+    const int win = opt->slow_window > 15 ? 15 : opt->slow_window;
+    fhist[0] = F;
     while (it < opt->max_iter) {
       /* ---- lm_step ---- */
       double pgmax = 0.0;
@@ -449,6 +452,10 @@ static void solve_one(job_t* J, int b) {
         lam = fmin(opt->lambda_max, fmax(lam * nu, opt->lambda_reject));
         nu *= 2.0;
         if (lam >= opt->lambda_max) { status = GTO_STATUS_STALLED; break; }
+      }
+      if (win > 0) {  /* windowed progress test on the accepted cost (acceptable-level termination, same bookkeeping as k_step_cr) */
+        if (it >= win && fhist[(it - win) & 15] - F <= opt->slow_ftol * F) { status = GTO_STATUS_SLOW; break; }
+        fhist[it & 15] = F;
       }
     }
     /* ---- unpack ---- */

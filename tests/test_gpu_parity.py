@@ -219,16 +219,18 @@ def test_chunked_solve_is_identical(ctx, monkeypatch):
     assert 0 < pf["linearize_ms"] + pf["step_ms"] <= pf["solve_ms"] * 1.05
 
 
-@pytest.mark.parametrize("knobs", [{"step_fk": 1 << 30}, {"step_fk": 4}, {"pdl": 0}, {"launch_events": 1}, {"cull_nslot": 2}, {"cons_warps": 5}])
+@pytest.mark.parametrize("knobs", [{"fused": 1}, {"step_fk": 1 << 30}, {"step_fk": 4}, {"pdl": 0}, {"launch_events": 1}, {"cull_nslot": 2},
+                                   {"cons_warps": 5}])
 def test_launch_options_do_not_change_the_result(ctx, knobs):
-    """Optional launch structures (FK records written by the step kernel, plain stream-ordered launches, CUDA events between the
-    launches, a shorter brick ring) must reproduce the default path bit for bit; a different number of consumer warps changes
-    the summation order of the per-knot blocks only."""
+    """The persistent one-CTA-per-problem solver (k_solve_fused, "fused" = 1), the optional launch structures of the default path
+    (FK records written by the step kernel, plain stream-ordered launches, CUDA events between the launches) and a shorter
+    brick ring must reproduce the default path (k_item_fk -> k_linearize_cull -> k_step_cr per iteration) bit for bit; a different
+    number of consumer warps changes the summation order of the per-knot blocks only."""
     w = small_workload("C2", "panda_small", B=12, n_field=64)
     ctx.set_robot(w.table)
     upload_fields(ctx, w)
     ref = ctx.solve_batch(w.batch)
-    default = dict(step_fk=0, pdl=1, launch_events=0, cull_nslot=4, cons_warps=0)
+    default = dict(fused=0, step_fk=0, pdl=1, launch_events=0, cull_nslot=4, cons_warps=0)
     ctx.configure(**knobs)
     try:
         res = ctx.solve_batch(w.batch)
