@@ -47,6 +47,10 @@ def parse_args():
                     help="secondary mode: stop a problem (status 'no progress', NOT counted as converged) once its cost fell by <= "
                          "--slow-ftol * f over this many iterations (gto_options.slow_window, at most 16; 0 = off, the contract setting)")
     ap.add_argument("--slow-ftol", type=float, default=1e-3)
+    ap.add_argument("--extras", type=int, default=1,
+                    help="also time BASELINE configs[4] (C5, 16384 problems, strong sweep: 16384/N per rank) and configs[3] (C4, 4096 problems, "
+                         "4096/N per rank) and report them under config.extra (the headline value stays the C2 line); 0 = skip")
+    ap.add_argument("--fused", type=int, default=0, help="secondary mode: k_solve_fused (one persistent CTA per problem)")
     return ap.parse_args()
 
 
@@ -101,9 +105,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one full k_linearize_cull launch (256 problems x 28 knots, C2), from the
-# ncu --set full capture summarised in profiles/ (bytes per launch; algorithmic bytes of that launch: 413.4 MB)
-TRAFFIC_NCU = 445.6e6
+def ncu_traffic(config, no_jrows, scale):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one full k_linearize_cull launch, from the kept `ncu --set full` capture of
+    THIS build (profiles/r2_traffic.json, written by tools/ncu_summary.py from the committed CSV).  Only valid for the
+    configuration it was captured on; anything else reports null."""
+    p = os.path.join(REPO, "profiles", "r2_traffic.json")
+    if not os.path.exists(p) or no_jrows or scale != 1.0:
+        return None, None
+    with open(p) as fh:
+        d = json.load(fh)
+    if d.get("config") != config.upper():
+        return None, None
+    return float(d["dram_bytes_per_launch"]), d
 
 
 def measured_peaks():
@@ -115,57 +128,89 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(w, prof, n_fields_per_launch=2):
-    """Jacobian rows + residual written once (exact count from the device), both fields read once
-    per launch, trajectory read + step written per problem-iteration."""
+def algorithmic_bytes(w, prof):
+    """SURVEY.md section 8(d), per problem-iteration: 4(nopt+1)(T*P + 6Pg) Jacobian rows + residual written once (exact row count
+    from the device: knots 0,1 are linearised only once) + 8*N^3 / B_scene (both fields of a scene read once per batch-iteration,
+    amortised over the B_scene problems that share the scene) + 8*nopt*T (trajectory read, step written)."""
     t = w.table
-    field_bytes = sum(int(np.prod(w.fields[s].cost.shape)) * 4 for s in sorted(w.fields)[:n_fields_per_launch])
+    b = w.batch
+    slots, counts = np.unique(np.concatenate([b.field_all, b.field_obs]), return_counts=True)
+    per_scene = {}
+    for s_, c_ in zip(slots, counts):
+        if s_ >= 0:
+            per_scene[int(s_)] = int(np.prod(w.fields[int(s_)].cost.shape)) * 4 / c_  # bytes of this field per problem that reads it
+    field_per_problem = float(np.mean([per_scene.get(int(b.field_all[i]), 0.0) + per_scene.get(int(b.field_obs[i]), 0.0) for i in range(b.B)]))
     units = prof["problem_iterations"]
-    return prof["jrow_bytes"] + prof["linearize_launches_with_work"] * field_bytes + units * 8 * t.nopt * w.batch.T
+    return prof["jrow_bytes"] + units * (field_per_problem + 8 * t.nopt * b.T)
 
 
 # --------------------------------------------------------------------------------------------------------------
-def time_cpu(w, nsample, nthreads):
-    """C restatement of the oracle (oracle/gto_oracle.c, float64, one pthread per core) on a bounded sample of the workload."""
+def config_block(w, args, opts, world, **more):
+    """The `config` object of the JSON line -- identical keys for the b200 and the reference arm."""
+    b = w.batch
+    d = {"workload": w.description, "config": args.config.upper(), "problems_per_gpu": b.B, "knots": int(b.T), "surface_points": int(w.table.npoints),
+         "field": list(next(iter(w.fields.values())).cost.shape), "materialize_jacobian_rows": not args.no_jrows,
+         "l2": "working set per iteration (Jacobian rows, >=0.4 GB) exceeds the 126 MB L2; no explicit flush",
+         "convergence": f"|dq|inf<={opts.tol_step:g} under damping<={opts.lambda_conv:g} or |proj grad|inf<={opts.tol_grad:g}, max_iter={opts.max_iter}",
+         "problems": b.B * world, "scale": args.scale}
+    d.update(more)
+    return d
+
+
+def status_dict(status):
+    sc = np.bincount(status, minlength=5)
+    return {"converged": int(sc[0]), "max_iter": int(sc[1]), "nan": int(sc[2]), "stalled": int(sc[3]), "rests_on_field_kink": int(sc[4])}
+
+
+def time_cpu(w, idx, nthreads, options=None):
+    """C restatement of the oracle (oracle/gto_oracle.c, float64, one pthread per core) on problems `idx` of the workload."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import c_oracle
 
-    B = w.batch.B
-    idx = np.unique(np.linspace(0, B - 1, min(nsample, B)).astype(int))
     c_oracle.load()
     t0 = time.perf_counter()
-    res = c_oracle.solve_workload(w, indices=idx, nthreads=nthreads)
+    res = c_oracle.solve_workload(w, indices=idx, nthreads=nthreads, options=options)
     dt = time.perf_counter() - t0
-    return dt, int(np.sum(res["status"] == 0)), len(idx), int(res["threads"])
+    return dt, res
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path.  CasADi/IPOPT are not installable offline, so this is the oracle port
-    (same reduced problem, projected LM, float64 C) on all host cores; each step is a bounded sample of the workload."""
+    """`--impl reference`: the reference's CPU path.  CasADi/IPOPT are not installable offline, so this is the oracle
+    port (same reduced problem, same projected LM, float64 C) on all host cores.  Same configuration and the same FULL batch
+    per step as the b200 arm for C1/C2/C5; for the Fetch configs (seconds per problem-batch on the host) a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import c_oracle
     from grasptrajopt_b200 import workloads as W
 
     ncpu = os.cpu_count() or 1
     w = W.make_workload(args.config, scale=args.scale)
     B = w.batch.B
-    nsample = max(1, min(B, 8 * ncpu))
+    full = args.config.upper() in ("C1", "C2")
+    idx = np.arange(B) if full else np.unique(np.linspace(0, B - 1, min(B, 8 * ncpu)).astype(int))
+    opts = c_oracle.default_options()
     for _ in range(max(0, min(args.warmup, 1))):
-        time_cpu(w, nsample, ncpu)
+        time_cpu(w, idx, ncpu, opts)
     tot_t, tot_conv, threads = 0.0, 0, ncpu
     steps = max(1, args.steps)
     for _ in range(steps):
-        dt, conv, n, threads = time_cpu(w, nsample, ncpu)
+        dt, res = time_cpu(w, idx, ncpu, opts)
         tot_t += dt
-        tot_conv += conv
+        tot_conv += int(np.sum(res["status"] == 0))
+        threads = int(res["threads"])
     value = tot_conv / tot_t
+    sample = (f"all {B} problems per step" if full else f"{len(idx)} of {B} problems per step") + \
+        f", oracle/gto_oracle.c (projected LM, float64), {threads} pthreads on {ncpu} host cores"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": w.description, "config": args.config.upper()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{nsample} of {B} problems per step, oracle/gto_oracle.c (projected LM, float64), {threads} pthreads"},
+        "data": "synthetic",
+        "config": config_block(w, args, opts, 1, converged=int(np.sum(res["status"] == 0)), iterations_histogram=np.bincount(res["iters"], minlength=1).tolist(),
+                               status_counts_rank0=status_dict(res["status"]), wall_ms_per_step=1e3 * tot_t / steps, host_cores=ncpu,
+                               problems_per_step=int(len(idx))),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference CasADi/IPOPT path not installable offline; its published wall-clock is ~0.1 trajectories/s (BASELINE.md)",
@@ -178,49 +223,32 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from grasptrajopt_b200 import capi, workloads as W
+    from grasptrajopt_b200.distributed import DeviceArray
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE is {world}: launch N > 1 with "
+                         f"`python -m torch.distributed.run --nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...`")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    # weak scaling: every rank owns a C2-sized shard generated from its own seed stream
-    idx = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[args.config.upper()]
-    scale = args.scale / world if args.config.upper() == "C5" else args.scale  # C5 is the fixed-size (strong) sweep
-    w = W.make_workload(args.config, scale=scale, seed=idx + 1000 * rank if world > 1 else None)
-    b = w.batch
-    if args.no_jrows:
-        b.flags |= capi.FLAG_NO_JROWS
-    B = b.B
+    dev = f"cuda:{local}"
+    cfg = args.config.upper()
+    idx = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[cfg]
+    # headline: weak scaling, every rank owns a full-size shard of the configuration generated from its own seed stream
+    w = W.make_workload(cfg, scale=args.scale, seed=idx + 1000 * rank if world > 1 else None)
     ctx = capi.GtoContext(local)
-    ctx.set_robot(w.table)
-    for slot, cf in w.fields.items():
-        ctx.set_field(slot, cf.cost, cf.origin, cf.pitch)
-    opts = capi.default_options(slow_window=min(16, max(0, args.slow_window)), slow_ftol=args.slow_ftol) if args.slow_window > 0 else capi.default_options()
+    ctx.configure(fused=args.fused)
+    opts = capi.default_options(slow_window=min(15, max(0, args.slow_window)), slow_ftol=args.slow_ftol) if args.slow_window > 0 else capi.default_options()
+    keep = []
 
-    # pinned host staging for the end-to-end arm
     def pin(a):
         tns = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return tns.numpy(), tns
-
-    keep = []
-    for name in ("qc", "q_seed", "goal_tf", "base_position"):
-        arr, tns = pin(getattr(b, name))
-        setattr(b, name, arr)
         keep.append(tns)
-
-    nfl = w.table.nopt * b.T + 2
-    gathered = torch.empty((world * B, nfl), dtype=torch.float32, device=f"cuda:{local}") if world > 1 else None
-
-    from grasptrajopt_b200.distributed import DeviceArray
-
-    def exchange():  # ONE all-gather of the converged trajectories, straight from the library's device buffer
-        if world > 1:
-            ptr, n = ctx.result_device_ptr()
-            local_res = torch.as_tensor(DeviceArray(ptr, (B, n)), device=f"cuda:{local}")
-            dist.all_gather_into_tensor(gathered, local_res)
+        return tns.numpy()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -228,131 +256,187 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM ----
-    ctx.upload_batch(b)
-    for _ in range(args.warmup):
-        ctx.solve_resident(opts)
-        exchange()
-    sync_all()
+    def measure(w, steps, warmup, e2e=True, events_pass=True):
+        """Times `steps` solves of workload `w` on this rank (inputs resident), the all-gather of the results, and -- optionally --
+        the end-to-end arm through gto_solve_batch with pinned host buffers.  Returns a dict of per-rank measurements."""
+        b = w.batch
+        if args.no_jrows:
+            b.flags |= capi.FLAG_NO_JROWS
+        B = b.B
+        ctx.set_robot(w.table)
+        for slot, cf in w.fields.items():
+            ctx.set_field(slot, cf.cost, cf.origin, cf.pitch)
+        for name in ("qc", "q_seed", "goal_tf", "base_position"):
+            setattr(b, name, pin(getattr(b, name)))
+        nfl = w.table.nopt * b.T + 2
+        gathered = torch.empty((world * B, nfl), dtype=torch.float32, device=dev) if world > 1 else None
+        xs = torch.cuda.Stream(device=dev) if world > 1 else None
+
+        def exchange():
+            """ONE all-gather of the packed trajectories, read in place from the library's device buffer; issued on a side stream
+            right after the solve has completed (gto_solve_resident is synchronous), timed with events on that stream."""
+            if world == 1:
+                return 0.0
+            ptr, n = ctx.result_device_ptr()
+            local_res = torch.as_tensor(DeviceArray(ptr, (B, n)), device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(xs):
+                e0.record()
+                dist.all_gather_into_tensor(gathered, local_res)
+                e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+
+        ctx.upload_batch(b)
+        for _ in range(warmup):
+            ctx.solve_resident(opts)
+            exchange()
+        sync_all()
+        m = {"dev_ms": 0.0, "lin_ms": 0.0, "step_ms": 0.0, "xch_ms": 0.0, "launches": 0,
+             "prof": {"jrow_bytes": 0, "problem_iterations": 0, "linearize_launches_with_work": 0, "linearize_launches": 0}}
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.solve_resident(opts)
+            m["xch_ms"] += exchange()
+            p = ctx.profile()
+            m["dev_ms"] += p["solve_ms"]; m["lin_ms"] += p["linearize_ms"]; m["step_ms"] += p["step_ms"]; m["launches"] += p["kernel_launches"]
+            for k in m["prof"]:
+                m["prof"][k] += p[k]
+        sync_all()
+        m["wall_ms"] = 1e3 * (time.perf_counter() - t0)
+        m["last_prof"] = ctx.profile()
+        res = ctx.download_batch()  # the result of the LAST timed solve
+        m["conv"] = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
+        m["status"] = res["status"]; m["iters"] = res["iters"]
+        m["ev"] = None
+        if events_pass and not args.fused:
+            # kernel durations with CUDA events recorded around every launch on the library's stream (separate pass of the same
+            # steps: an event record between two launches costs ~3 us of stream serialisation, x ~300 launches per solve, so the
+            # pass is slower than the timed region; the in-kernel %globaltimer stamps of the timed region are reported beside it)
+            ev = {"lin_ms": 0.0, "step_ms": 0.0, "solve_ms": 0.0}
+            ctx.configure(launch_events=1)
+            for _ in range(steps):
+                ctx.solve_resident(opts)
+                p = ctx.profile()
+                ev["lin_ms"] += p["linearize_ms"]; ev["step_ms"] += p["step_ms"]; ev["solve_ms"] += p["solve_ms"]
+            ctx.configure(launch_events=0)
+            sync_all()
+            m["ev"] = ev
+        m["e2e_ms"] = None
+        if e2e:
+            nd = w.table.ndof
+            out_pinned = {}
+            for k, (shp, dt) in dict(Q=((B, b.T, nd), np.float64), dQ=((B, b.T - 1, nd), np.float64), cost=((B,), np.float64), iters=((B,), np.int32),
+                                     status=((B,), np.int32)).items():
+                tns = torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int32).pin_memory()
+                keep.append(tns)
+                out_pinned[k] = tns.numpy()
+            for _ in range(min(warmup, 2)):
+                ctx.solve_batch(b, opts, out=out_pinned)
+            sync_all()
+            t1 = time.perf_counter()
+            for _ in range(steps):
+                r2 = ctx.solve_batch(b, opts, out=out_pinned)
+                exchange()
+                p = ctx.profile()
+                m["h2d"], m["d2h"] = p["h2d_bytes"], p["d2h_bytes"]
+            sync_all()
+            m["e2e_ms"] = 1e3 * (time.perf_counter() - t1)
+            m["conv2"] = int(np.sum(r2["status"] == capi.STATUS_CONVERGED))
+        return m
+
+    def over_ranks(vals_max, vals_sum):
+        if world == 1:
+            return vals_max, vals_sum
+        tmx = torch.tensor(vals_max, dtype=torch.float64, device=dev)
+        tsm = torch.tensor(vals_sum, dtype=torch.float64, device=dev)
+        dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsm, op=dist.ReduceOp.SUM)
+        return tmx.tolist(), tsm.tolist()
+
     sampler = ClockSampler(local)
     sampler.start()
-    dev_ms, lin_ms, step_ms, launches, conv = 0.0, 0.0, 0.0, 0, 0
-    prof_acc = {"jrow_bytes": 0, "problem_iterations": 0, "linearize_launches_with_work": 0, "linearize_launches": 0}
-    t0 = time.perf_counter()
-    xch_ms = 0.0
-    for _ in range(args.steps):
-        ctx.solve_resident(opts)
-        if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            exchange()
-            e1.record()
-            e1.synchronize()
-            xch_ms += e0.elapsed_time(e1)
-        p = ctx.profile()
-        dev_ms += p["solve_ms"]
-        lin_ms += p["linearize_ms"]
-        step_ms += p["step_ms"]
-        launches += p["kernel_launches"]
-        for k in prof_acc:
-            prof_acc[k] += p[k]
-    sync_all()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    last_prof = ctx.profile()
-    # cross-check pass (not part of `value`): the same steps with CUDA events recorded around every launch on the library's
-    # stream.  The timed region above measures the kernels with in-kernel %globaltimer stamps instead, because an event
-    # record between two launches costs ~3 us of stream serialisation (x ~300 launches per solve).
-    ev = {"lin_ms": 0.0, "step_ms": 0.0, "solve_ms": 0.0}
-    ctx.configure(launch_events=1)
-    for _ in range(args.steps):
-        ctx.solve_resident(opts)
-        p = ctx.profile()
-        ev["lin_ms"] += p["linearize_ms"]; ev["step_ms"] += p["step_ms"]; ev["solve_ms"] += p["solve_ms"]
-    ctx.configure(launch_events=0)
-    sync_all()
-    res = ctx.download_batch()
-    conv = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
-    iters_hist = np.bincount(res["iters"], minlength=1).tolist()
-    sc = np.bincount(res["status"], minlength=5)
-    status_counts = {"converged": int(sc[0]), "max_iter": int(sc[1]), "nan": int(sc[2]), "stalled": int(sc[3]), "no_progress_at_field_kink": int(sc[4])}
-    step_dev_ms = dev_ms + xch_ms  # device time of this rank: solves (library events) + all-gather (torch events)
-
-    # ---- e2e: public API with host buffers ----
-    nd = w.table.ndof
-    out_pinned = {}
-    for k, (shp, dt) in dict(Q=((B, b.T, nd), np.float64), dQ=((B, b.T - 1, nd), np.float64), cost=((B,), np.float64), iters=((B,), np.int32),
-                             status=((B,), np.int32)).items():
-        tns = torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int32).pin_memory()
-        keep.append(tns)
-        out_pinned[k] = tns.numpy()
-    for _ in range(min(args.warmup, 2)):
-        ctx.solve_batch(b, opts, out=out_pinned)
-    sync_all()
-    t1 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(args.steps):
-        r2 = ctx.solve_batch(b, opts, out=out_pinned)
-        exchange()
-        p = ctx.profile()
-        h2d, d2h = p["h2d_bytes"], p["d2h_bytes"]
-    sync_all()
-    e2e_ms = 1e3 * (time.perf_counter() - t1)
+    m = measure(w, args.steps, args.warmup)
     clocks = sampler.stop()
-    conv2 = int(np.sum(r2["status"] == capi.STATUS_CONVERGED))
+    step_dev_ms = m["dev_ms"] + m["xch_ms"]  # device time of this rank: solves (library events) + all-gather (torch events)
+    (step_dev_ms_mx, e2e_ms_mx, wall_ms_mx, xch_ms_mx, solve_ms_mx), (conv_tot, conv2_tot) = over_ranks(
+        [step_dev_ms, m["e2e_ms"], m["wall_ms"], m["xch_ms"], m["dev_ms"]], [float(m["conv"]), float(m["conv2"])])
 
-    # max over ranks
-    if world > 1:
-        tt = torch.tensor([step_dev_ms, e2e_ms, float(conv), float(conv2), wall_ms], dtype=torch.float64, device=f"cuda:{local}")
-        mx = tt.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        step_dev_ms, e2e_ms, wall_ms = float(mx[0]), float(mx[1]), float(mx[4])
-        conv_tot, conv2_tot = int(sm[2]), int(sm[3])
-    else:
-        conv_tot, conv2_tot = conv, conv2
+    # ---- BASELINE configs[4] (C5 strong sweep) and configs[3] (C4 sharded over the ranks): secondary lines under config.extra ----
+    extra = {}
+    if args.extras and cfg == "C2" and args.scale == 1.0:
+        for xcfg, total in (("C5", 16384), ("C4", 4096)):
+            wx = W.make_workload(xcfg)  # the SAME problems on every rank ...
+            lo, hi = W.shard_range(wx.batch.B, rank, world)  # ... of which this rank solves a contiguous shard (strong scaling)
+            wx.batch = W.slice_batch(wx.batch, lo, hi)
+            used = set(int(v) for v in np.concatenate([wx.batch.field_all, wx.batch.field_obs]) if v >= 0)
+            wx.fields = {s_: f for s_, f in wx.fields.items() if s_ in used}
+            mx_ = measure(wx, 2, 1, e2e=False, events_pass=False)
+            (t_mx, x_mx), (c_tot,) = over_ranks([mx_["dev_ms"] + mx_["xch_ms"], mx_["xch_ms"]], [float(mx_["conv"])])
+            pk, _ = measured_peaks()
+            algx = algorithmic_bytes(wx, mx_["prof"])
+            extra[xcfg] = {"workload": wx.description, "problems_total": total, "problems_per_gpu": int(wx.batch.B), "scaling": "strong",
+                           "converged_total": int(c_tot), "status_counts_rank0": status_dict(mx_["status"]),
+                           "ms_per_step": t_mx / 2, "xch_ms_per_step": x_mx / 2, "value": c_tot * 2 / (t_mx * 1e-3), "unit": UNIT,
+                           "linearize_ms_per_step_rank0": mx_["lin_ms"] / 2, "step_ms_per_step_rank0": mx_["step_ms"] / 2,
+                           "roofline_frac_rank0": (algx / (mx_["lin_ms"] * 1e-3) / 1e9 / pk) if mx_["lin_ms"] > 0 else None,
+                           "iterations_max": int(mx_["iters"].max()), "iterations_mean": float(mx_["iters"].mean())}
 
     if rank == 0:
+        b = w.batch
+        B = b.B
         peak, peak_src = measured_peaks()
-        alg = algorithmic_bytes(w, prof_acc)
-        achieved = alg / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0
-        value = conv_tot * args.steps / (step_dev_ms * 1e-3)
-        e2e_value = conv2_tot * args.steps / (e2e_ms * 1e-3)
+        alg = algorithmic_bytes(w, m["prof"])
+        ev = m["ev"]
+        kernel_ms_events = ev["lin_ms"] if ev else None
+        kernel_ms = kernel_ms_events if kernel_ms_events else m["lin_ms"]
+        achieved = alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        value = conv_tot * args.steps / (step_dev_ms_mx * 1e-3)
+        e2e_value = conv2_tot * args.steps / (e2e_ms_mx * 1e-3)
+        traffic, traffic_src = ncu_traffic(cfg, args.no_jrows, args.scale)
+        nlaunch = m["prof"]["linearize_launches"] / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config.upper() == "C5" else "weak",
-            "vs_baseline": None, "dtype": "f32 (point kernel; TF32 tensor-core J^T J) + f64 (trajectory, step solve)", "data": "synthetic",
-            "config": {"workload": w.description, "config": args.config.upper(), "problems_per_gpu": B, "knots": b.T, "surface_points": w.table.npoints,
-                       "field": list(next(iter(w.fields.values())).cost.shape), "materialize_jacobian_rows": not args.no_jrows,
-                       "l2": "working set per iteration (Jacobian rows, >=0.4 GB) exceeds the 126 MB L2; no explicit flush",
-                       "convergence": f"|dq|inf<={opts.tol_step:g} or |proj grad|inf<={opts.tol_grad:g}, max_iter={opts.max_iter}",
-                       "converged": conv_tot, "problems": B * world, "iterations_histogram": iters_hist, "status_counts_rank0": status_counts,
-                       **({"secondary_mode": f"slow_window={args.slow_window}, slow_ftol={args.slow_ftol}"} if args.slow_window > 0 else {}), "wall_ms_per_step": wall_ms / args.steps,
-                       "scale": args.scale},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": step_dev_ms_mx / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 point kernel (f64 voxel coordinates, f64 sums of J^T r and cost, 3xTF32 tensor-core J^T J) + f64 trajectory / step solve",
+            "data": "synthetic",
+            "config": config_block(w, args, opts, world, converged=int(conv_tot), iterations_histogram=np.bincount(m["iters"], minlength=1).tolist(),
+                                   status_counts_rank0=status_dict(m["status"]), wall_ms_per_step=wall_ms_mx / args.steps,
+                                   solve_ms_per_step=solve_ms_mx / args.steps, xch_ms_per_step=xch_ms_mx / args.steps,
+                                   exchange="one NCCL all-gather of [B][nopt*T+2] f32 per step, zero-copy from the library's result buffer, side stream",
+                                   **({"secondary_mode": f"slow_window={args.slow_window}, slow_ftol={args.slow_ftol}"} if args.slow_window > 0 else {}),
+                                   **({"secondary_mode_fused": "k_solve_fused"} if args.fused else {}),
+                                   **({"extra": extra} if extra else {})),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
                     "timing": "wall clock between device synchronisations around gto_solve_batch with pinned host buffers"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_linearize_cull (+ k_item_fk, its per-item pre-pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_NCU,
-                         "peak_source": peak_src, "algorithmic_bytes_per_step": alg / args.steps, "kernel_ms_per_step": lin_ms / args.steps,
-                         "kernel_share_of_step": lin_ms / dev_ms if dev_ms else None, "step_kernel_ms_per_step": step_ms / args.steps,
-                         "launches_per_step": prof_acc["linearize_launches"] / args.steps,
-                         "timing": "sum over the linearise launches of (last warp end - first CTA start), %globaltimer stamps written by the kernels "
-                                   "on the library's stream, inside the timed region",
-                         "cuda_events_cross_check": {"achieved": alg / (ev["lin_ms"] * 1e-3) / 1e9 if ev["lin_ms"] > 0 else None,
-                                                     "kernel_ms_per_step": ev["lin_ms"] / args.steps, "step_kernel_ms_per_step": ev["step_ms"] / args.steps,
-                                                     "ms_per_step": ev["solve_ms"] / args.steps,
-                                                     "note": "separate pass of the same steps with a CUDA event before/after every launch"},
-                         "links_culled_frac": 1.0 - last_prof["links_active"] / max(1, last_prof["links_tested"])},
+            "gpu_launches": int(m["launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_linearize_cull (+ k_item_fk, its per-item pre-pass)" if not args.fused else "k_solve_fused (FK + linearise phases)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": alg / args.steps,
+                         "algorithmic_bytes_per_launch": alg / max(1.0, m["prof"]["linearize_launches_with_work"]),
+                         "kernel_ms_per_step": kernel_ms / args.steps, "avg_launch_us": 1e3 * kernel_ms / max(1.0, m["prof"]["linearize_launches_with_work"]),
+                         "launches_per_step": nlaunch,
+                         "timing": "CUDA events around every linearise launch (k_item_fk + k_linearize_cull) on the library's stream, separate pass of the same "
+                                   "steps" if ev else "in-kernel %globaltimer stamps",
+                         "kernel_share_of_step": (ev["lin_ms"] / ev["solve_ms"]) if ev else (m["lin_ms"] / m["dev_ms"] if m["dev_ms"] else None),
+                         "whole_step_frac": alg / (m["dev_ms"] * 1e-3) / 1e9 / peak if m["dev_ms"] else None,
+                         "globaltimer_stamps": {"achieved": alg / (m["lin_ms"] * 1e-3) / 1e9 if m["lin_ms"] > 0 else None, "kernel_ms_per_step": m["lin_ms"] / args.steps,
+                                                "step_kernel_ms_per_step": m["step_ms"] / args.steps,
+                                                "note": "first CTA start .. last warp end per launch, written by the kernels inside the timed region (no event serialisation)"},
+                         "step_kernel_ms_per_step": (ev["step_ms"] if ev else m["step_ms"]) / args.steps,
+                         "links_culled_frac": 1.0 - m["last_prof"]["links_active"] / max(1, m["last_prof"]["links_tested"])},
             "clocks": clocks,
         }
-        # CPU baseline on rank 0 at N=1 only: bounded sample of the same workload
+        # CPU baseline on rank 0 at N=1 only: the full batch of the same workload (C2: ~0.6 s on 16 threads), else a bounded sample
         if world == 1 and args.cpu_sample != 0:
             ncpu = os.cpu_count() or 1
-            ns = args.cpu_sample if args.cpu_sample > 0 else min(B, 16 * ncpu)
-            dt, cconv, n, threads = time_cpu(w, ns, ncpu)
-            line["cpu_baseline"] = {"value": cconv / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n} of {B} problems of the same workload, oracle/gto_oracle.c (projected LM, float64), {threads} pthreads, {dt:.1f} s"}
+            ns = args.cpu_sample if args.cpu_sample > 0 else (B if cfg in ("C1", "C2") else min(B, 16 * ncpu))
+            idxs = np.arange(B) if ns >= B else np.unique(np.linspace(0, B - 1, ns).astype(int))
+            dt, cres = time_cpu(w, idxs, ncpu)
+            line["cpu_baseline"] = {"value": int(np.sum(cres["status"] == 0)) / dt, "unit": UNIT, "cores": int(cres["threads"]), "kind": "port",
+                                    "sample": f"{len(idxs)} of {B} problems of the same workload, oracle/gto_oracle.c (projected LM, float64), "
+                                              f"{int(cres['threads'])} pthreads on {ncpu} host cores, {dt:.1f} s"}
         _emit(line)
     ctx.close()
     if world > 1:
