@@ -20,13 +20,13 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgto_b200.so")
 
 GTO_OK = 0
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN, STATUS_STALLED, STATUS_SLOW = 0, 1, 2, 3, 4
-FLAG_NO_JROWS, FLAG_NO_CULL = 1, 32
+FLAG_NO_JROWS, FLAG_OBS_LINEAR, FLAG_NO_CULL = 1, 2, 32
 
 SYMBOLS = [
     "gto_abi_version", "gto_create", "gto_destroy", "gto_last_error", "gto_default_options", "gto_set_robot",
     "gto_set_field", "gto_solve_batch", "gto_upload_batch", "gto_solve_resident", "gto_download_batch",
     "gto_result_device_ptr", "gto_eval_batch", "gto_get_profile", "gto_configure", "gto_plan_cost", "gto_cloud_set", "gto_cloud_query",
-    "gto_base_place",
+    "gto_cloud_backproject", "gto_base_place",
 ]
 
 
@@ -144,6 +144,7 @@ def load_library(path: Optional[str] = None):
     lib.gto_configure.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.gto_cloud_set.argtypes = [C.c_void_p, _dp, C.c_int64]
     lib.gto_cloud_query.argtypes = [C.c_void_p, _dp, C.c_int64, _fp, C.c_int32, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_double, _fp, _dp]
+    lib.gto_cloud_backproject.argtypes = [C.c_void_p, _fp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, _dp, _dp, C.c_double, _dp, C.POINTER(C.c_uint8)]
     lib.gto_plan_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp]
     lib.gto_base_place.argtypes = [C.c_void_p, C.POINTER(BaseIn), C.POINTER(Options), C.POINTER(BaseOut), _dp]
     if path == os.environ.get("GTO_B200_LIB", LIB_PATH):
@@ -223,6 +224,7 @@ class GtoContext:
             raise GtoError(rc, "gto_create failed (no CUDA device / not sm_100?) -- there is no CPU fallback")
         self.device = device
         self.table: Optional[RobotTable] = None
+        self.field_keys = {}  # slot -> caller-defined key of the field uploaded last (see B200Solver.upload_field_cached)
         self._keep = []
 
     def close(self):
@@ -267,6 +269,7 @@ class GtoContext:
             raise ValueError("cost field must be [Nx,Ny,Nz]")
         dims = _i(cost.shape)
         org = _d(np.asarray(origin).reshape(3))
+        self.field_keys.pop(int(slot), None)
         self._check(self._lib.gto_set_field(self._h, int(slot), _ptr(cost, _fp), _ptr(dims, _ip), _ptr(org, _dp), float(pitch)))
 
     # ------------------------------------------------------------------------------------------------
@@ -361,8 +364,20 @@ class GtoContext:
         pts = _d(points).reshape(-1, 3)
         self._check(self._lib.gto_cloud_set(self._h, _ptr(pts, _dp), pts.shape[0]))
 
+    def cloud_backproject(self, depth: np.ndarray, K: np.ndarray, cam_pose: np.ndarray, threshold: float, target_mask=None) -> np.ndarray:
+        """Depth image -> world-frame point cloud [M,3] on the device (reference ``DepthPointCloud.__init__`` / ``backproject_camera``)."""
+        dep = np.ascontiguousarray(depth, dtype=np.float32)
+        H, W = dep.shape
+        Kinv, pose = _d(np.linalg.inv(np.asarray(K, dtype=np.float64)).reshape(9)), _d(np.asarray(cam_pose, dtype=np.float64).reshape(16))
+        mask = None if target_mask is None else np.ascontiguousarray(np.asarray(target_mask).reshape(H, W) != 0, dtype=np.uint8)
+        pts, valid = np.zeros((H * W, 3)), np.zeros(H * W, np.uint8)
+        self._check(self._lib.gto_cloud_backproject(self._h, _ptr(dep, _fp), None if mask is None else mask.ctypes.data_as(C.POINTER(C.c_uint8)), H, W,
+                                                    _ptr(Kinv, _dp), _ptr(pose, _dp), float(threshold), _ptr(pts, _dp), valid.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return pts[valid != 0]
+
     def cloud_query(self, query: np.ndarray, depth: np.ndarray, K: np.ndarray, cam_inv: np.ndarray, mode: int, epsilon=0.02, w_inside=1.0):
-        """Signed distance (mode 0) or cost (mode 1) of ``query`` [N,3] w.r.t. the cloud; returns (float32 [N], kernel ms)."""
+        """Signed distance (mode 0), cost (mode 1) or visibility (mode 2: 1 = outside) of ``query`` [N,3] w.r.t. the cloud; returns
+        (float32 [N], kernel ms)."""
         q = _d(query).reshape(-1, 3)
         dep = np.ascontiguousarray(depth, dtype=np.float32)
         Km, Ri = _d(np.asarray(K).reshape(9)), _d(np.asarray(cam_inv).reshape(16))

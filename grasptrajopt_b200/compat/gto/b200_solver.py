@@ -23,6 +23,7 @@ import numpy as np
 
 from optas.dm import DM, _as2d
 from grasptrajopt_b200 import capi
+from grasptrajopt_b200.goalset import goalset_best
 
 _CONTEXTS: Dict[int, capi.GtoContext] = {}
 
@@ -40,7 +41,7 @@ class B200Solver:
     FIELD_ALL, FIELD_OBS = 0, 1  # field slots used by the planner
 
     def __init__(self, robot, link_ee, link_gripper, T, dt, *, standoff_distance=-0.1, standoff_offset=-10, use_standoff=False,
-                 axis_standoff="x", collision_avoidance=True, w_goal=1.0, w_obs=10.0, w_vel=0.01, device=0, options=None):
+                 axis_standoff="x", collision_avoidance=True, w_goal=1.0, w_obs=10.0, w_vel=0.01, device=0, options=None, obs_linear=False):
         self.robot = robot
         self.robot_name = robot.get_name()
         self.table = robot.to_table(link_ee, link_gripper)
@@ -49,12 +50,26 @@ class B200Solver:
         self.use_standoff, self.axis_standoff = bool(use_standoff), axis_standoff
         self.collision_avoidance = bool(collision_avoidance)
         self.w_goal, self.w_obs, self.w_vel = w_goal, w_obs, w_vel
+        self.flags = capi.FLAG_OBS_LINEAR if obs_linear else 0  # unsquared obstacle term of the IK solver (gto/ik_solver.py:69)
         self.device = device
         self.options = options
         self.x0: Optional[np.ndarray] = None
         self.p: Dict[str, np.ndarray] = {}
         self._stats = {"success": False, "iter_count": 0}
         self.batch_result = None
+
+    # one upload per distinct field: the planner re-sends both cost fields as parameters on every call (reference protocol), but
+    # gto_set_field (device copy, ~340 tensor maps, summed-volume table) costs more than a solve
+    @staticmethod
+    def upload_field_cached(ctx, device, slot, cost32, origin, pitch):
+        """``ctx.set_field`` unless the same field (shape, geometry and a content checksum) already sits in ``slot``."""
+        flat = cost32.reshape(-1)
+        key = (cost32.shape, tuple(float(v) for v in origin), float(pitch), float(flat.sum(dtype=np.float64)), float(flat[::7].sum(dtype=np.float64)),
+               float(np.dot(flat[::13], np.arange(flat[::13].size, dtype=np.float32) % 251)))
+        if ctx.field_keys.get(int(slot)) == key:
+            return
+        ctx.set_field(slot, cost32, origin, pitch)
+        ctx.field_keys[int(slot)] = key
 
     # -- CasADiSolver protocol ----------------------------------------------------------------------------------
     def setup(self, solver_name: str = "b200", solver_options: Optional[dict] = None):
@@ -84,7 +99,8 @@ class B200Solver:
             raise ValueError(f"{key} has {cost.size} entries, the robot's field has {int(np.prod(shape))}")
         if not np.any(cost):
             return -1
-        ctx.set_field(slot, cost.reshape(shape).astype(np.float32), np.asarray(self.robot.origin).reshape(3), float(self.robot.grid_resolution))
+        self.upload_field_cached(ctx, self.device, slot, cost.reshape(shape).astype(np.float32), np.asarray(self.robot.origin).reshape(3),
+                                 float(self.robot.grid_resolution))
         return slot
 
     def solve(self) -> Dict[str, DM]:
@@ -116,10 +132,10 @@ class B200Solver:
             base_position=np.tile(base, (n, 1)), field_all=np.full(n, fa, np.int32), field_obs=np.full(n, fo, np.int32),
             standoff_offset=self.standoff_offset, use_standoff=self.use_standoff,
             collision_avoidance=self.collision_avoidance and (fa >= 0 or fo >= 0),
-            w_goal=self.w_goal, w_obs=self.w_obs, w_vel=self.w_vel)
+            w_goal=self.w_goal, w_obs=self.w_obs, w_vel=self.w_vel, flags=self.flags)
         res = ctx.solve_batch(batch, self.options)
         self.batch_result = res
-        best = int(np.argmin(res["cost"]))
+        best = goalset_best(res["cost"], res["status"])  # converged goals first, never a NaN solve (grasptrajopt_b200/goalset.py)
         self._stats = {"success": bool(res["status"][best] == capi.STATUS_CONVERGED), "iter_count": int(res["iters"][best]),
                        "status": int(res["status"][best]), "best_goal": best, "profile": ctx.profile()}
         Q, dQ = res["Q"][best].T, res["dQ"][best].T  # ndof-by-T, ndof-by-(T-1)
@@ -143,7 +159,7 @@ class B200Solver:
             T=self.T, dt=self.dt, qc=np.asarray(qc, dtype=np.float64).reshape(n, t.ndof), q_seed=np.asarray(q_seed, dtype=np.float64).reshape(n, self.T, t.ndof),
             goal_tf=capi.goal_transforms(t, RT, self.standoff_distance, self.axis_standoff), base_position=np.ascontiguousarray(base),
             field_all=np.full(n, field_all, np.int32), field_obs=np.full(n, field_obs, np.int32), standoff_offset=self.standoff_offset,
-            use_standoff=self.use_standoff, collision_avoidance=collide, w_goal=self.w_goal, w_obs=self.w_obs, w_vel=self.w_vel)
+            use_standoff=self.use_standoff, collision_avoidance=collide, w_goal=self.w_goal, w_obs=self.w_obs, w_vel=self.w_vel, flags=self.flags)
         res = ctx.solve_batch(batch, self.options)
         self.batch_result = res
         res["profile"] = ctx.profile()

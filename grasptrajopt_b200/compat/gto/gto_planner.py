@@ -31,7 +31,8 @@ class GTOPlanner:
         self.device = device
         self.solver = None
 
-    # BASELINE's 30-knot configs set ``planner.T = 30``; the reference computes dt once in __init__ (Q13), here it follows T.
+    # ``planner.T = 30`` behaves as in the reference: T is a plain attribute there and dt is computed once in __init__ from T = 50
+    # (gto/gto_planner.py:25-28), so a changed T keeps dt = 10/49.  ``set_horizon`` is the explicit way to rescale dt with T.
     @property
     def T(self):
         return self._T
@@ -39,7 +40,12 @@ class GTOPlanner:
     @T.setter
     def T(self, value):
         self._T = int(value)
-        self.dt = self.Tmax / (self._T - 1)
+
+    def set_horizon(self, T, rescale_dt=True):
+        """Change the number of knots; ``rescale_dt`` also sets dt = Tmax / (T - 1) (what BASELINE's 30-knot configurations use)."""
+        self._T = int(T)
+        if rescale_dt:
+            self.dt = self.Tmax / (self._T - 1)
 
     def setup_optimization(self, goal_size=1, use_standoff=False, axis_standoff="x"):
         self.fk = self.robot.get_global_link_transform_function(self.link_gripper, n=self.T)
@@ -121,6 +127,6 @@ class GTOPlanner:
         if ctx.table is not table:
             ctx.set_robot(table)
         shape = tuple(int(s) for s in self.robot.field_shape)
-        ctx.set_field(B200Solver.FIELD_OBS, np.asarray(sdf_cost_obstacle, dtype=np.float32).reshape(shape),
-                      np.asarray(self.robot.origin).reshape(3), float(self.robot.grid_resolution))
+        B200Solver.upload_field_cached(ctx, self.device, B200Solver.FIELD_OBS, np.asarray(sdf_cost_obstacle, dtype=np.float32).reshape(shape),
+                                       np.asarray(self.robot.origin).reshape(3), float(self.robot.grid_resolution))
         return ctx.plan_cost(np.transpose(plans, (0, 2, 1)), B200Solver.FIELD_OBS, base_position)

@@ -5,13 +5,12 @@
 is the trajectory problem with one free knot, no velocity term and no stand-off, so it runs on the same kernels
 (3 knots: two pinned at the seed, one free).  Many goals can be solved in one batch with ``solve_ik_batch``.
 
-The reference's optional IK collision term ``10 * sum(c)`` (unsquared, :69) is disabled in every shipped experiment
-(``ik_collision_avoidance=False``, Q14) and is not available here; ``collision_avoidance=True`` uses the planner's squared
-term ``10 * sum(c^2)`` instead and says so once.
+``collision_avoidance=True`` adds the reference's IK collision term ``10 * sum(c)`` -- unsquared (:69), unlike the planner's
+``10 * sum(c^2)`` -- through ``GTO_FLAG_OBS_LINEAR`` (value ``w*c``, gradient ``w*dc/dq`` of the trilinear field, no Gauss-Newton
+curvature).  In the reference the term is a nearest-node gather with structurally zero gradient and it is
+disabled in every shipped experiment (``ik_collision_avoidance=False``, Q14).
 """
 from __future__ import annotations
-
-import warnings
 
 import numpy as np
 
@@ -35,11 +34,8 @@ class IKSolver:
 
     def setup_optimization(self):
         self.fk = self.robot.get_global_link_transform_function(link=self.link_ee)
-        if self.collision_avoidance:
-            warnings.warn("IKSolver(collision_avoidance=True): the B200 build uses the squared obstacle term 10*sum(c^2) "
-                          "instead of the reference's 10*sum(c)", stacklevel=2)
         self.solver = B200Solver(self.robot, self.link_ee, self.link_gripper, T=3, dt=1.0, use_standoff=False, standoff_offset=-1,
-                                 collision_avoidance=self.collision_avoidance, w_vel=0.0, device=self.device,
+                                 collision_avoidance=self.collision_avoidance, w_vel=0.0, device=self.device, obs_linear=True,
                                  options=capi.default_options(max_iter=50))  # reference: max_iter 50 (:75)
 
     def _errors(self, q, RT):

@@ -1,123 +1,70 @@
-"""``DepthPointCloud`` (reference ``mesh_to_sdf/depth_point_cloud.py:9-142``): depth image -> world point cloud -> signed
-distance by nearest neighbour + camera visibility -> CHOMP-style cost field (epsilon = 0.02).
+"""``DepthPointCloud`` on the GPU: depth image -> world point cloud -> signed distance (nearest cloud point, negative where the
+query is hidden behind the visible surface) -> CHOMP-style cost field.  Producer of the voxel fields the hot path consumes
+(SURVEY.md section 8(f) row 2).
 
-Producer of the voxel fields the hot path consumes (SURVEY.md section 8(f) "next #2").  Same constructor, attributes and method
-names as the reference.  ``backend="b200"`` (default): the nearest-neighbour queries, the visibility sign and the cost transform
-run in ``libgto_b200.so`` (``k_cloud_query``: exact tiled brute force on the GPU; fails loudly without a device).
-``backend="kdtree"``: the reference's own algorithm (scikit-learn KD-tree on the CPU), kept to validate the GPU path against.
-``pyrender`` is only imported by the visualisation branches (the reference imports it at module level, :4).
+Interface of the reference class (``mesh_to_sdf/depth_point_cloud.py:9-142``: constructor arguments, the attributes ``points``,
+``depth``, ``intrinsic_matrix``, ``camera_pose``, ``target_mask``, ``width``, ``height``, ``threshold`` and the methods below) with
+every computation in ``libgto_b200.so``:
+
+    back-projection            ``gto_cloud_backproject``  (k_cloud_backproject, one thread per pixel, float64)
+    get_sdf / get_sdf_cost     ``gto_cloud_query`` mode 0 / 1  (k_cloud_query_pruned: exact nearest neighbour over Morton-sorted tiles,
+                               visibility sign by float64 projection into the depth image, cost transform fused)
+    is_outside                 ``gto_cloud_query`` mode 2  (the visibility test alone)
+
+There is no CPU path: without a CUDA device the constructor raises (``GtoError``).  The KD-tree restatement of the reference's
+algorithm that the tests check this class against lives in ``oracle/dpc_oracle.py`` (test infrastructure).  The ``vis=True``
+branch of the reference (a pyrender viewer) is out of scope.
 """
 from __future__ import annotations
-
-import math
-
-import os
 
 import numpy as np
 
 
 class DepthPointCloud:
-    def __init__(self, depth, intrinsic_matrix, camera_pose, target_mask=None, threshold=1.5, backend=None, device=0):
+    def __init__(self, depth, intrinsic_matrix, camera_pose, target_mask=None, threshold=1.5, device=0):
+        from gto.b200_solver import get_context
+
         self.depth = depth
         self.intrinsic_matrix = intrinsic_matrix
         self.camera_pose = camera_pose
         self.target_mask = target_mask
-        self.width = depth.shape[1]
-        self.height = depth.shape[0]
+        self.height, self.width = depth.shape[0], depth.shape[1]
         self.threshold = threshold
-        pc = self.backproject_camera(depth, intrinsic_matrix)
-        pc_base = camera_pose[:3, :3] @ pc + camera_pose[:3, 3].reshape((3, 1))
-        self.points = pc_base.T
-        self.backend = backend or os.environ.get("GTO_DPC_BACKEND", "b200")
         self.device = device
-        self.kd_tree = None
         self.last_kernel_ms = None
-        if self.backend == "kdtree":
-            from sklearn.neighbors import KDTree
+        self._ctx = get_context(device)
+        self._cam_inv = np.linalg.inv(np.asarray(camera_pose, dtype=np.float64))
+        self._depth32 = np.ascontiguousarray(depth, dtype=np.float32)
+        self.points = self._ctx.cloud_backproject(self._depth32, intrinsic_matrix, camera_pose, threshold, target_mask)
+        self._make_resident()
 
-            self.kd_tree = KDTree(self.points)
-        elif self.backend == "b200":
-            from gto.b200_solver import get_context
+    def _make_resident(self):
+        # one cloud is resident per solver context; the last DepthPointCloud that used the context owns it
+        self._ctx.cloud_set(self.points)
+        self._ctx._cloud_owner = self
 
-            self._ctx = get_context(device)
-            self._ctx.cloud_set(self.points)
-            self._ctx._cloud_obj = self
-        else:
-            raise ValueError(f"unknown DepthPointCloud backend {self.backend!r}")
-
-    def _gpu_query(self, query_points, mode, epsilon=0.02, w_inside=1):
-        # one cloud is resident per context: re-upload if another DepthPointCloud used the context since
-        if getattr(self._ctx, "_cloud_obj", None) is not self:
-            self._ctx.cloud_set(self.points)
-            self._ctx._cloud_obj = self
-        out, ms = self._ctx.cloud_query(np.asarray(query_points, dtype=np.float64), np.asarray(self.depth, dtype=np.float32), self.intrinsic_matrix,
-                                        np.linalg.inv(self.camera_pose), mode, epsilon, w_inside)
-        self.last_kernel_ms = ms
+    def _query(self, query_points, mode, epsilon=0.02, w_inside=1):
+        if mode != 2 and getattr(self._ctx, "_cloud_owner", None) is not self:
+            self._make_resident()
+        out, self.last_kernel_ms = self._ctx.cloud_query(np.asarray(query_points, dtype=np.float64), self._depth32, self.intrinsic_matrix, self._cam_inv,
+                                                         mode, epsilon, w_inside)
         return out
 
     def get_random_surface_points(self, count):
-        return self.points[np.random.choice(self.points.shape[0], count), :]
-
-    def backproject_camera(self, im_depth, K):
-        Kinv = np.linalg.inv(K)
-        width, height = im_depth.shape[1], im_depth.shape[0]
-        depth = im_depth.astype(np.float32, copy=True).flatten()
-        mask = (depth > 0) & (depth < self.threshold)
-        if self.target_mask is not None:
-            mask &= self.target_mask.flatten() == 0
-        x, y = np.meshgrid(np.arange(width), np.arange(height))
-        ones = np.ones((height, width), dtype=np.float32)
-        x2d = np.stack((x, y, ones), axis=2).reshape(width * height, 3)
-        R = Kinv.dot(x2d.transpose())
-        X = np.multiply(np.tile(depth.reshape(1, width * height), (3, 1)), R)
-        return X[:, mask]
+        return self.points[np.random.choice(len(self.points), count)]
 
     def is_outside(self, points):
-        RT = np.linalg.inv(self.camera_pose)
-        pc_camera = RT[:3, :3] @ points.T + RT[:3, 3].reshape((3, 1))
-        x2d = self.intrinsic_matrix @ pc_camera
-        x2d[0, :] /= x2d[2, :]
-        x2d[1, :] /= x2d[2, :]
-        pixels = x2d[:2].T.astype(int)
-        in_viewport = (pixels[:, 0] >= 0) & (pixels[:, 1] >= 0) & (pixels[:, 0] < self.width) & (pixels[:, 1] < self.height)
-        pc_camera = pc_camera.T
-        result = np.ones(points.shape[0], dtype=bool)
-        result[in_viewport] = pc_camera[in_viewport, 2] < self.depth[pixels[in_viewport, 1], pixels[in_viewport, 0]]
-        return result
+        """True where a point is visible from the camera or projects outside the image."""
+        return self._query(points, 2) > 0.5
 
     def get_sdf(self, query_points):
-        if self.backend == "b200":
-            return self._gpu_query(query_points, 0)
-        distances, _ = self.kd_tree.query(query_points)
-        distances = distances.astype(np.float32).reshape(-1)
-        inside = ~self.is_outside(query_points)
-        distances[inside] *= -1
-        return distances
+        return self._query(query_points, 0)
 
     def get_sdf_cost(self, query_points, epsilon=0.02, w_inside=1, vis=False):
-        if self.backend == "b200" and not vis:
-            return self._gpu_query(query_points, 1, epsilon, w_inside)
-        distances = self.get_sdf(query_points)
-        inside = distances < 0
-        if vis:  # pragma: no cover - rendering only
-            import pyrender
-
-            index = np.absolute(distances) < 0.03
-            colors = np.zeros((int(index.sum()), 3))
-            colors[distances[index] < 0, 2] = 1
-            colors[distances[index] > 0, 0] = 1
-            scene = pyrender.Scene()
-            scene.add(pyrender.Mesh.from_points(query_points[index], colors=colors))
-            scene.add(pyrender.Mesh.from_points(self.points[::100]))
-            pyrender.Viewer(scene, use_raymond_lighting=True, point_size=5)
-        cost = np.zeros_like(distances)
-        cost[inside] = w_inside * (-distances[inside] + epsilon / 2)
-        index = (distances > 0) & (distances < epsilon)
-        cost[index] = np.square(distances[index] - epsilon) / (2 * epsilon)
-        return cost
+        if vis:
+            raise NotImplementedError("the pyrender viewer of the reference (vis=True) is not part of the B200 build")
+        return self._query(query_points, 1, epsilon, w_inside)
 
     def get_sdf_in_batches(self, query_points, batch_size=1000000):
-        if query_points.shape[0] <= batch_size:
-            return self.get_sdf(query_points)
-        n_batches = int(math.ceil(query_points.shape[0] / batch_size))
-        return np.concatenate([self.get_sdf(p) for p in np.array_split(query_points, n_batches)])
+        query_points = np.asarray(query_points)
+        return np.concatenate([self.get_sdf(query_points[i : i + batch_size]) for i in range(0, len(query_points), batch_size)])

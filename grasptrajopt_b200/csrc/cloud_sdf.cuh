@@ -65,6 +65,40 @@ __device__ __forceinline__ float cloud_value(const CloudParams& p, float d2, boo
   return c;
 }
 
+// mode 2: the visibility test alone (DepthPointCloud.is_outside, :127-142), 1.0 = outside / visible, 0.0 = hidden
+__global__ void k_cloud_outside(const __grid_constant__ CloudParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.N) p.out[i] = cloud_outside(p, i) ? 1.f : 0.f;
+}
+
+// Back-projection of a depth image into a world-frame point cloud (DepthPointCloud.__init__ / backproject_camera, :15-19,32-52):
+// pixel (u, v) with 0 < depth < threshold (and outside the target mask) -> X = depth * Kinv [u v 1]^T -> world = R X + t, float64.
+// One thread per pixel; `valid` marks the pixels that pass the test (the caller compacts, keeping the row-major pixel order).
+struct BackprojParams {
+  const float* depth;          // [H][W]
+  const unsigned char* mask;   // [H][W] non-zero: pixel belongs to the target object (excluded), or NULL
+  int H, W;
+  double Kinv[9], pose[12];    // inverse intrinsics (row-major), camera pose rows of [R|t]
+  float threshold;
+  double* points;              // [H*W][3]
+  unsigned char* valid;        // [H*W]
+};
+__global__ void k_cloud_backproject(const __grid_constant__ BackprojParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.H * p.W) return;
+  const int v = (int)(i / p.W), u = (int)(i - (long long)v * p.W);
+  const float d = p.depth[i];
+  const bool ok = d > 0.f && d < p.threshold && (p.mask == nullptr || p.mask[i] == 0);
+  const double dd = (double)d, uu = (double)u, vv = (double)v;
+  const double x = dd * (p.Kinv[0] * uu + p.Kinv[1] * vv + p.Kinv[2]);
+  const double y = dd * (p.Kinv[3] * uu + p.Kinv[4] * vv + p.Kinv[5]);
+  const double z = dd * (p.Kinv[6] * uu + p.Kinv[7] * vv + p.Kinv[8]);
+  p.points[3 * i + 0] = p.pose[0] * x + p.pose[1] * y + p.pose[2] * z + p.pose[3];
+  p.points[3 * i + 1] = p.pose[4] * x + p.pose[5] * y + p.pose[6] * z + p.pose[7];
+  p.points[3 * i + 2] = p.pose[8] * x + p.pose[9] * y + p.pose[10] * z + p.pose[11];
+  p.valid[i] = ok ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(CLOUD_THREADS) k_cloud_query(const __grid_constant__ CloudParams p) {
   __shared__ float4 tile[CLOUD_TILE];
   const int tid = threadIdx.x;

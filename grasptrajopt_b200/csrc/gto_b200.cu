@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <math_constants.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -512,6 +513,7 @@ struct gto_ctx {
   long long cloud_n = 0;
   DevBuf<double> cloud_q;
   DevBuf<float> cloud_depth, cloud_out, cloud_tiles;
+  DevBuf<unsigned char> cloud_mask;
   DevBuf<unsigned long long> tstamps;
   double grip_mom[16] = {0};  // sum_k [x_k;1][x_k;1]^T over the gripper point set (base placement)
   DevBuf<double> base_d;      // base placement: inputs and outputs, one allocation
@@ -666,7 +668,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
   ctx->status.release(); ctx->active.release(); ctx->nactive.release(); ctx->work_ctr.release(); ctx->stats.release(); ctx->dbg.release(); ctx->tstamps.release();
-  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->cloud_tiles.release(); ctx->recs.release(); ctx->rec_dummy.release(); ctx->queue.release(); ctx->phase_ns.release();
+  ctx->cloud.release(); ctx->cloud_q.release(); ctx->cloud_depth.release(); ctx->cloud_out.release(); ctx->cloud_tiles.release(); ctx->cloud_mask.release(); ctx->recs.release(); ctx->rec_dummy.release(); ctx->queue.release(); ctx->phase_ns.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1471,7 +1473,8 @@ static inline unsigned morton_spread10(unsigned v) {  // 10 bits -> every third 
 }
 
 extern "C" int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M) {
-  if (!ctx || !points || M < 1) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!points || M < 1) return fail(ctx, GTO_ERR_INVALID, "gto_cloud_set: needs at least one point");
   CK(cudaSetDevice(ctx->device));
   const size_t Mpad = ((size_t)M + CLOUD_TILE - 1) / CLOUD_TILE * CLOUD_TILE;
   // order the cloud along a Morton curve (10 bits per axis over its bounding box): consecutive points are neighbours in
@@ -1516,8 +1519,10 @@ extern "C" int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M) {
 
 extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, const float* depth, int32_t H, int32_t W, const double K[9],
                                const double cam_inv[16], int32_t mode, double epsilon, double w_inside, float* out, double* kernel_ms) {
-  if (!ctx || !query || !depth || !K || !cam_inv || !out || N < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return GTO_ERR_INVALID;
-  if (ctx->cloud_n < 1) return fail(ctx, GTO_ERR_STATE, "gto_cloud_set has not been called");
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!query || !depth || !K || !cam_inv || !out || N < 1 || H < 1 || W < 1 || mode < 0 || mode > 2)
+    return fail(ctx, GTO_ERR_INVALID, "gto_cloud_query: null argument, empty query / image or unknown mode");
+  if (mode != 2 && ctx->cloud_n < 1) return fail(ctx, GTO_ERR_STATE, "gto_cloud_set has not been called");
   CK(cudaSetDevice(ctx->device));
   CK(ctx->cloud_q.ensure((size_t)N * 3));
   CK(ctx->cloud_out.ensure((size_t)N));
@@ -1539,7 +1544,9 @@ extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, con
   CK(cudaEventRecord(ev.a, ctx->stream));
   p.tiles = ctx->cloud_tiles.p;
   p.ntiles = (int)(((size_t)ctx->cloud_n + CLOUD_PTILE - 1) / CLOUD_PTILE);
-  if (getenv("GTO_CLOUD_BRUTE")) {  // A/B reference: every query against every point
+  if (mode == 2) {  // visibility test only (is_outside)
+    k_cloud_outside<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(p);
+  } else if (getenv("GTO_CLOUD_BRUTE")) {  // A/B reference: every query against every point
     const long long per = (long long)CLOUD_THREADS * CLOUD_QPT;
     k_cloud_query<<<(unsigned)((N + per - 1) / per), CLOUD_THREADS, 0, ctx->stream>>>(p);
   } else {
@@ -1553,6 +1560,32 @@ extern "C" int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, con
   float ms = 0;
   cudaEventElapsedTime(&ms, ev.a, ev.b);
   if (kernel_ms) *kernel_ms = ms;
+  return GTO_OK;
+}
+
+extern "C" int gto_cloud_backproject(gto_ctx* ctx, const float* depth, const uint8_t* target_mask, int32_t H, int32_t W, const double Kinv[9],
+                                     const double cam_pose[16], double threshold, double* points, uint8_t* valid) {
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!depth || !Kinv || !cam_pose || !points || !valid || H < 1 || W < 1) return fail(ctx, GTO_ERR_INVALID, "gto_cloud_backproject: null argument or empty image");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)H * W;
+  CK(ctx->cloud_depth.ensure(n));
+  CK(ctx->cloud_q.ensure(n * 3));
+  CK(ctx->cloud_mask.ensure(2 * n));
+  CK(cudaMemcpyAsync(ctx->cloud_depth.p, depth, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (target_mask) CK(cudaMemcpyAsync(ctx->cloud_mask.p, target_mask, n, cudaMemcpyHostToDevice, ctx->stream));
+  BackprojParams p;
+  memset(&p, 0, sizeof(p));
+  p.depth = ctx->cloud_depth.p; p.mask = target_mask ? ctx->cloud_mask.p : nullptr; p.H = H; p.W = W;
+  for (int i = 0; i < 9; ++i) p.Kinv[i] = Kinv[i];
+  for (int i = 0; i < 12; ++i) p.pose[i] = cam_pose[i];
+  p.threshold = (float)threshold;
+  p.points = ctx->cloud_q.p; p.valid = ctx->cloud_mask.p + n;
+  k_cloud_backproject<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(points, ctx->cloud_q.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(valid, ctx->cloud_mask.p + n, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return GTO_OK;
 }
 

@@ -607,6 +607,7 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
   // =============================== CONSUMER WARPS ===============================
   float* stage = stage_base + warp * st_floats;
   const int gq = lane >> 2, tq = lane & 3;
+  const bool obs_linear = (p.flags & GTO_FLAG_OBS_LINEAR) != 0;
   unsigned ic = 0, bc = 0;
   for (;; ++ic) {
     const int ci = ic & 1;
@@ -697,10 +698,17 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
           }
           if (act) {  // (inactive lanes hold zeros)
             const double rd = (double)r;
-            cacc = fma(rd, rd, cacc);
+            if (!obs_linear) {
+              cacc = fma(rd, rd, cacc);
 #pragma unroll
-            for (int k = 0; k < NP; ++k)
-              if (k < nopt) gacc[k] = fma((double)J[k], rd, gacc[k]);
+              for (int k = 0; k < NP; ++k)
+                if (k < nopt) gacc[k] = fma((double)J[k], rd, gacc[k]);
+            } else {  // unsquared term w*c (gto/ik_solver.py:69): value w*c, half gradient (w/2) dc/dq, no curvature
+              cacc = fma((double)p.sw_obs, rd, cacc);
+#pragma unroll
+              for (int k = 0; k < NP; ++k)
+                if (k < nopt) gacc[k] = fma(0.5 * (double)p.sw_obs, (double)J[k], gacc[k]);
+            }
           }
           if (NOPT_CT == 7) {  // row = [J0..J6 | r] = 32 bytes: two 128-bit shared stores
             float4* s4 = reinterpret_cast<float4*>(stage + lane * 8);
@@ -713,7 +721,7 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
             stage[lane * RS + nopt] = r;
           }
           __syncwarp();
-          mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
+          if (!obs_linear) mma_rows<NP>(stage, RS, cnt, acc0, acc1, lane);
           if (rows_b) {
             float* dst = rows_b + ((long long)t * R.npoints + p0) * RS;
             if (NOPT_CT == 7 && cnt == 32) {  // 1 KB tile, 16-byte aligned by construction

@@ -159,6 +159,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     int done = -1;  // -1: keep running, otherwise final status
     if (!isfinite(Ft)) {
       done = GTO_STATUS_NAN;
+      if (it == 0 && tid == 0) p.F[b] = CUDART_INF;  // no accepted point yet: the reported cost must not be the initial 0
     } else if (it == 0) {  // initial point: accept unconditionally
       // knots 0 and 1 never move and are linearised only once: keep their cost in both buffers
       if (tid < 2) {

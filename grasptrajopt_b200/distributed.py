@@ -66,24 +66,20 @@ def goalset_argmin(local_cost, lo: int, world: int, local_status=None):
     import torch
     import torch.distributed as dist
 
+    from .goalset import goalset_best, status_class
+
     cost = torch.as_tensor(local_cost, dtype=torch.float64)
     dev = cost.device
     n = cost.shape[0]
     big = torch.finfo(torch.float64).max
     if n == 0:
-        pair = torch.tensor([big, -1.0, 1.0], dtype=torch.float64, device=dev)
-    else:
-        if local_status is not None:
-            bad = torch.as_tensor(local_status, device=dev) != 0
-        else:
-            bad = torch.zeros(n, dtype=torch.bool, device=dev)
-        key = torch.where(bad, torch.full_like(cost, big), cost)
-        if bool(bad.all()):
-            i = int(torch.argmin(cost))
-            pair = torch.tensor([float(cost[i]), float(lo + i), 1.0], dtype=torch.float64, device=dev)
-        else:
-            i = int(torch.argmin(key))
-            pair = torch.tensor([float(cost[i]), float(lo + i), 0.0], dtype=torch.float64, device=dev)
+        pair = torch.tensor([big, -1.0, 3.0], dtype=torch.float64, device=dev)
+    else:  # the same ranking as the single-GPU planner (goalset.py): converged first, never a NaN solve
+        c_np = cost.detach().cpu().numpy()
+        s_np = np.zeros(n, np.int64) if local_status is None else torch.as_tensor(local_status).detach().cpu().numpy()
+        i = goalset_best(c_np, s_np)
+        ci = float(c_np[i]) if np.isfinite(c_np[i]) else big
+        pair = torch.tensor([ci, float(lo + i), float(status_class(c_np[i : i + 1], s_np[i : i + 1])[0])], dtype=torch.float64, device=dev)
     if world > 1:
         if dist.get_backend() == "nccl" and not pair.is_cuda:  # host-side costs (the C-ABI returns NumPy arrays): NCCL needs device memory
             pair = pair.to(torch.device("cuda", torch.cuda.current_device()))
@@ -92,7 +88,7 @@ def goalset_argmin(local_cost, lo: int, world: int, local_status=None):
     else:
         allp = pair.reshape(1, 3)
     allp = allp.cpu().numpy()
-    # converged candidates first, then cost, then index
+    # status class first (converged, finite but not converged, NaN), then cost, then index
     order = sorted(range(world), key=lambda r: (allp[r, 2], allp[r, 0], allp[r, 1] if allp[r, 1] >= 0 else np.inf))
     r = order[0]
     return int(allp[r, 1]), float(allp[r, 0]), int(r)

@@ -54,6 +54,9 @@ extern "C" {
 
 /* flags for gto_batch_in.flags */
 #define GTO_FLAG_NO_JROWS 1u      /* do not materialise the Jacobian rows in HBM (assembly still fused) */
+#define GTO_FLAG_OBS_LINEAR 2u    /* obstacle term w_obs * sum c(W) instead of w_obs * sum c(W)^2: the reference IK solver's term
+                                     (gto/ik_solver.py:69).  Value w*c, gradient w*dc/dq, no Gauss-Newton curvature; the row block
+                                     still holds sqrt(w)*dc/dq | sqrt(w)*c */
 #define GTO_FLAG_NO_CULL 32u      /* every link is treated as touching a non-zero node of the field (A-B check of the culling) */
 
 typedef struct gto_ctx gto_ctx;
@@ -238,9 +241,15 @@ int gto_plan_cost(gto_ctx* ctx, int32_t n, int32_t T, const double* plans, int32
  * gto_cloud_set uploads the world-frame point cloud of a depth image (what the reference puts into a scikit-learn KD-tree, :20-25);
  * gto_cloud_query returns, for N query points, the distance to the nearest cloud point, negative where the query is hidden behind
  * the visible surface (is_outside, :127-142: projection with the intrinsics K into the depth image through cam_inv, the inverse
- * camera pose, row-major 4x4) -- mode 0, get_sdf :57-62 -- or the CHOMP-style cost of that distance -- mode 1, get_sdf_cost :65-91.
+ * camera pose, row-major 4x4) -- mode 0, get_sdf :57-62 -- or the CHOMP-style cost of that distance -- mode 1, get_sdf_cost :65-91 --
+ * or the visibility test alone, 1.0 = visible / outside, 0.0 = hidden -- mode 2, is_outside :127-142 (needs no cloud).
  * kernel_ms (may be NULL) receives the device time of the query kernel.
+ * gto_cloud_backproject turns a depth image into the world-frame cloud (DepthPointCloud.__init__ / backproject_camera, :15-19,32-52):
+ * pixels with 0 < depth < threshold and target_mask == 0 (target_mask may be NULL); points[H*W][3] receives every pixel's point,
+ * valid[H*W] which of them pass the test (compact in row-major pixel order to get the reference's `points`).
  */
+int gto_cloud_backproject(gto_ctx* ctx, const float* depth, const uint8_t* target_mask, int32_t H, int32_t W, const double Kinv[9],
+                          const double cam_pose[16], double threshold, double* points, uint8_t* valid);
 int gto_cloud_set(gto_ctx* ctx, const double* points, int64_t M);
 int gto_cloud_query(gto_ctx* ctx, const double* query, int64_t N, const float* depth, int32_t H, int32_t W, const double K[9],
                     const double cam_inv[16], int32_t mode, double epsilon, double w_inside, float* out, double* kernel_ms);

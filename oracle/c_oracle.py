@@ -106,7 +106,7 @@ def solve_workload(w, indices=None, nthreads=0, options=None):
     s.qc, s.q_seed, s.goal_tf, s.base_position = (keep[k].ctypes.data_as(_dp) for k in ("qc", "q_seed", "goal_tf", "base"))
     s.field_all, s.field_obs = keep["fa"].ctypes.data_as(_ip), keep["fo"].ctypes.data_as(_ip)
     s.standoff_offset, s.use_standoff, s.collision_avoidance = int(b.standoff_offset), int(bool(b.use_standoff)), int(bool(b.collision_avoidance))
-    s.w_goal, s.w_obs, s.w_vel, s.flags = float(b.w_goal), float(b.w_obs), float(b.w_vel), 0
+    s.w_goal, s.w_obs, s.w_vel, s.flags = float(b.w_goal), float(b.w_obs), float(b.w_vel), int(getattr(w.batch, 'flags', 0)) & capi.FLAG_OBS_LINEAR
     res = dict(Q=np.zeros((B, T, t.ndof)), dQ=np.zeros((B, T - 1, t.ndof)), cost=np.zeros(B), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32))
     o = capi.BatchOut()
     o.Q, o.dQ, o.cost = res["Q"].ctypes.data_as(_dp), res["dQ"].ctypes.data_as(_dp), res["cost"].ctypes.data_as(_dp)

@@ -145,12 +145,17 @@ static void linearize(const prob_ctx* P, const double* Q, int t_lo, double* H, d
             double val, gr[3];
             trilinear(f, w[0] + (base ? base[0] : 0), w[1] + (base ? base[1] : 0), w[2] + (base ? base[2] : 0), &val, gr);
             const double r = sw * val;
-            ct += r * r;
+            if (in->flags & GTO_FLAG_OBS_LINEAR) ct += sw * r;  /* unsquared term w*c (gto/ik_solver.py:69) */
+            else ct += r * r;
             if (gr[0] == 0.0 && gr[1] == 0.0 && gr[2] == 0.0) continue;
             gr[0] *= sw; gr[1] *= sw; gr[2] *= sw;
             const double nx = w[1] * gr[2] - w[2] * gr[1], ny = w[2] * gr[0] - w[0] * gr[2], nz = w[0] * gr[1] - w[1] * gr[0];
             for (int k = 0; k < n; ++k)
               J[k] = ((mask >> k) & 1u) ? P->om[3 * k] * nx + P->om[3 * k + 1] * ny + P->om[3 * k + 2] * nz + P->mm[3 * k] * gr[0] + P->mm[3 * k + 1] * gr[1] + P->mm[3 * k + 2] * gr[2] : 0.0;
+            if (in->flags & GTO_FLAG_OBS_LINEAR) {  /* half gradient (w/2) dc/dq, no Gauss-Newton curvature */
+              for (int a = 0; a < n; ++a) gt[a] += 0.5 * sw * J[a];
+              continue;
+            }
             for (int a = 0; a < n; ++a) {
               if (J[a] == 0.0) continue;
               gt[a] += J[a] * r;

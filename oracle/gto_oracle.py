@@ -302,6 +302,7 @@ class Problem:
     w_obs: float = 10.0
     w_vel: float = 0.01
     sdf_mode: str = "trilinear"  # "trilinear" (build) | "nearest" (A5, zero gradient)
+    obs_linear: bool = False  # obstacle term w_obs * sum c instead of w_obs * sum c^2 (the IK solver's term, gto/ik_solver.py:69)
 
     def __post_init__(self):
         self.qc = np.asarray(self.qc, dtype=np.float64).reshape(-1)
@@ -417,12 +418,20 @@ def linearize(p: Problem, Q: np.ndarray, need_jac: bool = True) -> Linearization
         if t == p.knot_standoff and p.use_standoff:
             rows_r.append(r_stand.reshape(-1))
             rows_J.append(J_stand.reshape(-1, n))
-        rr_ = np.concatenate(rows_r)
-        JJ_ = np.concatenate(rows_J, axis=0)
+        if p.obs_linear:
+            # unsquared obstacle term w*sum(c) (gto/ik_solver.py:69): value w*c, half gradient (w/2) dc/dq, no Gauss-Newton
+            # curvature (c is piecewise trilinear).  r_obs / J_obs still hold sqrt(w)*c and sqrt(w)*dc/dq.
+            rows_r, rows_J = rows_r[1:], rows_J[1:]
+        rr_ = np.concatenate(rows_r) if rows_r else np.zeros(0)
+        JJ_ = np.concatenate(rows_J, axis=0) if rows_J else np.zeros((0, n))
         cost[t] = rr_ @ rr_
         if need_jac:
             H[t] = JJ_.T @ JJ_
             g[t] = JJ_.T @ rr_
+        if p.obs_linear:
+            cost[t] += sw * float(np.sum(r_obs[t]))
+            if need_jac:
+                g[t] += 0.5 * sw * J_obs[t].sum(axis=0)
     return Linearization(r_obs, J_obs, r_goal, J_goal, r_stand, J_stand, H, g, cost)
 
 

@@ -21,7 +21,7 @@ def problems_from_workload(w, indices=None, sdf_mode="trilinear"):
                 base_position=np.zeros(3) if b.base_position is None else b.base_position[i],
                 field_all=fa, field_obs=fo, standoff_offset=b.standoff_offset, standoff_distance=w.standoff_distance,
                 axis_standoff=w.axis_standoff, use_standoff=b.use_standoff, collision_avoidance=b.collision_avoidance,
-                w_goal=b.w_goal, w_obs=b.w_obs, w_vel=b.w_vel, sdf_mode=sdf_mode,
+                w_goal=b.w_goal, w_obs=b.w_obs, w_vel=b.w_vel, sdf_mode=sdf_mode, obs_linear=bool(int(b.flags) & 2),
             )
         )
     return out

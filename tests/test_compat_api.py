@@ -117,9 +117,12 @@ def test_field_geometry_matches_reference_run(model):
     assert tuple(model.field_shape) == tuple(z["pf_shape"])
 
 
-def test_depth_point_cloud_matches_reference_run():
+def test_depth_point_cloud_oracle_matches_reference_run():
+    """oracle/dpc_oracle.py (the checker of the GPU DepthPointCloud) against the outputs of the reference's own class."""
+    from dpc_oracle import KDTreeDepthPointCloud
+
     z = np.load(os.path.join(GOLDEN, "ref_field.npz"))
-    dpc = DepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5, backend="kdtree")
+    dpc = KDTreeDepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5)
     np.testing.assert_allclose(dpc.points, z["dpc_points"], atol=1e-12)
     np.testing.assert_array_equal(dpc.get_sdf(z["dpc_query"]), z["dpc_sdf"])
     np.testing.assert_array_equal(dpc.get_sdf_cost(z["dpc_query"], epsilon=0.02), z["dpc_cost"])
@@ -212,16 +215,18 @@ def test_base_planner_pose_errors(model):
     assert ep2[0, 0] == pytest.approx(0.05, abs=1e-6) and er2[0, 1] == pytest.approx(10.0, abs=1e-2)
 
 
-def test_plan_collision_audit_kdtree_backend(model):
-    """gto.utils.plan_collision_audit against the reference's per-knot loop (examples/pybullet_evaluate_plans.py:219-237), CPU backend."""
+def test_plan_collision_audit_host_logic(model):
+    """gto.utils.plan_collision_audit against the reference's per-knot loop (examples/pybullet_evaluate_plans.py:219-237); the
+    distance queries come from the KD-tree oracle here (the GPU class is exercised in tests/test_gpu_cloud.py)."""
     from gto.utils import plan_collision_audit
+    from dpc_oracle import KDTreeDepthPointCloud
 
     H, Wd, f = 60, 80, 70.0
     K = np.array([[f, 0, Wd / 2], [0, f, H / 2], [0, 0, 1.0]])
     cam = np.eye(4); cam[:3, :3] = np.array([[1.0, 0, 0], [0, -1, 0], [0, 0, -1]]); cam[:3, 3] = [0.3, 0.0, 1.0]
     depth = np.full((H, Wd), 1.0, np.float32)
     depth[20:40, 30:60] = 0.8  # a box on the table
-    dpc = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
+    dpc = KDTreeDepthPointCloud(depth, K, cam, threshold=1.5)
     T = 6
     plan = np.stack([np.linspace(-1.5, 1.5, T), np.linspace(0.0, 3.0, T), np.full(T, 0.01)])
     base = np.array([0.2, 0.0, 0.12])

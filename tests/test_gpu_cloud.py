@@ -1,6 +1,6 @@
 """SURVEY.md section 8(f) row 2 on the GPU: DepthPointCloud.get_sdf / get_sdf_cost through libgto_b200 (k_cloud_query) against
 (1) the outputs of the reference's own DepthPointCloud stored in tests/golden/ref_field.npz and (2) the reference algorithm
-(scikit-learn KD-tree backend) on a larger synthetic depth image.  Run with -m gpu."""
+(oracle/dpc_oracle.py: scikit-learn KD-tree) on a larger synthetic depth image.  Run with -m gpu."""
 import os
 import time
 
@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from mesh_to_sdf.depth_point_cloud import DepthPointCloud
+from dpc_oracle import KDTreeDepthPointCloud
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -15,7 +16,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def test_cloud_query_matches_reference_run():
     z = np.load(os.path.join(GOLDEN, "ref_field.npz"))
-    dpc = DepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5, backend="b200")
+    dpc = DepthPointCloud(z["dpc_depth"], z["dpc_K"], z["dpc_cam"], target_mask=None, threshold=1.5)
+    np.testing.assert_allclose(dpc.points, z["dpc_points"], atol=1e-12)  # back-projection on the device (k_cloud_backproject)
     sdf = dpc.get_sdf(z["dpc_query"])
     assert sdf.dtype == np.float32 and sdf.shape == z["dpc_sdf"].shape
     np.testing.assert_array_equal(np.sign(sdf), np.sign(z["dpc_sdf"]))
@@ -41,9 +43,13 @@ def _scene_depth(H=120, W=160):
 
 def test_cloud_query_matches_kdtree_backend_on_a_grid():
     depth, K, cam = _scene_depth()
-    gpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="b200")
-    cpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
-    np.testing.assert_array_equal(gpu.points, cpu.points)
+    mask = np.zeros(depth.shape, np.uint8)
+    mask[45:60, 55:70] = 1  # target object pixels are left out of the cloud
+    for tm in (None, mask):
+        gpu = DepthPointCloud(depth, K, cam, target_mask=tm, threshold=1.5)
+        cpu = KDTreeDepthPointCloud(depth, K, cam, target_mask=tm, threshold=1.5)
+        assert gpu.points.shape == cpu.points.shape
+        np.testing.assert_allclose(gpu.points, cpu.points, rtol=0, atol=1e-14)
     n = 56
     g = np.stack(np.meshgrid(np.linspace(0.0, 1.0, n), np.linspace(-0.5, 0.5, n), np.linspace(-0.2, 0.8, n), indexing="ij"), axis=-1).reshape(-1, 3)
     t0 = time.time(); s_gpu = gpu.get_sdf(g); t1 = time.time(); s_cpu = cpu.get_sdf(g); t2 = time.time()
@@ -55,6 +61,9 @@ def test_cloud_query_matches_kdtree_backend_on_a_grid():
     ok = ~flip
     np.testing.assert_allclose(c_gpu[ok], c_cpu[ok], rtol=0, atol=2e-6)
     assert (c_cpu > 0).mean() > 0.05 and (s_cpu < 0).any()
+    # is_outside on the device (mode 2 of gto_cloud_query) against the restated reference test
+    vis_g, vis_c = gpu.is_outside(g), cpu.is_outside(g)
+    assert vis_g.dtype == bool and (vis_g != vis_c).mean() < 1e-4 and (~vis_c).any()
     # the pruned search visits every tile that could hold a nearer point: bit-identical to the brute-force kernel
     os.environ["GTO_CLOUD_BRUTE"] = "1"
     try:
@@ -80,8 +89,8 @@ def test_plan_collision_audit_matches_kdtree_backend(tmp_path):
     robot = GTORobotModel(str(tmp_path), urdf_filename=str(tmp_path / "arm3.urdf"), time_derivs=[0, 1], param_joints=["slide"],
                           collision_link_names=["base", "l1", "l2", "tool"], sample_point_count=64, seed=2)
     depth, K, cam = _scene_depth()
-    gpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="b200")
-    cpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
+    gpu = DepthPointCloud(depth, K, cam, threshold=1.5)
+    cpu = KDTreeDepthPointCloud(depth, K, cam, threshold=1.5)
     T = 12
     plan = np.stack([np.linspace(-2.0, 2.0, T), np.linspace(0.0, 6.0, T), np.full(T, 0.01)])  # the arm starts inside the box on the table
     base = np.array([0.2, 0.0, 0.12])

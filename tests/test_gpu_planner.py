@@ -37,6 +37,8 @@ def _problem(robot, planner, qc, RT, seed, field_all, field_obs, use_standoff, a
 def test_plan_matches_oracle(robot):
     planner = GTOPlanner(robot, "tool", "tool", standoff_distance=-0.05)
     planner.T = 30
+    assert planner.dt == pytest.approx(10.0 / 49)  # reference semantics: dt is fixed at construction (gto_planner.py:25-28)
+    planner.set_horizon(30)
     assert planner.dt == pytest.approx(10.0 / 29)
     qc = np.array([0.2, -0.3, 0.01])
     q_star = np.array([1.1, 0.6, 0.01])
@@ -54,7 +56,7 @@ def test_plan_matches_oracle(robot):
 
 def test_plan_goalset_returns_cheapest_goal(robot):
     planner = GTOPlanner(robot, "tool", "tool", standoff_distance=-0.05)
-    planner.T = 30
+    planner.set_horizon(30)
     qc = np.array([0.2, -0.3, 0.01])
     q_goals = np.array([[1.1, 0.6, 0.01], [-1.4, 1.3, 0.01], [0.4, -0.9, 0.01]])
     RTs = np.stack([robot.get_global_link_transform("tool", q).toarray() for q in q_goals])
@@ -152,3 +154,68 @@ def test_base_planner_rejection_loop(robot):
     # the returned draw, solved alone through the reference signature, gives the same placement
     Q1, y1, _, _, c1 = bp.plan_goalset(qc, draw)
     assert np.array_equal(y1, y) and np.array_equal(Q1, Q) and c1 == cost
+
+
+def _ik_batch_from_workload(w, n, linear_obstacle):
+    """The batch ``IKSolver.solve_ik_batch`` hands to the solver (gto/ik_solver.py:30-76 as a 3-knot trajectory: two knots pinned
+    at the seed, one free, no velocity term, no stand-off), for the first n grasps of a workload."""
+    import dataclasses
+    from grasptrajopt_b200 import workloads as W
+
+    b = W.slice_batch(w.batch, 0, n)
+    seeds = np.repeat(b.qc[:, None, :], 3, axis=1)
+    return dataclasses.replace(b, T=3, dt=1.0, q_seed=seeds, use_standoff=False, standoff_offset=-1, w_vel=0.0,
+                               field_all=b.field_obs.copy(), flags=capi.FLAG_OBS_LINEAR if linear_obstacle else 0)
+
+
+@pytest.mark.parametrize("linear_obstacle", [False, True])
+def test_ik_batch_matches_oracle(linear_obstacle):
+    """SURVEY 8(f) row 1 against the oracle: batched IK of 48 Panda grasps (7 joints, 6-DoF goal: one redundant direction, so the
+    joint vector is not unique but the gripper point positions and the objective are) -- CUDA vs the C oracle on identical inputs;
+    ``linear_obstacle``: the reference IK solver's unsquared collision term 10*sum(c) (gto/ik_solver.py:69)."""
+    import c_oracle
+    import gto_oracle as O
+    from helpers import small_workload, upload_fields, problems_from_workload
+    from grasptrajopt_b200 import kinematics as K
+
+    w = small_workload("C2", "panda_small", B=48, n_field=64)
+    b = _ik_batch_from_workload(w, 48, linear_obstacle)
+    w.batch = b
+    ctx = capi.GtoContext(0)
+    try:
+        ctx.set_robot(w.table)
+        upload_fields(ctx, w)
+        opts = capi.default_options(max_iter=50)  # reference: max_iter 50 (:75)
+        res = ctx.solve_batch(b, opts)
+    finally:
+        ctx.close()
+    ora = c_oracle.solve_workload(w, options=c_oracle.default_options(max_iter=50))
+    t = w.table
+    xg = t.points[t.grip_pt_start : t.grip_pt_start + t.grip_pt_count]
+
+    def gripper_points(q):
+        F = np.stack([O.gripper_frame(t, qi) for qi in q])
+        return np.einsum("bij,kj->bki", F[:, :3, :3], xg) + F[:, None, :3, 3]
+
+    Wg, Wo = gripper_points(res["Q"][:, 2]), gripper_points(ora["Q"][:, 2])
+    both = (res["status"] == 0) & (ora["status"] == 0)
+    # (the unsquared term has a piecewise-constant gradient: most of its solutions rest on a cell face and are not "converged")
+    assert both.sum() >= (8 if linear_obstacle else 24), (res["status"], ora["status"])
+    assert np.abs(Wg - Wo)[both].max() < 1e-4  # metres
+    rel = np.abs(res["cost"] - ora["cost"]) / np.maximum(ora["cost"], 1e-9)
+    assert rel[both].max() < 1e-4
+    assert np.mean((res["status"] == 0) == (ora["status"] == 0)) >= 0.9
+    # the NumPy oracle (the one pinned against the reference's own code) agrees with the C port on this problem family
+    p0 = problems_from_workload(w, [0, 5])
+    for i, p in zip((0, 5), p0):
+        r = O.solve_lm(p, O.SolverOptions(max_iter=50))
+        assert r.status == ora["status"][i] and abs(r.cost - ora["cost"][i]) <= 1e-9 * max(1.0, r.cost)
+    if linear_obstacle:  # objective = goal term + 10 * sum(c) at the solution (trilinear c), not 10 * sum(c^2)
+        p = p0[0]
+        lin = O.linearize(p, ora["Q"][0], need_jac=False)
+        goal = float(np.sum(lin.r_goal ** 2))
+        c = lin.r_obs[2] / np.sqrt(p.w_obs)
+        # knots 0,1 (pinned at the seed) carry their constant obstacle cost as well
+        c_all = lin.r_obs / np.sqrt(p.w_obs)
+        assert ora["cost"][0] == pytest.approx(goal + p.w_obs * float(c_all.sum()), rel=1e-9)
+        assert c.sum() >= 0

@@ -47,6 +47,7 @@ except Exception as e:  # pragma: no cover
 
 # ---- row 2: cost field from a depth image ----
 from mesh_to_sdf.depth_point_cloud import DepthPointCloud
+from dpc_oracle import KDTreeDepthPointCloud
 H, Wd, f = 480, 640, 550.0
 K = np.array([[f, 0, Wd / 2], [0, f, H / 2], [0, 0, 1.0]])
 cam = np.eye(4); cam[:3, :3] = np.array([[1.0, 0, 0], [0, -1, 0], [0, 0, -1]]); cam[:3, 3] = [0.5, 0.0, 1.2]
@@ -56,13 +57,13 @@ depth[180:300, 250:390] = 1.05
 depth[60:140, 80:560] = (1.15 - 0.0002 * (u[60:140, 80:560] - 80)).astype(np.float32)
 for n in (64, 128):
     g = np.stack(np.meshgrid(np.linspace(-0.4, 1.4, n), np.linspace(-1.4, 1.4, n), np.linspace(-0.4, 1.4, n), indexing="ij"), axis=-1).reshape(-1, 3)
-    gpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="b200")
+    gpu = DepthPointCloud(depth, K, cam, threshold=1.5)
     gpu.get_sdf_cost(g[:4096])
     t0 = time.perf_counter(); c_gpu = gpu.get_sdf_cost(g); t1 = time.perf_counter()
     rec = {"cloud_points": int(gpu.points.shape[0]), "queries": int(g.shape[0]), "gpu_kernel_ms": gpu.last_kernel_ms, "gpu_call_ms": 1e3 * (t1 - t0),
            "pairs_per_s": gpu.points.shape[0] * g.shape[0] / (gpu.last_kernel_ms * 1e-3)}
     if n == 64:
-        cpu = DepthPointCloud(depth, K, cam, threshold=1.5, backend="kdtree")
+        cpu = KDTreeDepthPointCloud(depth, K, cam, threshold=1.5)
         t0 = time.perf_counter(); c_cpu = cpu.get_sdf_cost(g); t1 = time.perf_counter()
         rec["kdtree_cpu_ms"] = 1e3 * (t1 - t0)
         rec["max_abs_cost_diff"] = float(np.abs(c_gpu - c_cpu).max())
