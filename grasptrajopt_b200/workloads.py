@@ -38,6 +38,7 @@ class Workload:
     axis_standoff: str
     q_star: np.ndarray  # [B,ndof] configurations the goals were generated from
     description: str = ""
+    field_specs: Dict[int, tuple] = field(default_factory=dict)  # slot -> (boxes, lo, hi, n): what the field was built from
 
 
 def _table(name: str) -> RobotTable:
@@ -63,13 +64,52 @@ def _obj_box(center, size=(0.06, 0.06, 0.12)):
     return [((float(center[0]), float(center[1]), float(center[2])), tuple(size))]
 
 
-def make_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n_field: Optional[int] = None) -> Workload:
+def make_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n_field: Optional[int] = None, cache: bool = True) -> Workload:
+    """The seeded workload of a BASELINE configuration (see ``_build_workload``).  Rejection sampling of thousands of reachable grasps
+    takes tens of seconds on the host (C4: 38 s, C5: 51 s), so large workloads are kept in the temp directory -- everything but the
+    cost fields, which are rebuilt from their boxes (milliseconds) -- and shared by later runs and by the ranks of one run."""
+    import pickle
+    import tempfile
+
+    full = {"C1": 1, "C2": 256, "C3": 1024, "C4": 4096, "C5": 16384}[config.upper()]
+    if not cache or full * scale < 1000:
+        return _build_workload(config, scale, seed, n_field)
+    path = os.path.join(tempfile.gettempdir(), f"gto_b200_workload_v3_{config.upper()}_{scale:.6f}_{seed}_{n_field}.pkl")
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as fh:
+                w = pickle.load(fh)
+            w.fields = {slot: S.make_field(*spec) for slot, spec in w.field_specs.items()}
+            return w
+        except Exception:
+            pass
+    w = _build_workload(config, scale, seed, n_field)
+    try:
+        fields, w.fields = w.fields, {}
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "wb") as fh:
+            pickle.dump(w, fh, protocol=4)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    finally:
+        w.fields = fields
+    return w
+
+
+def _build_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n_field: Optional[int] = None) -> Workload:
     """Scenes follow the reference pipeline (``examples/pybullet_gto_planning.py:178-190``): ``sdf_cost_all`` (slot 2s)
     contains every obstacle *and* the target object, ``sdf_cost_obstacle`` (slot 2s+1) everything but the target; the
     first T-10 knots read the former, the approach knots the latter (``gto/gto_planner.py:117-131``)."""
     config = config.upper()
     idx = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[config]
     rng = np.random.default_rng(idx if seed is None else seed)
+    specs = {}
+
+    def done(w, slot_boxes, lo_, hi_, n_):
+        w.field_specs = {slot: (list(bx), np.asarray(lo_), np.asarray(hi_), n_) for slot, bx in slot_boxes.items()}
+        return w
+
     if config in ("C1", "C2"):
         t = _table("panda_c2")
         B = 1 if config == "C1" else max(1, int(round(256 * scale)))
@@ -80,9 +120,10 @@ def make_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n
         lo, hi = S.workspace_box(1.0, 0.0)
         f_obs = S.make_field(boxes, lo, hi, n)
         f_all = S.make_field(boxes + _obj_box(target), lo, hi, n)
+        specs = {0: boxes + _obj_box(target), 1: boxes}
         RT, QS, QG = S.sample_grasps_around(t, PANDA_QC, target, B, rng, approach_axis="z", reach=0.10, boxes=boxes)
-        return _assemble(config, t, {0: f_all, 1: f_obs}, PANDA_QC, RT, QG, 30, [0] * B, [1] * B, -0.1, "z",
-                         f"Panda tabletop, {B} candidate grasps x 30 knots, P={t.npoints}, {n}^3 SDF", QS, rng=rng)
+        return done(_assemble(config, t, {0: f_all, 1: f_obs}, PANDA_QC, RT, QG, 30, [0] * B, [1] * B, -0.1, "z",
+                         f"Panda tabletop, {B} candidate grasps x 30 knots, P={t.npoints}, {n}^3 SDF", QS, rng=rng), specs, lo, hi, n)
     if config == "C3":
         t = _table("fetch8_c3")
         B = max(1, int(round(1024 * scale)))
@@ -93,10 +134,11 @@ def make_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n
         lo, hi = S.workspace_box(1.1, 1.1)
         f_obs = S.make_field(boxes, lo, hi, n)
         f_all = S.make_field(boxes + _obj_box(target), lo, hi, n)
+        specs = {0: boxes + _obj_box(target), 1: boxes}
         RT, QS, QG = S.sample_grasps_around(t, FETCH_QC, target, B, rng, approach_axis="x", reach=0.0, approach_dir=(1, 0, 0),
                                             min_cos=0.6, boxes=boxes)
-        return _assemble(config, t, {0: f_all, 1: f_obs}, FETCH_QC, RT, QG, 50, [0] * B, [1] * B, -0.2, "x",
-                         f"Fetch 8-DoF shelf, {B} grasps x 50 knots, P={t.npoints}, {n}^3 SDF", QS, rng=rng)
+        return done(_assemble(config, t, {0: f_all, 1: f_obs}, FETCH_QC, RT, QG, 50, [0] * B, [1] * B, -0.2, "x",
+                         f"Fetch 8-DoF shelf, {B} grasps x 50 knots, P={t.npoints}, {n}^3 SDF", QS, rng=rng), specs, lo, hi, n)
     if config == "C4":
         t = _table("fetch10_c4")
         B = max(1, int(round(4096 * scale)))
@@ -106,11 +148,12 @@ def make_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n
         lo, hi = np.array([-0.75, -1.5, 0.0]), np.array([1.6, 1.5, 2.2])
         f_obs = S.make_field(boxes, lo, hi, n)
         f_all = S.make_field(boxes + _obj_box(target), lo, hi, n)
+        specs = {0: boxes + _obj_box(target), 1: boxes}
         qc = np.concatenate([[0.0, 0.0, 0.0], FETCH_QC])
         RT, QS, QG = S.sample_grasps_around(t, qc, target, B, rng, approach_axis="x", reach=0.0, approach_dir=(0, 0, -1), min_cos=0.2,
                                             boxes=boxes)
-        return _assemble(config, t, {0: f_all, 1: f_obs}, qc, RT, QG, 50, [0] * B, [1] * B, -0.1, "x",
-                         f"Fetch mobile 10-DoF tabletop, {B} seeds x 50 knots, P={t.npoints}, {n}^3 SDF", QS, qc_noise=0.1, rng=rng)
+        return done(_assemble(config, t, {0: f_all, 1: f_obs}, qc, RT, QG, 50, [0] * B, [1] * B, -0.1, "x",
+                         f"Fetch mobile 10-DoF tabletop, {B} seeds x 50 knots, P={t.npoints}, {n}^3 SDF", QS, qc_noise=0.1, rng=rng), specs, lo, hi, n)
     if config == "C5":
         t = _table("panda_c2")
         nscene = max(1, int(round(64 * scale)))
@@ -124,13 +167,14 @@ def make_workload(config: str, scale: float = 1.0, seed: Optional[int] = None, n
             boxes_t = boxes + [((target[0], target[1], 0.10), (0.08, 0.08, 0.20))]  # pedestal keeps the target above the clutter
             fields[2 * s] = S.make_field(boxes_t + _obj_box(target), lo, hi, n)
             fields[2 * s + 1] = S.make_field(boxes_t, lo, hi, n)
+            specs[2 * s], specs[2 * s + 1] = boxes_t + _obj_box(target), boxes_t
             RT, QS, QG = S.sample_grasps_around(t, PANDA_QC, target, per, rng, approach_axis="z", reach=0.10, boxes=boxes_t)
             RTs.append(RT); QSs.append(QS); QGs.append(QG)
             fa += [2 * s] * per
             fo += [2 * s + 1] * per
         RT, QS, QG = np.concatenate(RTs), np.concatenate(QSs), np.concatenate(QGs)
-        return _assemble(config, t, fields, PANDA_QC, RT, QG, 30, fa, fo, -0.1, "z",
-                         f"Panda clutter, {nscene} scenes x {per} problems x 30 knots, P={t.npoints}, {n}^3 SDF", QS, qc_noise=0.1, rng=rng)
+        return done(_assemble(config, t, fields, PANDA_QC, RT, QG, 30, fa, fo, -0.1, "z",
+                         f"Panda clutter, {nscene} scenes x {per} problems x 30 knots, P={t.npoints}, {n}^3 SDF", QS, qc_noise=0.1, rng=rng), specs, lo, hi, n)
     raise ValueError(config)
 
 
