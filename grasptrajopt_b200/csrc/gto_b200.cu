@@ -74,6 +74,8 @@ struct LinParams {
   const RobotDev* robot;
   const int* chunk_start;  // [nchunks] first point of each 32-point chunk
   const int* chunk_count;  // [nchunks]
+  const float* pts3;       // [3][npad] surface points x | y | z (one bulk copy into shared memory per CTA)
+  int npad;                // npoints rounded up to a multiple of 4
   const float* px;
   const float* py;
   const float* pz;
@@ -480,6 +482,7 @@ struct gto_ctx {
   int device = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
+  int smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   PFN_encodeTiled encode = nullptr;
@@ -487,7 +490,8 @@ struct gto_ctx {
   bool has_robot = false;
   RobotDev robot_h;
   RobotDev* robot_d = nullptr;
-  DevBuf<float> px, py, pz;
+  DevBuf<float> pts3;  // [3][npad]: x | y | z of the surface points
+  int npad = 0;
   DevBuf<int> chunk_start, chunk_count;
   int pipe_cons = 8;
   double max_link_diag = 0.0;  // largest |half extent|_2 over links
@@ -621,6 +625,7 @@ extern "C" int gto_create(gto_ctx** out, int device) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GTO_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
@@ -661,7 +666,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   if (ctx->robot_d) cudaFree(ctx->robot_d);
   if (ctx->fields_d) cudaFree(ctx->fields_d);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
-  ctx->px.release(); ctx->py.release(); ctx->pz.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
+  ctx->pts3.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
   ctx->qc.release(); ctx->q_seed.release(); ctx->Qc.release(); ctx->Qt.release(); ctx->F.release(); ctx->Fp.release();
   ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Fhist.release();
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
@@ -676,7 +681,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
 extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
   if (!ctx || !r) return GTO_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  if (r->nopt < 1 || r->nopt > GTO_MAX_OPT || r->nmov < 1 || r->nmov > GTO_MAX_MOV || r->nlinks < 1 || r->nlinks > GTO_MAX_LINKS ||
+  if (r->nopt < 1 || r->nopt > GTO_MAX_OPT || r->nmov < 1 || r->nmov > GTO_MAX_MOV || r->nlinks < 1 || r->nlinks > GTO_MAX_LINKS || r->nlinks > CULL_REC_LINKS ||
       r->ndof < r->nopt || r->npoints < 1)
     return fail(ctx, GTO_ERR_INVALID, "robot table sizes out of range");
   RobotDev& h = ctx->robot_h;
@@ -748,11 +753,13 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
     }
     ctx->pipe_cons = bestc;
   }
-  CK(ctx->px.ensure(r->npoints)); CK(ctx->py.ensure(r->npoints)); CK(ctx->pz.ensure(r->npoints));
+  ctx->npad = (r->npoints + 3) & ~3;
+  CK(ctx->pts3.ensure((size_t)3 * ctx->npad));
+  CK(cudaMemset(ctx->pts3.p, 0, sizeof(float) * 3 * ctx->npad));
   CK(ctx->chunk_start.ensure(cs.size())); CK(ctx->chunk_count.ensure(cs.size()));
-  CK(cudaMemcpy(ctx->px.p, hx.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->py.p, hy.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->pz.p, hz.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->pts3.p, hx.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->pts3.p + ctx->npad, hy.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->pts3.p + 2 * ctx->npad, hz.data(), sizeof(float) * r->npoints, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->chunk_start.p, cs.data(), sizeof(int) * cs.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->chunk_count.p, cc.data(), sizeof(int) * cc.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->robot_d, &h, sizeof(RobotDev), cudaMemcpyHostToDevice));
@@ -929,7 +936,8 @@ static void fill_lin_params(gto_ctx* ctx, LinParams& p, const double* q, const i
   const RobotDev& R = ctx->robot_h;
   memset(&p, 0, sizeof(p));
   p.robot = ctx->robot_d; p.chunk_start = ctx->chunk_start.p; p.chunk_count = ctx->chunk_count.p;
-  p.px = ctx->px.p; p.py = ctx->py.p; p.pz = ctx->pz.p;
+  p.pts3 = ctx->pts3.p; p.npad = ctx->npad;
+  p.px = ctx->pts3.p; p.py = ctx->pts3.p + ctx->npad; p.pz = ctx->pts3.p + 2 * ctx->npad;
   p.q = q; p.goal_tf = ctx->goal_tf.p; p.base = ctx->base.p; p.field_ids = ctx->field_ids.p;
   p.fields = ctx->fields_d;
   p.active = active; p.nactive = nactive; p.nproblems = nproblems; p.b0 = b0; p.bufsel = bufsel;
@@ -956,6 +964,14 @@ static int brick_slot_floats(const gto_ctx* ctx) {
   return n3 <= 24 ? 4096 : (n3 <= 32 ? 8192 : 12288);
 }
 
+// brick ring slots: as many as requested, but not so many that a second CTA no longer fits on the SM
+static int pick_nslot(const gto_ctx* ctx, int nopt, int nc, int slot_floats, size_t extra) {
+  const int want = std::min(CULL_NSLOT_MAX, std::max(2, ctx->tune_nslot));
+  for (int ns = want; ns >= 2; --ns)
+    if (2 * (cull_smem_bytes(nopt, nc, ns, slot_floats, ctx->npad) + extra + 1024) <= (size_t)ctx->smem_per_sm) return ns;
+  return want;
+}
+
 typedef void (*cull_kernel_t)(const CullParams);
 static cull_kernel_t pick_cull_kernel(int nopt) {
   if (nopt == 7) return k_linearize_cull<8, 7>;
@@ -978,12 +994,12 @@ static int launch_linearize(gto_ctx* ctx, const double* q, const int* active, co
   cp.slot_floats = slot_floats;
   const int nc = ctx->tune_cons > 0 ? std::min(CULL_MAX_CONS, ctx->tune_cons) : ctx->pipe_cons;
   cp.ncons = nc;
-  const int nslot = std::min(CULL_NSLOT_MAX, std::max(2, ctx->tune_nslot));
+  const int nslot = pick_nslot(ctx, R.nopt, nc, slot_floats, 0);
   cp.nslot = nslot;
   cp.count_early = have_recs ? 0 : 1;
   cp.work_counter = work_counter;
   cp.stats = ctx->stats.p;
-  const size_t sm = cull_smem_bytes(R.nopt, nc, nslot, slot_floats);
+  const size_t sm = cull_smem_bytes(R.nopt, nc, nslot, slot_floats, ctx->npad);
   const int threads = (nc + 2) * 32;  // consumers + producer + zero-row warp
   cull_kernel_t kern = pick_cull_kernel(R.nopt);
   if (ctx->cull_smem_set != (long long)sm) {
@@ -1117,9 +1133,9 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     memset(&fp, 0, sizeof(fp));
     const int slot_floats = brick_slot_floats(ctx);
     const int nc = ctx->tune_cons > 0 ? std::min(CULL_MAX_CONS, ctx->tune_cons) : ctx->pipe_cons;
-    const int nslot = std::min(CULL_NSLOT_MAX, std::max(2, ctx->tune_nslot));
+    const int nslot = pick_nslot(ctx, n, nc, slot_floats, fused_robot_bytes());
     const int threads = (nc + 2) * 32;
-    const size_t phase_smem = std::max(std::max(cull_smem_bytes(n, nc, nslot, slot_floats), (cr_smem + 127) & ~(size_t)127),
+    const size_t phase_smem = std::max(std::max(cull_smem_bytes(n, nc, nslot, slot_floats, ctx->npad), (cr_smem + 127) & ~(size_t)127),
                                        (fused_fk_smem_bytes(R.nmov, threads) + 127) & ~(size_t)127);
     const size_t smem = fused_robot_bytes() + phase_smem;
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, GTO_ERR_INVALID, "fused solver kernel does not fit in shared memory");
@@ -1441,7 +1457,7 @@ extern "C" int gto_plan_cost(gto_ctx* ctx, int32_t nplans, int32_t T, const doub
   cudaStreamSynchronize(ctx->stream);
   const float bx = base_position ? (float)base_position[0] : 0.f, by = base_position ? (float)base_position[1] : 0.f,
               bz = base_position ? (float)base_position[2] : 0.f;
-  k_plan_cost<<<nplans * T, 128, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, dq, T, f, bx, by, bz, dc);
+  k_plan_cost<<<nplans * T, 128, 0, ctx->stream>>>(ctx->robot_d, ctx->pts3.p, ctx->pts3.p + ctx->npad, ctx->pts3.p + 2 * ctx->npad, dq, T, f, bx, by, bz, dc);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(cost, dc, nplans * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1638,7 +1654,7 @@ extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_opt
   EventPair ev;
   CK(ev.create());
   CK(cudaEventRecord(ev.a, ctx->stream));
-  if (in->occupancy) k_base_points<<<1, 256, 0, ctx->stream>>>(ctx->robot_d, ctx->px.p, ctx->py.p, ctx->pz.p, p.qc, d + o_wp);
+  if (in->occupancy) k_base_points<<<1, 256, 0, ctx->stream>>>(ctx->robot_d, ctx->pts3.p, ctx->pts3.p + ctx->npad, ctx->pts3.p + 2 * ctx->npad, p.qc, d + o_wp);
   const bool v1 = getenv("GTO_BASE_V1") != nullptr || nopt > 12;  // local-memory kernel: A/B reference, and robots with > 12 optimised joints
   if (v1) {
     if (nopt <= 8) k_base_place<8><<<B, 32, 0, ctx->stream>>>(p);

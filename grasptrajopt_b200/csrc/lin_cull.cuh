@@ -19,6 +19,8 @@
 
 #define CULL_NSLOT_MAX 8  // brick ring slots: run-time (CullParams.nslot), default 4
 #define CULL_ZERO_BYTES 8192
+#define CULL_NCTX 4        // item records in flight per CTA (the producer runs up to this many items ahead of the consumers)
+#define CULL_REC_LINKS 16  // collision links per item record (Panda 12, Fetch 10); gto_set_robot rejects more
 
 struct LinkMeta {
   int c0, c1, pt_start, pt_end;
@@ -85,29 +87,29 @@ __device__ __forceinline__ void sdf_trilinear_box(const FieldDev& f, const float
 }
 
 struct __align__(16) CullCtx {
-  float frames[GTO_MAX_LINKS][12];  // visual frame of each collision link (robot base frame)
+  float frames[CULL_REC_LINKS][12];  // visual frame of each collision link (robot base frame)
   float tw[GTO_MAX_OPT][8];         // (omega.xyz, -, m.xyz, -) per optimised joint
   float gripf[12];
   float goal[2][12];                // gripper frame minus goal / stand-off frame
-  double vf[GTO_MAX_LINKS][12];     // float64 3x4 map: point in the link's visual frame -> brick-local voxel coordinate
-  int blo[GTO_MAX_LINKS][4];        // brick lower corner (grid index) per link
-  int bdim[GTO_MAX_LINKS][4];       // brick dims (x, y, z) and fast flag
+  double vf[CULL_REC_LINKS][12];     // float64 3x4 map: point in the link's visual frame -> brick-local voxel coordinate
+  int blo[CULL_REC_LINKS][4];        // brick lower corner (grid index) per link
+  int bdim[CULL_REC_LINKS][4];       // brick dims (x, y, z) and fast flag
   float basep[4];
   int b, t, fid, obuf;
   int nact, kind;                   // surviving links; kind bit 0: goal rows, bit 1: stand-off rows
   unsigned amask;                   // bit l: link l survived the culling test
   int pad_;
-  int act[GTO_MAX_LINKS];           // surviving link ids, ascending
+  int act[CULL_REC_LINKS];           // surviving link ids, ascending
 };
 
 #define CULL_ZQ 16  // entries of the producer -> zero-row warp queue
 struct CullShared {
-  CullCtx ctx[2];
-  LinkMeta links[GTO_MAX_LINKS];
-  unsigned long long slot_full[CULL_NSLOT_MAX], slot_empty[CULL_NSLOT_MAX], ctx_full[2], ctx_empty[2];
+  CullCtx ctx[CULL_NCTX];
+  LinkMeta links[CULL_REC_LINKS];
+  unsigned long long slot_full[CULL_NSLOT_MAX], slot_empty[CULL_NSLOT_MAX], ctx_full[CULL_NCTX], ctx_empty[CULL_NCTX];
   int4 zq[CULL_ZQ];            // (b, t, amask, -) of the items whose culled links still need their zero rows; b < 0: stop
-  volatile unsigned zq_tail;   // entries written by the producer warp
-  volatile unsigned zq_head;   // entries consumed by the zero-row warp
+  unsigned long long zq_full[CULL_ZQ], zq_empty[CULL_ZQ];  // producer -> zero-row warp hand-over (mbarriers: waiting threads are parked)
+  unsigned long long pts_full;                             // the robot's surface points have arrived in shared memory
 };
 
 struct CullParams {
@@ -382,15 +384,41 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
                : "memory");
 }
 
+// Warp sum of NP values per lane by recursive halving (see the use in cull_body).  On return gacc[0] of lane l holds the total of
+// value warp_multi_owner<NP>(l) when that is >= 0.
+template <int NP>
+__device__ __forceinline__ void warp_reduce_multi(double (&v)[NP], int lane) {
+  static_assert(NP == 8 || NP == 16, "8 or 16 values");
+  int m = 16;
+#pragma unroll
+  for (int half = NP / 2; half >= 1; half >>= 1, m >>= 1) {
+    const bool upper = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  for (; m >= 1; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+}
+template <int NP>
+__device__ __forceinline__ int warp_multi_owner(int lane) {
+  if (NP == 8) return (lane & 3) == 0 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) : -1;
+  return (lane & 1) == 0 ? ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1) : -1;
+}
+
 // per-warp reduction record: [nopt*nopt] float (J^T J), then [nopt + 1] double (J^T r, sum r^2), 8-byte aligned
 __host__ __device__ inline int cull_red_floats(int nopt) { return ((nopt * nopt + 1) & ~1) + 2 * (nopt + 1); }
-__host__ __device__ inline size_t cull_smem_bytes(int nopt, int ncons, int nslot, int slot_floats) {
+__host__ __device__ inline size_t cull_smem_bytes(int nopt, int ncons, int nslot, int slot_floats, int npad) {
   const int RS = nopt + 1;
   size_t sm = (sizeof(CullShared) + 127) & ~(size_t)127;
   sm += CULL_ZERO_BYTES;
   sm += (size_t)nslot * slot_floats * sizeof(float);
   sm += (size_t)ncons * (((32 * RS + 16 + 31) / 32) * 32) * sizeof(float);
   sm += (size_t)2 * ncons * cull_red_floats(nopt) * sizeof(float);
+  sm = (sm + 127) & ~(size_t)127;
+  sm += (size_t)3 * npad * sizeof(float);  // surface points
   return (sm + 127) & ~(size_t)127;
 }
 
@@ -419,23 +447,33 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
   off += (size_t)NC * st_floats * sizeof(float);
   const int red_floats = cull_red_floats(nopt), red_g0 = (nopt * nopt + 1) & ~1;  // doubles start at an even float index
   float* red_base = reinterpret_cast<float*>(smem_raw + off);  // [2][NC][red_floats]
+  off += (size_t)2 * NC * red_floats * sizeof(float);
+  off = (off + 127) & ~(size_t)127;
+  float* spts = reinterpret_cast<float*>(smem_raw + off);      // [3][npad] surface points x | y | z
+  const float *spx = spts, *spy = spts + p.npad, *spz = spts + 2 * p.npad;
   uint64_t* slot_full = reinterpret_cast<uint64_t*>(S.slot_full);
   uint64_t* slot_empty = reinterpret_cast<uint64_t*>(S.slot_empty);
   uint64_t* ctx_full = reinterpret_cast<uint64_t*>(S.ctx_full);
   uint64_t* ctx_empty = reinterpret_cast<uint64_t*>(S.ctx_empty);
+  uint64_t* zq_full = reinterpret_cast<uint64_t*>(S.zq_full);
+  uint64_t* zq_empty = reinterpret_cast<uint64_t*>(S.zq_empty);
+  uint64_t* pts_full = reinterpret_cast<uint64_t*>(&S.pts_full);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < (int)CULL_NSLOT; ++s) {
       mbar_init(slot_full + s, 1);
       mbar_init(slot_empty + s, NC);
     }
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < CULL_NCTX; ++c) {
       mbar_init(ctx_full + c, 1);
       mbar_init(ctx_empty + c, NC);
     }
+    for (int s = 0; s < CULL_ZQ; ++s) {
+      mbar_init(reinterpret_cast<uint64_t*>(S.zq_full) + s, 1);
+      mbar_init(reinterpret_cast<uint64_t*>(S.zq_empty) + s, 1);
+    }
+    mbar_init(reinterpret_cast<uint64_t*>(&S.pts_full), 1);
     mbar_fence_init();
-    S.zq_tail = 0u;
-    S.zq_head = 0u;
   }
   if ((int)threadIdx.x < R.nlinks) {
     LinkMeta m;
@@ -468,8 +506,13 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
     // per item: read the header of its record, write the zero rows of the culled links (bulk stores), and -- if anything
     // is left for the point kernel -- pull the record into shared memory (one bulk copy) and the surviving links' bricks
     // into the ring (one TMA tile each).  The next item index is fetched one item ahead.
-    unsigned pub = 0, bc = 0;
+    unsigned pub = 0, bc = 0, zq_tail = 0;
     int next_item = 0;
+    if (lane == 0) {  // the robot's surface point set, staged once per call by ONE bulk copy (x | y | z, 16-byte padded)
+      const uint32_t bytes = (uint32_t)(3 * p.npad * sizeof(float));
+      mbar_expect_tx(pts_full, bytes);
+      bulk_load(spts, p.pts3, bytes, pts_full);
+    }
     if (!FUSED && lane == 0) next_item = atomicAdd(pp.work_counter, 1);
     for (;;) {
       const int item = FUSED ? next_item : __shfl_sync(0xffffffffu, next_item, 0);
@@ -490,19 +533,16 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
       // ---- the zero rows of the culled links are handed to the zero-row warp (nobody waits for them) ----
       if (p.collision && p.rows) {
         if (lane == 0) {
-          unsigned tail = S.zq_tail;
-          for (int tries = 0; tail - S.zq_head >= CULL_ZQ; ++tries) {  // queue full: the zero-row warp is behind
-            __nanosleep(200);
-            if (tries > (1 << 22)) __trap();
-          }
-          S.zq[tail % CULL_ZQ] = make_int4(b, t, (int)amask, 0);
-          __threadfence_block();
-          S.zq_tail = tail + 1;
+          const unsigned zs = zq_tail % CULL_ZQ;
+          if (zq_tail >= CULL_ZQ) mbar_wait_sleep(zq_empty + zs, ((zq_tail / CULL_ZQ) - 1) & 1);  // queue full: the zero-row warp is behind
+          S.zq[zs] = make_int4(b, t, (int)amask, 0);
+          mbar_arrive(zq_full + zs);  // (release: the entry is visible to the waiter)
         }
+        ++zq_tail;
       }
       if (amask == 0u && h1.y == 0) continue;  // k_item_fk wrote the zero Gauss-Newton block
-      const int ci = pub & 1;
-      if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
+      const int ci = pub % CULL_NCTX;
+      if (pub >= CULL_NCTX) mbar_wait_sleep(ctx_empty + ci, ((pub / CULL_NCTX) - 1) & 1);
       if (lane == 0) {
         mbar_expect_tx(ctx_full + ci, (uint32_t)sizeof(CullCtx));
         bulk_load(&S.ctx[ci], G, (uint32_t)sizeof(CullCtx), ctx_full + ci);
@@ -532,22 +572,18 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
     }
     // ---- tell the consumers to stop, drain the bulk stores ----
     {
-      const int ci = pub & 1;
-      if (pub >= 2) mbar_wait_sleep(ctx_empty + ci, ((pub >> 1) - 1) & 1);
+      const int ci = pub % CULL_NCTX;
+      if (pub >= CULL_NCTX) mbar_wait_sleep(ctx_empty + ci, ((pub / CULL_NCTX) - 1) & 1);
       if (lane == 0) {
         S.ctx[ci].b = -1;
         mbar_arrive(ctx_full + ci);
       }
     }
     if (p.collision && p.rows && lane == 0) {  // stop record for the zero-row warp
-      unsigned tail = S.zq_tail;
-      for (int tries = 0; tail - S.zq_head >= CULL_ZQ; ++tries) {
-        __nanosleep(200);
-        if (tries > (1 << 22)) __trap();
-      }
-      S.zq[tail % CULL_ZQ] = make_int4(-1, 0, 0, 0);
-      __threadfence_block();
-      S.zq_tail = tail + 1;
+      const unsigned zs = zq_tail % CULL_ZQ;
+      if (zq_tail >= CULL_ZQ) mbar_wait_sleep(zq_empty + zs, ((zq_tail / CULL_ZQ) - 1) & 1);
+      S.zq[zs] = make_int4(-1, 0, 0, 0);
+      mbar_arrive(zq_full + zs);
     }
     if (!FUSED) stamp_end(pp.ts_lin);
     return;
@@ -561,17 +597,11 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
     int my_start = 0, my_cnt = 0;
     if (lane < nlinks) { my_start = S.links[lane].pt_start; my_cnt = S.links[lane].pt_end - my_start; }
     for (unsigned head = 0;; ++head) {
-      if (lane == 0) {
-        for (int tries = 0; S.zq_tail == head; ++tries) {
-          __nanosleep(100);
-          if (tries > (1 << 23)) __trap();
-        }
-        __threadfence_block();
-      }
+      const unsigned zs = head % CULL_ZQ;
+      mbar_wait_sleep(zq_full + zs, (head / CULL_ZQ) & 1);
+      const int4 e = S.zq[zs];
       __syncwarp();
-      const int4 e = S.zq[head % CULL_ZQ];
-      __syncwarp();
-      if (lane == 0) S.zq_head = head + 1;
+      if (lane == 0) mbar_arrive(zq_empty + zs);
       const int b = e.x, t = e.y;
       if (b < 0) break;
       const unsigned amask = (unsigned)e.z;
@@ -609,9 +639,10 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
   const int gq = lane >> 2, tq = lane & 3;
   const bool obs_linear = (p.flags & GTO_FLAG_OBS_LINEAR) != 0;
   unsigned ic = 0, bc = 0;
+  mbar_wait_sleep(pts_full, 0);
   for (;; ++ic) {
-    const int ci = ic & 1;
-    mbar_wait_sleep(ctx_full + ci, (ic >> 1) & 1);
+    const int ci = ic % CULL_NCTX, ri = ic & 1;  // record slot, reduction buffer
+    mbar_wait_sleep(ctx_full + ci, (ic / CULL_NCTX) & 1);
     const CullCtx& C = S.ctx[ci];
     const int b = C.b;
     if (b < 0) break;
@@ -654,7 +685,7 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
           for (int k = 0; k < NP; ++k) J[k] = 0.f;
           float r = 0.f;
           if (act) {
-            const float x = __ldg(p.px + p0 + lane), y = __ldg(p.py + p0 + lane), z = __ldg(p.pz + p0 + lane);
+            const float x = spx[p0 + lane], y = spy[p0 + lane], z = spz[p0 + lane];
             const float wbx = F[0] * x + F[1] * y + F[2] * z + F[3];
             const float wby = F[4] * x + F[5] * y + F[6] * z + F[7];
             const float wbz = F[8] * x + F[9] * y + F[10] * z + F[11];
@@ -761,7 +792,7 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
           float w3[3] = {0.f, 0.f, 0.f}, r3[3] = {0.f, 0.f, 0.f};
           if (act) {
             const int pi = R.grip_pt_start + k0 + lane;
-            const float x = __ldg(p.px + pi), y = __ldg(p.py + pi), z = __ldg(p.pz + pi);
+            const float x = spx[pi], y = spy[pi], z = spz[pi];
 #pragma unroll
             for (int a3 = 0; a3 < 3; ++a3) {
               w3[a3] = Fg[a3 * 4 + 0] * x + Fg[a3 * 4 + 1] * y + Fg[a3 * 4 + 2] * z + Fg[a3 * 4 + 3];
@@ -804,15 +835,18 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
     }
 
     // ---- reduce over lanes / consumer warps, write the per-knot Gauss-Newton block ----
+    // sum over the 32 lanes by recursive halving: at every stage a lane keeps half of its values and hands the other half to its
+    // partner (NP/2 + NP/4 + ... + 1 shuffles, then plain butterfly steps; 9 instead of 40 for 8 values).  sum r^2 rides in the
+    // first free slot when nopt < NP.  Afterwards value k sits in the lanes selected by warp_multi_owner.
+    constexpr bool kCostRides = NOPT_CT > 0 && NOPT_CT < NP;
+    if (kCostRides) gacc[kCostRides ? NOPT_CT : 0] = cacc;
+    warp_reduce_multi<NP>(gacc, lane);
+    if (!kCostRides) {
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
+      for (int o = 16; o > 0; o >>= 1) cacc += __shfl_xor_sync(0xffffffffu, cacc, o);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cacc += __shfl_xor_sync(0xffffffffu, cacc, o);
     {
-      float* red = red_base + ((size_t)ci * NC + warp) * red_floats;
+      float* red = red_base + ((size_t)ri * NC + warp) * red_floats;
       const int c0 = 2 * tq;
       if (gq < nopt) {
         if (c0 < nopt) red[gq * nopt + c0] = acc0[0];
@@ -832,12 +866,15 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
           if (c0 + 9 < nopt) red[(gq + 8) * nopt + c0 + 9] = acc1[3];
         }
       }
-      if (lane == 0) {
+      {
         double* redd = reinterpret_cast<double*>(red + red_g0);
-#pragma unroll
-        for (int k = 0; k < NP; ++k)
-          if (k < nopt) redd[k] = gacc[k];
-        redd[nopt] = cacc;
+        const int kown = warp_multi_owner<NP>(lane);  // the value this lane holds in gacc[0] (< 0: none)
+        if (kCostRides) {
+          if (kown >= 0 && kown <= nopt) redd[kown] = gacc[0];
+        } else {
+          if (kown >= 0 && kown < nopt) redd[kown] = gacc[0];
+          if (lane == 0) redd[nopt] = cacc;
+        }
       }
     }
     const int obuf = C.obuf;
@@ -848,11 +885,11 @@ __device__ __forceinline__ void cull_body(const CullParams& pp, unsigned char* s
       for (int i = threadIdx.x; i < ntot; i += NC * 32) {
         if (i < nH) {
           float s = 0.f;
-          for (int w = 0; w < NC; ++w) s += red_base[((size_t)ci * NC + w) * red_floats + i];
+          for (int w = 0; w < NC; ++w) s += red_base[((size_t)ri * NC + w) * red_floats + i];
           p.H[obuf * p.buf_stride_H + bt * nH + i] = s;
         } else {
           double s = 0.0;
-          for (int w = 0; w < NC; ++w) s += reinterpret_cast<const double*>(red_base + ((size_t)ci * NC + w) * red_floats + red_g0)[i - nH];
+          for (int w = 0; w < NC; ++w) s += reinterpret_cast<const double*>(red_base + ((size_t)ri * NC + w) * red_floats + red_g0)[i - nH];
           if (i < nH + nopt) p.g[obuf * p.buf_stride_g + bt * nopt + (i - nH)] = s;
           else p.costp[obuf * p.buf_stride_c + bt] = s;
         }

@@ -85,10 +85,15 @@ __global__ void __launch_bounds__((CULL_MAX_CONS + 2) * 32, 2) k_solve_fused(con
           asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.slot_full[s])) : "memory");
           asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.slot_empty[s])) : "memory");
         }
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < CULL_NCTX; ++c) {
           asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.ctx_full[c])) : "memory");
           asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.ctx_empty[c])) : "memory");
         }
+        for (int z = 0; z < CULL_ZQ; ++z) {
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.zq_full[z])) : "memory");
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.zq_empty[z])) : "memory");
+        }
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.pts_full)) : "memory");
       }
       __syncthreads();
       unsigned long long c2 = prof ? gto_globaltimer() : 0ull;

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import gto_oracle as O
+from grasptrajopt_b200 import capi
 from gto.gto_models import GTORobotModel
 from gto.gto_planner import GTOPlanner
 from gto.ik_solver import IKSolver
