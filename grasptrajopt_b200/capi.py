@@ -65,6 +65,7 @@ class Options(C.Structure):
         ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("eta", C.c_double), ("noise_rel", C.c_double),
         ("bound_eps", C.c_double), ("check_every", C.c_int32), ("ftol", C.c_double), ("lambda_slow", C.c_double),
         ("slow_window", C.c_int32), ("slow_ftol", C.c_double), ("as_rounds", C.c_int32), ("lambda_reject", C.c_double), ("lambda_conv", C.c_double),
+        ("bundle", C.c_int32), ("bundle_radius", C.c_double),
     ]
 
 

@@ -324,6 +324,12 @@ struct StepParams {
   int slow_window;
   int as_rounds;
   double lambda_reject, lambda_conv;
+  int bundle;      // pieces of the gradient bundle (0 .. GTO_BUNDLE_MAX)
+  double bundle_radius;  // pieces further than this (|.|_inf, rad) from the standing point are not used
+  double* gB;      // [B][GTO_BUNDLE_MAX][T-2][n] half gradients at the bundle points
+  double* dyB;     // [B][GTO_BUNDLE_MAX][T-2][n] bundle point - standing point
+  double* FB;      // [B][GTO_BUNDLE_MAX] cost at the bundle points
+  int* nbund;      // [B] pieces held
   double* Fhist;  // [B][16] accepted cost per iteration (ring)
   double* Qc;
   double* Qt;
@@ -506,7 +512,8 @@ struct gto_ctx {
   double dt = 0, w_goal = 1, w_obs = 10, w_vel = 0.01;
   int standoff_offset = -10, use_standoff = 1, collision = 1;
   unsigned flags = 0;
-  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Fhist, outQ, outdQ, outcost;
+  DevBuf<double> qc, q_seed, Qc, Qt, F, Fp, lam, nu, pred, stepn, Fhist, outQ, outdQ, outcost, gB, dyB, FB;
+  DevBuf<int> nbund;
   DevBuf<double> q_trial, goal_tf;
   DevBuf<float> base, H, rows, result;
   DevBuf<double> g, costp;
@@ -587,6 +594,8 @@ extern "C" void gto_default_options(gto_options* o) {
   o->as_rounds = 1;
   o->lambda_reject = 1e-4;
   o->lambda_conv = 1e-2;
+  o->bundle = 3;
+  o->bundle_radius = 3e-3;
 }
 
 extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
@@ -668,7 +677,7 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   ctx->pts3.release(); ctx->chunk_start.release(); ctx->chunk_count.release();
   ctx->qc.release(); ctx->q_seed.release(); ctx->Qc.release(); ctx->Qt.release(); ctx->F.release(); ctx->Fp.release();
-  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Fhist.release();
+  ctx->lam.release(); ctx->nu.release(); ctx->pred.release(); ctx->stepn.release(); ctx->Fhist.release(); ctx->gB.release(); ctx->dyB.release(); ctx->FB.release(); ctx->nbund.release();
   ctx->outQ.release(); ctx->outdQ.release(); ctx->outcost.release();
   ctx->q_trial.release(); ctx->goal_tf.release(); ctx->base.release(); ctx->H.release(); ctx->g.release(); ctx->costp.release();
   ctx->rows.release(); ctx->result.release(); ctx->field_ids.release(); ctx->bufsel.release(); ctx->iters.release();
@@ -1092,13 +1101,21 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   st.as_rounds = std::min(4, std::max(0, (int)o.as_rounds)); st.lambda_reject = o.lambda_reject; st.lambda_conv = o.lambda_conv;
   CK(ctx->Fhist.ensure((size_t)B * 16));
   st.Fhist = ctx->Fhist.p;
+  st.bundle = std::min(GTO_BUNDLE_MAX, std::max(0, (int)o.bundle));
+  st.bundle_radius = o.bundle_radius;
+  CK(ctx->gB.ensure((size_t)B * GTO_BUNDLE_MAX * (T - 2) * n));
+  CK(ctx->dyB.ensure((size_t)B * GTO_BUNDLE_MAX * (T - 2) * n));
+  CK(ctx->FB.ensure((size_t)B * GTO_BUNDLE_MAX));
+  CK(ctx->nbund.ensure((size_t)B));
+  CK(cudaMemsetAsync(ctx->nbund.p, 0, sizeof(int) * B, ctx->stream));
+  st.gB = ctx->gB.p; st.dyB = ctx->dyB.p; st.FB = ctx->FB.p; st.nbund = ctx->nbund.p;
   st.Qc = ctx->Qc.p; st.Qt = ctx->Qt.p; st.q_trial = ctx->q_trial.p; st.H = ctx->H.p; st.g = ctx->g.p; st.costp = ctx->costp.p;
   st.buf_stride_H = (long long)B * T * n * n; st.buf_stride_g = (long long)B * T * n; st.buf_stride_c = (long long)B * T;
   st.bufsel = ctx->bufsel.p; st.F = ctx->F.p; st.Fp = ctx->Fp.p; st.lam = ctx->lam.p; st.nu = ctx->nu.p; st.pred = ctx->pred.p;
   st.stepn = ctx->stepn.p; st.iters = ctx->iters.p; st.status = ctx->status.p;
   // LM step: block cyclic reduction, one CTA per problem (k_step_cr)
   step_kernel_t step_kern = pick_step_kernel(n);
-  const size_t cr_smem = step_cr_smem_bytes(T, n);
+  const size_t cr_smem = step_cr_smem_bytes(T, n, st.bundle);
   if (cr_smem > (size_t)ctx->max_smem_optin)
     return fail(ctx, GTO_ERR_INVALID, "(T-2) * nopt^2 too large: the block-tridiagonal factor must fit in shared memory");
   if (ctx->step_smem_set != (long long)cr_smem) {

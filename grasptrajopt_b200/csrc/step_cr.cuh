@@ -10,13 +10,22 @@
 // latency bound (a few thousand flops per problem), so the depth of the dependency chain is what sets its duration.
 // Elimination in any symmetric order is stable for an SPD matrix; a non-positive pivot means the damped matrix is not
 // positive definite and the factorisation is retried with more damping, exactly as in k_step.
+//
+// Gradient bundle (gto_options.bundle, oracle lm_step / solve_lm): the trilinear field makes the objective piecewise smooth,
+// and a minimiser usually lies on a gradient jump (cell face) where a one-sided quadratic model keeps predicting a descent that
+// the other side takes back.  The (cost, gradient) of up to `bundle` points that were evaluated but are not stood on --
+// rejected trial points, iterates that were left -- are kept per problem as cutting planes piece_k(s) = e_k + g_k.s, and the
+// step minimises  max_k piece_k(s) + s'(H + lambda D)s/2 : the SAME factorisation is applied to bundle+1 right-hand sides
+// (-g_0 .. -g_K), a (K+1)-variable dual QP gives the convex weights, the step is the weighted sum.  Both gradients are already
+// there: the linearise kernel writes J^T r of the accepted AND of the trial point (double buffer).
 #pragma once
 
 #define STEP_CR_THREADS 256
+#define STEP_RED2 (16 * (GTO_BUNDLE_MAX + GTO_BUNDLE_MAX * GTO_BUNDLE_MAX))  // scratch of cta_sum_n: [values][<= 16 warps]
 
-__host__ __device__ inline size_t step_cr_smem_bytes(int T, int n) {
-  const size_t m = (size_t)(T - 2), nn = (size_t)n * n;
-  const size_t d = (size_t)2 * T * n + 7 * m * n + 3 * m * nn + 64;
+__host__ __device__ inline size_t step_cr_smem_bytes(int T, int n, int bundle) {
+  const size_t m = (size_t)(T - 2), nn = (size_t)n * n, nr = (size_t)bundle + 1;
+  const size_t d = (size_t)2 * T * n + (5 + 2 * nr) * m * n + 3 * m * nn + 64 + STEP_RED2 + 8;
   return ((d * sizeof(double) + 2 * (m * nn) * sizeof(float) + (m + 4) * sizeof(unsigned)) + 15) & ~(size_t)15;
 }
 
@@ -49,6 +58,83 @@ __device__ __forceinline__ double cta_max(double v, double* red) {
   double s = red[0];
   for (int w = 1; w < nw; ++w) s = fmax(s, red[w]);
   return s;
+}
+
+// Up to NV reductions at once (fixed tree): value i takes part when bit i of `mask` is set (uniform over the CTA); bit i of
+// `maxmask` selects max instead of sum.  red2: [NV][16]
+template <int NV>
+__device__ __forceinline__ void cta_reduce_n(double (&v)[NV], unsigned mask, unsigned maxmask, double* red2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if ((mask >> i) & 1u) v[i] = ((maxmask >> i) & 1u) ? warp_max(v[i]) : warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if ((mask >> i) & 1u) red2[i * 16 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if ((mask >> i) & 1u) {
+      double s = red2[i * 16];
+      if ((maxmask >> i) & 1u)
+        for (int w = 1; w < nw; ++w) s = fmax(s, red2[i * 16 + w]);
+      else
+        for (int w = 1; w < nw; ++w) s += red2[i * 16 + w];
+      v[i] = s;
+    }
+}
+
+// Dual of the bundle model (oracle bundle_dual / _bundle_dual, same loop): maximise b.theta + theta' M theta / 2 over
+// theta_1..K >= 0, sum <= 1 by pairwise exchange; theta_0 = 1 - sum.  Row / column 0 of M and b_0 are zero, entries beyond K
+// are zero.  Every array index is a compile-time constant (selects instead of M[ib][jb]) so that all of it stays in registers.
+__device__ __forceinline__ void bundle_dual(int K, const double (&bq)[GTO_BUNDLE_MAX + 1], const double (&M)[GTO_BUNDLE_MAX + 1][GTO_BUNDLE_MAX + 1],
+                                            double (&theta)[GTO_BUNDLE_MAX + 1]) {
+  constexpr int KM = GTO_BUNDLE_MAX;
+#pragma unroll
+  for (int k = 0; k <= KM; ++k) theta[k] = (k == 0) ? 1.0 : 0.0;
+  for (int iter = 0; iter < 24; ++iter) {
+    double G[KM + 1];
+#pragma unroll
+    for (int k = 0; k <= KM; ++k) {
+      double g = bq[k];
+#pragma unroll
+      for (int j = 1; j <= KM; ++j) g += M[k][j] * theta[j];
+      G[k] = g;
+    }
+    int ib = 0, jb = -1;
+    double Gi = G[0], Gj = 0.0, thj = 0.0;
+#pragma unroll
+    for (int k = 1; k <= KM; ++k)
+      if (k <= K && G[k] > Gi) { ib = k; Gi = G[k]; }
+#pragma unroll
+    for (int k = 0; k <= KM; ++k)
+      if (theta[k] > 0.0 && (jb < 0 || G[k] < Gj)) { jb = k; Gj = G[k]; thj = theta[k]; }
+    if (jb < 0 || ib == jb || Gi - Gj <= 1e-12 * (fabs(Gi) + fabs(Gj) + 1e-300)) break;
+    double Mii = 0.0, Mij = 0.0, Mjj = 0.0;
+#pragma unroll
+    for (int k = 0; k <= KM; ++k)
+#pragma unroll
+      for (int j = 0; j <= KM; ++j) {
+        const double mv = M[k][j];
+        if (k == ib && j == ib) Mii = mv;
+        if (k == ib && j == jb) Mij = mv;
+        if (k == jb && j == jb) Mjj = mv;
+      }
+    const double curv = -(Mii - 2.0 * Mij + Mjj);
+    double delta = curv > 0.0 ? (Gi - Gj) / curv : thj;
+    if (delta > thj) delta = thj;
+#pragma unroll
+    for (int k = 0; k <= KM; ++k) {
+      if (k == ib) theta[k] += delta;
+      if (k == jb) {
+        theta[k] -= delta;
+        if (theta[k] < 1e-15) theta[k] = 0.0;
+      }
+    }
+  }
 }
 
 // In-register Gauss-Jordan inverse of an SPD block: lane r < NP owns row r.  Returns false (uniformly) on a
@@ -94,16 +180,19 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   STEP_MARK();
   const int n = EXACT ? NP : R.nopt, T = p.T, m = T - 2, nn = n * n;
   const double a2 = p.w_vel / (p.dt * p.dt);
+  const int KB = p.bundle, mn = m * n;
   double* X = reinterpret_cast<double*>(step_smem);  // [T][n] accepted point
   double* gt = X + (size_t)T * n;                    // [m][n] gradient
   double* dd = gt + (size_t)m * n;                   // [m][n] clipped step
-  double* xs = dd + (size_t)m * n;                   // [m][n] solution of the linear system
-  double* bb = xs + (size_t)m * n;                   // [m][n] right-hand side -> D^-1 b of eliminated blocks
-  double* Dm = bb + (size_t)m * n;                   // [m][n*n] diagonal blocks -> their inverses
+  double* xs = dd + (size_t)m * n;                   // [KB+1][m][n] solutions of the linear system (0: LM step -> combined step)
+  double* bb = xs + (size_t)(KB + 1) * mn;           // [KB+1][m][n] right-hand sides -> D^-1 b of eliminated blocks
+  double* Dm = bb + (size_t)(KB + 1) * mn;           // [m][n*n] diagonal blocks -> their inverses
   double* Lm = Dm + (size_t)m * nn;                  // [m][n*n] coupling to block i - s -> D^-1 L
   double* Um = Lm + (size_t)m * nn;                  // [m][n*n] coupling to block i + s -> D^-1 U
   double* red = Um + (size_t)m * nn;                 // [64] reduction scratch
-  double* X2 = red + 64;                             // [T][n] the other of (accepted, trial) point while the decision is open
+  double* red2 = red + 64;                           // [STEP_RED2] scratch of cta_sum_n
+  double* thS = red2 + STEP_RED2;                    // [8] convex weights of the bundle pieces
+  double* X2 = thS + 8;                              // [T][n] the other of (accepted, trial) point while the decision is open
   double* dfix = X2 + (size_t)T * n;                 // [m][n] prescribed step of the variables held at a joint limit
   double* gS = dfix + (size_t)m * n;                 // [2][m][n] J^T r of both buffers (knots 2..T-1)
   float* HS = reinterpret_cast<float*>(gS + (size_t)2 * m * n);  // [2][m][n*n] Gauss-Newton blocks of both buffers
@@ -115,6 +204,14 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   // ---- everything that only depends on b is requested in one batch: the launch is latency bound, and every dependent
   //      round trip to L2 / HBM costs the better part of a microsecond ----
   int cur = p.bufsel[b];
+  const int cur0 = cur;
+  double* gBb = p.gB + (long long)b * GTO_BUNDLE_MAX * mn;    // [KB][m][n] half gradients at the bundle points y_k
+  double* dyBb = p.dyB + (long long)b * GTO_BUNDLE_MAX * mn;  // [KB][m][n] y_k - x
+  double* FBb = p.FB + (long long)b * GTO_BUNDLE_MAX;
+  int nb = (KB > 0 && it > 0) ? p.nbund[b] : 0;
+  double eB[GTO_BUNDLE_MAX + 1];  // value of piece k at the standing point (half-cost units, <= 0); uniform over the CTA
+#pragma unroll
+  for (int k = 0; k <= GTO_BUNDLE_MAX; ++k) eB[k] = 0.0;
   double lam = p.lam[b], nu = p.nu[b];
   const double Fcur = p.F[b], Fpcur = p.Fp[b], pred = p.pred[b], step = p.stepn[b];
   const int tri = 1 - cur;
@@ -209,6 +306,67 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     }
     if (it == 0 && done < 0 && p.slow_window > 0 && tid == 0) p.Fhist[(long long)b * 16] = Ft;
     if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
+    // ---- bundle update (oracle solve_lm): the point we do not stand on after this decision becomes a cutting plane; kept
+    //      pieces are re-based to the new standing point; a full bundle replaces its least active piece ----
+    if (done < 0 && it > 0 && KB > 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const double Fnew = accepted ? Ft : Fcur, Fpiece = accepted ? Fcur : Ft;
+      const double sgn = accepted ? -1.0 : 1.0;            // dy of the new piece = sgn * (trial - old)
+      const double* Xp = accepted ? X2 : X;                 // the point the piece is taken at: old iterate / rejected trial
+      const double* gp = gS + (size_t)(accepted ? cur0 : tri) * mn;
+      constexpr int KM = GTO_BUNDLE_MAX;
+      double sr[2 * KM];  // [k]: g_k . dy_k, [KM + k]: |dy_k|_inf
+      double FBv[KM];
+#pragma unroll
+      for (int k = 0; k < KM; ++k) { sr[k] = 0.0; sr[KM + k] = 0.0; FBv[k] = (k < nb) ? FBb[k] : 0.0; }
+      for (int idx = tid; idx < mn; idx += NT) {
+        const double dprev = X[2 * n + idx] - X2[2 * n + idx];
+#pragma unroll
+        for (int k = 0; k < KM; ++k)
+          if (k < nb) {
+            double dy = dyBb[(size_t)k * mn + idx];
+            if (accepted) { dy -= dprev; dyBb[(size_t)k * mn + idx] = dy; }
+            sr[k] = fma(gBb[(size_t)k * mn + idx], dy, sr[k]);
+            sr[KM + k] = fmax(sr[KM + k], fabs(dy));
+          }
+      }
+      if (nb > 0) {
+        const unsigned used = (1u << nb) - 1u;
+        cta_reduce_n<2 * KM>(sr, used | (used << KM), used << KM, red2);
+      }
+      int slot = nb;
+      double worst = 0.0;
+#pragma unroll
+      for (int k = 0; k < KM; ++k)
+        if (k < nb) {  // a piece further than bundle_radius from the standing point is not used (and is the first to be replaced)
+          const double e = sr[KM + k] > p.bundle_radius ? -1e300 : -fabs(0.5 * (FBv[k] - Fnew) - sr[k]);
+          eB[k + 1] = e;
+          if (nb >= KB && (k == 0 || e < worst)) { worst = e; slot = k; }
+        }
+      double sn = 0.0;
+      for (int idx = tid; idx < mn; idx += NT) {
+        const int i = idx / n, k = idx - i * n, t = i + 2;
+        const double x = Xp[t * n + k];
+        double gv = x - Xp[(t - 1) * n + k];
+        if (t < T - 1) gv -= Xp[(t + 1) * n + k] - x;
+        const double gtot = gp[idx] + a2 * gv;
+        const double dy = sgn * (X[t * n + k] - X2[t * n + k]);
+        gBb[(size_t)slot * mn + idx] = gtot;
+        dyBb[(size_t)slot * mn + idx] = dy;
+        sn = fma(gtot, dy, sn);
+      }
+      sn = cta_sum(sn, red);
+      {
+        const double e = step > p.bundle_radius ? -1e300 : -fabs(0.5 * (Fpiece - Fnew) - sn);
+#pragma unroll
+        for (int k = 0; k < KM; ++k)
+          if (k == slot) eB[k + 1] = e;
+      }
+      if (nb < KB) ++nb;
+      if (tid == 0) { FBb[slot] = Fpiece; p.nbund[b] = nb; }
+      __syncthreads();  // the new piece is visible to the whole CTA (global memory, same block)
+    }
     // the accepted point (the trial point becomes the accepted one)
     for (int i = tid; i < T * n; i += NT) {  // same thread -> same entries as in the staging loop above
       if (accepted) {
@@ -258,8 +416,18 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   STEP_MARK();  // 4: gradient, active set
 
   // ---------------- damped projected Gauss-Newton step: block cyclic reduction in float64 ----------------
-  constexpr int OUT_A = (2 * NP * NP + NP + 31) / 32;  // results a lane holds in phase A / B before they are written back
-  constexpr int OUT_B = (3 * NP * NP + NP + 31) / 32;
+  constexpr int OUT_A = (2 * NP * NP + (GTO_BUNDLE_MAX + 1) * NP + 31) / 32;  // results a lane holds in phase A / B before they are written back
+  constexpr int OUT_B = (3 * NP * NP + (GTO_BUNDLE_MAX + 1) * NP + 31) / 32;
+  // no piece within bundle_radius of the standing point (the usual case while the steps are long): plain Levenberg-Marquardt step.
+  // Pieces that are switched off (e = -1e300) never get weight in the dual, so skipping their solves does not change the result.
+  {
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < GTO_BUNDLE_MAX; ++k)
+      if (k < nb && eB[k + 1] > -1e299) any = true;
+    if (!any) nb = 0;
+  }
+  const int nrhs = nb + 1;  // right-hand side 0: -g (the Levenberg-Marquardt step); k: -g_k of bundle piece k
   // Active-set rounds (gto_options.as_rounds, oracle lm_step): a free variable that the step pushes beyond a joint limit is
   // moved exactly onto the limit (prescribed step dfix) and the other variables are re-solved with that step on the
   // right-hand side.  Clipping alone distorts the coupled step (the model then often predicts an increase).
@@ -289,20 +457,20 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     for (int idx = tid; idx < m * n; idx += NT) {
       const int i = idx / n, k = idx - i * n;
       const unsigned mi = fm[i];
-      double v;
       if ((mi >> k) & 1u) {
-        v = dfix[idx];
+        for (int q = 0; q < nrhs; ++q) bb[(size_t)q * mn + idx] = dfix[idx];
       } else {  // free row: -g - (coupling to the prescribed steps of the held variables)
-        v = -gt[idx];
+        double cpl = 0.0;
         if (as_round > 0) {
           const float* Hr = Hc + (size_t)i * nn + k * n;
           for (int c = 0; c < n; ++c)
-            if (c != k && ((mi >> c) & 1u)) v -= (double)Hr[c] * dfix[i * n + c];
-          if (i > 0 && ((fm[i - 1] >> k) & 1u)) v += a2 * dfix[idx - n];
-          if (i < m - 1 && ((fm[i + 1] >> k) & 1u)) v += a2 * dfix[idx + n];
+            if (c != k && ((mi >> c) & 1u)) cpl -= (double)Hr[c] * dfix[i * n + c];
+          if (i > 0 && ((fm[i - 1] >> k) & 1u)) cpl += a2 * dfix[idx - n];
+          if (i < m - 1 && ((fm[i + 1] >> k) & 1u)) cpl += a2 * dfix[idx + n];
         }
+        bb[idx] = -gt[idx] + cpl;
+        for (int q = 1; q < nrhs; ++q) bb[(size_t)q * mn + idx] = -gBb[(size_t)(q - 1) * mn + idx] + cpl;
       }
-      bb[idx] = v;
     }
     if (tid == 0) sflag[0] = 0;
     __syncthreads();
@@ -336,7 +504,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
         __syncwarp();
         // W_L = D^-1 L, W_U = D^-1 U, w = D^-1 b : outputs dealt over the 32 lanes, written back in place afterwards
         double outv[OUT_A];
-        const int nout = 2 * nn + n;
+        const int nout = 2 * nn + nrhs * n;
 #pragma unroll
         for (int o = 0; o < OUT_A; ++o) {
           const int id = lane + 32 * o;
@@ -352,8 +520,9 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
                   for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], M[k * n + c], acc);
               }
             } else {
-              const int r = id - 2 * nn;
-              for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], bi[k], acc);
+              const int qr = id - 2 * nn, q = qr / n, r = qr - q * n;
+              const double* bq = bi + (size_t)q * mn;
+              for (int k = 0; k < n; ++k) acc = fma(Di[r * n + k], bq[k], acc);
             }
           }
           outv[o] = acc;
@@ -364,7 +533,10 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
           const int id = lane + 32 * o;
           if (id < nn) Li[id] = outv[o];
           else if (id < 2 * nn) Ui[id - nn] = outv[o];
-          else if (id < nout) bi[id - 2 * nn] = outv[o];
+          else if (id < nout) {
+            const int qr = id - 2 * nn, q = qr / n, r = qr - q * n;
+            bi[(size_t)q * mn + r] = outv[o];
+          }
         }
       }
       __syncthreads();
@@ -390,7 +562,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
         const bool has1L = has1 && (i1 - s >= 0);  // j - 2s exists
         const bool has2U = has2 && (i2 + s < m);   // j + 2s exists
         double outv[OUT_B];
-        const int nout = 3 * nn + n;
+        const int nout = 3 * nn + nrhs * n;
 #pragma unroll
         for (int o = 0; o < OUT_B; ++o) {
           const int id = lane + 32 * o;
@@ -409,10 +581,11 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
                 const int rc = id - 2 * nn, r = rc / n, c = rc - r * n;
                 if (has2U) acc = -Uj[r * n + r] * WU2[r * n + c];
               } else {
-                const int r = id - 3 * nn;
-                acc = bj[r];
-                if (has2) acc = fma(-Uj[r * n + r], w2[r], acc);
-                if (has1) acc = fma(-Lj[r * n + r], w1[r], acc);
+                const int qr = id - 3 * nn, q = qr / n, r = qr - q * n;
+                const size_t qo = (size_t)q * mn;
+                acc = bj[qo + r];
+                if (has2) acc = fma(-Uj[r * n + r], w2[qo + r], acc);
+                if (has1) acc = fma(-Lj[r * n + r], w1[qo + r], acc);
               }
             } else if (id < nn) {  // D_j - U_j W_L(j+s) - L_j W_U(j-s)
               const int r = id / n, c = id - r * n;
@@ -430,12 +603,13 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
               if (has2U)
                 for (int k = 0; k < n; ++k) acc = fma(-Uj[r * n + k], WU2[k * n + c], acc);
             } else {  // b_j - U_j w(j+s) - L_j w(j-s)
-              const int r = id - 3 * nn;
-              acc = bj[r];
+              const int qr = id - 3 * nn, q = qr / n, r = qr - q * n;
+              const size_t qo = (size_t)q * mn;
+              acc = bj[qo + r];
               if (has2)
-                for (int k = 0; k < n; ++k) acc = fma(-Uj[r * n + k], w2[k], acc);
+                for (int k = 0; k < n; ++k) acc = fma(-Uj[r * n + k], w2[qo + k], acc);
               if (has1)
-                for (int k = 0; k < n; ++k) acc = fma(-Lj[r * n + k], w1[k], acc);
+                for (int k = 0; k < n; ++k) acc = fma(-Lj[r * n + k], w1[qo + k], acc);
             }
           }
           outv[o] = acc;
@@ -447,7 +621,10 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
           if (id < nn) Dj[id] = outv[o];
           else if (id < 2 * nn) Lj[id - nn] = outv[o];
           else if (id < 3 * nn) Uj[id - 2 * nn] = outv[o];
-          else if (id < nout) bj[id - 3 * nn] = outv[o];
+          else if (id < nout) {
+            const int qr = id - 3 * nn, q = qr / n, r = qr - q * n;
+            bj[(size_t)q * mn + r] = outv[o];
+          }
         }
       }
       __syncthreads();
@@ -460,23 +637,80 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       continue;
     }
     // back substitution: x_0 = w_0, then the eliminated blocks level by level, coarsest first
-    if (tid < n) xs[tid] = bb[tid];
+    for (int idx = tid; idx < nrhs * n; idx += NT) {
+      const int q = idx / n, r = idx - q * n;
+      xs[(size_t)q * mn + r] = bb[(size_t)q * mn + r];
+    }
     __syncthreads();
     for (s >>= 1; s >= 1; s >>= 1) {
       const int nel = (m - s + 2 * s - 1) / (2 * s);
-      for (int idx = tid; idx < nel * n; idx += NT) {
-        const int e = idx / n, r = idx - e * n;
+      for (int idx = tid; idx < nrhs * nel * n; idx += NT) {
+        const int q = idx / (nel * n), er = idx - q * nel * n;
+        const int e = er / n, r = er - e * n;
         const int i = s + 2 * s * e;
+        const size_t qo = (size_t)q * mn;
         const double* WL = Lm + (size_t)i * nn + r * n;
         const double* WU = Um + (size_t)i * nn + r * n;
-        double acc = bb[i * n + r];
-        const double* xl = xs + (size_t)(i - s) * n;
+        double acc = bb[qo + i * n + r];
+        const double* xl = xs + qo + (size_t)(i - s) * n;
         for (int k = 0; k < n; ++k) acc = fma(-WL[k], xl[k], acc);
         if (i + s < m) {
-          const double* xu = xs + (size_t)(i + s) * n;
+          const double* xu = xs + qo + (size_t)(i + s) * n;
           for (int k = 0; k < n; ++k) acc = fma(-WU[k], xu[k], acc);
         }
-        xs[i * n + r] = acc;
+        xs[qo + i * n + r] = acc;
+      }
+      __syncthreads();
+    }
+    if (nb > 0) {  // convex weights of the pieces (dual QP of the bundle model), combined step into xs[0]
+      constexpr int KM = GTO_BUNDLE_MAX, NV = KM + KM * KM;
+      double acc[NV];  // [k]: (g_k - g).d_0, [KM + k KM + j]: (g_k - g).(d_j - d_0)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+      for (int idx = tid; idx < mn; idx += NT) {
+        const double g0 = gt[idx], x0 = xs[idx];
+#pragma unroll
+        for (int k = 0; k < KM; ++k)
+          if (k < nb) {
+            const double dg = gBb[(size_t)k * mn + idx] - g0;
+            acc[k] = fma(dg, x0, acc[k]);
+#pragma unroll
+            for (int j = 0; j < KM; ++j)
+              if (j < nb) acc[KM + k * KM + j] = fma(dg, xs[(size_t)(j + 1) * mn + idx] - x0, acc[KM + k * KM + j]);
+          }
+      }
+      unsigned used = 0u;
+#pragma unroll
+      for (int k = 0; k < KM; ++k)
+        if (k < nb) {
+          used |= 1u << k;
+#pragma unroll
+          for (int j = 0; j < KM; ++j)
+            if (j < nb) used |= 1u << (KM + k * KM + j);
+        }
+      cta_reduce_n<NV>(acc, used, 0u, red2);
+      if (tid == 0) {
+        double bq[KM + 1], M[KM + 1][KM + 1], th[KM + 1];
+#pragma unroll
+        for (int k = 0; k <= KM; ++k) {
+          bq[k] = (k >= 1 && k <= nb) ? eB[k] + acc[k >= 1 ? k - 1 : 0] : 0.0;
+#pragma unroll
+          for (int j = 0; j <= KM; ++j)
+            M[k][j] = (k >= 1 && j >= 1 && k <= nb && j <= nb) ? 0.5 * (acc[KM + (k >= 1 ? k - 1 : 0) * KM + (j >= 1 ? j - 1 : 0)] + acc[KM + (j >= 1 ? j - 1 : 0) * KM + (k >= 1 ? k - 1 : 0)]) : 0.0;
+        }
+        bundle_dual(nb, bq, M, th);
+#pragma unroll
+        for (int k = 0; k <= KM; ++k) thS[k] = th[k];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < mn; idx += NT) {
+        const double x0 = xs[idx];
+        double sx = x0;
+        for (int k = 1; k <= nb; ++k) {
+          const double th = thS[k];
+          if (th != 0.0) sx = fma(th, xs[(size_t)k * mn + idx] - x0, sx);
+        }
+        xs[idx] = sx;
       }
       __syncthreads();
     }
@@ -519,6 +753,22 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   }
   stepmax = cta_max(stepmax, red);
   gdot = cta_sum(gdot, red);  // (the barriers inside also publish dd)
+  if (nb > 0) {  // linear part of the bundle model: max over the pieces
+    constexpr int KM = GTO_BUNDLE_MAX;
+    double lk[KM];
+#pragma unroll
+    for (int k = 0; k < KM; ++k) lk[k] = 0.0;
+    for (int idx = tid; idx < mn; idx += NT) {
+      const double dr = dd[idx];
+#pragma unroll
+      for (int k = 0; k < KM; ++k)
+        if (k < nb) lk[k] = fma(gBb[(size_t)k * mn + idx], dr, lk[k]);
+    }
+    cta_reduce_n<KM>(lk, (1u << nb) - 1u, 0u, red2);
+#pragma unroll
+    for (int k = 0; k < KM; ++k)
+      if (k < nb) gdot = fmax(gdot, eB[k + 1] + lk[k]);
+  }
   double quad = 0.0;
   for (int idx = tid; idx < m * n; idx += NT) {
     const int i = idx / n, r = idx - i * n;
@@ -576,7 +826,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
 }
 
 template <int NP, bool EXACT>
-__global__ void __launch_bounds__(STEP_CR_THREADS) k_step_cr(const StepParams p) {
+__global__ void __launch_bounds__(STEP_CR_THREADS, 2) k_step_cr(const StepParams p) {
   extern __shared__ __align__(16) unsigned char step_smem[];
   if ((int)blockIdx.x >= *p.nactive_in) return;  // written by the step kernel two launches back: may be read ahead of pdl_wait
   step_body<NP, EXACT, false>(p, step_smem, *p.robot, p.active_in[blockIdx.x], p.iter);

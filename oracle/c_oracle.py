@@ -41,7 +41,7 @@ def default_options(**kw):
     """Same defaults as gto_default_options / gto_oracle.SolverOptions (no libgto_b200 needed)."""
     o = capi.Options()
     vals = dict(max_iter=100, tol_step=1e-6, tol_grad=1e-6, lambda0=1e-3, lambda_min=1e-9, lambda_max=1e9, eta=1e-4, noise_rel=1e-6,
-                bound_eps=1e-12, check_every=4, ftol=1e-6, lambda_slow=1e30, slow_window=0, slow_ftol=1e-3, as_rounds=1, lambda_reject=1e-4, lambda_conv=1e-2)
+                bound_eps=1e-12, check_every=4, ftol=1e-6, lambda_slow=1e30, slow_window=0, slow_ftol=1e-3, as_rounds=1, lambda_reject=1e-4, lambda_conv=1e-2, bundle=3, bundle_radius=3e-3)
     vals.update(kw)
     for k, v in vals.items():
         setattr(o, k, v)

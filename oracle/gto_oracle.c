@@ -243,240 +243,375 @@ typedef struct {
   atomic_int failed;
 } job_t;
 
+/* Block-tridiagonal solve (block Thomas) of the masked, damped Gauss-Newton system with `nr` right-hand sides:
+ * diagonal blocks (H_t + a2 c_t I)(1 + lam on the diagonal), couplings -a2 I, rows / columns of held variables replaced by
+ * identity.  rhs, x: [nr][m*n]; vv: scratch [nr][m*n]; Sinv: scratch [m][n*n].  Returns 0 when a pivot block is not
+ * positive definite. */
+static int solve_masked(int m, int n, int T, const double* H /* [T][n][n] */, double a2, double lam, const unsigned char* fx,
+                        double* Sinv, int nr, double* const* rhs, double* const* x, double* vv) {
+  const int nn = n * n;
+  double u[16];
+  for (int i = 0; i < m; ++i) {
+    const int t = i + 2;
+    const double cnt = (t < T - 1) ? 2.0 : 1.0;
+    double* S = Sinv + (size_t)i * nn;
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) {
+        const int fr = fx[i * n + r], fc = fx[i * n + c];
+        double v = H[(size_t)t * nn + r * n + c];
+        if (r == c) { v += a2 * cnt; v += lam * v; }
+        if (fr || fc) v = (r == c) ? 1.0 : 0.0;
+        if (i > 0) {
+          const double cr = (fr || fx[(i - 1) * n + r]) ? 0.0 : a2, cc = (fc || fx[(i - 1) * n + c]) ? 0.0 : a2;
+          v -= cr * cc * Sinv[(size_t)(i - 1) * nn + r * n + c];
+        }
+        S[r * n + c] = v;
+      }
+    if (!gj_inverse(S, n)) return 0;
+    for (int q = 0; q < nr; ++q) {
+      double* v = vv + (size_t)q * m * n;
+      for (int r = 0; r < n; ++r) {
+        double uu = rhs[q][i * n + r];
+        if (i > 0) uu += ((fx[i * n + r] || fx[(i - 1) * n + r]) ? 0.0 : a2) * v[(i - 1) * n + r];
+        u[r] = uu;
+      }
+      for (int r = 0; r < n; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < n; ++c) s += S[r * n + c] * u[c];
+        v[i * n + r] = s;
+      }
+    }
+  }
+  for (int q = 0; q < nr; ++q) {
+    const double* v = vv + (size_t)q * m * n;
+    double* xq = x[q];
+    for (int i = m - 1; i >= 0; --i)
+      for (int r = 0; r < n; ++r) {
+        double s = v[i * n + r];
+        if (i < m - 1)
+          for (int c = 0; c < n; ++c)
+            s += Sinv[(size_t)i * nn + r * n + c] * ((fx[i * n + c] || fx[(i + 1) * n + c]) ? 0.0 : a2) * xq[(i + 1) * n + c];
+        xq[i * n + r] = s;
+      }
+  }
+  return 1;
+}
+
+/* half gradient of f over the free knots 2..T-1: J^T r of the point rows + the analytic velocity term */
+static void total_gradient(int T, int n, double a2, const double* X, const double* g, double* gt) {
+  for (int i = 0; i < T - 2; ++i)
+    for (int k = 0; k < n; ++k) {
+      const int t = i + 2;
+      double gv = X[t * n + k] - X[(t - 1) * n + k];
+      if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
+      gt[i * n + k] = g[t * n + k] + a2 * gv;
+    }
+}
+
+/* Dual of the bundle model: maximise  b.theta + theta' M theta / 2  over theta_1..K >= 0, sum <= 1 (theta_0 = 1 - sum is the
+ * weight of the model at the standing point; row / column 0 of M and b_0 are zero).  Pairwise exchange (SMO): move weight
+ * from the active piece with the smallest dual gradient to the piece with the largest.  Same loop in gto_oracle.py and
+ * step_cr.cuh. */
+static void bundle_dual(int K, const double* bq, double M[][GTO_BUNDLE_MAX + 1], double* theta) {
+  theta[0] = 1.0;
+  for (int k = 1; k <= K; ++k) theta[k] = 0.0;
+  for (int iter = 0; iter < 24; ++iter) {
+    double G[GTO_BUNDLE_MAX + 1];
+    for (int k = 0; k <= K; ++k) {
+      G[k] = bq[k];
+      for (int j = 1; j <= K; ++j) G[k] += M[k][j] * theta[j];
+    }
+    int ib = 0, jb = -1;
+    for (int k = 1; k <= K; ++k)
+      if (G[k] > G[ib]) ib = k;
+    for (int k = 0; k <= K; ++k)
+      if (theta[k] > 0.0 && (jb < 0 || G[k] < G[jb])) jb = k;
+    if (jb < 0 || ib == jb || G[ib] - G[jb] <= 1e-12 * (fabs(G[ib]) + fabs(G[jb]) + 1e-300)) break;
+    const double curv = -(M[ib][ib] - 2.0 * M[ib][jb] + M[jb][jb]);
+    double delta = curv > 0.0 ? (G[ib] - G[jb]) / curv : theta[jb];
+    if (delta > theta[jb]) delta = theta[jb];
+    theta[ib] += delta;
+    theta[jb] -= delta;
+    if (theta[jb] < 1e-15) theta[jb] = 0.0;
+  }
+}
+
 static void solve_one(job_t* J, int b) {
   const gto_robot_desc* R = J->R;
   const oracle_field* fields = J->fields;
   const gto_batch_in* in = J->in;
   const gto_options* opt = J->opt;
   gto_batch_out* out = J->out;
-  const int T = in->T, n = R->nopt, nd = R->ndof, m = T - 2, nn = n * n;
+  const int T = in->T, n = R->nopt, nd = R->ndof, m = T - 2, nn = n * n, mn = m * n;
   const double a2 = in->w_vel / (in->dt * in->dt);
-  {
-    prob_ctx P;
-    P.R = R; P.fields = fields; P.in = in; P.b = b;
-    const size_t wsz = (size_t)R->nmov * 12 + 6 * n + 2 * ((size_t)T * nd + (size_t)T * nn + (size_t)T * n + T) + 2 * (size_t)T * n +
-                       (size_t)m * nn + 5 * (size_t)m * n + 4 * n;
-    double* W = (double*)calloc(wsz, sizeof(double));
-    unsigned char* fx = (unsigned char*)calloc((size_t)m * n + 1, 1);
-    if (!W || !fx) {
-      atomic_store(&J->failed, 1);
-      free(W);
-      free(fx);
-      return;
+  const int KB = opt->bundle < 0 ? 0 : (opt->bundle > GTO_BUNDLE_MAX ? GTO_BUNDLE_MAX : opt->bundle);
+  prob_ctx P;
+  P.R = R; P.fields = fields; P.in = in; P.b = b;
+  const size_t wsz = (size_t)R->nmov * 12 + 6 * n + 2 * ((size_t)T * nd + (size_t)T * nn + (size_t)T * n + T) + 2 * (size_t)T * n +
+                     (size_t)m * nn + (size_t)mn * (5 + 3 * (GTO_BUNDLE_MAX + 1) + 2 * GTO_BUNDLE_MAX);
+  double* W = (double*)calloc(wsz, sizeof(double));
+  unsigned char* fx = (unsigned char*)calloc((size_t)mn + 1, 1);
+  if (!W || !fx) {
+    atomic_store(&J->failed, 1);
+    free(W);
+    free(fx);
+    return;
+  }
+  double* w = W;
+  P.Tm = w; w += (size_t)R->nmov * 12;
+  P.om = w; w += 3 * n;
+  P.mm = w; w += 3 * n;
+  double* Q = w; w += (size_t)T * nd;
+  double* Qt = w; w += (size_t)T * nd;
+  double* H = w; w += (size_t)T * nn;
+  double* Ht = w; w += (size_t)T * nn;
+  double* g = w; w += (size_t)T * n;
+  double* gtr = w; w += (size_t)T * n;
+  double* cp = w; w += T;
+  double* cpt = w; w += T;
+  double* X = w; w += (size_t)T * n;
+  double* Xt = w; w += (size_t)T * n;
+  double* Sinv = w; w += (size_t)m * nn;
+  double* gt = w; w += mn;    /* half gradient at the standing point */
+  double* gtt = w; w += mn;   /* half gradient at the trial point */
+  double* dd = w; w += mn;    /* clipped step */
+  double* dfix = w; w += mn;  /* prescribed step of the variables held at a bound */
+  double* sst = w; w += mn;   /* combined step before clipping */
+  double* rhsb = w; w += (size_t)mn * (GTO_BUNDLE_MAX + 1);
+  double* solb = w; w += (size_t)mn * (GTO_BUNDLE_MAX + 1);
+  double* vvb = w; w += (size_t)mn * (GTO_BUNDLE_MAX + 1);
+  double* gB = w; w += (size_t)mn * GTO_BUNDLE_MAX;   /* bundle: half gradients at the other points y_k */
+  double* dyB = w; w += (size_t)mn * GTO_BUNDLE_MAX;  /* y_k - x */
+  double FB[GTO_BUNDLE_MAX], eB[GTO_BUNDLE_MAX + 1];
+  int nb = 0;
+  double* rhs[GTO_BUNDLE_MAX + 1];
+  double* sol[GTO_BUNDLE_MAX + 1];
+  for (int q = 0; q <= GTO_BUNDLE_MAX; ++q) { rhs[q] = rhsb + (size_t)q * mn; sol[q] = solb + (size_t)q * mn; }
+  /* initial trajectory: seed projected on the constraints */
+  memcpy(Q, in->q_seed + (size_t)b * T * nd, sizeof(double) * T * nd);
+  for (int t = 0; t < T; ++t)
+    for (int k = 0; k < n; ++k) {
+      const int j = R->opt_qidx[k];
+      double v = Q[(size_t)t * nd + j];
+      if (v < R->lo[k]) v = R->lo[k];
+      if (v > R->hi[k]) v = R->hi[k];
+      if (t < 2) v = in->qc[(size_t)b * nd + j];
+      Q[(size_t)t * nd + j] = v;
+      X[(size_t)t * n + k] = v;
     }
-    double* w = W;
-    P.Tm = w; w += (size_t)R->nmov * 12;
-    P.om = w; w += 3 * n;
-    P.mm = w; w += 3 * n;
-    double* Q = w; w += (size_t)T * nd;
-    double* Qt = w; w += (size_t)T * nd;
-    double* H = w; w += (size_t)T * nn;
-    double* Ht = w; w += (size_t)T * nn;
-    double* g = w; w += (size_t)T * n;
-    double* gtr = w; w += (size_t)T * n;
-    double* cp = w; w += T;
-    double* cpt = w; w += T;
-    double* X = w; w += (size_t)T * n;
-    double* Xt = w; w += (size_t)T * n;
-    double* Sinv = w; w += (size_t)m * nn;
-    double* gt = w; w += (size_t)m * n;
-    double* vv = w; w += (size_t)m * n;
-    double* dd = w; w += (size_t)m * n;
-    double* xs = w; w += (size_t)m * n;
-    double* u = w; w += n;
-    double* xnext = w; w += n;
-    double* dfix = w; w += (size_t)m * n;  /* prescribed step of the variables held at a bound */
-    /* initial trajectory: seed projected on the constraints */
-    memcpy(Q, in->q_seed + (size_t)b * T * nd, sizeof(double) * T * nd);
-    for (int t = 0; t < T; ++t)
-      for (int k = 0; k < n; ++k) {
-        const int j = R->opt_qidx[k];
-        double v = Q[(size_t)t * nd + j];
-        if (v < R->lo[k]) v = R->lo[k];
-        if (v > R->hi[k]) v = R->hi[k];
-        if (t < 2) v = in->qc[(size_t)b * nd + j];
-        Q[(size_t)t * nd + j] = v;
-        X[(size_t)t * n + k] = v;
-      }
-    linearize(&P, Q, 0, H, g, cp);
-    double Fp = 0;
-    for (int t = 0; t < T; ++t) Fp += cp[t];
-    double F = Fp + velocity_cost(in, X, n);
-    double lam = opt->lambda0, nu = 2.0;
-    int status = GTO_STATUS_MAX_ITER, it = 0;
-    double fhist[16];
-    const int win = opt->slow_window > 15 ? 15 : opt->slow_window;
-    fhist[0] = F;
-    while (it < opt->max_iter) {
-      /* ---- lm_step ---- */
-      double pgmax = 0.0;
-      for (int i = 0; i < m; ++i)
-        for (int k = 0; k < n; ++k) {
-          const int t = i + 2;
-          double gv = X[t * n + k] - X[(t - 1) * n + k];
-          if (t < T - 1) gv -= X[(t + 1) * n + k] - X[t * n + k];
-          const double gtv = g[t * n + k] + a2 * gv;
-          const double x = X[t * n + k];
-          const int fixed = (x <= R->lo[k] + opt->bound_eps && gtv > 0.0) || (x >= R->hi[k] - opt->bound_eps && gtv < 0.0);
-          gt[i * n + k] = gtv;
-          fx[i * n + k] = (unsigned char)fixed;
-          if (!fixed && fabs(gtv) > pgmax) pgmax = fabs(gtv);
-        }
-      if (2.0 * pgmax <= opt->tol_grad) { status = GTO_STATUS_CONVERGED; break; }
-      /* Active-set rounds (gto_options.as_rounds): a free variable that the damped Gauss-Newton step pushes beyond a joint
-       * limit is moved exactly onto the limit (prescribed step dfix) and the remaining variables are re-solved with that
-       * step on the right-hand side -- one round of an active-set method for the bound-constrained quadratic model.
-       * Clipping alone (round 0) distorts the coupled step: the model then often predicts an increase and the step is
-       * rejected again and again while the damping rises. */
-      for (int i = 0; i < m * n; ++i) dfix[i] = 0.0;
-      int as_round = 0, ok;
-    resolve:
-      ok = 0;
-      for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
-        ok = 1;
-        for (int i = 0; i < m && ok; ++i) {
-          const int t = i + 2;
-          const double cnt = (t < T - 1) ? 2.0 : 1.0;
-          double* S = Sinv + (size_t)i * nn;
-          for (int r = 0; r < n; ++r)
-            for (int c = 0; c < n; ++c) {
-              const int fr = fx[i * n + r], fc = fx[i * n + c];
-              double v = H[(size_t)t * nn + r * n + c];
-              if (r == c) { v += a2 * cnt; v += lam * v; }
-              if (fr || fc) v = (r == c) ? 1.0 : 0.0;
-              if (i > 0) {
-                const double cr = (fr || fx[(i - 1) * n + r]) ? 0.0 : a2, cc = (fc || fx[(i - 1) * n + c]) ? 0.0 : a2;
-                v -= cr * cc * Sinv[(size_t)(i - 1) * nn + r * n + c];
-              }
-              S[r * n + c] = v;
-            }
+  linearize(&P, Q, 0, H, g, cp);
+  double Fp = 0;
+  for (int t = 0; t < T; ++t) Fp += cp[t];
+  double F = Fp + velocity_cost(in, X, n);
+  double lam = opt->lambda0, nu = 2.0;
+  int status = GTO_STATUS_MAX_ITER, it = 0;
+  double fhist[16];
+  const int win = opt->slow_window > 15 ? 15 : opt->slow_window;
+  fhist[0] = F;
+  eB[0] = 0.0;
+  while (it < opt->max_iter) {
+    /* ---- gradient, active set, projected-gradient test ---- */
+    double pgmax = 0.0;
+    total_gradient(T, n, a2, X, g, gt);
+    for (int i = 0; i < mn; ++i) {
+      const int k = i % n;
+      const double x = X[2 * n + i];
+      const int fixed = (x <= R->lo[k] + opt->bound_eps && gt[i] > 0.0) || (x >= R->hi[k] - opt->bound_eps && gt[i] < 0.0);
+      fx[i] = (unsigned char)fixed;
+      if (!fixed && fabs(gt[i]) > pgmax) pgmax = fabs(gt[i]);
+    }
+    if (2.0 * pgmax <= opt->tol_grad) { status = GTO_STATUS_CONVERGED; break; }
+    /* ---- bundle step: d_0 = Levenberg-Marquardt step, d_k = the same system solved for the gradient of bundle piece k;
+     *      piece_k(s) = e_k + g_k.s in half-cost units relative to f/2 (e_k <= 0: its value at the standing point).
+     * Active-set rounds (gto_options.as_rounds): a free variable that the step pushes beyond a joint limit is moved exactly onto
+     * the limit (prescribed step dfix) and the remaining variables are re-solved with that step on the right-hand side. ---- */
+    for (int i = 0; i < mn; ++i) dfix[i] = 0.0;
+    int as_round = 0, ok;
+    double theta[GTO_BUNDLE_MAX + 1];
+  resolve:
+    ok = 0;
+    for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
+      for (int q = 0; q <= nb; ++q) {
+        const double* gq = q == 0 ? gt : gB + (size_t)(q - 1) * mn;
+        for (int i = 0; i < m; ++i)
           for (int r = 0; r < n; ++r) {
-            const int fr = fx[i * n + r];
+            const int t = i + 2;
             double uu;
-            if (fr) {
+            if (fx[i * n + r]) {
               uu = dfix[i * n + r];
-            } else {  /* free row: -g - (coupling to the prescribed steps of held variables) */
-              uu = -gt[i * n + r];
+            } else { /* free row: -g - (coupling to the prescribed steps of held variables) */
+              uu = -gq[i * n + r];
               for (int c = 0; c < n; ++c)
                 if (c != r && fx[i * n + c]) uu -= H[(size_t)t * nn + r * n + c] * dfix[i * n + c];
               if (i > 0 && fx[(i - 1) * n + r]) uu += a2 * dfix[(i - 1) * n + r];
               if (i < m - 1 && fx[(i + 1) * n + r]) uu += a2 * dfix[(i + 1) * n + r];
             }
-            if (i > 0) uu += ((fr || fx[(i - 1) * n + r]) ? 0.0 : a2) * vv[(i - 1) * n + r];
-            u[r] = uu;
+            rhs[q][i * n + r] = uu;
           }
-          if (!gj_inverse(S, n)) { ok = 0; break; }
-          for (int r = 0; r < n; ++r) {
-            double v = 0.0;
-            for (int c = 0; c < n; ++c) v += S[r * n + c] * u[c];
-            vv[i * n + r] = v;
-          }
-        }
-        if (!ok) lam = fmin(opt->lambda_max, lam * 10.0);
       }
-      if (!ok) { status = GTO_STATUS_NAN; break; }
-      double stepmax = 0.0, gdot = 0.0;
-      memcpy(Xt, X, sizeof(double) * T * n);
-      for (int i = m - 1; i >= 0; --i) {
-        const int t = i + 2;
-        for (int r = 0; r < n; ++r) {
-          double x = vv[i * n + r];
-          if (i < m - 1)
-            for (int c = 0; c < n; ++c)
-              x += Sinv[(size_t)i * nn + r * n + c] * ((fx[i * n + c] || fx[(i + 1) * n + c]) ? 0.0 : a2) * xnext[c];
-          xs[i * n + r] = x;
-        }
-        for (int r = 0; r < n; ++r) {
-          xnext[r] = xs[i * n + r];
-          const double xc = X[t * n + r];
-          double xn = xc + xnext[r];
-          if (xn < R->lo[r]) xn = R->lo[r];
-          if (xn > R->hi[r]) xn = R->hi[r];
-          const double d = xn - xc;
-          Xt[t * n + r] = xn;
-          dd[i * n + r] = d;
-          if (fabs(d) > stepmax) stepmax = fabs(d);
-          gdot += gt[i * n + r] * d;
+      ok = solve_masked(m, n, T, H, a2, lam, fx, Sinv, nb + 1, rhs, sol, vvb);
+      if (!ok) lam = fmin(opt->lambda_max, lam * 10.0);
+    }
+    if (!ok) { status = GTO_STATUS_NAN; break; }
+    theta[0] = 1.0;
+    for (int k = 1; k <= nb; ++k) theta[k] = 0.0;
+    if (nb > 0) {
+      double bq[GTO_BUNDLE_MAX + 1], M[GTO_BUNDLE_MAX + 1][GTO_BUNDLE_MAX + 1];
+      for (int k = 0; k <= nb; ++k) { bq[k] = 0.0; for (int j = 0; j <= nb; ++j) M[k][j] = 0.0; }
+      for (int k = 1; k <= nb; ++k) {
+        const double* gk = gB + (size_t)(k - 1) * mn;
+        double s = eB[k];
+        for (int i = 0; i < mn; ++i) s += (gk[i] - gt[i]) * sol[0][i];
+        bq[k] = s;
+        for (int j = 1; j <= nb; ++j) {
+          double mm_ = 0.0;
+          for (int i = 0; i < mn; ++i) mm_ += (gk[i] - gt[i]) * (sol[j][i] - sol[0][i]);
+          M[k][j] = mm_;
         }
       }
-      if (as_round < opt->as_rounds) {
-        int nviol = 0;
-        for (int i = 0; i < m; ++i)
-          for (int r = 0; r < n; ++r) {
-            if (fx[i * n + r]) continue;
-            const double xc = X[(i + 2) * n + r], xn = xc + xs[i * n + r];
-            if (xn < R->lo[r]) { fx[i * n + r] = 1; dfix[i * n + r] = R->lo[r] - xc; ++nviol; }
-            else if (xn > R->hi[r]) { fx[i * n + r] = 1; dfix[i * n + r] = R->hi[r] - xc; ++nviol; }
-          }
-        if (nviol) { ++as_round; goto resolve; }
+      for (int k = 1; k <= nb; ++k)
+        for (int j = k + 1; j <= nb; ++j) { const double s = 0.5 * (M[k][j] + M[j][k]); M[k][j] = M[j][k] = s; }
+      bundle_dual(nb, bq, M, theta);
+    }
+    for (int i = 0; i < mn; ++i) {
+      double s = sol[0][i];
+      for (int k = 1; k <= nb; ++k)
+        if (theta[k] != 0.0) s += theta[k] * (sol[k][i] - sol[0][i]);
+      sst[i] = s;
+    }
+    if (as_round < opt->as_rounds) {
+      int nviol = 0;
+      for (int i = 0; i < mn; ++i) {
+        if (fx[i]) continue;
+        const int r = i % n;
+        const double xc = X[2 * n + i], xn = xc + sst[i];
+        if (xn < R->lo[r]) { fx[i] = 1; dfix[i] = R->lo[r] - xc; ++nviol; }
+        else if (xn > R->hi[r]) { fx[i] = 1; dfix[i] = R->hi[r] - xc; ++nviol; }
       }
-      double quad = 0.0;
-      for (int i = 0; i < m; ++i) {
-        const int t = i + 2;
-        const double dg = a2 * ((t < T - 1) ? 2.0 : 1.0);
-        for (int r = 0; r < n; ++r) {
-          double hd = dg * dd[i * n + r];
-          for (int c = 0; c < n; ++c) hd += H[(size_t)t * nn + r * n + c] * dd[i * n + c];
-          quad += dd[i * n + r] * hd;
-          if (i < m - 1) quad -= 2.0 * a2 * dd[i * n + r] * dd[(i + 1) * n + r];
+      if (nviol) { ++as_round; goto resolve; }
+    }
+    /* ---- trial point = clip(X + s); predicted reduction with the undamped, unmasked bundle model ---- */
+    double stepmax = 0.0;
+    memcpy(Xt, X, sizeof(double) * T * n);
+    for (int i = 0; i < mn; ++i) {
+      const int r = i % n;
+      const double xc = X[2 * n + i];
+      double xn = xc + sst[i];
+      if (xn < R->lo[r]) xn = R->lo[r];
+      if (xn > R->hi[r]) xn = R->hi[r];
+      Xt[2 * n + i] = xn;
+      dd[i] = xn - xc;
+      if (fabs(dd[i]) > stepmax) stepmax = fabs(dd[i]);
+    }
+    double lin = 0.0, quad = 0.0;
+    for (int i = 0; i < mn; ++i) lin += gt[i] * dd[i];
+    for (int k = 1; k <= nb; ++k) {
+      const double* gk = gB + (size_t)(k - 1) * mn;
+      double s = eB[k];
+      for (int i = 0; i < mn; ++i) s += gk[i] * dd[i];
+      if (s > lin) lin = s;
+    }
+    for (int i = 0; i < m; ++i) {
+      const int t = i + 2;
+      const double dg = a2 * ((t < T - 1) ? 2.0 : 1.0);
+      for (int r = 0; r < n; ++r) {
+        double hd = dg * dd[i * n + r];
+        for (int c = 0; c < n; ++c) hd += H[(size_t)t * nn + r * n + c] * dd[i * n + c];
+        quad += dd[i * n + r] * hd;
+        if (i < m - 1) quad -= 2.0 * a2 * dd[i * n + r] * dd[(i + 1) * n + r];
+      }
+    }
+    const double pred = -(lin + 0.5 * quad);
+    it += 1;
+    /* ---- evaluate the trial ---- */
+    memcpy(Qt, Q, sizeof(double) * T * nd);
+    for (int t = 2; t < T; ++t)
+      for (int k = 0; k < n; ++k) Qt[(size_t)t * nd + R->opt_qidx[k]] = Xt[t * n + k];
+    cpt[0] = cp[0]; cpt[1] = cp[1];
+    linearize(&P, Qt, 2, Ht, gtr, cpt);
+    double Fp_t = 0;
+    for (int t = 0; t < T; ++t) Fp_t += cpt[t];
+    const double Ft = Fp_t + velocity_cost(in, Xt, n);
+    if (!isfinite(Ft)) { status = GTO_STATUS_NAN; break; }
+    const double ared = 0.5 * (F - Ft), noise = opt->noise_rel * fmax(Fp, Fp_t);
+    const int acc = pred > 0.0 && ared + noise >= opt->eta * pred;
+    /* ---- bundle update: the point we do not stand on after this decision becomes a cutting plane.  Kept pieces are re-based to
+     *      the new standing point; when the bundle is full the least active piece (most negative value e_k there) is replaced ---- */
+    if (KB > 0) {
+      const double Fnew = acc ? Ft : F;
+      int slot = nb;
+      double worst = 0.0;
+      for (int k = 0; k < nb; ++k) {
+        double* dk = dyB + (size_t)k * mn;
+        const double* gk = gB + (size_t)k * mn;
+        double s1 = 0.0;
+        if (acc)
+          for (int i = 0; i < mn; ++i) dk[i] -= dd[i];
+        double rk = 0.0;
+        for (int i = 0; i < mn; ++i) {
+          s1 += gk[i] * dk[i];
+          if (fabs(dk[i]) > rk) rk = fabs(dk[i]);
         }
+        /* a piece further than bundle_radius from the standing point is not used (and is the first to be replaced) */
+        eB[k + 1] = rk > opt->bundle_radius ? -1e300 : -fabs(0.5 * (FB[k] - Fnew) - s1);
+        if (nb >= KB && (k == 0 || eB[k + 1] < worst)) { worst = eB[k + 1]; slot = k; }
       }
-      const double pred = -(gdot + 0.5 * quad);
-      it += 1;
-      /* ---- evaluate the trial ---- */
-      memcpy(Qt, Q, sizeof(double) * T * nd);
-      for (int t = 2; t < T; ++t)
-        for (int k = 0; k < n; ++k) Qt[(size_t)t * nd + R->opt_qidx[k]] = Xt[t * n + k];
-      cpt[0] = cp[0]; cpt[1] = cp[1];
-      linearize(&P, Qt, 2, Ht, gtr, cpt);
-      double Fp_t = 0;
-      for (int t = 0; t < T; ++t) Fp_t += cpt[t];
-      const double Ft = Fp_t + velocity_cost(in, Xt, n);
-      if (!isfinite(Ft)) { status = GTO_STATUS_NAN; break; }
-      const double ared = 0.5 * (F - Ft), noise = opt->noise_rel * fmax(Fp, Fp_t);
-      if (pred > 0.0 && ared + noise >= opt->eta * pred) {
-        const double rho = ared / pred, lam_used = lam, F_before = F;
-        double* tmp;
-        tmp = Q; Q = Qt; Qt = tmp;
-        tmp = X; X = Xt; Xt = tmp;
-        tmp = H; H = Ht; Ht = tmp;
-        tmp = g; g = gtr; gtr = tmp;
-        tmp = cp; cp = cpt; cpt = tmp;
-        F = Ft; Fp = Fp_t;
-        /* gain ratio clamped to [0, 1]: a step accepted only thanks to the noise allowance can have rho << 0, and Nielsen's
-         * cubic would then multiply the damping by hundreds in one step */
-        const double ww = 2.0 * fmin(fmax(rho, 0.0), 1.0) - 1.0;
-        lam = fmax(opt->lambda_min, lam * fmax(1.0 / 3.0, 1.0 - ww * ww * ww));
-        nu = 2.0;
-        /* a small step certifies a stationary point only when it was (nearly) the undamped Gauss-Newton step; under heavy
-         * damping the iterate rests on a gradient jump of the trilinear field (GTO_STATUS_SLOW, not converged) */
-        if (stepmax <= opt->tol_step) { status = (lam_used <= opt->lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW; break; }
-        if (lam_used >= opt->lambda_slow && ared <= opt->ftol * F_before) { status = GTO_STATUS_SLOW; break; }
+      double* gs = gB + (size_t)slot * mn;
+      double* ds = dyB + (size_t)slot * mn;
+      double s1 = 0.0;
+      if (acc) {
+        for (int i = 0; i < mn; ++i) { gs[i] = gt[i]; ds[i] = -dd[i]; s1 += gs[i] * ds[i]; }
+        FB[slot] = F;
       } else {
-        if (pred <= 0.0 && stepmax <= opt->tol_step) { status = (lam <= opt->lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW; break; }
-        lam = fmin(opt->lambda_max, fmax(lam * nu, opt->lambda_reject));
-        nu *= 2.0;
-        if (lam >= opt->lambda_max) { status = GTO_STATUS_STALLED; break; }
+        total_gradient(T, n, a2, Xt, gtr, gtt);
+        for (int i = 0; i < mn; ++i) { gs[i] = gtt[i]; ds[i] = dd[i]; s1 += gs[i] * ds[i]; }
+        FB[slot] = Ft;
       }
-      if (win > 0) {  /* windowed progress test on the accepted cost (acceptable-level termination, same bookkeeping as k_step_cr) */
-        if (it >= win && fhist[(it - win) & 15] - F <= opt->slow_ftol * F) { status = GTO_STATUS_SLOW; break; }
-        fhist[it & 15] = F;
-      }
+      eB[slot + 1] = stepmax > opt->bundle_radius ? -1e300 : -fabs(0.5 * (FB[slot] - Fnew) - s1);
+      if (nb < KB) ++nb;
     }
-    /* ---- unpack ---- */
-    if (out->Q) memcpy(out->Q + (size_t)b * T * nd, Q, sizeof(double) * T * nd);
-    if (out->dQ) {
-      double* dQ = out->dQ + (size_t)b * (T - 1) * nd;
-      memset(dQ, 0, sizeof(double) * (T - 1) * nd);
-      for (int t = 0; t < T - 1; ++t)
-        for (int k = 0; k < n; ++k) dQ[(size_t)t * nd + R->opt_qidx[k]] = (X[(t + 1) * n + k] - X[t * n + k]) / in->dt;
+    if (acc) {
+      const double rho = ared / pred, lam_used = lam, F_before = F;
+      double* tmp;
+      tmp = Q; Q = Qt; Qt = tmp;
+      tmp = X; X = Xt; Xt = tmp;
+      tmp = H; H = Ht; Ht = tmp;
+      tmp = g; g = gtr; gtr = tmp;
+      tmp = cp; cp = cpt; cpt = tmp;
+      F = Ft; Fp = Fp_t;
+      /* gain ratio clamped to [0, 1]: a step accepted only thanks to the noise allowance can have rho << 0, and Nielsen's
+       * cubic would then multiply the damping by hundreds in one step */
+      const double ww = 2.0 * fmin(fmax(rho, 0.0), 1.0) - 1.0;
+      lam = fmax(opt->lambda_min, lam * fmax(1.0 / 3.0, 1.0 - ww * ww * ww));
+      nu = 2.0;
+      /* a small step certifies a stationary point only when it was (nearly) the undamped step of the bundle model; under heavy
+       * damping the iterate rests on gradient jumps of the trilinear field that the bundle does not resolve (GTO_STATUS_SLOW) */
+      if (stepmax <= opt->tol_step) { status = (lam_used <= opt->lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW; break; }
+      if (lam_used >= opt->lambda_slow && ared <= opt->ftol * F_before) { status = GTO_STATUS_SLOW; break; }
+    } else {
+      if (pred <= 0.0 && stepmax <= opt->tol_step) { status = (lam <= opt->lambda_conv) ? GTO_STATUS_CONVERGED : GTO_STATUS_SLOW; break; }
+      lam = fmin(opt->lambda_max, fmax(lam * nu, opt->lambda_reject));
+      nu *= 2.0;
+      if (lam >= opt->lambda_max) { status = GTO_STATUS_STALLED; break; }
     }
-    if (out->cost) out->cost[b] = F;
-    if (out->iters) out->iters[b] = it;
-    if (out->status) out->status[b] = status;
-    free(W);
-    free(fx);
+    if (win > 0) {  /* windowed progress test on the accepted cost (acceptable-level termination, same bookkeeping as k_step_cr) */
+      if (it >= win && fhist[(it - win) & 15] - F <= opt->slow_ftol * F) { status = GTO_STATUS_SLOW; break; }
+      fhist[it & 15] = F;
+    }
   }
+  /* ---- unpack ---- */
+  if (out->Q) memcpy(out->Q + (size_t)b * T * nd, Q, sizeof(double) * T * nd);
+  if (out->dQ) {
+    double* dQ = out->dQ + (size_t)b * (T - 1) * nd;
+    memset(dQ, 0, sizeof(double) * (T - 1) * nd);
+    for (int t = 0; t < T - 1; ++t)
+      for (int k = 0; k < n; ++k) dQ[(size_t)t * nd + R->opt_qidx[k]] = (X[(t + 1) * n + k] - X[t * n + k]) / in->dt;
+  }
+  if (out->cost) out->cost[b] = F;
+  if (out->iters) out->iters[b] = it;
+  if (out->status) out->status[b] = status;
+  free(W);
+  free(fx);
 }
 
 static void* worker(void* arg) {

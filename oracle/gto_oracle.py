@@ -488,6 +488,8 @@ class SolverOptions:
     as_rounds: int = 1  # active-set rounds per step: variables pushed beyond a limit are put on it, the rest re-solved
     lambda_reject: float = 1e-4  # a rejected step raises the damping to at least this value
     lambda_conv: float = 1e-2  # |dq| <= tol_step counts as converged only if the damping that produced the step was <= this
+    bundle_radius: float = 3e-3  # pieces further than this (|.|_inf, rad) from the standing point are ignored (replaced first)
+    bundle: int = 3  # cutting planes kept from points evaluated but not stood on (0: plain LM); see include/gto_b200.h gto_options.bundle
 
 
 STATUS_CONVERGED = 0
@@ -551,8 +553,46 @@ def _matvec(D, off, x):
     return y
 
 
-def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: SolverOptions):
-    """One damped projected Gauss-Newton step.  Returns (trial Qx, d [m,n], pred, |proj grad|_inf);
+BUNDLE_MAX = 4
+
+
+def _total_gradient(p: Problem, Qx: np.ndarray, lin: Linearization) -> np.ndarray:
+    """Half gradient of f over the free knots: J^T r of the point rows + the analytic velocity term."""
+    return _system(p, Qx, lin)[2]
+
+
+def _bundle_dual(bq: np.ndarray, M: np.ndarray) -> np.ndarray:
+    """Dual of the bundle model: maximise ``b.theta + theta' M theta / 2`` over ``theta_1..K >= 0, sum <= 1`` (theta_0 = 1 - sum is
+    the weight of the model at the standing point; row / column 0 of M and b_0 are zero) by pairwise exchange.  Same loop as
+    bundle_dual() in gto_oracle.c and step_cr.cuh."""
+    K = len(bq) - 1
+    theta = np.zeros(K + 1)
+    theta[0] = 1.0
+    for _ in range(24):
+        G = bq + M[:, 1:] @ theta[1:]
+        ib = 0
+        for k in range(1, K + 1):
+            if G[k] > G[ib]:
+                ib = k
+        jb = -1
+        for k in range(K + 1):
+            if theta[k] > 0.0 and (jb < 0 or G[k] < G[jb]):
+                jb = k
+        if jb < 0 or ib == jb or G[ib] - G[jb] <= 1e-12 * (abs(G[ib]) + abs(G[jb]) + 1e-300):
+            break
+        curv = -(M[ib, ib] - 2.0 * M[ib, jb] + M[jb, jb])
+        delta = (G[ib] - G[jb]) / curv if curv > 0.0 else theta[jb]
+        delta = min(delta, theta[jb])
+        theta[ib] += delta
+        theta[jb] -= delta
+        if theta[jb] < 1e-15:
+            theta[jb] = 0.0
+    return theta
+
+
+def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: SolverOptions, bundle=None):
+    """One damped projected Gauss-Newton step of the bundle model.  ``bundle``: list of ``(g_k [m,n], e_k)`` cutting planes
+    ``piece_k(s) = e_k + g_k.s`` (half-cost units relative to f/2, e_k <= 0).  Returns (trial Qx, d [m,n], pred, |proj grad|_inf);
     the trial is ``None`` when the projected gradient is already below ``tol_grad``."""
     tb = p.table
     D, a2, gt = _system(p, Qx, lin)
@@ -564,27 +604,59 @@ def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: So
     pgnorm = 2.0 * float(np.max(np.abs(pg))) if pg.size else 0.0
     if pgnorm <= opts.tol_grad:
         return None, np.zeros_like(gt), 0.0, pgnorm
-    Dd = D.copy()
     m, n = gt.shape
-    for i in range(m):
-        dg = np.diag(Dd[i]).copy()
-        Dd[i] += lam * np.diag(dg)
-        fi = fixed[i]
-        if fi.any():
-            Dd[i][fi, :] = 0.0
-            Dd[i][:, fi] = 0.0
-            Dd[i][fi, fi] = 1.0
-    # off-diagonal blocks are -a2*I; rows/cols of fixed variables must vanish there too.  With a
-    # scalar*I coupling this is handled by solving in the free subspace: zero the rhs of fixed
-    # variables and note that a fixed variable has d=0, so its coupling contributes nothing as long
-    # as its own equation is decoupled.  We decouple by masking in the block factorisation.
-    d = _solve_masked(Dd, -a2, -pg, fixed)
+    bundle = bundle or []
+    grads = [gt] + [gk for gk, _ in bundle]
+    evals = [0.0] + [ek for _, ek in bundle]
     # Active-set rounds: a free variable that the step pushes beyond a joint limit is moved exactly onto the limit
     # (prescribed step dfix) and the other variables are re-solved with that step on the right-hand side -- one round of an
     # active-set method for the bound-constrained quadratic model.  Clipping alone distorts the coupled step: the model
     # then often predicts an increase and the step is rejected again and again while the damping rises.
     dfix = np.zeros_like(gt)
-    for _ in range(opts.as_rounds):
+    as_round = 0
+    while True:
+        Dd = D.copy()
+        for i in range(m):
+            dg = np.diag(Dd[i]).copy()
+            Dd[i] += lam * np.diag(dg)
+            fi = fixed[i]
+            if fi.any():
+                Dd[i][fi, :] = 0.0
+                Dd[i][:, fi] = 0.0
+                Dd[i][fi, fi] = 1.0
+        sols = []
+        for gq in grads:
+            rhs = np.zeros_like(gt)
+            for i in range(m):
+                fi = fixed[i]
+                # free rows: -g - H[free, held] dfix[held] + a2 (dfix of the same joint at the neighbouring knots)
+                Hoff = D[i] - np.diag(np.diag(D[i]))
+                r = -gq[i] - Hoff @ (dfix[i] * fi)
+                if i > 0:
+                    r = r + a2 * dfix[i - 1] * fixed[i - 1]
+                if i + 1 < m:
+                    r = r + a2 * dfix[i + 1] * fixed[i + 1]
+                rhs[i] = np.where(fi, dfix[i], r)
+            sols.append(_solve_masked(Dd, -a2, rhs, fixed))
+        K = len(bundle)
+        theta = np.zeros(K + 1)
+        theta[0] = 1.0
+        if K > 0:
+            bq = np.zeros(K + 1)
+            M = np.zeros((K + 1, K + 1))
+            for k in range(1, K + 1):
+                dgk = grads[k] - gt
+                bq[k] = evals[k] + float(np.sum(dgk * sols[0]))
+                for j in range(1, K + 1):
+                    M[k, j] = float(np.sum(dgk * (sols[j] - sols[0])))
+            M = 0.5 * (M + M.T)
+            theta = _bundle_dual(bq, M)
+        d = sols[0].copy()
+        for k in range(1, K + 1):
+            if theta[k] != 0.0:
+                d += theta[k] * (sols[k] - sols[0])
+        if as_round >= opts.as_rounds:
+            break
         Xn = X + d
         viol_lo = (~fixed) & (Xn < tb.lo)
         viol_hi = (~fixed) & (Xn > tb.hi)
@@ -592,25 +664,14 @@ def lm_step(p: Problem, Qx: np.ndarray, lin: Linearization, lam: float, opts: So
             break
         dfix = np.where(viol_lo, tb.lo - X, np.where(viol_hi, tb.hi - X, dfix))
         fixed = fixed | viol_lo | viol_hi
-        rhs = np.zeros_like(gt)
-        for i in range(m):
-            fi = fixed[i]
-            Dd[i][fi, :] = 0.0
-            Dd[i][:, fi] = 0.0
-            Dd[i][fi, fi] = 1.0
-            # free rows: -g - H[free, held] dfix[held] + a2 (dfix of the same joint at the neighbouring knots)
-            Hoff = D[i] - np.diag(np.diag(D[i]))
-            r = -gt[i] - Hoff @ dfix[i]
-            if i > 0:
-                r = r + a2 * dfix[i - 1]
-            if i + 1 < m:
-                r = r + a2 * dfix[i + 1]
-            rhs[i] = np.where(fi, dfix[i], r)
-        d = _solve_masked(Dd, -a2, rhs, fixed)
+        as_round += 1
     Xn = np.clip(X + d, tb.lo, tb.hi)
     d = Xn - X
     Ad = _matvec(D, -a2, d)
-    pred = -(float(np.sum(gt * d)) + 0.5 * float(np.sum(d * Ad)))
+    lin_term = float(np.sum(gt * d))
+    for k in range(1, len(grads)):
+        lin_term = max(lin_term, evals[k] + float(np.sum(grads[k] * d)))
+    pred = -(lin_term + 0.5 * float(np.sum(d * Ad)))
     Qn = Qx.copy()
     Qn[2:] = Xn
     return Qn, d, pred, pgnorm
@@ -666,6 +727,14 @@ def unpack_solution(p: Problem, Q: np.ndarray):
     return Q, dQ
 
 
+def _piece_value(gk, Fk, dyk, F, opts) -> float:
+    """Value at the standing point (half-cost units, forced <= 0) of the cutting plane taken at ``x + dyk``; a plane further than
+    ``bundle_radius`` away is switched off."""
+    if float(np.max(np.abs(dyk))) > opts.bundle_radius:
+        return -1e300
+    return -abs(0.5 * (Fk - F) - float(np.sum(gk * dyk)))
+
+
 def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
     opts = opts or SolverOptions()
     tb = p.table
@@ -679,8 +748,11 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
     fhist = [0.0] * 16
     fhist[0] = F
     it = 0
+    KB = min(max(int(opts.bundle), 0), BUNDLE_MAX)
+    bun = []  # cutting planes [g_k, f_k, y_k - x] of points evaluated but not stood on (rejected trials, iterates left)
     while it < opts.max_iter:
-        Qx_trial, d, pred, pgnorm = lm_step(p, Q[:, oi], lin, lam, opts)
+        pieces = [(gk, _piece_value(gk, Fk, dyk, F, opts)) for gk, Fk, dyk in bun]
+        Qx_trial, d, pred, pgnorm = lm_step(p, Q[:, oi], lin, lam, opts, pieces)
         if Qx_trial is None:
             status = STATUS_CONVERGED
             break
@@ -696,7 +768,27 @@ def solve_lm(p: Problem, opts: Optional[SolverOptions] = None) -> SolveResult:
         ared = 0.5 * (F - Ft)
         noise = opts.noise_rel * max(float(np.sum(lin.cost_pts)), Fp_t)
         step = float(np.max(np.abs(d))) if d.size else 0.0
-        if pred > 0 and ared + noise >= opts.eta * pred:
+        acc = pred > 0 and ared + noise >= opts.eta * pred
+        if KB > 0:
+            # bundle update: the point we do not stand on after this decision becomes a cutting plane; kept pieces are re-based
+            # to the new standing point; a full bundle replaces its least active piece (most negative value there)
+            Fnew = Ft if acc else F
+            if acc:
+                for piece in bun:
+                    piece[2] = piece[2] - d
+                new_piece = [_total_gradient(p, Q[:, oi], lin), F, -d]
+            else:
+                new_piece = [_total_gradient(p, Qx_trial, lin_t), Ft, d.copy()]
+            if len(bun) < KB:
+                bun.append(new_piece)
+            else:
+                ev = [_piece_value(gk, Fk, dyk, Fnew, opts) for gk, Fk, dyk in bun]
+                slot = 0
+                for k in range(1, len(bun)):
+                    if ev[k] < ev[slot]:
+                        slot = k
+                bun[slot] = new_piece
+        if acc:
             rho = ared / pred if pred > 0 else 1.0
             F_before, lam_used = F, lam
             Q, lin, F = Qt, lin_t, Ft
