@@ -9,8 +9,9 @@ N=1 workload: BASELINE config C2 (Panda tabletop, 256 candidate grasps x 30 knot
 N>1 (launched by torchrun, one rank per GPU): every rank solves its own C2-sized shard (weak scaling; problems are
 independent, no collective inside the solve) and the converged trajectories are exchanged with ONE NCCL all-gather.
 
-`value`  = converged trajectories / device time of the solves, inputs already resident in HBM (CUDA events on the
-           library's stream, max over ranks).
+`value`  = converged trajectories / device time of the K solves, inputs already resident in HBM (CUDA events around the
+           timed region, max over ranks).  The K steps are issued with `--in-flight` batches at a time (continuous batching at
+           batch granularity: every batch is an independent planning call, as in the reference's per-scene loop).
 `e2e`    = the same through the public C-ABI call gto_solve_batch with pinned HOST buffers: H2D of the per-problem
            inputs, solve, D2H of Q/dQ/cost inside the timed region (wall clock between device synchronisations).
 `--impl reference` times the CPU oracle port of the same path on the host cores (the reference's CasADi/IPOPT path
@@ -51,6 +52,10 @@ def parse_args():
                     help="also time BASELINE configs[4] (C5, 16384 problems, strong sweep: 16384/N per rank) and configs[3] (C4, 4096 problems, "
                          "4096/N per rank) and report them under config.extra (the headline value stays the C2 line); 0 = skip")
     ap.add_argument("--fused", type=int, default=0, help="secondary mode: k_solve_fused (one persistent CTA per problem)")
+    ap.add_argument("--in-flight", type=int, default=3,
+                    help="batches in flight: the K steps are issued from this many host threads, each with its own context (own stream, own "
+                         "resident copy of the batch), so that the latency-bound tail of one batch (a handful of problems still iterating) "
+                         "overlaps the head of the next; 1 = one batch at a time (its latency is reported as solve_ms_per_step either way)")
     return ap.parse_args()
 
 
@@ -240,8 +245,12 @@ def run_b200(args):
     idx = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[cfg]
     # headline: weak scaling, every rank owns a full-size shard of the configuration generated from its own seed stream
     w = W.make_workload(cfg, scale=args.scale, seed=idx + 1000 * rank if world > 1 else None)
-    ctx = capi.GtoContext(local)
-    ctx.configure(fused=args.fused)
+    NF = max(1, args.in_flight)
+    ctxs = [capi.GtoContext(local) for _ in range(NF)]
+    for c in ctxs:
+        c.configure(fused=args.fused)
+    ctx = ctxs[0]
+    xch_lock = threading.Lock()
     opts = capi.default_options(slow_window=min(15, max(0, args.slow_window)), slow_ftol=args.slow_ftol) if args.slow_window > 0 else capi.default_options()
     keep = []
 
@@ -263,49 +272,88 @@ def run_b200(args):
         if args.no_jrows:
             b.flags |= capi.FLAG_NO_JROWS
         B = b.B
-        ctx.set_robot(w.table)
-        for slot, cf in w.fields.items():
-            ctx.set_field(slot, cf.cost, cf.origin, cf.pitch)
+        nf = max(1, min(NF, steps))
+        for c in ctxs[:nf]:
+            c.set_robot(w.table)
+            for slot, cf in w.fields.items():
+                c.set_field(slot, cf.cost, cf.origin, cf.pitch)
         for name in ("qc", "q_seed", "goal_tf", "base_position"):
             setattr(b, name, pin(getattr(b, name)))
         nfl = w.table.nopt * b.T + 2
-        gathered = torch.empty((world * B, nfl), dtype=torch.float32, device=dev) if world > 1 else None
+        gathered = [torch.empty((world * B, nfl), dtype=torch.float32, device=dev) for _ in range(nf)] if world > 1 else None
         xs = torch.cuda.Stream(device=dev) if world > 1 else None
 
-        def exchange():
-            """ONE all-gather of the packed trajectories, read in place from the library's device buffer; issued on a side stream
-            right after the solve has completed (gto_solve_resident is synchronous), timed with events on that stream."""
+        def exchange(i):
+            """ONE all-gather of the packed trajectories of the solve that just finished on context i, read in place from the
+            library's device buffer; issued on a side stream (gto_solve_resident is synchronous), timed with events on that
+            stream.  Collectives of the in-flight batches are serialised by a lock (identical calls, so any order matches)."""
             if world == 1:
                 return 0.0
-            ptr, n = ctx.result_device_ptr()
-            local_res = torch.as_tensor(DeviceArray(ptr, (B, n)), device=dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(xs):
-                e0.record()
-                dist.all_gather_into_tensor(gathered, local_res)
-                e1.record()
-            e1.synchronize()
-            return e0.elapsed_time(e1)
+            with xch_lock:
+                ptr, n = ctxs[i].result_device_ptr()
+                local_res = torch.as_tensor(DeviceArray(ptr, (B, n)), device=dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(xs):
+                    e0.record()
+                    dist.all_gather_into_tensor(gathered[i], local_res)
+                    e1.record()
+                e1.synchronize()
+                return e0.elapsed_time(e1)
 
-        ctx.upload_batch(b)
-        for _ in range(warmup):
-            ctx.solve_resident(opts)
-            exchange()
-        sync_all()
-        m = {"dev_ms": 0.0, "lin_ms": 0.0, "step_ms": 0.0, "xch_ms": 0.0, "launches": 0,
+        def in_flight(fn, nsteps):
+            """Runs fn(i) nsteps times in total from nf host threads (thread i owns context i); returns the CUDA-event time of
+            the region: both events are recorded on an otherwise idle stream after a device synchronisation, and every solve
+            has completed on the device when its call returns, so the interval covers all of the work."""
+            share = [nsteps // nf + (1 if i < nsteps % nf else 0) for i in range(nf)]
+            errs = []
+
+            def work(i):
+                try:
+                    torch.cuda.set_device(local)
+                    for _ in range(share[i]):
+                        fn(i)
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
+
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            th = [threading.Thread(target=work, args=(i,)) for i in range(nf)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            e1.record()
+            sync_all()
+            wall = 1e3 * (time.perf_counter() - t0)
+            if errs:
+                raise errs[0]
+            return e0.elapsed_time(e1), wall
+
+        for c in ctxs[:nf]:
+            c.upload_batch(b)
+        for i in range(nf):
+            for _ in range(warmup):
+                ctxs[i].solve_resident(opts)
+                exchange(i)
+        m = {"dev_ms": 0.0, "lin_ms": 0.0, "step_ms": 0.0, "xch_ms": 0.0, "launches": 0, "solve_ms": 0.0, "in_flight": nf,
              "prof": {"jrow_bytes": 0, "problem_iterations": 0, "linearize_launches_with_work": 0, "linearize_launches": 0}}
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            ctx.solve_resident(opts)
-            m["xch_ms"] += exchange()
-            p = ctx.profile()
-            m["dev_ms"] += p["solve_ms"]; m["lin_ms"] += p["linearize_ms"]; m["step_ms"] += p["step_ms"]; m["launches"] += p["kernel_launches"]
-            for k in m["prof"]:
-                m["prof"][k] += p[k]
-        sync_all()
-        m["wall_ms"] = 1e3 * (time.perf_counter() - t0)
+        acc_lock = threading.Lock()
+
+        def one_step(i):
+            ctxs[i].solve_resident(opts)
+            x = exchange(i)
+            p = ctxs[i].profile()
+            with acc_lock:
+                m["xch_ms"] += x
+                m["solve_ms"] += p["solve_ms"]; m["lin_ms"] += p["linearize_ms"]; m["step_ms"] += p["step_ms"]; m["launches"] += p["kernel_launches"]
+                for k in m["prof"]:
+                    m["prof"][k] += p[k]
+
+        m["dev_ms"], m["wall_ms"] = in_flight(one_step, steps)
         m["last_prof"] = ctx.profile()
-        res = ctx.download_batch()  # the result of the LAST timed solve
+        res = ctx.download_batch()  # the result of the last timed solve of context 0
         m["conv"] = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
         m["status"] = res["status"]; m["iters"] = res["iters"]
         m["ev"] = None
@@ -331,18 +379,27 @@ def run_b200(args):
                 tns = torch.empty(shp, dtype=torch.float64 if dt == np.float64 else torch.int32).pin_memory()
                 keep.append(tns)
                 out_pinned[k] = tns.numpy()
-            for _ in range(min(warmup, 2)):
-                ctx.solve_batch(b, opts, out=out_pinned)
-            sync_all()
-            t1 = time.perf_counter()
-            for _ in range(steps):
-                r2 = ctx.solve_batch(b, opts, out=out_pinned)
-                exchange()
-                p = ctx.profile()
-                m["h2d"], m["d2h"] = p["h2d_bytes"], p["d2h_bytes"]
-            sync_all()
-            m["e2e_ms"] = 1e3 * (time.perf_counter() - t1)
-            m["conv2"] = int(np.sum(r2["status"] == capi.STATUS_CONVERGED))
+            outs = [out_pinned]
+            for _ in range(1, nf):
+                o2 = {}
+                for k, v in out_pinned.items():
+                    tns = torch.empty(v.shape, dtype=torch.float64 if v.dtype == np.float64 else torch.int32).pin_memory()
+                    keep.append(tns)
+                    o2[k] = tns.numpy()
+                outs.append(o2)
+            for i in range(nf):
+                for _ in range(min(warmup, 2)):
+                    ctxs[i].solve_batch(b, opts, out=outs[i])
+            last = {}
+
+            def one_e2e(i):
+                last[i] = ctxs[i].solve_batch(b, opts, out=outs[i])
+                exchange(i)
+
+            _, m["e2e_ms"] = in_flight(one_e2e, steps)
+            p = ctx.profile()
+            m["h2d"], m["d2h"] = p["h2d_bytes"], p["d2h_bytes"]
+            m["conv2"] = int(np.sum(last[0]["status"] == capi.STATUS_CONVERGED))
         return m
 
     def over_ranks(vals_max, vals_sum):
@@ -358,9 +415,9 @@ def run_b200(args):
     sampler.start()
     m = measure(w, args.steps, args.warmup)
     clocks = sampler.stop()
-    step_dev_ms = m["dev_ms"] + m["xch_ms"]  # device time of this rank: solves (library events) + all-gather (torch events)
+    step_dev_ms = m["dev_ms"]  # device time of this rank for the K steps (CUDA events around the region: solves + all-gathers)
     (step_dev_ms_mx, e2e_ms_mx, wall_ms_mx, xch_ms_mx, solve_ms_mx), (conv_tot, conv2_tot) = over_ranks(
-        [step_dev_ms, m["e2e_ms"], m["wall_ms"], m["xch_ms"], m["dev_ms"]], [float(m["conv"]), float(m["conv2"])])
+        [step_dev_ms, m["e2e_ms"], m["wall_ms"], m["xch_ms"], m["solve_ms"]], [float(m["conv"]), float(m["conv2"])])
 
     # ---- BASELINE configs[4] (C5 strong sweep) and configs[3] (C4 sharded over the ranks): secondary lines under config.extra ----
     extra = {}
@@ -372,10 +429,10 @@ def run_b200(args):
             used = set(int(v) for v in np.concatenate([wx.batch.field_all, wx.batch.field_obs]) if v >= 0)
             wx.fields = {s_: f for s_, f in wx.fields.items() if s_ in used}
             mx_ = measure(wx, 2, 1, e2e=False, events_pass=False)
-            (t_mx, x_mx), (c_tot,) = over_ranks([mx_["dev_ms"] + mx_["xch_ms"], mx_["xch_ms"]], [float(mx_["conv"])])
+            (t_mx, x_mx), (c_tot,) = over_ranks([mx_["dev_ms"], mx_["xch_ms"]], [float(mx_["conv"])])
             pk, _ = measured_peaks()
             algx = algorithmic_bytes(wx, mx_["prof"])
-            extra[xcfg] = {"workload": wx.description, "problems_total": total, "problems_per_gpu": int(wx.batch.B), "scaling": "strong",
+            extra[xcfg] = {"workload": wx.description, "problems_total": total, "problems_per_gpu": int(wx.batch.B), "scaling": "strong", "batches_in_flight": mx_["in_flight"],
                            "converged_total": int(c_tot), "status_counts_rank0": status_dict(mx_["status"]),
                            "ms_per_step": t_mx / 2, "xch_ms_per_step": x_mx / 2, "value": c_tot * 2 / (t_mx * 1e-3), "unit": UNIT,
                            "linearize_ms_per_step_rank0": mx_["lin_ms"] / 2, "step_ms_per_step_rank0": mx_["step_ms"] / 2,
@@ -402,13 +459,17 @@ def run_b200(args):
             "data": "synthetic",
             "config": config_block(w, args, opts, world, converged=int(conv_tot), iterations_histogram=np.bincount(m["iters"], minlength=1).tolist(),
                                    status_counts_rank0=status_dict(m["status"]), wall_ms_per_step=wall_ms_mx / args.steps,
-                                   solve_ms_per_step=solve_ms_mx / args.steps, xch_ms_per_step=xch_ms_mx / args.steps,
+                                   batches_in_flight=m["in_flight"],
+                                   solve_ms_per_step=solve_ms_mx / args.steps, solve_ms_note="mean latency of one batch solve (library events on its stream) with "
+                                   f"{m['in_flight']} batches in flight; ms_per_step is the device time of the region / steps",
+                                   xch_ms_per_step=xch_ms_mx / args.steps,
                                    exchange="one NCCL all-gather of [B][nopt*T+2] f32 per step, zero-copy from the library's result buffer, side stream",
                                    **({"secondary_mode": f"slow_window={args.slow_window}, slow_ftol={args.slow_ftol}"} if args.slow_window > 0 else {}),
                                    **({"secondary_mode_fused": "k_solve_fused"} if args.fused else {}),
                                    **({"extra": extra} if extra else {})),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
-                    "timing": "wall clock between device synchronisations around gto_solve_batch with pinned host buffers"},
+                    "timing": "wall clock between device synchronisations around the K gto_solve_batch calls with pinned host buffers, "
+                              f"{m['in_flight']} calls in flight (one host thread + context each)"},
             "gpu_launches": int(m["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_linearize_cull (+ k_item_fk, its per-item pre-pass)" if not args.fused else "k_solve_fused (FK + linearise phases)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -421,6 +482,8 @@ def run_b200(args):
                                    "steps" if ev else "in-kernel %globaltimer stamps",
                          "kernel_share_of_step": (ev["lin_ms"] / ev["solve_ms"]) if ev else (m["lin_ms"] / m["dev_ms"] if m["dev_ms"] else None),
                          "whole_step_frac": alg / (m["dev_ms"] * 1e-3) / 1e9 / peak if m["dev_ms"] else None,
+                         "kernel_timing_note": "linearise / step kernel times are taken with ONE batch in flight (events pass on context 0); the stamps of the "
+                                               "timed region overlap between the in-flight batches",
                          "globaltimer_stamps": {"achieved": alg / (m["lin_ms"] * 1e-3) / 1e9 if m["lin_ms"] > 0 else None, "kernel_ms_per_step": m["lin_ms"] / args.steps,
                                                 "step_kernel_ms_per_step": m["step_ms"] / args.steps,
                                                 "note": "first CTA start .. last warp end per launch, written by the kernels inside the timed region (no event serialisation)"},
@@ -438,7 +501,8 @@ def run_b200(args):
                                     "sample": f"{len(idxs)} of {B} problems of the same workload, oracle/gto_oracle.c (projected LM, float64), "
                                               f"{int(cres['threads'])} pthreads on {ncpu} host cores, {dt:.1f} s"}
         _emit(line)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -346,7 +346,8 @@ struct StepParams {
   int* active_out;
   int* nactive_out;
   int iter;        // number of LM steps already taken by the problems in the active list
-  long long* dbg;  // k_step_cr: clock64() at phase boundaries of CTA 0 (diagnostics, NULL: off)
+  long long* dbg;  // k_step_cr: clock64() at phase boundaries of CTA 0 in the launch of iteration dbg_iter (diagnostics, NULL: off)
+  int dbg_iter;
   unsigned long long* ts;  // k_step_cr: launch time stamps (NULL: off)
   int fk_robot_smem;  // k_step_cr: the robot table fits into the shared storage that is free during the FK phase
   int do_fk;       // k_step_cr: also write the item records (FK, brick placement, culling test) of the new trial point
@@ -608,7 +609,7 @@ extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
   else if (k == "cull_nslot") { ctx->tune_nslot = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
   else if (k == "cons_warps") { ctx->tune_cons = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
   else if (k == "slot_floats") { ctx->tune_slot_floats = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
-  else if (k == "step_dbg") ctx->tune_step_dbg = value != 0;
+  else if (k == "step_dbg") ctx->tune_step_dbg = (int)value;  // iteration whose step launch records its phase clocks (0: off)
   else if (k == "fused") ctx->tune_fused = value != 0;
   else return fail(ctx, GTO_ERR_INVALID, "gto_configure: unknown key '" + k + "'");
   return GTO_OK;
@@ -1235,6 +1236,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(ctx->dbg.ensure(64));
     CK(cudaMemsetAsync(ctx->dbg.p, 0, 64 * sizeof(long long), ctx->stream));
     st.dbg = ctx->dbg.p;
+    st.dbg_iter = ctx->tune_step_dbg;
   }
   std::vector<int> h_nact(cstride);
   // per-launch durations for the profile (linearize_ms / step_ms): in-kernel %globaltimer stamps by default; CUDA events
@@ -1358,8 +1360,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   if (st.dbg) {
     long long hd[64];
     CK(cudaMemcpy(hd, ctx->dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[gto] k_step_cr phase clocks (cycles since kernel start, last launch with work, CTA 0):");
-    for (int i = 1; i < 64 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[0]);
+    fprintf(stderr, "[gto] k_step_cr phase clocks (cycles between marks, launch of iteration %d, CTA 0):", ctx->tune_step_dbg);
+    for (int i = 1; i < 32 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[i - 1]);
     fprintf(stderr, "\n[gto] k_item_fk phase clocks (cycles since pdl_wait):");
     for (int i = 33; i < 40 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[32]);
     fprintf(stderr, "\n");

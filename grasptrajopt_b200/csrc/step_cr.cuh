@@ -173,7 +173,7 @@ template <int NP, bool EXACT, bool FUSED>
 __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* step_smem, const RobotDev& R, const int b, const int it) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
   int dbg_i = 0;
-#define STEP_MARK() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
+#define STEP_MARK() do { if (p.dbg && p.iter == p.dbg_iter && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
   // Programmatic dependent launch: the per-problem solver state read below (active list, damping, accepted / trial point) was
   // written by the PREVIOUS step kernel, which completed before the linearise kernel ahead of us even started -- only the
   // Gauss-Newton blocks and costs need pdl_wait(), so the dependent round trips for the state overlap the linearise kernel.
@@ -367,6 +367,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       if (tid == 0) { FBb[slot] = Fpiece; p.nbund[b] = nb; }
       __syncthreads();  // the new piece is visible to the whole CTA (global memory, same block)
     }
+    STEP_MARK();  // 3: bundle updated
     // the accepted point (the trial point becomes the accepted one)
     for (int i = tid; i < T * n; i += NT) {  // same thread -> same entries as in the staging loop above
       if (accepted) {
@@ -385,7 +386,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   for (int i = tid; i < m; i += NT) fm[i] = 0u;
   for (int i = tid; i < m * n; i += NT) dfix[i] = 0.0;
   __syncthreads();
-  STEP_MARK();  // 3: accept / reject done
+  STEP_MARK();  // 4: accept / reject done
 
   // ---------------- gradient with the analytic velocity terms, active set, projected-gradient test ----------------
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -413,7 +414,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     }
   }
   __syncthreads();
-  STEP_MARK();  // 4: gradient, active set
+  STEP_MARK();  // 5: gradient, active set
 
   // ---------------- damped projected Gauss-Newton step: block cyclic reduction in float64 ----------------
   constexpr int OUT_A = (2 * NP * NP + (GTO_BUNDLE_MAX + 1) * NP + 31) / 32;  // results a lane holds in phase A / B before they are written back
@@ -474,7 +475,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     }
     if (tid == 0) sflag[0] = 0;
     __syncthreads();
-    STEP_MARK();  // 5: system built
+    STEP_MARK();  // 6: system built
 
     // forward: strides 1, 2, 4, ...; the last pass (s >= m) eliminates block 0, which has no neighbour left
     int s = 1;
@@ -662,6 +663,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       }
       __syncthreads();
     }
+    STEP_MARK();  // bundle weights, combined step, active-set round
     if (nb > 0) {  // convex weights of the pieces (dual QP of the bundle model), combined step into xs[0]
       constexpr int KM = GTO_BUNDLE_MAX, NV = KM + KM * KM;
       double acc[NV];  // [k]: (g_k - g).d_0, [KM + k KM + j]: (g_k - g).(d_j - d_0)

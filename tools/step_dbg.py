@@ -20,7 +20,7 @@ for bundle in (3, 0):
     o.bundle = bundle
     ctx.configure(step_dbg=0)
     ctx.solve_resident(o)
-    ctx.configure(step_dbg=1)
+    ctx.configure(step_dbg=int(os.environ.get("STEP_DBG_ITER", "30")))
     ctx.solve_resident(o)
     p = ctx.profile()
     res = ctx.download_batch()
