@@ -226,6 +226,31 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       sv += d * d;
     }
   }
+  // Bundle sums that do not depend on the decision about the trial point (the bundle was written by the previous step kernel):
+  // [k] g_k.dy_k, [KM+k] g_k.(trial - accepted), [2KM+k] |dy_k|_inf, [3KM+k] |dy_k - (trial - accepted)|_inf -- ahead of pdl_wait().
+  constexpr int KM = GTO_BUNDLE_MAX;
+  double pre[4 * KM], FBv[KM];
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    pre[k] = 0.0; pre[KM + k] = 0.0; pre[2 * KM + k] = 0.0; pre[3 * KM + k] = 0.0;
+    FBv[k] = (k < nb) ? FBb[k] : 0.0;
+  }
+  if (nb > 0) {
+    for (int idx = tid; idx < mn; idx += NT) {
+      const double dprev = Xt[2 * n + idx] - Xc[2 * n + idx];
+#pragma unroll
+      for (int k = 0; k < KM; ++k)
+        if (k < nb) {
+          const double gk = gBb[(size_t)k * mn + idx], dy = dyBb[(size_t)k * mn + idx];
+          pre[k] = fma(gk, dy, pre[k]);
+          pre[KM + k] = fma(gk, dprev, pre[KM + k]);
+          pre[2 * KM + k] = fmax(pre[2 * KM + k], fabs(dy));
+          pre[3 * KM + k] = fmax(pre[3 * KM + k], fabs(dy - dprev));
+        }
+    }
+    const unsigned used = (1u << nb) - 1u;
+    cta_reduce_n<4 * KM>(pre, used | (used << KM) | (used << (2 * KM)) | (used << (3 * KM)), (used << (2 * KM)) | (used << (3 * KM)), red2);
+  }
   if (!FUSED) {
     pdl_wait();     // from here on: results of the linearise kernel before us
     pdl_trigger();  // the successor may be scheduled (it blocks in its own pdl_wait until we are done)
@@ -242,6 +267,8 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   // ---------------- evaluate the trial point produced by the previous call ----------------
+  int slot = -1;    // bundle slot that receives the new cutting plane (-1: none)
+  double Ft0 = 0.0;  // cost of the trial point
   {
     for (int t = tid; t < T; t += NT) {
       s0 += p.costp[(long long)b * T + t];
@@ -253,6 +280,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     double* ct = p.costp + tri * p.buf_stride_c + (long long)b * T;
     const double Fp_t = tri ? s1 : s0;
     const double Ft = Fp_t + a2 * sv;
+    Ft0 = Ft;
     int done = -1;  // -1: keep running, otherwise final status
     if (!isfinite(Ft)) {
       done = GTO_STATUS_NAN;
@@ -306,76 +334,34 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
     }
     if (it == 0 && done < 0 && p.slow_window > 0 && tid == 0) p.Fhist[(long long)b * 16] = Ft;
     if (done < 0 && it >= p.max_iter) done = GTO_STATUS_MAX_ITER;
-    // ---- bundle update (oracle solve_lm): the point we do not stand on after this decision becomes a cutting plane; kept
-    //      pieces are re-based to the new standing point; a full bundle replaces its least active piece ----
+    // ---- bundle update, part 1 (oracle solve_lm): kept pieces are re-based to the new standing point; the point we do not stand on
+    //      after this decision becomes a cutting plane (its gradient is formed in the gradient loop below); a full bundle replaces
+    //      its least active piece ----
     if (done < 0 && it > 0 && KB > 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-      const double Fnew = accepted ? Ft : Fcur, Fpiece = accepted ? Fcur : Ft;
-      const double sgn = accepted ? -1.0 : 1.0;            // dy of the new piece = sgn * (trial - old)
-      const double* Xp = accepted ? X2 : X;                 // the point the piece is taken at: old iterate / rejected trial
-      const double* gp = gS + (size_t)(accepted ? cur0 : tri) * mn;
-      constexpr int KM = GTO_BUNDLE_MAX;
-      double sr[2 * KM];  // [k]: g_k . dy_k, [KM + k]: |dy_k|_inf
-      double FBv[KM];
-#pragma unroll
-      for (int k = 0; k < KM; ++k) { sr[k] = 0.0; sr[KM + k] = 0.0; FBv[k] = (k < nb) ? FBb[k] : 0.0; }
-      for (int idx = tid; idx < mn; idx += NT) {
-        const double dprev = X[2 * n + idx] - X2[2 * n + idx];
-#pragma unroll
-        for (int k = 0; k < KM; ++k)
-          if (k < nb) {
-            double dy = dyBb[(size_t)k * mn + idx];
-            if (accepted) { dy -= dprev; dyBb[(size_t)k * mn + idx] = dy; }
-            sr[k] = fma(gBb[(size_t)k * mn + idx], dy, sr[k]);
-            sr[KM + k] = fmax(sr[KM + k], fabs(dy));
-          }
-      }
-      if (nb > 0) {
-        const unsigned used = (1u << nb) - 1u;
-        cta_reduce_n<2 * KM>(sr, used | (used << KM), used << KM, red2);
-      }
-      int slot = nb;
+      const double Fnew = accepted ? Ft : Fcur;
+      slot = nb;
       double worst = 0.0;
 #pragma unroll
       for (int k = 0; k < KM; ++k)
         if (k < nb) {  // a piece further than bundle_radius from the standing point is not used (and is the first to be replaced)
-          const double e = sr[KM + k] > p.bundle_radius ? -1e300 : -fabs(0.5 * (FBv[k] - Fnew) - sr[k]);
+          const double s1 = accepted ? pre[k] - pre[KM + k] : pre[k], rk = accepted ? pre[3 * KM + k] : pre[2 * KM + k];
+          const double e = rk > p.bundle_radius ? -1e300 : -fabs(0.5 * (FBv[k] - Fnew) - s1);
           eB[k + 1] = e;
           if (nb >= KB && (k == 0 || e < worst)) { worst = e; slot = k; }
         }
-      double sn = 0.0;
-      for (int idx = tid; idx < mn; idx += NT) {
-        const int i = idx / n, k = idx - i * n, t = i + 2;
-        const double x = Xp[t * n + k];
-        double gv = x - Xp[(t - 1) * n + k];
-        if (t < T - 1) gv -= Xp[(t + 1) * n + k] - x;
-        const double gtot = gp[idx] + a2 * gv;
-        const double dy = sgn * (X[t * n + k] - X2[t * n + k]);
-        gBb[(size_t)slot * mn + idx] = gtot;
-        dyBb[(size_t)slot * mn + idx] = dy;
-        sn = fma(gtot, dy, sn);
-      }
-      sn = cta_sum(sn, red);
-      {
-        const double e = step > p.bundle_radius ? -1e300 : -fabs(0.5 * (Fpiece - Fnew) - sn);
-#pragma unroll
-        for (int k = 0; k < KM; ++k)
-          if (k == slot) eB[k + 1] = e;
-      }
-      if (nb < KB) ++nb;
-      if (tid == 0) { FBb[slot] = Fpiece; p.nbund[b] = nb; }
-      __syncthreads();  // the new piece is visible to the whole CTA (global memory, same block)
-    }
-    STEP_MARK();  // 3: bundle updated
-    // the accepted point (the trial point becomes the accepted one)
-    for (int i = tid; i < T * n; i += NT) {  // same thread -> same entries as in the staging loop above
       if (accepted) {
-        if (it > 0) Xc[i] = X[i];
-      } else {
-        X[i] = X2[i];
+        for (int idx = tid; idx < mn; idx += NT) {
+          const double dprev = X[2 * n + idx] - X2[2 * n + idx];
+#pragma unroll
+          for (int k = 0; k < KM; ++k)
+            if (k < nb && k != slot) dyBb[(size_t)k * mn + idx] -= dprev;
+        }
       }
     }
+    STEP_MARK();  // 3: bundle re-based
+    // the accepted point (the trial point becomes the accepted one)
+    if (accepted && it > 0)
+      for (int i = tid; i < T * n; i += NT) Xc[i] = X[i];  // same thread -> same entries as in the staging loop above
     if (done >= 0) {
       if (tid == 0) { p.status[b] = done; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -383,6 +369,8 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       return false;
     }
   }
+  const double* Xst = accepted ? X : X2;  // the standing point (accepted trial, or the old accepted point after a rejection)
+  const double* Xot = accepted ? X2 : X;  // the other one of the two: the iterate that was left / the rejected trial
   for (int i = tid; i < m; i += NT) fm[i] = 0u;
   for (int i = tid; i < m * n; i += NT) dfix[i] = 0.0;
   __syncthreads();
@@ -394,23 +382,44 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   const float* Hc = HS + (size_t)cur * m * nn;  // knots 2..T-1 of the accepted buffer
   const double* gc = gS + (size_t)cur * m * n;
   {
-    double pgmax = 0.0;
+    // bundle update, part 2: the new cutting plane (gradient of the point we do not stand on: the other Gauss-Newton buffer + the
+    // analytic velocity term there) is formed in the same pass as the gradient of the standing point
+    const double* go = gS + (size_t)(1 - cur) * mn;
+    double pr[2] = {0.0, 0.0};  // [0] |projected gradient|_inf, [1] g_new . dy_new
     for (int idx = tid; idx < m * n; idx += NT) {
       const int i = idx / n, k = idx - i * n, t = i + 2;
-      const double x = X[t * n + k];
-      double gv = x - X[(t - 1) * n + k];
-      if (t < T - 1) gv -= X[(t + 1) * n + k] - x;
+      const double x = Xst[t * n + k];
+      double gv = x - Xst[(t - 1) * n + k];
+      if (t < T - 1) gv -= Xst[(t + 1) * n + k] - x;
       const double gtv = gc[idx] + a2 * gv;
       const bool fixed = (x <= R.lo[k] + p.bound_eps && gtv > 0.0) || (x >= R.hi[k] - p.bound_eps && gtv < 0.0);
       gt[idx] = gtv;
       if (fixed) atomicOr(fm + i, 1u << k);
-      else pgmax = fmax(pgmax, fabs(gtv));
+      else pr[0] = fmax(pr[0], fabs(gtv));
+      if (slot >= 0) {
+        const double xo = Xot[t * n + k];
+        double go_v = xo - Xot[(t - 1) * n + k];
+        if (t < T - 1) go_v -= Xot[(t + 1) * n + k] - xo;
+        const double gtot = go[idx] + a2 * go_v, dy = xo - x;
+        gBb[(size_t)slot * mn + idx] = gtot;
+        dyBb[(size_t)slot * mn + idx] = dy;
+        pr[1] = fma(gtot, dy, pr[1]);
+      }
     }
-    pgmax = cta_max(pgmax, red);
-    if (2.0 * pgmax <= p.tol_grad) {
+    cta_reduce_n<2>(pr, slot >= 0 ? 3u : 1u, 1u, red2);  // (the barriers inside also make the new piece visible to the whole CTA)
+    if (2.0 * pr[0] <= p.tol_grad) {
       if (tid == 0) { p.status[b] = GTO_STATUS_CONVERGED; p.iters[b] = it; p.lam[b] = lam; p.nu[b] = nu; }
       if (!FUSED) stamp_end(p.ts);
       return false;
+    }
+    if (slot >= 0) {
+      const double Fst = accepted ? Ft0 : Fcur, Fot = accepted ? Fcur : Ft0;
+      const double e = step > p.bundle_radius ? -1e300 : -fabs(0.5 * (Fot - Fst) - pr[1]);
+#pragma unroll
+      for (int k = 0; k < KM; ++k)
+        if (k == slot) eB[k + 1] = e;
+      if (nb < KB) ++nb;
+      if (tid == 0) { FBb[slot] = Fot; p.nbund[b] = nb; }
     }
   }
   __syncthreads();
@@ -721,7 +730,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       for (int idx = tid; idx < m * n; idx += NT) {
         const int i = idx / n, r = idx - i * n;
         if ((fm[i] >> r) & 1u) continue;
-        const double xc = X[(i + 2) * n + r], xn = xc + xs[idx];
+        const double xc = Xst[(i + 2) * n + r], xn = xc + xs[idx];
         if (xn < R.lo[r]) { dfix[idx] = R.lo[r] - xc; viol = 1; }
         else if (xn > R.hi[r]) { dfix[idx] = R.hi[r] - xc; viol = 1; }
         if (xn < R.lo[r] || xn > R.hi[r]) atomicOr(fm + i, 1u << r);
@@ -744,7 +753,7 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
   double stepmax = 0.0, gdot = 0.0;
   for (int idx = tid; idx < m * n; idx += NT) {
     const int i = idx / n, r = idx - i * n, t = i + 2;
-    const double xc = X[t * n + r];
+    const double xc = Xst[t * n + r];
     const double xn = fmin(fmax(xc + xs[idx], R.lo[r]), R.hi[r]);
     const double d = xn - xc;
     Xt[t * n + r] = xn;

@@ -1,0 +1,106 @@
+"""Bundle Levenberg-Marquardt (gto_options.bundle / bundle_radius), CPU side: the dual QP of the bundle model against an
+exhaustive solution, the cutting-plane step on a hand-made kink, and the effect on BASELINE-shaped problems (C oracle).
+The GPU-vs-oracle comparison of the same algorithm is tests/test_gpu_parity_configs.py."""
+import itertools
+
+import numpy as np
+
+import c_oracle
+import gto_oracle as O
+from helpers import small_workload
+
+
+def _dual_value(theta, bq, M):
+    return float(bq @ theta + 0.5 * theta @ M @ theta)
+
+
+def _exhaustive(bq, M):
+    """max b.theta + theta'M theta/2 over theta_1..K >= 0, sum <= 1 by enumerating the active sets (KKT on every face)."""
+    K = len(bq) - 1
+    best, best_th = 0.0, np.zeros(K + 1)
+    best_th[0] = 1.0
+    for r in range(1, K + 1):
+        for S in itertools.combinations(range(1, K + 1), r):
+            S = list(S)
+            for tight in (False, True):  # sum constraint inactive / active (theta_0 = 0)
+                A = M[np.ix_(S, S)]
+                if tight:
+                    kkt = np.block([[A, -np.ones((r, 1))], [np.ones((1, r)), np.zeros((1, 1))]])
+                    rhs = np.concatenate([-bq[S], [1.0]])
+                else:
+                    kkt, rhs = A, -bq[S]
+                try:
+                    sol = np.linalg.solve(kkt, rhs)
+                except np.linalg.LinAlgError:
+                    continue
+                th = np.zeros(K + 1)
+                th[S] = sol[:r]
+                if np.any(th < -1e-12) or th[1:].sum() > 1 + 1e-12:
+                    continue
+                th[0] = 1.0 - th[1:].sum()
+                v = _dual_value(th, bq, M)
+                if v > best + 1e-15:
+                    best, best_th = v, th
+    return best, best_th
+
+
+def test_bundle_dual_matches_exhaustive_active_set_solution():
+    rng = np.random.default_rng(5)
+    for K in (1, 2, 3, 4):
+        for _ in range(40):
+            # M = -(G A^-1 G') with rows g_k - g_0: negative semidefinite, row / column 0 zero
+            G = rng.normal(size=(K, 6)) * rng.choice([1e-3, 1.0, 30.0])
+            M = np.zeros((K + 1, K + 1))
+            M[1:, 1:] = -G @ G.T
+            bq = np.zeros(K + 1)
+            bq[1:] = rng.normal(size=K) * np.abs(M[1:, 1:]).max() - rng.random(K) * 0.1
+            th = O._bundle_dual(bq, M)
+            assert np.all(th >= 0) and abs(th.sum() - 1.0) < 1e-12
+            ref, _ = _exhaustive(bq, M)
+            got = _dual_value(th, bq, M)
+            assert got >= ref - 1e-9 * max(1.0, abs(ref)), (K, got, ref)
+
+
+def test_cutting_plane_step_stops_at_a_kink():
+    """f(x) = |x| + x^2/2 seen through the bundle model: standing at x = 0.1 (gradient 1.1) with a plane taken at the rejected
+    trial x = -0.05 (gradient -1.05, value there), the model minimiser is where the two pieces intersect -- 1.7e-3 from the kink
+    x = 0 (the plane underestimates the curved branch) -- where a one-sided Newton step would land at -1.0."""
+    x, y = 0.1, -0.05
+    f = lambda t: abs(t) + 0.5 * t * t  # noqa: E731
+    g0, g1 = 1.0 + x, -1.0 + y  # half-cost convention of the solver: model of f itself here
+    e1 = -abs((f(y) - f(x)) - g1 * (y - x))
+    a = 1.0  # model curvature
+    d0, d1 = -g0 / a, -g1 / a
+    bq = np.array([0.0, e1 + (g1 - g0) * d0])
+    M = np.array([[0.0, 0.0], [0.0, (g1 - g0) * (d1 - d0)]])
+    th = O._bundle_dual(bq, M)
+    s = d0 + th[1] * (d1 - d0)
+    s_cross = e1 / (g0 - g1)  # g0 s = e1 + g1 s
+    assert abs(s - s_cross) < 1e-12 and abs(x + s) < 2e-3 and 0.0 < th[1] < 1.0
+
+
+def test_bundle_converges_more_kink_problems_and_radius_switches_pieces_off():
+    w = small_workload("C2", None, B=32, n_field=96)
+    plain = c_oracle.solve_workload(w, options=c_oracle.default_options(bundle=0))
+    bun = c_oracle.solve_workload(w, options=c_oracle.default_options())
+    assert np.sum(bun["status"] == 0) > np.sum(plain["status"] == 0)
+    assert bun["iters"].mean() < plain["iters"].mean()
+    # both solvers minimise the same objective: wherever both converge the cost agrees, and the bundle never ends higher overall
+    both = (plain["status"] == 0) & (bun["status"] == 0)
+    assert np.abs(bun["cost"][both] - plain["cost"][both]).max() < 1e-6
+    assert bun["cost"].sum() <= plain["cost"].sum() * (1 + 1e-6)
+    # a radius of zero switches every piece off: bit-identical to the plain solver
+    off = c_oracle.solve_workload(w, options=c_oracle.default_options(bundle_radius=0.0))
+    np.testing.assert_array_equal(off["Q"], plain["Q"])
+    np.testing.assert_array_equal(off["iters"], plain["iters"])
+
+
+def test_numpy_and_c_bundle_walk_the_same_path():
+    w = small_workload("C2", "panda_small", B=3, n_field=48)
+    from helpers import problems_from_workload
+
+    c = c_oracle.solve_workload(w, nthreads=1, options=c_oracle.default_options(max_iter=30))
+    for i, p in enumerate(problems_from_workload(w)):
+        r = O.solve_lm(p, O.SolverOptions(max_iter=30))
+        assert c["iters"][i] == r.iters and c["status"][i] == r.status
+        np.testing.assert_allclose(c["Q"][i], r.Q, atol=1e-9)

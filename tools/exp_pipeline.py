@@ -12,10 +12,10 @@ import torch
 from grasptrajopt_b200 import capi, workloads as W
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 w = W.make_workload(cfg)
 ctxs = []
-for i in range(4):
+for i in range(8):
     c = capi.GtoContext(0)
     c.set_robot(w.table)
     for slot, cf in w.fields.items():
@@ -23,7 +23,7 @@ for i in range(4):
     c.upload_batch(w.batch)
     c.solve_resident()
     ctxs.append(c)
-for nf in (1, 2, 3, 4):
+for nf in (1, 2, 3, 4, 6, 8):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lat = []
