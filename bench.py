@@ -52,7 +52,7 @@ def parse_args():
                     help="also time BASELINE configs[4] (C5, 16384 problems, strong sweep: 16384/N per rank) and configs[3] (C4, 4096 problems, "
                          "4096/N per rank) and report them under config.extra (the headline value stays the C2 line); 0 = skip")
     ap.add_argument("--fused", type=int, default=0, help="secondary mode: k_solve_fused (one persistent CTA per problem)")
-    ap.add_argument("--in-flight", type=int, default=3,
+    ap.add_argument("--in-flight", type=int, default=4,
                     help="batches in flight: the K steps are issued from this many host threads, each with its own context (own stream, own "
                          "resident copy of the batch), so that the latency-bound tail of one batch (a handful of problems still iterating) "
                          "overlaps the head of the next; 1 = one batch at a time (its latency is reported as solve_ms_per_step either way)")

@@ -600,7 +600,8 @@ extern "C" void gto_default_options(gto_options* o) {
 }
 
 extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
-  if (!ctx || !key) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!key) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   const std::string k(key);
   if (k == "jrows_budget_mb") ctx->tune_jrows_budget_mb = value > 0 ? value : 24576.0;
   else if (k == "pdl") ctx->use_pdl = value != 0;
@@ -689,7 +690,8 @@ extern "C" void gto_destroy(gto_ctx* ctx) {
 }
 
 extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
-  if (!ctx || !r) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!r) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   CK(cudaSetDevice(ctx->device));
   if (r->nopt < 1 || r->nopt > GTO_MAX_OPT || r->nmov < 1 || r->nmov > GTO_MAX_MOV || r->nlinks < 1 || r->nlinks > GTO_MAX_LINKS || r->nlinks > CULL_REC_LINKS ||
       r->ndof < r->nopt || r->npoints < 1)
@@ -779,7 +781,8 @@ extern "C" int gto_set_robot(gto_ctx* ctx, const gto_robot_desc* r) {
 }
 
 extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const int32_t dims[3], const double origin[3], double pitch) {
-  if (!ctx || !cost || !dims || !origin) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!cost || !dims || !origin) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   if (slot < 0 || slot >= MAX_FIELDS) return fail(ctx, GTO_ERR_INVALID, "field slot out of range");
   if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2 || !(pitch > 0)) return fail(ctx, GTO_ERR_INVALID, "field needs >= 2 nodes per axis and pitch > 0");
   CK(cudaSetDevice(ctx->device));
@@ -1381,7 +1384,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
 }
 
 extern "C" int gto_download_batch(gto_ctx* ctx, gto_batch_out* out) {
-  if (!ctx || !out) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!out) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   if (!ctx->solved) return fail(ctx, GTO_ERR_STATE, "no solved batch to download");
   CK(cudaSetDevice(ctx->device));
   const int B = ctx->B, T = ctx->T, nd = ctx->robot_h.ndof;
@@ -1413,7 +1417,8 @@ extern "C" int gto_solve_batch(gto_ctx* ctx, const gto_batch_in* in, const gto_o
 }
 
 extern "C" int gto_result_device_ptr(gto_ctx* ctx, void** ptr, int64_t* nfloats) {
-  if (!ctx || !ptr) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!ptr) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   if (!ctx->solved) return fail(ctx, GTO_ERR_STATE, "no solved batch");
   *ptr = (void*)ctx->result.p;
   if (nfloats) *nfloats = (int64_t)ctx->robot_h.nopt * ctx->T + 2;
@@ -1421,7 +1426,8 @@ extern "C" int gto_result_device_ptr(gto_ctx* ctx, void** ptr, int64_t* nfloats)
 }
 
 extern "C" int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out* out) {
-  if (!ctx || !out) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!out) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   int rc = gto_upload_batch(ctx, in);
   if (rc) return rc;
   const RobotDev& R = ctx->robot_h;
@@ -1450,14 +1456,16 @@ extern "C" int gto_eval_batch(gto_ctx* ctx, const gto_batch_in* in, gto_eval_out
 }
 
 extern "C" int gto_get_profile(gto_ctx* ctx, gto_profile* prof) {
-  if (!ctx || !prof) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!prof) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   *prof = ctx->prof;
   return GTO_OK;
 }
 
 extern "C" int gto_plan_cost(gto_ctx* ctx, int32_t nplans, int32_t T, const double* plans, int32_t slot, const double base_position[3],
                              double* cost, double* dist) {
-  if (!ctx || !plans || !cost || nplans < 1 || T < 1) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!plans || !cost || nplans < 1 || T < 1) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   if (!ctx->has_robot) return fail(ctx, GTO_ERR_STATE, "gto_set_robot has not been called");
   if (slot < 0 || slot >= MAX_FIELDS || !ctx->fields[slot].set) return fail(ctx, GTO_ERR_INVALID, "field slot not set");
   CK(cudaSetDevice(ctx->device));
@@ -1628,7 +1636,8 @@ extern "C" int gto_cloud_backproject(gto_ctx* ctx, const float* depth, const uin
 // Mobile-base placement (BasePlanner): B problems x n goals in one launch
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" int gto_base_place(gto_ctx* ctx, const gto_base_in* in, const gto_options* user_opts, gto_base_out* out, double* kernel_ms) {
-  if (!ctx || !in || !out || !in->qc || !in->goal_tf || !out->Q || !out->y) return GTO_ERR_INVALID;
+  if (!ctx) return GTO_ERR_INVALID;
+  if (!in || !out || !in->qc || !in->goal_tf || !out->Q || !out->y) return fail(ctx, GTO_ERR_INVALID, "null or out-of-range argument");
   if (!ctx->has_robot) return fail(ctx, GTO_ERR_STATE, "gto_set_robot has not been called");
   if (in->B < 1 || in->n_goals < 1 || in->n_goals > 32) return fail(ctx, GTO_ERR_INVALID, "base placement: need B >= 1 and 1 <= n_goals <= 32");
   if (in->occupancy && (in->occ_dims[0] < 1 || in->occ_dims[1] < 1 || !(in->occ_resolution > 0)))
