@@ -244,6 +244,49 @@ def test_launch_options_do_not_change_the_result(ctx, knobs):
             np.testing.assert_array_equal(res[k], ref[k], err_msg=f"{knobs} {k}")
 
 
+def test_contexts_in_flight_give_identical_results(ctx):
+    """Several contexts solving concurrently from their own host threads (what bench.py --in-flight does: the tail of one batch
+    overlaps the head of the next) return the bits of a context running alone, and the bundle option 0 / radius 0 are the plain
+    Levenberg-Marquardt path."""
+    import threading
+
+    w = small_workload("C2", "panda_small", B=24, n_field=64)
+    ctx.set_robot(w.table)
+    upload_fields(ctx, w)
+    ref = ctx.solve_batch(w.batch)
+    others = [capi.GtoContext(0) for _ in range(3)]
+    out, errs = {}, []
+
+    def work(i, c):
+        try:
+            c.set_robot(w.table)
+            upload_fields(c, w)
+            for _ in range(3):
+                out[i] = c.solve_batch(w.batch)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i, c)) for i, c in enumerate(others)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in others:
+        c.close()
+    assert not errs, errs
+    for i in range(3):
+        for k in ("Q", "dQ", "cost", "iters", "status"):
+            np.testing.assert_array_equal(out[i][k], ref[k], err_msg=f"context {i} {k}")
+    o0 = capi.default_options()
+    o0.bundle = 0
+    o1 = capi.default_options()
+    o1.bundle_radius = 0.0
+    r0, r1 = ctx.solve_batch(w.batch, o0), ctx.solve_batch(w.batch, o1)
+    for k in ("Q", "iters", "status"):
+        np.testing.assert_array_equal(r0[k], r1[k])
+    assert np.any(r0["iters"] != ref["iters"])  # (the bundle does change the path of some problems)
+
+
 def _sub_batch(b, idx):
     import dataclasses
     idx = np.asarray(idx, dtype=np.int64)
