@@ -283,22 +283,38 @@ def run_b200(args):
         gathered = [torch.empty((world * B, nfl), dtype=torch.float32, device=dev) for _ in range(nf)] if world > 1 else None
         xs = torch.cuda.Stream(device=dev) if world > 1 else None
 
+        staging = [torch.empty((B, nfl), dtype=torch.float32, device=dev) for _ in range(nf)] if world > 1 else None
+        pending = [None] * nf
+        xch_events = []
+
         def exchange(i):
-            """ONE all-gather of the packed trajectories of the solve that just finished on context i, read in place from the
-            library's device buffer; issued on a side stream (gto_solve_resident is synchronous), timed with events on that
-            stream.  Collectives of the in-flight batches are serialised by a lock (identical calls, so any order matches)."""
+            """ONE all-gather of the packed trajectories of the solve that just finished on context i (gto_solve_resident is
+            synchronous), issued on a side stream and NOT waited for: the worker goes on with its next solve while NCCL moves the
+            data.  The library's result buffer is copied (device to device, 0.2 MB) into a per-context staging tensor first and
+            only that copy is waited for, so the next solve may overwrite the buffer.  Collectives of the in-flight batches are
+            serialised by a lock (identical calls, so any order matches across ranks); timed with events on the side stream."""
             if world == 1:
-                return 0.0
+                return
             with xch_lock:
+                if pending[i] is not None:
+                    pending[i].synchronize()  # the previous all-gather out of this staging tensor has finished
                 ptr, n = ctxs[i].result_device_ptr()
                 local_res = torch.as_tensor(DeviceArray(ptr, (B, n)), device=dev)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0, e1, ec = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
                 with torch.cuda.stream(xs):
+                    staging[i].copy_(local_res)
+                    ec.record()
                     e0.record()
-                    dist.all_gather_into_tensor(gathered[i], local_res)
+                    dist.all_gather_into_tensor(gathered[i], staging[i])
                     e1.record()
-                e1.synchronize()
-                return e0.elapsed_time(e1)
+                ec.synchronize()
+                pending[i] = e1
+                xch_events.append((e0, e1))
+
+        def xch_ms_total():
+            t = sum(e0.elapsed_time(e1) for e0, e1 in xch_events)
+            xch_events.clear()
+            return t
 
         def in_flight(fn, nsteps):
             """Runs fn(i) nsteps times in total from nf host threads (thread i owns context i); returns the CUDA-event time of
@@ -337,21 +353,23 @@ def run_b200(args):
             for _ in range(warmup):
                 ctxs[i].solve_resident(opts)
                 exchange(i)
+        sync_all()
+        xch_ms_total()
         m = {"dev_ms": 0.0, "lin_ms": 0.0, "step_ms": 0.0, "xch_ms": 0.0, "launches": 0, "solve_ms": 0.0, "in_flight": nf,
              "prof": {"jrow_bytes": 0, "problem_iterations": 0, "linearize_launches_with_work": 0, "linearize_launches": 0}}
         acc_lock = threading.Lock()
 
         def one_step(i):
             ctxs[i].solve_resident(opts)
-            x = exchange(i)
+            exchange(i)
             p = ctxs[i].profile()
             with acc_lock:
-                m["xch_ms"] += x
                 m["solve_ms"] += p["solve_ms"]; m["lin_ms"] += p["linearize_ms"]; m["step_ms"] += p["step_ms"]; m["launches"] += p["kernel_launches"]
                 for k in m["prof"]:
                     m["prof"][k] += p[k]
 
         m["dev_ms"], m["wall_ms"] = in_flight(one_step, steps)
+        m["xch_ms"] = xch_ms_total()
         m["last_prof"] = ctx.profile()
         res = ctx.download_batch()  # the result of the last timed solve of context 0
         m["conv"] = int(np.sum(res["status"] == capi.STATUS_CONVERGED))
@@ -397,6 +415,7 @@ def run_b200(args):
                 exchange(i)
 
             _, m["e2e_ms"] = in_flight(one_e2e, steps)
+            xch_ms_total()
             p = ctx.profile()
             m["h2d"], m["d2h"] = p["h2d_bytes"], p["d2h_bytes"]
             m["conv2"] = int(np.sum(last[0]["status"] == capi.STATUS_CONVERGED))
@@ -464,7 +483,7 @@ def run_b200(args):
                                    solve_ms_per_step=solve_ms_mx / args.steps, solve_ms_note="mean latency of one batch solve (library events on its stream) with "
                                    f"{m['in_flight']} batches in flight; ms_per_step is the device time of the region / steps",
                                    xch_ms_per_step=xch_ms_mx / args.steps,
-                                   exchange="one NCCL all-gather of [B][nopt*T+2] f32 per step, zero-copy from the library's result buffer, side stream",
+                                   exchange="one NCCL all-gather of [B][nopt*T+2] f32 per batch on a side stream, overlapped with the next solves (the library's result buffer is staged by one device-to-device copy)",
                                    **({"secondary_mode": f"slow_window={args.slow_window}, slow_ftol={args.slow_ftol}"} if args.slow_window > 0 else {}),
                                    **({"secondary_mode_fused": "k_solve_fused"} if args.fused else {}),
                                    **({"extra": extra} if extra else {})),

@@ -1365,6 +1365,8 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(cudaMemcpy(hd, ctx->dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[gto] k_step_cr phase clocks (cycles between marks, launch of iteration %d, CTA 0):", ctx->tune_step_dbg);
     for (int i = 1; i < 32 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[i - 1]);
+    fprintf(stderr, "\n[gto] k_step_cr launch of iteration %d: %lld CTAs reached the solve, %lld re-solved for the active set, %lld used bundle planes", ctx->tune_step_dbg,
+            hd[40], hd[41], hd[42]);
     fprintf(stderr, "\n[gto] k_item_fk phase clocks (cycles since pdl_wait):");
     for (int i = 33; i < 40 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[32]);
     fprintf(stderr, "\n");

@@ -673,6 +673,11 @@ __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* st
       __syncthreads();
     }
     STEP_MARK();  // bundle weights, combined step, active-set round
+  if (p.dbg && p.iter == p.dbg_iter && tid == 0) {  // counters of this launch: CTAs, CTAs that re-solved for the active set, CTAs with planes in use
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 40), 1ull);
+    if (as_round > 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 41), 1ull);
+    if (nb > 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 42), 1ull);
+  }
     if (nb > 0) {  // convex weights of the pieces (dual QP of the bundle model), combined step into xs[0]
       constexpr int KM = GTO_BUNDLE_MAX, NV = KM + KM * KM;
       double acc[NV];  // [k]: (g_k - g).d_0, [KM + k KM + j]: (g_k - g).(d_j - d_0)
