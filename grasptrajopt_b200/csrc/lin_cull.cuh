@@ -27,6 +27,9 @@ struct LinkMeta {
   unsigned mask;
 };
 
+#ifndef GTO_MBAR_HINT_NS
+#define GTO_MBAR_HINT_NS 2000
+#endif
 // try_wait with a suspend-time hint: the hardware parks the thread instead of burning issue slots on polling
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -37,7 +40,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(2000u)
+        : "r"(addr), "r"(parity), "r"((unsigned)GTO_MBAR_HINT_NS)
         : "memory");
     if (ok) return;
   }
