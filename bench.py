@@ -247,8 +247,10 @@ def run_b200(args):
     w = W.make_workload(cfg, scale=args.scale, seed=idx + 1000 * rank if world > 1 else None)
     NF = max(1, args.in_flight)
     ctxs = [capi.GtoContext(local) for _ in range(NF)]
+    # more solving host threads on the box than cores (8 ranks x 4 in flight on 32 cores): sleep in the polls instead of spinning
+    blocking = int(NF * world >= (os.cpu_count() or 1))
     for c in ctxs:
-        c.configure(fused=args.fused)
+        c.configure(fused=args.fused, blocking_sync=blocking)
     ctx = ctxs[0]
     xch_lock = threading.Lock()
     opts = capi.default_options(slow_window=min(15, max(0, args.slow_window)), slow_ftol=args.slow_ftol) if args.slow_window > 0 else capi.default_options()
@@ -479,7 +481,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": config_block(w, args, opts, world, converged=int(conv_tot), iterations_histogram=np.bincount(m["iters"], minlength=1).tolist(),
                                    status_counts_rank0=status_dict(m["status"]), wall_ms_per_step=wall_ms_mx / args.steps,
-                                   batches_in_flight=m["in_flight"],
+                                   batches_in_flight=m["in_flight"], host_blocking_sync=bool(blocking),
                                    solve_ms_per_step=solve_ms_mx / args.steps, solve_ms_note="mean latency of one batch solve (library events on its stream) with "
                                    f"{m['in_flight']} batches in flight; ms_per_step is the device time of the region / steps",
                                    xch_ms_per_step=xch_ms_mx / args.steps,

@@ -351,7 +351,8 @@ class GtoContext:
 
     def configure(self, **knobs):
         """Run-time tuning knobs (``gto_configure``): jrows_budget_mb, pdl, launch_events, step_fk, cull_nslot, cons_warps,
-        slot_floats, step_dbg."""
+        slot_floats, step_dbg (iteration whose step launch reports its phase clocks), fused, blocking_sync (the host thread sleeps
+        in the convergence polls instead of spinning: for more solving threads than cores)."""
         for k, v in knobs.items():
             self._check(self._lib.gto_configure(self._h, k.encode(), float(v)))
 

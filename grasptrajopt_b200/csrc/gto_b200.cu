@@ -545,6 +545,7 @@ struct gto_ctx {
   int cull_occ = 0;
   int* h_counter = nullptr;  // pinned, 16 ints
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};  // convergence polls in flight (two parities)
+  int tune_blocking_sync = 0;  // 1: the host thread sleeps in the convergence polls instead of spinning (many contexts per core)
   long long rows_per_problem = 0;
   int Bchunk = 0;
   // profiling
@@ -612,6 +613,11 @@ extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
   else if (k == "slot_floats") { ctx->tune_slot_floats = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
   else if (k == "step_dbg") ctx->tune_step_dbg = (int)value;  // iteration whose step launch records its phase clocks (0: off)
   else if (k == "fused") ctx->tune_fused = value != 0;
+  else if (k == "blocking_sync") {  // the poll events are re-created with / without cudaEventBlockingSync at the next solve
+    ctx->tune_blocking_sync = value != 0;
+    for (int i = 0; i < 2; ++i)
+      if (ctx->ev_poll[i]) { cudaEventDestroy(ctx->ev_poll[i]); ctx->ev_poll[i] = nullptr; }
+  }
   else return fail(ctx, GTO_ERR_INVALID, "gto_configure: unknown key '" + k + "'");
   return GTO_OK;
 }
@@ -643,7 +649,7 @@ extern "C" int gto_create(gto_ctx** out, int device) {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     ctx->encode = (PFN_encodeTiled)fn;
   {  // tuning defaults from the environment (read once; gto_configure changes them afterwards)
-    static const char* keys[] = {"jrows_budget_mb", "pdl", "launch_events", "step_fk", "cull_nslot", "cons_warps", "slot_floats", "step_dbg", "fused"};
+    static const char* keys[] = {"jrows_budget_mb", "pdl", "launch_events", "step_fk", "cull_nslot", "cons_warps", "slot_floats", "step_dbg", "fused", "blocking_sync"};
     for (const char* k : keys) {
       std::string e = std::string("GTO_") + k;
       for (auto& ch : e) ch = (char)toupper((unsigned char)ch);
@@ -1231,7 +1237,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   std::vector<int> ident(B);
   for (int b = 0; b < B; ++b) ident[b] = b;
   for (int i = 0; i < 2; ++i)
-    if (!ctx->ev_poll[i]) CK(cudaEventCreateWithFlags(&ctx->ev_poll[i], cudaEventDisableTiming));
+    if (!ctx->ev_poll[i]) CK(cudaEventCreateWithFlags(&ctx->ev_poll[i], cudaEventDisableTiming | (ctx->tune_blocking_sync ? cudaEventBlockingSync : 0)));
   const size_t cstride = (size_t)o.max_iter + 3;  // one counter per iteration
   CK(ctx->nactive.ensure(cstride));
   CK(ctx->work_ctr.ensure(cstride));
