@@ -347,7 +347,7 @@ struct StepParams {
   int* nactive_out;
   int iter;        // number of LM steps already taken by the problems in the active list
   long long* dbg;  // k_step_cr: clock64() at phase boundaries of CTA 0 in the launch of iteration dbg_iter (diagnostics, NULL: off)
-  int dbg_iter;
+  int dbg_iter, dbg_cta;
   unsigned long long* ts;  // k_step_cr: launch time stamps (NULL: off)
   int fk_robot_smem;  // k_step_cr: the robot table fits into the shared storage that is free during the FK phase
   int do_fk;       // k_step_cr: also write the item records (FK, brick placement, culling test) of the new trial point
@@ -545,6 +545,7 @@ struct gto_ctx {
   int cull_occ = 0;
   int* h_counter = nullptr;  // pinned, 16 ints
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};  // convergence polls in flight (two parities)
+  int tune_step_dbg_cta = 0;  // CTA (position in the active list) whose phase clocks step_dbg records
   int tune_blocking_sync = 0;  // 1: the host thread sleeps in the convergence polls instead of spinning (many contexts per core)
   long long rows_per_problem = 0;
   int Bchunk = 0;
@@ -613,6 +614,7 @@ extern "C" int gto_configure(gto_ctx* ctx, const char* key, double value) {
   else if (k == "slot_floats") { ctx->tune_slot_floats = (int)value; ctx->cull_smem_set = ctx->fused_smem_set = -1; }
   else if (k == "step_dbg") ctx->tune_step_dbg = (int)value;  // iteration whose step launch records its phase clocks (0: off)
   else if (k == "fused") ctx->tune_fused = value != 0;
+  else if (k == "step_dbg_cta") ctx->tune_step_dbg_cta = (int)value;
   else if (k == "blocking_sync") {  // the poll events are re-created with / without cudaEventBlockingSync at the next solve
     ctx->tune_blocking_sync = value != 0;
     for (int i = 0; i < 2; ++i)
@@ -1246,6 +1248,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
     CK(cudaMemsetAsync(ctx->dbg.p, 0, 64 * sizeof(long long), ctx->stream));
     st.dbg = ctx->dbg.p;
     st.dbg_iter = ctx->tune_step_dbg;
+    st.dbg_cta = ctx->tune_step_dbg_cta;
   }
   std::vector<int> h_nact(cstride);
   // per-launch durations for the profile (linearize_ms / step_ms): in-kernel %globaltimer stamps by default; CUDA events
@@ -1369,7 +1372,7 @@ extern "C" int gto_solve_resident(gto_ctx* ctx, const gto_options* user_opts) {
   if (st.dbg) {
     long long hd[64];
     CK(cudaMemcpy(hd, ctx->dbg.p, sizeof(hd), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[gto] k_step_cr phase clocks (cycles between marks, launch of iteration %d, CTA 0):", ctx->tune_step_dbg);
+    fprintf(stderr, "[gto] k_step_cr phase clocks (cycles between marks, launch of iteration %d, CTA %d):", ctx->tune_step_dbg, ctx->tune_step_dbg_cta);
     for (int i = 1; i < 32 && hd[i]; ++i) fprintf(stderr, " %lld", hd[i] - hd[i - 1]);
     fprintf(stderr, "\n[gto] k_step_cr launch of iteration %d: %lld CTAs reached the solve, %lld re-solved for the active set, %lld used bundle planes", ctx->tune_step_dbg,
             hd[40], hd[41], hd[42]);

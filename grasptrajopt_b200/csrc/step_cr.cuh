@@ -95,6 +95,11 @@ __device__ __forceinline__ void bundle_dual(int K, const double (&bq)[GTO_BUNDLE
   constexpr int KM = GTO_BUNDLE_MAX;
 #pragma unroll
   for (int k = 0; k <= KM; ++k) theta[k] = (k == 0) ? 1.0 : 0.0;
+  // the dual gradients of the pieces with weight all vanish at an interior optimum: the stopping tolerance is relative to the
+  // largest |b_k|, not to the gradients themselves (which would never pass it and always run into the iteration cap)
+  double scale = 0.0;
+#pragma unroll
+  for (int k = 1; k <= KM; ++k) scale = fmax(scale, fabs(bq[k]));
   for (int iter = 0; iter < 24; ++iter) {
     double G[KM + 1];
 #pragma unroll
@@ -112,7 +117,7 @@ __device__ __forceinline__ void bundle_dual(int K, const double (&bq)[GTO_BUNDLE
 #pragma unroll
     for (int k = 0; k <= KM; ++k)
       if (theta[k] > 0.0 && (jb < 0 || G[k] < Gj)) { jb = k; Gj = G[k]; thj = theta[k]; }
-    if (jb < 0 || ib == jb || Gi - Gj <= 1e-12 * (fabs(Gi) + fabs(Gj) + 1e-300)) break;
+    if (jb < 0 || ib == jb || Gi - Gj <= 1e-13 * scale) break;
     double Mii = 0.0, Mij = 0.0, Mjj = 0.0;
 #pragma unroll
     for (int k = 0; k <= KM; ++k)
@@ -173,7 +178,7 @@ template <int NP, bool EXACT, bool FUSED>
 __device__ __forceinline__ bool step_body(const StepParams& p, unsigned char* step_smem, const RobotDev& R, const int b, const int it) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, NW = NT >> 5;
   int dbg_i = 0;
-#define STEP_MARK() do { if (p.dbg && p.iter == p.dbg_iter && blockIdx.x == 0 && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
+#define STEP_MARK() do { if (p.dbg && p.iter == p.dbg_iter && (int)blockIdx.x == p.dbg_cta && tid == 0 && dbg_i < 63) p.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
   // Programmatic dependent launch: the per-problem solver state read below (active list, damping, accepted / trial point) was
   // written by the PREVIOUS step kernel, which completed before the linearise kernel ahead of us even started -- only the
   // Gauss-Newton blocks and costs need pdl_wait(), so the dependent round trips for the state overlap the linearise kernel.

@@ -315,6 +315,10 @@ static void total_gradient(int T, int n, double a2, const double* X, const doubl
 static void bundle_dual(int K, const double* bq, double M[][GTO_BUNDLE_MAX + 1], double* theta) {
   theta[0] = 1.0;
   for (int k = 1; k <= K; ++k) theta[k] = 0.0;
+  /* the dual gradients of the pieces with weight all vanish at an interior optimum: the stopping tolerance is relative to the
+   * largest |b_k|, not to the gradients themselves (which would never pass it and always run into the iteration cap) */
+  double scale = 0.0;
+  for (int k = 1; k <= K; ++k) scale = fmax(scale, fabs(bq[k]));
   for (int iter = 0; iter < 24; ++iter) {
     double G[GTO_BUNDLE_MAX + 1];
     for (int k = 0; k <= K; ++k) {
@@ -326,7 +330,7 @@ static void bundle_dual(int K, const double* bq, double M[][GTO_BUNDLE_MAX + 1],
       if (G[k] > G[ib]) ib = k;
     for (int k = 0; k <= K; ++k)
       if (theta[k] > 0.0 && (jb < 0 || G[k] < G[jb])) jb = k;
-    if (jb < 0 || ib == jb || G[ib] - G[jb] <= 1e-12 * (fabs(G[ib]) + fabs(G[jb]) + 1e-300)) break;
+    if (jb < 0 || ib == jb || G[ib] - G[jb] <= 1e-13 * scale) break;
     const double curv = -(M[ib][ib] - 2.0 * M[ib][jb] + M[jb][jb]);
     double delta = curv > 0.0 ? (G[ib] - G[jb]) / curv : theta[jb];
     if (delta > theta[jb]) delta = theta[jb];

@@ -568,6 +568,8 @@ def _bundle_dual(bq: np.ndarray, M: np.ndarray) -> np.ndarray:
     K = len(bq) - 1
     theta = np.zeros(K + 1)
     theta[0] = 1.0
+    # the dual gradients of the pieces with weight all vanish at an interior optimum: the tolerance is relative to the largest |b_k|
+    scale = float(np.max(np.abs(bq[1:]))) if K > 0 else 0.0
     for _ in range(24):
         G = bq + M[:, 1:] @ theta[1:]
         ib = 0
@@ -578,7 +580,7 @@ def _bundle_dual(bq: np.ndarray, M: np.ndarray) -> np.ndarray:
         for k in range(K + 1):
             if theta[k] > 0.0 and (jb < 0 or G[k] < G[jb]):
                 jb = k
-        if jb < 0 or ib == jb or G[ib] - G[jb] <= 1e-12 * (abs(G[ib]) + abs(G[jb]) + 1e-300):
+        if jb < 0 or ib == jb or G[ib] - G[jb] <= 1e-13 * scale:
             break
         curv = -(M[ib, ib] - 2.0 * M[ib, jb] + M[jb, jb])
         delta = (G[ib] - G[jb]) / curv if curv > 0.0 else theta[jb]

@@ -17,7 +17,7 @@ FULL = {"C2": 256, "C3": 1024, "C4": 4096, "C5": 16384}
 CASES = (("C2", 256), ("C3", 64), ("C4", 64), ("C5", 64))
 TOL_Q = 1e-4  # rad, north-star tolerance
 # fraction of the both-converged problems that may end in a neighbouring kink minimiser (tests/test_gpu_parity_configs.py)
-OUT_FRAC = {"C2": 0.02, "C3": 0.15, "C4": 0.15, "C5": 0.02}
+OUT_FRAC = {"C2": 0.02, "C3": 0.20, "C4": 0.20, "C5": 0.02}
 
 
 def shard_workload(cfg, B):

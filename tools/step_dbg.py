@@ -15,12 +15,12 @@ ctx.set_robot(w.table)
 for slot, cf in w.fields.items():
     ctx.set_field(slot, cf.cost, cf.origin, cf.pitch)
 ctx.upload_batch(w.batch)
-for bundle in (3, 0):
+for bundle in (3, 1, 0):
     o = capi.default_options()
     o.bundle = bundle
     ctx.configure(step_dbg=0)
     ctx.solve_resident(o)
-    ctx.configure(step_dbg=int(os.environ.get("STEP_DBG_ITER", "30")))
+    ctx.configure(step_dbg=int(os.environ.get("STEP_DBG_ITER", "30")), step_dbg_cta=int(os.environ.get("STEP_DBG_CTA", "0")))
     ctx.solve_resident(o)
     p = ctx.profile()
     res = ctx.download_batch()
