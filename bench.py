@@ -52,7 +52,7 @@ def parse_args():
                     help="also time BASELINE configs[4] (C5, 16384 problems, strong sweep: 16384/N per rank) and configs[3] (C4, 4096 problems, "
                          "4096/N per rank) and report them under config.extra (the headline value stays the C2 line); 0 = skip")
     ap.add_argument("--fused", type=int, default=0, help="secondary mode: k_solve_fused (one persistent CTA per problem)")
-    ap.add_argument("--in-flight", type=int, default=4,
+    ap.add_argument("--in-flight", type=int, default=6,
                     help="batches in flight: the K steps are issued from this many host threads, each with its own context (own stream, own "
                          "resident copy of the batch), so that the latency-bound tail of one batch (a handful of problems still iterating) "
                          "overlaps the head of the next; 1 = one batch at a time (its latency is reported as solve_ms_per_step either way)")
@@ -449,7 +449,7 @@ def run_b200(args):
             wx.batch = W.slice_batch(wx.batch, lo, hi)
             used = set(int(v) for v in np.concatenate([wx.batch.field_all, wx.batch.field_obs]) if v >= 0)
             wx.fields = {s_: f for s_, f in wx.fields.items() if s_ in used}
-            xsteps = max(2, NF)  # as many steps as batches in flight, so that the extras overlap their tails like the headline
+            xsteps = min(4, max(2, NF))  # as many steps as batches in flight (at most 4 contexts: each holds a row buffer of up to 24 GiB)
             mx_ = measure(wx, xsteps, 1, e2e=False, events_pass=False)
             (t_mx, x_mx), (c_tot,) = over_ranks([mx_["dev_ms"], mx_["xch_ms"]], [float(mx_["conv"])])
             pk, _ = measured_peaks()
