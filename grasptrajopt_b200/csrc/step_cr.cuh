@@ -100,7 +100,7 @@ __device__ __forceinline__ void bundle_dual(int K, const double (&bq)[GTO_BUNDLE
   double scale = 0.0;
 #pragma unroll
   for (int k = 1; k <= KM; ++k) scale = fmax(scale, fabs(bq[k]));
-  for (int iter = 0; iter < 24; ++iter) {
+  for (int iter = 0; iter < 12; ++iter) {
     double G[KM + 1];
 #pragma unroll
     for (int k = 0; k <= KM; ++k) {

@@ -319,7 +319,7 @@ static void bundle_dual(int K, const double* bq, double M[][GTO_BUNDLE_MAX + 1],
    * largest |b_k|, not to the gradients themselves (which would never pass it and always run into the iteration cap) */
   double scale = 0.0;
   for (int k = 1; k <= K; ++k) scale = fmax(scale, fabs(bq[k]));
-  for (int iter = 0; iter < 24; ++iter) {
+  for (int iter = 0; iter < 12; ++iter) {
     double G[GTO_BUNDLE_MAX + 1];
     for (int k = 0; k <= K; ++k) {
       G[k] = bq[k];

@@ -570,7 +570,7 @@ def _bundle_dual(bq: np.ndarray, M: np.ndarray) -> np.ndarray:
     theta[0] = 1.0
     # the dual gradients of the pieces with weight all vanish at an interior optimum: the tolerance is relative to the largest |b_k|
     scale = float(np.max(np.abs(bq[1:]))) if K > 0 else 0.0
-    for _ in range(24):
+    for _ in range(12):
         G = bq + M[:, 1:] @ theta[1:]
         ib = 0
         for k in range(1, K + 1):
