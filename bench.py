@@ -6,8 +6,9 @@
 A "step" is one pass of the hot path over one batch of synthetic problems: all problems of the batch are solved
 to convergence (LM iterations of the fused linearise kernel + the block-tridiagonal step kernel).
 N=1 workload: BASELINE config C2 (Panda tabletop, 256 candidate grasps x 30 knots, 2000 surface points, 128^3 SDF).
-N>1 (launched by torchrun, one rank per GPU): every rank solves its own C2-sized shard (weak scaling; problems are
-independent, no collective inside the solve) and the converged trajectories are exchanged with ONE NCCL all-gather.
+N>1 (launched by torchrun, one rank per GPU): every rank solves a C2-sized batch (weak scaling with equal work per GPU: the
+same batch on every rank; --distinct-shards 1 for differently seeded ones; problems are independent, no collective inside the
+solve) and the converged trajectories are exchanged with ONE NCCL all-gather per batch.
 
 `value`  = converged trajectories / device time of the K solves, inputs already resident in HBM (CUDA events around the
            timed region, max over ranks).  The K steps are issued with `--in-flight` batches at a time (continuous batching at
@@ -52,6 +53,14 @@ def parse_args():
                     help="also time BASELINE configs[4] (C5, 16384 problems, strong sweep: 16384/N per rank) and configs[3] (C4, 4096 problems, "
                          "4096/N per rank) and report them under config.extra (the headline value stays the C2 line); 0 = skip")
     ap.add_argument("--fused", type=int, default=0, help="secondary mode: k_solve_fused (one persistent CTA per problem)")
+    ap.add_argument("--distinct-shards", type=int, default=0,
+                    help="N > 1: 1 = every rank generates its own C2-sized shard from its own seed (round-1 behaviour).  Default 0: every rank "
+                         "solves the SAME batch, the N = 1 workload -- weak scaling with exactly equal work per GPU.  The differently seeded "
+                         "shards differ in difficulty (on one GPU alone they run at 30.7 .. 40.0 k traj/s, tools/exp_rank_shards.py; rank 0's is "
+                         "the easiest), so with them the step time of an N-GPU run is that of the hardest shard and says nothing about scaling")
+    ap.add_argument("--shard-seed-of-rank", type=int, default=-1,
+                    help="diagnostic (1 GPU): solve the shard that this rank of a multi-GPU run generates (seed = config index + 1000 * rank), to "
+                         "separate the difficulty of the shards from the cost of running N ranks")
     ap.add_argument("--in-flight", type=int, default=6,
                     help="batches in flight: the K steps are issued from this many host threads, each with its own context (own stream, own "
                          "resident copy of the batch), so that the latency-bound tail of one batch (a handful of problems still iterating) "
@@ -243,8 +252,11 @@ def run_b200(args):
     dev = f"cuda:{local}"
     cfg = args.config.upper()
     idx = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[cfg]
-    # headline: weak scaling, every rank owns a full-size shard of the configuration generated from its own seed stream
-    w = W.make_workload(cfg, scale=args.scale, seed=idx + 1000 * rank if world > 1 else None)
+    # headline: weak scaling, every rank solves a full-size batch of the configuration (the same batch on every rank by default:
+    # equal work per GPU; --distinct-shards 1: a batch generated from the rank's own seed stream)
+    shard_rank = args.shard_seed_of_rank if (world == 1 and args.shard_seed_of_rank >= 0) else rank
+    distinct = (world > 1 and args.distinct_shards) or args.shard_seed_of_rank >= 0
+    w = W.make_workload(cfg, scale=args.scale, seed=idx + 1000 * shard_rank if distinct else None)
     NF = max(1, args.in_flight)
     ctxs = [capi.GtoContext(local) for _ in range(NF)]
     # more solving host threads on the box than cores (8 ranks x 4 in flight on 32 cores): sleep in the polls instead of spinning
@@ -482,6 +494,7 @@ def run_b200(args):
             "config": config_block(w, args, opts, world, converged=int(conv_tot), iterations_histogram=np.bincount(m["iters"], minlength=1).tolist(),
                                    status_counts_rank0=status_dict(m["status"]), wall_ms_per_step=wall_ms_mx / args.steps,
                                    batches_in_flight=m["in_flight"], host_blocking_sync=bool(blocking),
+                                   shards=("a differently seeded batch per rank" if distinct else "the same batch (the N = 1 workload) on every rank: equal work per GPU") if world > 1 else "one batch",
                                    solve_ms_per_step=solve_ms_mx / args.steps, solve_ms_note="mean latency of one batch solve (library events on its stream) with "
                                    f"{m['in_flight']} batches in flight; ms_per_step is the device time of the region / steps",
                                    xch_ms_per_step=xch_ms_mx / args.steps,
