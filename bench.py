@@ -222,8 +222,10 @@ def run_reference(args):
         "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": config_block(w, args, opts, 1, converged=int(np.sum(res["status"] == 0)), iterations_histogram=np.bincount(res["iters"], minlength=1).tolist(),
-                               status_counts_rank0=status_dict(res["status"]), wall_ms_per_step=1e3 * tot_t / steps, host_cores=ncpu,
-                               problems_per_step=int(len(idx))),
+                               status_counts_rank0=status_dict(res["status"]), wall_ms_per_step=1e3 * tot_t / steps,
+                               batches_in_flight=1, host_blocking_sync=False, shards="one batch", solve_ms_per_step=1e3 * tot_t / steps,
+                               solve_ms_note="wall clock of one batch on the host cores", xch_ms_per_step=0.0, exchange="none (rank 0 only)",
+                               host_cores=ncpu, problems_per_step=int(len(idx))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
