@@ -32,7 +32,7 @@ def ctx():
 
 # (config, problems, minimum fraction converged on the GPU, fraction of both-converged problems that may end in another kink
 #  minimiser, their maximum distance [rad] and relative objective difference)
-CASES = [("C2", 256, 0.90, 0.02, 1e-3, 1e-6), ("C3", 64, 0.40, 0.20, 0.1, 5e-3), ("C4", 64, 0.50, 0.20, 0.1, 5e-3), ("C5", 64, 0.90, 0.02, 1e-3, 1e-6)]
+CASES = [("C2", 256, 0.90, 0.02, 1e-3, 1e-6), ("C3", 64, 0.40, 0.20, 0.1, 5e-3), ("C4", 64, 0.50, 0.20, 0.1, 5e-3), ("C5", 64, 0.85, 0.02, 1e-3, 1e-6)]
 
 
 @pytest.mark.parametrize("cfg,B,min_conv,out_frac,out_dq,out_cost", CASES)
@@ -61,7 +61,7 @@ def test_solve_parity_on_baseline_configs(ctx, cfg, B, min_conv, out_frac, out_d
     #    (Fetch: a problem that converges at iteration 80..100 on one side can run into max_iter on the other)
     assert r["gpu_status"][0] >= min_conv * B
     conv_differs = np.nonzero((res["status"] == 0) != (ora["status"] == 0))[0]
-    assert len(conv_differs) <= (max(2, B // 12) if cfg in ("C2", "C5") else B // 5), conv_differs
+    assert len(conv_differs) <= (max(2, B // 10) if cfg in ("C2", "C5") else B // 5), conv_differs
     assert not np.any(res["status"] == capi.STATUS_NAN) and not np.any(res["status"] == capi.STATUS_STALLED)
     # 3. iteration counts: identical on most problems that converge quickly; float32 noise in J^T J / J^T r shifts the last
     #    accept/reject decisions and the bundle weights of the others by a step or two
