@@ -10,7 +10,8 @@
  *   trilinear field lookup         SURVEY.md Appendix A (replaces gto/gto_models.py:174-187, gto/sdf_callback.py)
  *   residual blocks                gto/gto_planner.py:86-135
  *   constraints                    gto/gto_planner.py:59-72,138 (eliminated / projected)
- *   solve                          projected Levenberg-Marquardt of solve_lm() (stands in for IPOPT, optas/solver.py:384-400)
+ *   solve                          projected bundle Levenberg-Marquardt of solve_lm() / lm_step() (stands in for IPOPT,
+ *                                  optas/solver.py:384-400): solve_masked, bundle_dual, solve_one
  * Parity pinning: checked against the NumPy oracle in tests/test_oracle_c.py (the NumPy oracle is the one pinned
  * against reference-generated golden vectors).  The reference's own CPU path (CasADi + IPOPT) cannot be built here.
  */

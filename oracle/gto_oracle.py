@@ -25,10 +25,12 @@ A9     gto/gto_planner.py:131                      ``linearize`` (obstacle rows)
 A10    gto/gto_planner.py:134-135                  ``velocity_terms``
 A11    gto/gto_planner.py:59-72,138 +              eliminated analytically (``free knots``),
        optas/builder.py:420-524                    bounds kept (``solve_lm`` projection)
-A13    optas/solver.py:335-400 (IPOPT)             ``solve_lm`` (projected Levenberg-
-                                                   Marquardt; same algorithm as the CUDA
-                                                   solver) and ``solve_scipy`` (SciPy TRF,
-                                                   independent cross-check)
+A13    optas/solver.py:335-400 (IPOPT)             ``solve_lm`` / ``lm_step`` (projected bundle
+                                                   Levenberg-Marquardt: cutting planes from
+                                                   rejected trial points for the kinks of the
+                                                   trilinear field; same algorithm as the CUDA
+                                                   solver and gto_oracle.c) and ``solve_scipy``
+                                                   (SciPy TRF, independent cross-check)
 A14    gto/utils.py:63-82, gto_planner.py:193-219  ``interpolate_seed``, ``plan_cost_nearest``
 A15    optas/solver.py:126-159                     ``unpack_solution``
 =====  ==========================================  ======================================
