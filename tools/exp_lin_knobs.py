@@ -10,8 +10,11 @@ from grasptrajopt_b200 import capi, workloads as W
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 w = W.make_workload(cfg, scale=float(sys.argv[2]) if len(sys.argv) > 2 else 1.0)
-for knobs in ({}, {"cull_nslot": 2}, {"cull_nslot": 3}, {"cull_nslot": 6}, {"cull_nslot": 8}, {"cons_warps": 4}, {"cons_warps": 6}, {"cons_warps": 4, "cull_nslot": 6},
-              {"slot_floats": 2048}, {"slot_floats": 8192}):
+SETS = {"a": ({}, {"cull_nslot": 2}, {"cull_nslot": 3}, {"cull_nslot": 6}, {"cull_nslot": 8}, {"cons_warps": 4}, {"cons_warps": 6}, {"cons_warps": 4, "cull_nslot": 6},
+              {"slot_floats": 2048}, {"slot_floats": 8192}),
+        "b": ({}, {"cons_warps": 4, "cull_nslot": 2, "slot_floats": 2048}, {"cons_warps": 4, "cull_nslot": 3, "slot_floats": 2048}, {"cons_warps": 5, "cull_nslot": 2, "slot_floats": 2048},
+              {"cons_warps": 6, "cull_nslot": 2, "slot_floats": 2048}, {"cons_warps": 4, "cull_nslot": 2, "slot_floats": 3072}, {"cons_warps": 3, "cull_nslot": 2, "slot_floats": 2048})}
+for knobs in SETS[sys.argv[3] if len(sys.argv) > 3 else "a"]:
     ctx = capi.GtoContext(0)
     try:
         ctx.configure(**knobs)
