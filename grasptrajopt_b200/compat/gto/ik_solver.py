@@ -34,9 +34,12 @@ class IKSolver:
 
     def setup_optimization(self):
         self.fk = self.robot.get_global_link_transform_function(link=self.link_ee)
+        options = capi.default_options(max_iter=50)  # reference: max_iter 50 (:75)
+        if not self.collision_avoidance:
+            options.bundle = 0  # goal rows only: a smooth problem, no field kinks for the cutting planes to resolve -> plain LM
         self.solver = B200Solver(self.robot, self.link_ee, self.link_gripper, T=3, dt=1.0, use_standoff=False, standoff_offset=-1,
                                  collision_avoidance=self.collision_avoidance, w_vel=0.0, device=self.device, obs_linear=True,
-                                 options=capi.default_options(max_iter=50))  # reference: max_iter 50 (:75)
+                                 options=options)
 
     def _errors(self, q, RT):
         tf = self.fk(q).toarray()

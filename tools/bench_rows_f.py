@@ -21,6 +21,7 @@ ik = capi.Batch(T=3, dt=1.0, qc=b.qc, q_seed=np.repeat(b.qc[:, None, :], 3, axis
 ctx = capi.GtoContext(0)
 ctx.set_robot(t)
 opts = capi.default_options(max_iter=50)
+opts.bundle = 0  # as gto.IKSolver without collision avoidance: goal rows only, a smooth problem (no field kinks)
 for _ in range(3):
     res = ctx.solve_batch(ik, opts)
 t0 = time.perf_counter()
@@ -34,7 +35,7 @@ try:
     import c_oracle as CO
     wk = W.Workload(w.name, t, {}, ik, w.RT, 0.0, "z", w.q_star)
     idx = np.arange(0, B, 8)
-    t0 = time.perf_counter(); ro = CO.solve_workload(wk, indices=idx, options=CO.default_options(max_iter=50)); dtc = time.perf_counter() - t0
+    t0 = time.perf_counter(); ro = CO.solve_workload(wk, indices=idx, options=CO.default_options(max_iter=50, bundle=0)); dtc = time.perf_counter() - t0
     dq = np.abs(ro["Q"][:, 2] - res["Q"][idx, 2]).max(axis=1)
     both = (ro["status"] == 0) & (res["status"][idx] == 0)
     out["ik_batch"]["cpu_port"] = {"ik_solves_per_s": len(idx) / dtc, "threads": int(ro["threads"]), "sample": int(len(idx)),
