@@ -3,8 +3,10 @@
 Layout:
   csrc/        CUDA kernels (sm_100a) + the C-ABI (``libgto_b200.so``; header ``include/gto_b200.h``)
   capi.py      ctypes binding of the C-ABI
-  batch.py     batched problem container + solver front-end
-  robot_table.py, urdf.py, meshio.py, spatial.py, scenes.py   host-side model/input preparation
+  workloads.py, scenes.py     synthetic BASELINE configurations (C1..C5), scenes and cost fields
+  robot_table.py, urdf.py, meshio.py, spatial.py, kinematics.py   host-side model/input preparation
+  distributed.py, goalset.py  sharding, NCCL all-gather of results, goal-set arg-min
+  run_reference.py            launcher that runs the reference's own scripts unchanged against compat/
   compat/      host-side mirror of the reference interface: top-level ``optas``, ``gto``, ``mesh_to_sdf``
 """
 import os
