@@ -23,6 +23,8 @@
 #include <math_constants.h>
 #include <string>
 #include <vector>
+#include <thread>
+#include <functional>
 #include <algorithm>
 
 #include "../../include/gto_b200.h"
@@ -834,19 +836,40 @@ extern "C" int gto_set_field(gto_ctx* ctx, int slot, const float* cost, const in
   {  // summed-volume table of the non-zero nodes: S[i][j][k] = #{cost != 0 in [0,i) x [0,j) x [0,k)} (culling test of k_linearize_cull)
     const size_t ex = (size_t)f.nx + 1, ey = (size_t)f.ny + 1, ez = (size_t)f.nz + 1, ns = ex * ey * ez;
     std::vector<unsigned> S(ns, 0u);
-    for (size_t i = 1; i < ex; ++i)
-      for (size_t j = 1; j < ey; ++j) {
-        const float* src = cost + ((i - 1) * f.ny + (j - 1)) * f.nz;
-        unsigned* row = S.data() + (i * ey + j) * ez;
-        const unsigned* up = S.data() + (i * ey + (j - 1)) * ez;             // S[i][j-1][.]
-        const unsigned* back = S.data() + ((i - 1) * ey + j) * ez;           // S[i-1][j][.]
-        const unsigned* diag = S.data() + ((i - 1) * ey + (j - 1)) * ez;     // S[i-1][j-1][.]
-        unsigned run = 0;  // non-zero nodes of this z-line so far
-        for (size_t k = 1; k < ez; ++k) {
-          run += (src[k - 1] != 0.0f) ? 1u : 0u;
-          row[k] = run + up[k] + back[k] - diag[k];
-        }
+    // two passes on the host cores (a 256^3 field has 17 M entries): (1) the 2-D prefix sums of every x-slab, slabs in parallel;
+    // (2) the running sum over the slabs, (y, z) rows in parallel.  Integer arithmetic: the same table as a single sweep.
+    const unsigned nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto parallel_for = [&](size_t n, const std::function<void(size_t, size_t)>& body) {
+      std::vector<std::thread> th;
+      const size_t chunk = (n + nth - 1) / nth;
+      for (unsigned w = 0; w < nth; ++w) {
+        const size_t lo = std::min(n, w * chunk), hi = std::min(n, lo + chunk);
+        if (lo < hi) th.emplace_back(body, lo, hi);
       }
+      for (auto& t : th) t.join();
+    };
+    unsigned* Sp = S.data();
+    parallel_for(ex - 1, [&](size_t lo, size_t hi) {
+      for (size_t i = lo + 1; i <= hi; ++i)
+        for (size_t j = 1; j < ey; ++j) {
+          const float* src = cost + ((i - 1) * f.ny + (j - 1)) * f.nz;
+          unsigned* row = Sp + (i * ey + j) * ez;
+          const unsigned* up = Sp + (i * ey + (j - 1)) * ez;  // this slab, row j-1
+          unsigned run = 0;                                   // non-zero nodes of this z-line so far
+          for (size_t k = 1; k < ez; ++k) {
+            run += (src[k - 1] != 0.0f) ? 1u : 0u;
+            row[k] = run + up[k];
+          }
+        }
+    });
+    parallel_for(ey - 1, [&](size_t lo, size_t hi) {
+      for (size_t i = 2; i < ex; ++i)
+        for (size_t j = lo + 1; j <= hi; ++j) {
+          unsigned* row = Sp + (i * ey + j) * ez;
+          const unsigned* back = Sp + ((i - 1) * ey + j) * ez;  // previous slab, same row
+          for (size_t k = 1; k < ez; ++k) row[k] += back[k];
+        }
+    });
     if (f.svt && f.svt_n != ns) { cudaFree(f.svt); f.svt = nullptr; }
     if (!f.svt) CK(cudaMalloc((void**)&f.svt, ns * sizeof(unsigned)));
     f.svt_n = ns;
